@@ -1,0 +1,159 @@
+"""ctypes binding of ``libdriftb200.so`` (see include/driftscan_b200.h).
+
+The library is built in-tree by ``driftscan_b200.build`` (nvcc, sm_100a).
+There is no CPU fallback: if the shared object is missing the import of this
+module fails loudly, and every compute entry point fails without a CUDA device.
+"""
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdriftb200.so")
+
+DSB_PREC_FP64 = 0
+DSB_PREC_FP32X3 = 1
+
+DSB_OUT_TARRAY_C128 = 0
+DSB_OUT_MMAJOR_C128 = 1
+DSB_OUT_MMAJOR_C64 = 2
+
+PRECISIONS = {"fp64": DSB_PREC_FP64, "fp32x3": DSB_PREC_FP32X3}
+
+
+class DsbUnit(ctypes.Structure):
+    _fields_ = [
+        ("uvec", ctypes.c_double * 3),
+        ("prefactor", ctypes.c_double),
+        ("beam_i", ctypes.c_int32),
+        ("beam_j", ctypes.c_int32),
+        ("lmax", ctypes.c_int32),
+        ("out0", ctypes.c_int32),
+        ("out1", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
+UNIT_DTYPE = np.dtype(
+    [
+        ("uvec", "f8", 3),
+        ("prefactor", "f8"),
+        ("beam_i", "i4"),
+        ("beam_j", "i4"),
+        ("lmax", "i4"),
+        ("out0", "i4"),
+        ("out1", "i4"),
+        ("reserved", "i4"),
+    ],
+    align=True,
+)
+assert UNIT_DTYPE.itemsize == ctypes.sizeof(DsbUnit)
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m driftscan_b200.build` "
+            "(the B200 path has no CPU fallback)"
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, u64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double
+    P = ctypes.POINTER
+    sig = {
+        "dsb_version": (i32, []),
+        "dsb_last_error": (ctypes.c_char_p, []),
+        "dsb_launch_count": (u64, []),
+        "dsb_plan_create": (i32, [i32, vp, P(vp)]),
+        "dsb_plan_destroy": (i32, [vp]),
+        "dsb_beam_upload": (i32, [vp, i32, vp, i32, i32, P(dbl), vp]),
+        "dsb_beam_slots": (i32, [vp, i32]),
+        "dsb_plan_build_tables": (i32, [vp, i32, i32, i32, i32, vp]),
+        "dsb_transfer_units": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, P(i64), vp, i32, vp]),
+        "dsb_mmajor_size": (i64, [i32, i32, i32, i32, i32, P(i64)]),
+        "dsb_set_workspace_limit": (i32, [ctypes.c_size_t]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+_ERRORS = {-1: ValueError, -2: RuntimeError, -3: MemoryError, -4: NotImplementedError, -5: ArithmeticError}
+
+
+def check(rc):
+    """Raise the Python exception matching a negative dsb_status."""
+    if rc != 0:
+        msg = lib.dsb_last_error().decode(errors="replace")
+        raise _ERRORS.get(rc, RuntimeError)(f"libdriftb200: {msg} (status {rc})")
+
+
+def launch_count():
+    return int(lib.dsb_launch_count())
+
+
+def mmajor_offsets(n0, n1, npol, lside, mmax):
+    off = (ctypes.c_int64 * (mmax + 2))()
+    tot = lib.dsb_mmajor_size(n0, n1, npol, lside, mmax, off)
+    return int(tot), np.array(off[:], dtype=np.int64)
+
+
+class Plan:
+    """Per-nside device plan (ring geometry, horizon mask, beams, Legendre tables)."""
+
+    def __init__(self, nside, horizon):
+        horizon = np.ascontiguousarray(np.asarray(horizon).astype(np.uint8))
+        if horizon.shape != (12 * nside * nside,):
+            raise ValueError("horizon map has the wrong number of pixels")
+        self.nside = nside
+        self._h = ctypes.c_void_p()
+        check(lib.dsb_plan_create(nside, horizon.ctypes.data_as(ctypes.c_void_p), ctypes.byref(self._h)))
+        self.omega = {}
+
+    def close(self):
+        if self._h:
+            lib.dsb_plan_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload_beam(self, slot, beam, stream=None):
+        beam = np.asarray(beam)
+        is_complex = np.iscomplexobj(beam)
+        if is_complex and np.all(beam.imag == 0):
+            beam, is_complex = beam.real, False
+        beam = np.ascontiguousarray(beam, dtype=np.complex128 if is_complex else np.float64)
+        ncomp = 1 if beam.ndim == 1 else beam.shape[1]
+        om = ctypes.c_double()
+        check(
+            lib.dsb_beam_upload(
+                self._h, slot, beam.ctypes.data_as(ctypes.c_void_p), ncomp, int(is_complex),
+                ctypes.byref(om), ctypes.c_void_p(stream or 0),
+            )
+        )
+        self.omega[slot] = om.value
+        return om.value
+
+    def build_tables(self, lmax, mmax, spin2, precision, stream=None):
+        check(lib.dsb_plan_build_tables(self._h, lmax, mmax, int(spin2), precision, ctypes.c_void_p(stream or 0)))
+
+    def transfer_units(self, units, npol_sky, polarised, mmax, precision, out_kind, dims, out_ptr,
+                       out_is_host, stream=None):
+        units = np.ascontiguousarray(units, dtype=UNIT_DTYPE)
+        d = (ctypes.c_int64 * len(dims))(*[int(x) for x in dims])
+        check(
+            lib.dsb_transfer_units(
+                self._h, units.ctypes.data_as(ctypes.c_void_p), len(units), npol_sky, int(polarised), mmax,
+                precision, out_kind, d, ctypes.c_void_p(out_ptr), int(out_is_host),
+                ctypes.c_void_p(stream or 0),
+            )
+        )

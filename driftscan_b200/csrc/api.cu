@@ -1,0 +1,267 @@
+// C-ABI orchestration of the transfer path: bucket of units -> ring spectra ->
+// Legendre contraction -> packed output.  Replaces the unit loop of
+// TransitTelescope.transfer_matrices (drift/core/telescope.py:818-828) and the
+// +-m packing of BeamTransfer._generate_mfiles (drift/core/beamtransfer.py:610-624).
+#include <algorithm>
+#include <numeric>
+
+#include "dsb_common.cuh"
+
+using namespace dsb;
+
+extern "C" int64_t dsb_mmajor_size(int n_out0, int n_out1, int npol, int lside, int mmax, int64_t *offsets) {
+  int64_t tot = 0;
+  for (int m = 0; m <= mmax; ++m) {
+    if (offsets) offsets[m] = tot;
+    const int nl = lside + 1 - m;
+    if (nl > 0) tot += (int64_t)n_out0 * 2 * n_out1 * npol * nl;
+  }
+  if (offsets) offsets[mmax + 1] = tot;
+  return tot;
+}
+
+namespace {
+
+struct Carve {
+  char *base;
+  size_t off = 0;
+  explicit Carve(void *b) : base((char *)b) {}
+  template <typename T>
+  T *take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T *p = base ? (T *)(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+}  // namespace
+
+extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, int nunits, int npol_sky,
+                                  int polarised, int mmax, int precision, int out_kind, const int64_t *dims,
+                                  void *out, int out_is_host, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSB_CHECK(plan && units_host && dims && out, DSB_ERR_INVALID, "dsb_transfer_units: NULL argument");
+  DSB_CHECK(nunits >= 0, DSB_ERR_INVALID, "dsb_transfer_units: negative unit count");
+  DSB_CHECK(npol_sky == 1 || npol_sky == 3 || npol_sky == 4, DSB_ERR_INVALID,
+            "dsb_transfer_units: npol_sky must be 1, 3 or 4 (got %d)", npol_sky);
+  DSB_CHECK(polarised || npol_sky == 1, DSB_ERR_INVALID,
+            "dsb_transfer_units: an unpolarised telescope has a single sky polarisation");
+  DSB_CHECK(precision == DSB_PREC_FP64 || precision == DSB_PREC_FP32X3, DSB_ERR_INVALID,
+            "dsb_transfer_units: unknown precision %d", precision);
+  DSB_CHECK(out_kind >= DSB_OUT_TARRAY_C128 && out_kind <= DSB_OUT_MMAJOR_C64, DSB_ERR_INVALID,
+            "dsb_transfer_units: unknown output kind %d", out_kind);
+  if (nunits == 0) return DSB_OK;
+
+  const bool tarray = out_kind == DSB_OUT_TARRAY_C128;
+  const int64_t d0 = dims[0];
+  const int64_t d1 = tarray ? 0 : dims[1];
+  const int npol_out = (int)(tarray ? dims[1] : dims[2]);
+  const int lside = (int)(tarray ? dims[2] : dims[3]);
+  const int mmax_out = tarray ? lside : (int)dims[4];
+  DSB_CHECK(npol_out >= npol_sky || !tarray, DSB_ERR_INVALID, "dsb_transfer_units: npol_out < npol_sky");
+  DSB_CHECK(tarray || npol_out == npol_sky, DSB_ERR_INVALID,
+            "dsb_transfer_units: m-major output stores exactly the computed polarisations");
+
+  // ---- validate units (mirrors the ValueError of telescope.py:784-788) and sort by lmax
+  int lmax_b = 0;
+  for (int i = 0; i < nunits; ++i) {
+    const dsb_unit &u = units_host[i];
+    DSB_CHECK(u.lmax >= 0 && u.lmax <= lside, DSB_ERR_INVALID,
+              "dsb_transfer_units: unit %d has lmax %d outside [0, lside=%d]", i, u.lmax, lside);
+    DSB_CHECK(u.beam_i >= 0 && u.beam_i < (int)plan->beams.size() && plan->beams[u.beam_i].valid &&
+                  u.beam_j >= 0 && u.beam_j < (int)plan->beams.size() && plan->beams[u.beam_j].valid,
+              DSB_ERR_INVALID, "dsb_transfer_units: unit %d references an empty beam slot", i);
+    DSB_CHECK(plan->beams[u.beam_i].ncomp == (polarised ? 2 : 1) &&
+                  plan->beams[u.beam_j].ncomp == (polarised ? 2 : 1),
+              DSB_ERR_INVALID, "dsb_transfer_units: unit %d beam component count mismatch", i);
+    DSB_CHECK(u.out0 >= 0 && u.out0 < d0 && (tarray || (u.out1 >= 0 && u.out1 < d1)), DSB_ERR_INVALID,
+              "dsb_transfer_units: unit %d output index out of range", i);
+    lmax_b = std::max(lmax_b, u.lmax);
+  }
+  std::vector<int> order(nunits);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(),
+                   [&](int a, int b) { return units_host[a].lmax > units_host[b].lmax; });
+
+  BucketLayout lay;
+  lay.npol_sky = npol_sky;
+  lay.polarised = polarised;
+  lay.nsp0 = npol_sky == 4 ? 2 : 1;
+  lay.has2 = npol_sky >= 3 ? 1 : 0;
+  lay.cpu0 = 4 * lay.nsp0;
+  lay.cpu2 = 8;
+  lay.mcap = std::min(std::min(mmax, mmax_out), lmax_b);
+  lay.lmax_b = lmax_b;
+  lay.Kp = plan->Kp;
+
+  const Tables *tab = find_tables(plan, lmax_b, lay.mcap, lay.has2, precision);
+  if (!tab) {
+    DSB_TRY(dsb_plan_build_tables(plan, lmax_b, lay.mcap, lay.has2, precision, stream_));
+    tab = find_tables(plan, lmax_b, lay.mcap, lay.has2, precision);
+    DSB_CHECK(tab != nullptr, DSB_ERR_CUDA, "dsb_transfer_units: table construction failed");
+  }
+  const Tables &t = *tab;
+
+  // ---- chunk size from the workspace budget
+  const bool f64 = precision == DSB_PREC_FP64;
+  const size_t nprob = 2 * ((size_t)lay.mcap + 1);
+  const size_t es = f64 ? 8 : 6, cs = f64 ? 8 : 4;
+  const size_t per_unit = nprob * lay.Kp * lay.cpu0 * es + (lay.has2 ? nprob * 2 * lay.Kp * 8 * es : 0) +
+                          nprob * t.NP * (lay.cpu0 + (lay.has2 ? 8 : 0)) * cs;
+  const size_t plane_out = (size_t)npol_out * (lside + 1) * (2 * lside + 1) * 16;
+  const size_t per_unit_tot = per_unit + ((tarray && out_is_host) ? plane_out : 0);
+  size_t budget = workspace_limit();
+  size_t free_b = 0, total_b = 0;
+  DSB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  budget = std::min(budget, plan->ws_bytes + free_b * 8 / 10);
+  const int gran = 128 / std::min(lay.cpu0, 8);  // units per 128-column tile of the narrower block
+  long chunk = (long)((budget - (8 << 20)) / (per_unit_tot + 4096));
+  if (chunk >= gran) chunk = chunk / gran * gran;
+  DSB_CHECK(chunk >= 1, DSB_ERR_NOMEM,
+            "dsb_transfer_units: one unit needs %zu bytes of workspace, budget is %zu", per_unit_tot, budget);
+  chunk = std::min<long>(chunk, nunits);
+  if (chunk < nunits && chunk > 4096) chunk = 4096;
+
+  // m-major host output is staged through a device copy of the whole array
+  std::vector<int64_t> moff(mmax_out + 2, 0);
+  void *out_dev = out;
+  size_t out_elem = out_kind == DSB_OUT_MMAJOR_C64 ? 8 : 16;
+  int64_t mm_total = 0;
+  if (!tarray) {
+    mm_total = dsb_mmajor_size((int)d0, (int)d1, npol_out, lside, mmax_out, moff.data());
+    if (out_is_host) {
+      DSB_CUDA(cudaMallocAsync(&out_dev, (size_t)mm_total * out_elem, stream));
+      DSB_CUDA(cudaMemcpyAsync(out_dev, out, (size_t)mm_total * out_elem, cudaMemcpyHostToDevice, stream));
+    }
+  }
+
+  int rc = DSB_OK;
+  for (long c0 = 0; c0 < nunits && rc == DSB_OK; c0 += chunk) {
+    const int nu = (int)std::min<long>(chunk, nunits - c0);
+    lay.nunits = nu;
+    lay.ncols0 = (int)round_up((int64_t)nu * lay.cpu0, 128);
+    lay.ncols2 = lay.has2 ? (int)round_up((int64_t)nu * 8, 128) : 0;
+
+    // work items
+    std::vector<WorkItem> items;
+    std::vector<UnitDev> ud(nu);
+    std::vector<int32_t> o0(nu), o1(nu);
+    for (int i = 0; i < nu; ++i) {
+      const dsb_unit &u = units_host[order[c0 + i]];
+      ud[i] = {u.uvec[0], u.uvec[1], u.uvec[2], u.prefactor, u.beam_i, u.beam_j, u.lmax,
+               std::min(u.lmax, lay.mcap)};
+      o0[i] = (tarray && out_is_host) ? i : u.out0;
+      o1[i] = u.out1;
+    }
+    for (int s = 0; s <= (lay.has2 ? 2 : 0); s += 2) {
+      const int cpu = s == 0 ? lay.cpu0 : 8;
+      const int upt = 128 / cpu;
+      for (int ct = 0; ct * upt < nu; ++ct) {
+        const int Lt = ud[ct * upt].lmax;  // units are sorted by descending lmax
+        for (int m = 0; m <= std::min(lay.mcap, Lt); ++m)
+          for (int p = 0; p < 2; ++p) {
+            const int nr = nrows_mp(Lt, m, p);
+            if (nr > 0) items.push_back({2 * m + p, ct, nr, s});
+          }
+      }
+    }
+
+    // carve the workspace
+    size_t need;
+    {
+      Carve cv(nullptr);
+      cv.take<char>(nprob * lay.Kp * lay.ncols0 * es);
+      cv.take<char>(lay.has2 ? nprob * 2 * lay.Kp * lay.ncols2 * es : 0);
+      cv.take<char>(nprob * lay.ncols0 * t.NP * cs);
+      cv.take<char>(lay.has2 ? nprob * lay.ncols2 * t.NP * cs : 0);
+      cv.take<UnitDev>(nu);
+      cv.take<int32_t>(nu);
+      cv.take<int32_t>(nu);
+      cv.take<WorkItem>(items.size());
+      cv.take<int64_t>(moff.size());
+      if (tarray && out_is_host) cv.take<char>((size_t)nu * plane_out);
+      need = cv.off + 256;
+    }
+    if ((rc = ensure_workspace(plan, need)) != DSB_OK) break;
+    Carve cv(plan->ws);
+    const size_t f0_bytes = nprob * lay.Kp * lay.ncols0 * es;
+    const size_t f2_bytes = lay.has2 ? nprob * 2 * lay.Kp * lay.ncols2 * es : 0;
+    char *F0 = cv.take<char>(f0_bytes);
+    char *F2 = cv.take<char>(f2_bytes);
+    char *C0 = cv.take<char>(nprob * lay.ncols0 * t.NP * cs);
+    char *C2 = cv.take<char>(lay.has2 ? nprob * lay.ncols2 * t.NP * cs : 0);
+    UnitDev *ud_dev = cv.take<UnitDev>(nu);
+    int32_t *o0_dev = cv.take<int32_t>(nu);
+    int32_t *o1_dev = cv.take<int32_t>(nu);
+    WorkItem *items_dev = cv.take<WorkItem>(items.size());
+    int64_t *moff_dev = cv.take<int64_t>(moff.size());
+    char *stage = (tarray && out_is_host) ? cv.take<char>((size_t)nu * plane_out) : nullptr;
+
+    // Rows of the operand that no ring writes (padding of the fold-ring count, columns of
+    // the last partial tile) must be finite: clear whenever the layout leaves such holes.
+    const bool holes = plan->Kp != plan->nfold || lay.ncols0 != nu * lay.cpu0 ||
+                       (lay.has2 && lay.ncols2 != nu * 8);
+    if (holes) {
+      DSB_CUDA(cudaMemsetAsync(F0, 0, f0_bytes, stream));
+      if (f2_bytes) DSB_CUDA(cudaMemsetAsync(F2, 0, f2_bytes, stream));
+    }
+    DSB_CUDA(cudaMemcpyAsync(ud_dev, ud.data(), nu * sizeof(UnitDev), cudaMemcpyHostToDevice, stream));
+    DSB_CUDA(cudaMemcpyAsync(o0_dev, o0.data(), nu * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    DSB_CUDA(cudaMemcpyAsync(o1_dev, o1.data(), nu * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    DSB_CUDA(cudaMemcpyAsync(items_dev, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice,
+                             stream));
+    DSB_CUDA(cudaMemcpyAsync(moff_dev, moff.data(), moff.size() * sizeof(int64_t), cudaMemcpyHostToDevice,
+                             stream));
+
+    if ((rc = launch_ringfft(plan, lay, ud_dev, precision, F0, F2, stream)) != DSB_OK) break;
+    if (f64)
+      rc = launch_legendre_f64(plan, t, lay, items, items_dev, (const double *)F0, (const double *)F2,
+                               (double *)C0, (double *)C2, stream);
+    else
+      rc = launch_legendre_tc(plan, t, lay, items, items_dev, (const __nv_bfloat16 *)F0,
+                              (const __nv_bfloat16 *)F2, (float *)C0, (float *)C2, stream);
+    if (rc != DSB_OK) break;
+
+    PackParams pp;
+    pp.out_kind = out_kind;
+    pp.nunits = nu;
+    pp.npol_sky = npol_sky;
+    pp.nsp0 = lay.nsp0;
+    pp.has2 = lay.has2;
+    pp.cpu0 = lay.cpu0;
+    pp.cpu2 = 8;
+    pp.ncols0 = lay.ncols0;
+    pp.ncols2 = lay.ncols2;
+    pp.NP = t.NP;
+    pp.mcap = lay.mcap;
+    pp.lside = lside;
+    pp.d0 = d0;
+    pp.d1 = d1;
+    pp.npol_out = npol_out;
+    pp.mmax_out = mmax_out;
+    void *pack_out = (tarray && out_is_host) ? (void *)stage : out_dev;
+    if ((rc = launch_pack(pp, ud_dev, o0_dev, o1_dev, moff_dev, C0, C2, f64 ? 1 : 0, pack_out, stream)) !=
+        DSB_OK)
+      break;
+    if (tarray && out_is_host) {
+      for (int i = 0; i < nu; ++i) {
+        const dsb_unit &u = units_host[order[c0 + i]];
+        DSB_CUDA(cudaMemcpyAsync((char *)out + (size_t)u.out0 * plane_out, stage + (size_t)i * plane_out,
+                                 plane_out, cudaMemcpyDeviceToHost, stream));
+      }
+    }
+    // host-side vectors (ud, items, ...) are consumed by async copies from pageable memory,
+    // which the runtime stages synchronously; chunk buffers are reused, so drain the stream.
+    DSB_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  if (!tarray && out_is_host) {
+    if (rc == DSB_OK)
+      DSB_CUDA(cudaMemcpyAsync(out, out_dev, (size_t)mm_total * out_elem, cudaMemcpyDeviceToHost, stream));
+    DSB_CUDA(cudaStreamSynchronize(stream));
+    DSB_CUDA(cudaFreeAsync(out_dev, stream));
+  }
+  if (rc == DSB_OK && out_is_host) DSB_CUDA(cudaStreamSynchronize(stream));
+  return rc;
+}

@@ -1,0 +1,229 @@
+// Shared declarations of the driftscan_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/driftscan_b200.h"
+
+namespace dsb {
+
+// ---- error handling --------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern thread_local std::string g_last_error;
+void count_launch(int n = 1);
+
+#define DSB_CUDA(call)                                                                \
+  do {                                                                                \
+    cudaError_t _e = (call);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      dsb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,               \
+                     cudaGetErrorString(_e));                                         \
+      return DSB_ERR_CUDA;                                                            \
+    }                                                                                 \
+  } while (0)
+
+#define DSB_CHECK(cond, code, ...)                                                    \
+  do {                                                                                \
+    if (!(cond)) {                                                                    \
+      dsb::set_error(__VA_ARGS__);                                                    \
+      return (code);                                                                  \
+    }                                                                                 \
+  } while (0)
+
+#define DSB_LAUNCH_CHECK()                                                            \
+  do {                                                                                \
+    dsb::count_launch();                                                              \
+    cudaError_t _e = cudaGetLastError();                                              \
+    if (_e != cudaSuccess) {                                                          \
+      dsb::set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__,           \
+                     cudaGetErrorString(_e));                                         \
+      return DSB_ERR_CUDA;                                                            \
+    }                                                                                 \
+  } while (0)
+
+#define DSB_TRY(expr)                                                                 \
+  do {                                                                                \
+    int _s = (expr);                                                                  \
+    if (_s != DSB_OK) return _s;                                                      \
+  } while (0)
+
+// ---- small device helpers ----------------------------------------------------
+template <typename T>
+struct cplx {
+  T x, y;
+};
+template <typename T>
+__host__ __device__ __forceinline__ cplx<T> cmul(cplx<T> a, cplx<T> b) {
+  return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+template <typename T>
+__host__ __device__ __forceinline__ cplx<T> cconj(cplx<T> a) {
+  return {a.x, -a.y};
+}
+template <typename T>
+__host__ __device__ __forceinline__ cplx<T> cadd(cplx<T> a, cplx<T> b) {
+  return {a.x + b.x, a.y + b.y};
+}
+template <typename T>
+__host__ __device__ __forceinline__ cplx<T> csub(cplx<T> a, cplx<T> b) {
+  return {a.x - b.x, a.y - b.y};
+}
+
+static inline int ilog2_ceil(int n) {
+  int l = 0;
+  while ((1 << l) < n) ++l;
+  return l;
+}
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ---- per-nside plan ------------------------------------------------------------
+// Fold ring k = 0 .. 2*nside-1 pairs northern ring i = k+1 with its southern mirror
+// 4*nside - i; k = 2*nside-1 is the equator (no mirror).
+struct RingDesc {
+  int32_t nphi;       // pixels in the ring
+  int32_t startN;     // first pixel of the northern ring
+  int32_t startS;     // first pixel of the southern ring, -1 for the equator
+  int32_t trig_off;   // offset into the (cos phi, sin phi) table
+  int32_t log2n;      // log2 of the FFT length actually run (nphi if power of two, else Bluestein)
+  int32_t bluestein;  // 1 if nphi is not a power of two
+  int32_t chirp_off;  // offset into chirp tables (Bluestein only)
+  int32_t dhat_off;   // offset into the transformed-chirp table (Bluestein only)
+  int32_t shifted;    // 1 if phi0 = pi/nphi (half-pixel shift), 0 if phi0 = 0
+  int32_t pad;
+  double cth, sth;    // cos / sin of the northern colatitude
+  double ch2, sh2;    // cos / sin of half the northern colatitude
+  double quad;        // quadrature weight 4 pi / npix (x ring weight)
+};
+
+struct BeamSlot {
+  double *d64 = nullptr;  // [npix][ncomp] fp64
+  float *d32 = nullptr;   // [npix][ncomp] fp32
+  int ncomp = 0;
+  double omega = 0.0;
+  bool valid = false;
+};
+
+// Legendre tables of one (lmax, mmax, spin2, precision) request.
+// Problem index prob = 2*m + p covers rows l = m + p + 2*n, n = 0 .. nrows(m,p)-1.
+// spin-0 table: [prob][NP rows][K0 = Kp] ; spin-2 table: [prob][NP rows][2*Kp] = [-W | -X].
+struct Tables {
+  int lmax = -1, mmax = -1, spin2 = 0, precision = -1;
+  int NP = 0;        // padded row pitch (max rows per problem, multiple of 16)
+  int Kp = 0;        // padded fold-ring count (multiple of 32)
+  // fp64
+  double *t0_f64 = nullptr, *t2_f64 = nullptr;
+  // bf16 x3 planes
+  __nv_bfloat16 *t0_bf = nullptr, *t2_bf = nullptr;  // [3][nprob][NP][K]
+  size_t plane0 = 0, plane2 = 0;                     // elements per plane
+};
+
+}  // namespace dsb
+
+struct dsb_plan {
+  int device = 0;
+  int nside = 0, npix = 0, nfold = 0, Kp = 0;
+  std::vector<dsb::RingDesc> rings_h;
+  dsb::RingDesc *rings = nullptr;
+  uint8_t *horizon = nullptr;
+  double2 *trig = nullptr;       // (cos phi_j, sin phi_j) per distinct ring pattern
+  int tw_log2 = 0;               // twiddle table size = 2^tw_log2
+  double2 *tw64 = nullptr;       // e^{+2 pi i j / Ntw}, j < Ntw/2
+  float2 *tw32 = nullptr;
+  double2 *chirp64 = nullptr;    // c_j = e^{+i pi j^2 / n} per Bluestein ring
+  float2 *chirp32 = nullptr;
+  double2 *dhat64 = nullptr;     // FFT(d wrapped)/Nb in DIF (bit-reversed) order
+  float2 *dhat32 = nullptr;
+  std::vector<dsb::BeamSlot> beams;
+  std::vector<dsb::Tables> tables;
+  // workspace (grown on demand, capped by dsb_set_workspace_limit)
+  void *ws = nullptr;
+  size_t ws_bytes = 0;
+  dsb::RingDesc *dummy = nullptr;
+};
+
+namespace dsb {
+
+// plan.cu
+int ensure_workspace(dsb_plan *plan, size_t bytes);
+size_t workspace_limit();
+
+// tables.cu
+int build_tables(dsb_plan *plan, Tables &t, cudaStream_t stream);
+const Tables *find_tables(const dsb_plan *plan, int lmax, int mmax, int spin2, int precision);
+__host__ __device__ inline int nrows_mp(int lmax, int m, int p) {
+  // rows l = m + p + 2n <= lmax
+  int span = lmax - m - p;
+  return span < 0 ? 0 : span / 2 + 1;
+}
+
+// Column layout of the ring spectra / GEMM operands.
+// spin-0 block: cols per unit = 4 * nsp0 :  [pol0 slot][+-][re,im]
+// spin-2 block: cols per unit = 8        :  [E,B][+-][re,im]
+struct BucketLayout {
+  int nunits = 0;
+  int npol_sky = 0;     // 1, 3 or 4
+  int polarised = 0;
+  int nsp0 = 0;         // spin-0 pols computed: 1 (I) or 2 (I,V)
+  int has2 = 0;         // spin-2 block present
+  int cpu0 = 0, cpu2 = 0;
+  int ncols0 = 0, ncols2 = 0;  // padded to a multiple of 128
+  int mcap = 0;         // largest m computed
+  int lmax_b = 0;       // largest unit lmax in the bucket
+  int Kp = 0;
+};
+
+struct UnitDev {
+  double ax, ay, az;  // uvec
+  double pref;
+  int32_t beam_i, beam_j;
+  int32_t lmax;
+  int32_t mmax;  // min(lmax, mcap)
+};
+
+// ringfft.cu -- fused fringe x beam -> ring FFT -> north/south fold -> spectra
+// F planes: spin-0 [nprob][Kp][ncols0], spin-2 [nprob][2*Kp][ncols2]; element type double
+// (precision fp64, 1 plane) or bf16 (3 planes, plane stride = nprob*K*ncols).
+int launch_ringfft(dsb_plan *plan, const BucketLayout &lay, const UnitDev *units_dev, int precision,
+                   void *F0, void *F2, cudaStream_t stream);
+
+// legendre_f64.cu / legendre_tc.cu -- grouped contraction
+//   C_s[prob][col][n] = sum_k F_s[prob][k][col] * T_s[prob][n][k]
+// C row pitch = t.NP, fp64 (precision 0) or fp32 (precision 1).
+struct WorkItem {
+  int32_t prob;     // 2*m + p
+  int32_t coltile;  // 128-column tile
+  int32_t nrows;    // valid rows (<= NP)
+  int32_t spin;     // 0 or 2
+};
+int launch_legendre_f64(dsb_plan *plan, const Tables &t, const BucketLayout &lay,
+                        const std::vector<WorkItem> &items, const WorkItem *items_dev, const double *F0,
+                        const double *F2, double *C0, double *C2, cudaStream_t stream);
+int launch_legendre_tc(dsb_plan *plan, const Tables &t, const BucketLayout &lay,
+                       const std::vector<WorkItem> &items, const WorkItem *items_dev,
+                       const __nv_bfloat16 *F0, const __nv_bfloat16 *F2, float *C0, float *C2,
+                       cudaStream_t stream);
+
+// pack.cu
+struct PackParams {
+  int out_kind;
+  int nunits;
+  int npol_sky, nsp0, has2;
+  int cpu0, cpu2, ncols0, ncols2;
+  int NP;
+  int mcap;
+  int lside;          // output lside (telescope lmax)
+  int64_t d0, d1;     // n_out0, n_out1
+  int npol_out;
+  int mmax_out;       // m-major: number of m blocks - 1
+};
+int launch_pack(const PackParams &pp, const UnitDev *units_dev, const int32_t *out0_dev,
+                const int32_t *out1_dev, const int64_t *moff_dev, const void *C0, const void *C2,
+                int c_is_f64, void *out, cudaStream_t stream);
+
+}  // namespace dsb

@@ -1,0 +1,128 @@
+// Stage 3: pack the contraction output into the reference's layouts.
+//   - dense  [unit][pol][l][m column]  (TransitTelescope.transfer_matrices,
+//     drift/core/telescope.py:809-828, negative m in the wrapped columns), or
+//   - m-major compact beam_m blocks [m][freq][+-][baseline][pol][l-m]
+//     (drift/core/beamtransfer.py:567, 620-624, 663).
+// The kernel interleaves the two l-parity problems, re/im columns, applies the
+// per-unit lmax truncation (telescope.py:792-802 -> zeros above the unit's lmax) and
+// the (-1)^m conj relation between the +-m slots (beamtransfer.py:622).
+#include "dsb_common.cuh"
+
+namespace dsb {
+
+template <typename CT>
+__device__ __forceinline__ void fetch(const PackParams &pp, const UnitDev &ud, int u, int X, int pm, int l,
+                                      int m, const CT *__restrict__ C0, const CT *__restrict__ C2, double &re,
+                                      double &im) {
+  re = 0.0;
+  im = 0.0;
+  if (X >= pp.npol_sky || l > ud.lmax || m > ud.mmax || l < m) return;
+  const int p = (l - m) & 1, n = (l - m) >> 1;
+  const size_t prob = 2 * (size_t)m + p;
+  if (X == 0 || X == 3) {
+    const size_t col = (size_t)u * pp.cpu0 + (X == 0 ? 0 : 4) + pm * 2;
+    const size_t base = (prob * pp.ncols0 + col) * pp.NP + n;
+    re = (double)C0[base];
+    im = (double)C0[base + pp.NP];
+  } else {
+    const size_t col = (size_t)u * 8 + (X == 1 ? 0 : 4) + pm * 2;
+    const size_t base = (prob * pp.ncols2 + col) * pp.NP + n;
+    re = (double)C2[base];
+    im = (double)C2[base + pp.NP];
+  }
+}
+
+template <typename CT>
+__global__ void pack_tarray_kernel(const PackParams pp, const UnitDev *__restrict__ units,
+                                   const int32_t *__restrict__ out0, const CT *__restrict__ C0,
+                                   const CT *__restrict__ C2, double2 *__restrict__ out) {
+  const int u = blockIdx.y / pp.npol_out, X = blockIdx.y % pp.npol_out;
+  const UnitDev ud = units[u];
+  const int ncol = 2 * pp.lside + 1;
+  const size_t plane = (size_t)(pp.lside + 1) * ncol;
+  double2 *o = out + ((size_t)out0[u] * pp.npol_out + X) * plane;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < plane;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int l = (int)(idx / ncol), mc = (int)(idx % ncol);
+    double re, im;
+    if (mc <= pp.lside) {
+      fetch<CT>(pp, ud, u, X, 0, l, mc, C0, C2, re, im);
+    } else {
+      const int mm = ncol - mc;
+      fetch<CT>(pp, ud, u, X, 1, l, mm, C0, C2, re, im);
+      // B_{l,-m} = (-1)^m conj(beam_m[-])
+      const double sg = (mm & 1) ? -1.0 : 1.0;
+      re = sg * re;
+      im = -sg * im;
+    }
+    o[idx] = make_double2(re, im);
+  }
+}
+
+template <typename CT, typename OT>
+__global__ void pack_mmajor_kernel(const PackParams pp, const UnitDev *__restrict__ units,
+                                   const int32_t *__restrict__ out0, const int32_t *__restrict__ out1,
+                                   const int64_t *__restrict__ moff, const CT *__restrict__ C0,
+                                   const CT *__restrict__ C2, OT *__restrict__ out) {
+  const int m = blockIdx.y;
+  const int nl = pp.lside + 1 - m;
+  if (nl <= 0) return;
+  const size_t per_unit = (size_t)2 * pp.npol_out * nl;
+  const size_t total = per_unit * pp.nunits;
+  OT *o = out + moff[m];
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int u = (int)(idx / per_unit);
+    size_t r = idx % per_unit;
+    const int pm = (int)(r / ((size_t)pp.npol_out * nl));
+    r %= (size_t)pp.npol_out * nl;
+    const int X = (int)(r / nl);
+    const int dl = (int)(r % nl);
+    const UnitDev ud = units[u];
+    double re, im;
+    fetch<CT>(pp, ud, u, X, pm, m + dl, m, C0, C2, re, im);
+    if (m == 0 && pm == 1) {  // the negative-m slot of m = 0 is left zero (beamtransfer.py:624)
+      re = 0.0;
+      im = 0.0;
+    }
+    const size_t oi = ((((size_t)out0[u] * 2 + pm) * pp.d1 + out1[u]) * pp.npol_out + X) * nl + dl;
+    o[oi].x = re;
+    o[oi].y = im;
+  }
+}
+
+int launch_pack(const PackParams &pp, const UnitDev *units_dev, const int32_t *out0_dev,
+                const int32_t *out1_dev, const int64_t *moff_dev, const void *C0, const void *C2,
+                int c_is_f64, void *out, cudaStream_t stream) {
+  if (pp.nunits == 0) return DSB_OK;
+  if (pp.out_kind == DSB_OUT_TARRAY_C128) {
+    const size_t plane = (size_t)(pp.lside + 1) * (2 * pp.lside + 1);
+    dim3 grid((unsigned)std::min<size_t>((plane + 255) / 256, 1024), pp.nunits * pp.npol_out);
+    if (c_is_f64)
+      pack_tarray_kernel<double><<<grid, 256, 0, stream>>>(pp, units_dev, out0_dev, (const double *)C0,
+                                                           (const double *)C2, (double2 *)out);
+    else
+      pack_tarray_kernel<float><<<grid, 256, 0, stream>>>(pp, units_dev, out0_dev, (const float *)C0,
+                                                          (const float *)C2, (double2 *)out);
+  } else {
+    const size_t per_m = (size_t)2 * pp.npol_out * (pp.lside + 1) * pp.nunits;
+    dim3 grid((unsigned)std::min<size_t>((per_m + 255) / 256, 2048), pp.mmax_out + 1);
+    const bool c128 = pp.out_kind == DSB_OUT_MMAJOR_C128;
+    if (c_is_f64 && c128)
+      pack_mmajor_kernel<double, double2><<<grid, 256, 0, stream>>>(
+          pp, units_dev, out0_dev, out1_dev, moff_dev, (const double *)C0, (const double *)C2, (double2 *)out);
+    else if (c_is_f64)
+      pack_mmajor_kernel<double, float2><<<grid, 256, 0, stream>>>(
+          pp, units_dev, out0_dev, out1_dev, moff_dev, (const double *)C0, (const double *)C2, (float2 *)out);
+    else if (c128)
+      pack_mmajor_kernel<float, double2><<<grid, 256, 0, stream>>>(
+          pp, units_dev, out0_dev, out1_dev, moff_dev, (const float *)C0, (const float *)C2, (double2 *)out);
+    else
+      pack_mmajor_kernel<float, float2><<<grid, 256, 0, stream>>>(
+          pp, units_dev, out0_dev, out1_dev, moff_dev, (const float *)C0, (const float *)C2, (float2 *)out);
+  }
+  DSB_LAUNCH_CHECK();
+  return DSB_OK;
+}
+
+}  // namespace dsb

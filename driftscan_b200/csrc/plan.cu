@@ -1,0 +1,326 @@
+// Plan = per-nside HEALPix ring geometry, FFT twiddles, Bluestein chirps, horizon
+// mask and primary-beam slots.  Replaces TransitTelescope._init_trans
+// (drift/core/telescope.py:943-952) and the beam cache (:956-974).
+#include <cmath>
+#include <cstdarg>
+#include <atomic>
+
+#include "dsb_common.cuh"
+#include "fft.cuh"
+
+namespace dsb {
+
+thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+static size_t g_ws_limit = (size_t)24 << 30;
+
+void set_error(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+void count_launch(int n) { g_launches += n; }
+size_t workspace_limit() { return g_ws_limit; }
+
+int ensure_workspace(dsb_plan *plan, size_t bytes) {
+  if (bytes <= plan->ws_bytes) return DSB_OK;
+  DSB_CHECK(bytes <= g_ws_limit, DSB_ERR_NOMEM, "workspace request %zu exceeds limit %zu", bytes,
+            g_ws_limit);
+  if (plan->ws) {
+    DSB_CUDA(cudaDeviceSynchronize());
+    DSB_CUDA(cudaFree(plan->ws));
+    plan->ws = nullptr;
+    plan->ws_bytes = 0;
+  }
+  DSB_CUDA(cudaMalloc(&plan->ws, bytes));
+  DSB_CUDA(cudaMemset(plan->ws, 0, bytes));
+  plan->ws_bytes = bytes;
+  return DSB_OK;
+}
+
+// Transformed Bluestein chirp, one block per non-power-of-two ring length.
+//   d_t = exp(-i pi t^2 / n);  D[t] = d_t (t < n), D[Nb - t] = d_t (0 < t < n), else 0
+//   dhat = DFT_-(D) / Nb, left in fft_dif (bit-reversed) order.
+__global__ void bluestein_prepare_kernel(const RingDesc *rings, int nrings_cap, const double2 *chirp,
+                                         double2 *dhat, const double2 *tw, int tw_log2) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx<double> *buf = reinterpret_cast<cplx<double> *>(smem_raw);
+  const RingDesc rd = rings[blockIdx.x];
+  if (!rd.bluestein) return;
+  const int n = rd.nphi;
+  const int Nb = 1 << rd.log2n;
+  for (int t = threadIdx.x; t < Nb; t += blockDim.x) buf[t] = {0.0, 0.0};
+  __syncthreads();
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    double2 c = chirp[rd.chirp_off + t];
+    cplx<double> d = {c.x, -c.y};
+    buf[t] = d;
+    if (t > 0) buf[Nb - t] = d;
+  }
+  __syncthreads();
+  fft_dif<double, -1>(buf, rd.log2n, 1, Nb, tw, tw_log2);
+  const double inv = 1.0 / Nb;
+  for (int t = threadIdx.x; t < Nb; t += blockDim.x)
+    dhat[rd.dhat_off + t] = make_double2(buf[t].x * inv, buf[t].y * inv);
+}
+
+__global__ void d2f2_kernel(const double2 *in, float2 *out, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_float2((float)in[i].x, (float)in[i].y);
+}
+
+// Beam solid angle: omega = (4 pi / npix) sum_p H_p sum_c |E_c,p|^2
+// (_fast_tools.pyx:124-137; telescope.py:1165-1169), deterministic two-pass reduction.
+__global__ void beam_power_partial_kernel(const double *beam, const uint8_t *horizon, int npix, int ncomp,
+                                          float *beam32, double *partial) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+    double t = 0.0;
+    for (int c = 0; c < ncomp; ++c) {
+      double v = beam[(size_t)p * ncomp + c];
+      beam32[(size_t)p * ncomp + c] = (float)v;
+      t += v * v;
+    }
+    acc += horizon[p] ? t : 0.0;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+}  // namespace dsb
+
+using namespace dsb;
+
+extern "C" int dsb_version(void) { return 100; }
+extern "C" const char *dsb_last_error(void) { return g_last_error.c_str(); }
+extern "C" uint64_t dsb_launch_count(void) { return g_launches.load(); }
+extern "C" int dsb_set_workspace_limit(size_t bytes) {
+  g_ws_limit = bytes;
+  return DSB_OK;
+}
+
+extern "C" int dsb_plan_create(int nside, const uint8_t *horizon_host, dsb_plan **out) {
+  DSB_CHECK(out != nullptr, DSB_ERR_INVALID, "dsb_plan_create: out is NULL");
+  DSB_CHECK(nside >= 1 && nside <= 1024 && (nside & (nside - 1)) == 0, DSB_ERR_INVALID,
+            "dsb_plan_create: nside %d is not a power of two in [1, 1024]", nside);
+  DSB_CHECK(horizon_host != nullptr, DSB_ERR_INVALID, "dsb_plan_create: horizon is NULL");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("dsb_plan_create: no CUDA device available (there is no CPU fallback)");
+    return DSB_ERR_CUDA;
+  }
+  dsb_plan *plan = new dsb_plan();
+  DSB_CUDA(cudaGetDevice(&plan->device));
+  plan->nside = nside;
+  plan->npix = 12 * nside * nside;
+  plan->nfold = 2 * nside;
+  plan->Kp = (int)round_up(plan->nfold, 32);
+
+  const int nfold = plan->nfold;
+  const int ncapring = nside - 1;  // fold rings 0 .. nside-2 are polar-cap rings
+  const long captotal = 2L * (nside - 1) * nside;
+  plan->tw_log2 = ilog2_ceil(8 * nside < 8 ? 8 : 8 * nside);
+
+  // ---- ring descriptors
+  plan->rings_h.resize(nfold);
+  int chirp_total = 0, dhat_total = 0;
+  const double quad = 4.0 * M_PI / plan->npix;
+  for (int k = 0; k < nfold; ++k) {
+    RingDesc &rd = plan->rings_h[k];
+    const long i = k + 1;
+    double z;
+    if (k < ncapring) {
+      rd.nphi = (int)(4 * i);
+      rd.startN = (int)(2 * i * (i - 1));
+      rd.startS = (int)(plan->npix - 2 * i * (i + 1));
+      z = 1.0 - (double)(i * i) / (3.0 * nside * nside);
+      rd.shifted = 1;
+      rd.trig_off = (int)(2 * (i - 1) * i);
+    } else {
+      rd.nphi = 4 * nside;
+      rd.startN = (int)(2L * nside * (nside - 1) + (i - nside) * 4L * nside);
+      const long imirror = 4L * nside - i;
+      rd.startS = (k == nfold - 1) ? -1
+                                   : (int)(2L * nside * (nside - 1) + (imirror - nside) * 4L * nside);
+      z = (2.0 * nside - i) * 2.0 / (3.0 * nside);
+      rd.shifted = ((i - nside) % 2 == 0) ? 1 : 0;
+      rd.trig_off = (int)(captotal + (rd.shifted ? 0 : 4 * nside));
+    }
+    // 1 - z is formed exactly in the caps so that sin(theta/2) keeps full precision
+    const long double omz = (k < ncapring) ? (long double)(i * i) / (3.0L * nside * nside)
+                                           : 1.0L - (long double)z;
+    rd.cth = z;
+    rd.sth = (double)sqrtl(omz * (2.0L - omz));
+    rd.sh2 = (double)sqrtl(0.5L * omz);
+    rd.ch2 = (double)sqrtl(1.0L - 0.5L * omz);
+    rd.quad = quad;
+    const int n = rd.nphi;
+    const bool pow2 = (n & (n - 1)) == 0;
+    rd.bluestein = pow2 ? 0 : 1;
+    rd.log2n = pow2 ? ilog2_ceil(n) : ilog2_ceil(2 * n - 1);
+    rd.chirp_off = chirp_total;
+    rd.dhat_off = dhat_total;
+    if (!pow2) {
+      chirp_total += n;
+      dhat_total += 1 << rd.log2n;
+    }
+    rd.pad = 0;
+  }
+
+  // ---- trig table (cos phi_j, sin phi_j)
+  const long ntrig = captotal + 8L * nside;
+  std::vector<double2> trig(ntrig);
+  for (int k = 0; k < ncapring; ++k) {
+    const int n = 4 * (k + 1);
+    const long off = 2L * k * (k + 1);
+    for (int j = 0; j < n; ++j) {
+      long double ang = 2.0L * M_PIl * ((long double)j + 0.5L) / n;
+      trig[off + j] = make_double2((double)cosl(ang), (double)sinl(ang));
+    }
+  }
+  for (int j = 0; j < 4 * nside; ++j) {
+    long double a1 = 2.0L * M_PIl * ((long double)j + 0.5L) / (4 * nside);
+    long double a0 = 2.0L * M_PIl * ((long double)j) / (4 * nside);
+    trig[captotal + j] = make_double2((double)cosl(a1), (double)sinl(a1));
+    trig[captotal + 4 * nside + j] = make_double2((double)cosl(a0), (double)sinl(a0));
+  }
+
+  // ---- FFT twiddles
+  const int Ntw = 1 << plan->tw_log2;
+  std::vector<double2> tw(Ntw / 2);
+  for (int j = 0; j < Ntw / 2; ++j) {
+    long double ang = 2.0L * M_PIl * j / Ntw;
+    tw[j] = make_double2((double)cosl(ang), (double)sinl(ang));
+  }
+
+  // ---- Bluestein chirps c_j = exp(+i pi j^2 / n) with exact phase reduction
+  std::vector<double2> chirp(chirp_total > 0 ? chirp_total : 1);
+  for (int k = 0; k < nfold; ++k) {
+    const RingDesc &rd = plan->rings_h[k];
+    if (!rd.bluestein) continue;
+    const long n = rd.nphi;
+    for (long j = 0; j < n; ++j) {
+      long q = (j * j) % (2 * n);
+      long double ang = M_PIl * (long double)q / n;
+      chirp[rd.chirp_off + j] = make_double2((double)cosl(ang), (double)sinl(ang));
+    }
+  }
+
+  DSB_CUDA(cudaMalloc(&plan->rings, sizeof(RingDesc) * nfold));
+  DSB_CUDA(cudaMemcpy(plan->rings, plan->rings_h.data(), sizeof(RingDesc) * nfold, cudaMemcpyHostToDevice));
+  DSB_CUDA(cudaMalloc(&plan->horizon, plan->npix));
+  DSB_CUDA(cudaMemcpy(plan->horizon, horizon_host, plan->npix, cudaMemcpyHostToDevice));
+  DSB_CUDA(cudaMalloc(&plan->trig, sizeof(double2) * ntrig));
+  DSB_CUDA(cudaMemcpy(plan->trig, trig.data(), sizeof(double2) * ntrig, cudaMemcpyHostToDevice));
+  DSB_CUDA(cudaMalloc(&plan->tw64, sizeof(double2) * (Ntw / 2)));
+  DSB_CUDA(cudaMemcpy(plan->tw64, tw.data(), sizeof(double2) * (Ntw / 2), cudaMemcpyHostToDevice));
+  DSB_CUDA(cudaMalloc(&plan->tw32, sizeof(float2) * (Ntw / 2)));
+  d2f2_kernel<<<(Ntw / 2 + 255) / 256, 256>>>(plan->tw64, plan->tw32, Ntw / 2);
+  DSB_LAUNCH_CHECK();
+  const size_t nch = chirp.size();
+  DSB_CUDA(cudaMalloc(&plan->chirp64, sizeof(double2) * nch));
+  DSB_CUDA(cudaMemcpy(plan->chirp64, chirp.data(), sizeof(double2) * nch, cudaMemcpyHostToDevice));
+  DSB_CUDA(cudaMalloc(&plan->chirp32, sizeof(float2) * nch));
+  d2f2_kernel<<<(unsigned)((nch + 255) / 256), 256>>>(plan->chirp64, plan->chirp32, nch);
+  DSB_LAUNCH_CHECK();
+  const size_t ndh = dhat_total > 0 ? dhat_total : 1;
+  DSB_CUDA(cudaMalloc(&plan->dhat64, sizeof(double2) * ndh));
+  DSB_CUDA(cudaMalloc(&plan->dhat32, sizeof(float2) * ndh));
+  if (dhat_total > 0) {
+    const size_t smem = sizeof(double2) * (size_t)(1 << plan->tw_log2);
+    DSB_CUDA(cudaFuncSetAttribute(bluestein_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    bluestein_prepare_kernel<<<ncapring, 256, smem>>>(plan->rings, ncapring, plan->chirp64, plan->dhat64,
+                                                      plan->tw64, plan->tw_log2);
+    DSB_LAUNCH_CHECK();
+    d2f2_kernel<<<(unsigned)((ndh + 255) / 256), 256>>>(plan->dhat64, plan->dhat32, ndh);
+    DSB_LAUNCH_CHECK();
+  }
+  DSB_CUDA(cudaDeviceSynchronize());
+  *out = plan;
+  return DSB_OK;
+}
+
+static void free_tables(Tables &t) {
+  cudaFree(t.t0_f64);
+  cudaFree(t.t2_f64);
+  cudaFree(t.t0_bf);
+  cudaFree(t.t2_bf);
+  t = Tables();
+}
+
+extern "C" int dsb_plan_destroy(dsb_plan *plan) {
+  if (!plan) return DSB_OK;
+  cudaDeviceSynchronize();
+  cudaFree(plan->rings);
+  cudaFree(plan->horizon);
+  cudaFree(plan->trig);
+  cudaFree(plan->tw64);
+  cudaFree(plan->tw32);
+  cudaFree(plan->chirp64);
+  cudaFree(plan->chirp32);
+  cudaFree(plan->dhat64);
+  cudaFree(plan->dhat32);
+  for (auto &b : plan->beams) {
+    cudaFree(b.d64);
+    cudaFree(b.d32);
+  }
+  for (auto &t : plan->tables) free_tables(t);
+  cudaFree(plan->ws);
+  delete plan;
+  return DSB_OK;
+}
+
+extern "C" int dsb_beam_slots(dsb_plan *plan, int nslots) {
+  DSB_CHECK(plan && nslots >= 0, DSB_ERR_INVALID, "dsb_beam_slots: bad arguments");
+  if ((int)plan->beams.size() < nslots) plan->beams.resize(nslots);
+  return DSB_OK;
+}
+
+extern "C" int dsb_beam_upload(dsb_plan *plan, int slot, const double *beam_host, int ncomp,
+                               int is_complex, double *omega_out, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSB_CHECK(plan && beam_host, DSB_ERR_INVALID, "dsb_beam_upload: NULL argument");
+  DSB_CHECK(ncomp == 1 || ncomp == 2, DSB_ERR_INVALID, "dsb_beam_upload: ncomp must be 1 or 2");
+  DSB_CHECK(!is_complex, DSB_ERR_UNSUPPORTED,
+            "dsb_beam_upload: complex primary beams are not supported by the device path yet");
+  DSB_CHECK(slot >= 0, DSB_ERR_INVALID, "dsb_beam_upload: negative slot");
+  if ((int)plan->beams.size() <= slot) plan->beams.resize(slot + 1);
+  BeamSlot &b = plan->beams[slot];
+  const size_t n = (size_t)plan->npix * ncomp;
+  if (b.ncomp != ncomp || !b.d64) {
+    cudaFree(b.d64);
+    cudaFree(b.d32);
+    b.d64 = nullptr;
+    b.d32 = nullptr;
+    DSB_CUDA(cudaMalloc(&b.d64, n * sizeof(double)));
+    DSB_CUDA(cudaMalloc(&b.d32, n * sizeof(float)));
+    b.ncomp = ncomp;
+  }
+  DSB_CUDA(cudaMemcpyAsync(b.d64, beam_host, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+  const int nblk = 128;
+  double *partial = nullptr;
+  DSB_CUDA(cudaMalloc(&partial, nblk * sizeof(double)));
+  beam_power_partial_kernel<<<nblk, 256, 0, stream>>>(b.d64, plan->horizon, plan->npix, ncomp, b.d32,
+                                                       partial);
+  DSB_LAUNCH_CHECK();
+  double hp[nblk];
+  DSB_CUDA(cudaMemcpyAsync(hp, partial, sizeof(hp), cudaMemcpyDeviceToHost, stream));
+  DSB_CUDA(cudaStreamSynchronize(stream));
+  DSB_CUDA(cudaFree(partial));
+  double tot = 0.0;
+  for (int i = 0; i < nblk; ++i) tot += hp[i];
+  b.omega = tot * 4.0 * M_PI / plan->npix;
+  b.valid = true;
+  if (omega_out) *omega_out = b.omega;
+  return DSB_OK;
+}

@@ -1,0 +1,162 @@
+/*
+ * driftscan_b200 -- C ABI of the B200 beam-transfer hot path.
+ *
+ * The reference (radiocosmology/driftscan) has no FFI/plugin registry: its hot
+ * path is entered through Python methods.  Each entry point below names the
+ * reference interface it replaces (file:line relative to the reference tree);
+ * INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative dsb_status otherwise;
+ *     dsb_last_error() returns a thread-local message for the last failure.
+ *   - "dev" pointers are CUDA device pointers owned by the caller; "host"
+ *     pointers are ordinary (preferably pinned) host memory.
+ *   - all kernels are enqueued on the `stream` argument (a cudaStream_t cast
+ *     to void*; NULL = the legacy default stream).  Host-buffer entry points
+ *     synchronise the stream before returning.
+ *   - complex numbers are interleaved (re, im).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with DSB_ERR_CUDA.
+ */
+#ifndef DRIFTSCAN_B200_H
+#define DRIFTSCAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  DSB_OK = 0,
+  DSB_ERR_INVALID = -1,   /* bad argument (mirrors the reference's ValueError) */
+  DSB_ERR_CUDA = -2,      /* CUDA runtime / driver failure                     */
+  DSB_ERR_NOMEM = -3,     /* workspace too small / allocation failed           */
+  DSB_ERR_UNSUPPORTED = -4,
+  DSB_ERR_NUMERIC = -5    /* an eigen/SVD iteration failed to converge         */
+} dsb_status;
+
+/* Arithmetic mode of the transfer path. */
+typedef enum {
+  DSB_PREC_FP64 = 0,   /* validation path: fp64 maps, fp64 ring FFT, fp64 SIMT contraction     */
+  DSB_PREC_FP32X3 = 1  /* production path: fp32 maps/FFT (fp64 phase), bf16x3 split operands,  */
+                       /* tcgen05 tensor-core contraction with fp32 TMEM accumulation          */
+} dsb_precision;
+
+typedef struct dsb_plan dsb_plan; /* one per (device, nside): HEALPix ring geometry + tables */
+
+int dsb_version(void);
+const char *dsb_last_error(void);
+/* Number of kernels this library has launched in the calling process. */
+uint64_t dsb_launch_count(void);
+
+/* ---- plan ---------------------------------------------------------------
+ * Replaces TransitTelescope._init_trans (drift/core/telescope.py:943-952):
+ * per-nside pixel geometry and the horizon mask.  `horizon_host` is the
+ * boolean map visibility.horizon() returns (drift/core/visibility.py:27-46),
+ * one byte per RING-ordered pixel, computed by the host so that pixels on the
+ * horizon are classified exactly as the reference does. */
+int dsb_plan_create(int nside, const uint8_t *horizon_host, dsb_plan **out);
+int dsb_plan_destroy(dsb_plan *plan);
+
+/* Upload one primary-beam map -- what TransitTelescope._beam caches per
+ * (nside, freq, beamclass) (drift/core/telescope.py:956-974).  `beam_host` is
+ * float64 [npix][ncomp] (ncomp = 1 unpolarised, 2 = (theta, phi) components).
+ * The beam solid angle Omega = (4 pi / npix) sum H |E|^2 of
+ * _fast_tools.pyx:124-137 / telescope.py:1165-1169 is reduced on the device and
+ * returned through `omega_out` (may be NULL). */
+int dsb_beam_upload(dsb_plan *plan, int slot, const double *beam_host, int ncomp,
+                    int is_complex, double *omega_out, void *stream);
+int dsb_beam_slots(dsb_plan *plan, int nslots); /* reserve `nslots` beam slots */
+
+/* Evaluate the analytic cylinder beam of drift/telescope/cylbeam.py:101-212 on
+ * the device into `slot` (pol = 0: beam_x, 1: beam_y, -1: unpolarised beam_amp).
+ * `pattern_k/pattern_f` is the host-computed 1-D Fraunhofer pattern of
+ * cylbeam.fraunhofer_cylinder (:52-95) as natural-cubic-spline knots. */
+int dsb_beam_cylinder(dsb_plan *plan, int slot, int pol, const double *zenith,
+                      const double *pattern_k, const double *pattern_f, const double *pattern_m2,
+                      int npattern, double fwhm_ns, double *omega_out, void *stream);
+
+/* Legendre / spin-2 tables for l <= lmax, m <= mmax (the part of
+ * healpy.map2alm that the reference reaches through cora.util.hputil,
+ * drift/core/telescope.py:1189,1300,1310). */
+int dsb_plan_build_tables(dsb_plan *plan, int lmax, int mmax, int want_spin2, int precision,
+                          void *stream);
+
+/* One (baseline, frequency) unit == one call of _transfer_single
+ * (drift/core/telescope.py:1178-1193, 1287-1316). */
+typedef struct {
+  double uvec[3];   /* u*uhat + v*vhat in wavelengths, Cartesian (_fast_tools.pyx:50-53) */
+  double prefactor; /* 1/sqrt(Omega_i Omega_j)                                          */
+  int32_t beam_i;   /* beam slot of feed i                                              */
+  int32_t beam_j;   /* beam slot of feed j                                              */
+  int32_t lmax;     /* per-unit lmax (telescope.py:792-802); l > lmax is zero           */
+  int32_t out0;     /* output index 0: unit row (tarray) or frequency slot (m-major)    */
+  int32_t out1;     /* output index 1: baseline slot (m-major)                          */
+  int32_t reserved;
+} dsb_unit;
+
+/* Output of dsb_transfer_units. */
+typedef enum {
+  /* complex128 [n_out0][npol_out][lside+1][2*lside+1], column m for m>=0 and
+   * 2*lside+1-|m| for m<0: what TransitTelescope.transfer_matrices returns
+   * (drift/core/telescope.py:809-828).  dims = {n_out0, npol_out, lside}. */
+  DSB_OUT_TARRAY_C128 = 0,
+  /* m-major compact beam_m blocks, the layout of <bt>/beam_m/<m>/beam.hdf5
+   * (drift/core/beamtransfer.py:567,620-624,663): for each m <= mmax a block
+   * [n_out0 (freq)][2 (+-)][n_out1 (baseline)][npol_out][lside+1-m], blocks
+   * concatenated in m order.  complex128 or complex64.  dims = {n_out0, n_out1,
+   * npol_out, lside, mmax}. */
+  DSB_OUT_MMAJOR_C128 = 1,
+  DSB_OUT_MMAJOR_C64 = 2
+} dsb_out_kind;
+
+/* Beam-transfer matrices for `nunits` units that all share the plan's nside.
+ * Replaces the loop body of TransitTelescope.transfer_matrices
+ * (drift/core/telescope.py:818-828) including fringe (_fast_tools.pyx:18-82),
+ * Stokes maps (_fast_tools.pyx:96-242 / telescope.py:1156-1176), the SHT and
+ * the +-m packing of beamtransfer.py:620-624.
+ *   npol_sky : 1 (unpolarised or skip_pol), 3 (skip_V) or 4
+ *   polarised: 0 -> beams have 1 component (UnpolarisedTelescope), 1 -> 2 components
+ *   out      : device pointer (out_is_host = 0) or host pointer (out_is_host = 1)
+ * Output entries of the given units are overwritten (zero where l > unit lmax);
+ * other entries are left untouched. */
+int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, int nunits, int npol_sky,
+                       int polarised, int mmax, int precision, int out_kind, const int64_t *dims,
+                       void *out, int out_is_host, void *stream);
+
+/* Size in elements (complex numbers) of an m-major buffer and the per-m block
+ * offsets (mmax+2 entries, last = total). */
+int64_t dsb_mmajor_size(int n_out0, int n_out1, int npol, int lside, int mmax, int64_t *offsets);
+
+/* Workspace cap (bytes) for the library-owned scratch (ring spectra, GEMM
+ * output).  Default 24 GiB. */
+int dsb_set_workspace_limit(size_t bytes);
+
+/* ---- per-(m, freq) SVD chain --------------------------------------------
+ * Replaces the frequency loop body of BeamTransfer._generate_svdfile_m
+ * (drift/core/beamtransfer.py:802-924): noise whitening, matrix_image (:68-104),
+ * matrix_nullspace (:107-143), final SVD, beam_ut / beam_svd / pinv.
+ *   bf_dev     : complex128 [batch][ntel][npol][nl]   (beam_m(mi, fi) reshaped)
+ *   noisew_dev : float64    [batch][ntel]
+ * outputs (device, zero-filled beyond nmodes):
+ *   beam_svd  c128 [batch][svd_len][npol][nl];  beam_ut c128 [batch][svd_len][ntel]
+ *   invbeam   c128 [batch][npol][nl][svd_len] (may be NULL);  sv f64 [batch][svd_len]
+ *   nmodes    int32 [batch] */
+int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int batch, int ntel, int npol,
+                  int nl, int svd_len, double rtol1, double polsvcut, void *beam_svd_dev,
+                  void *beam_ut_dev, void *invbeam_dev, double *sv_dev, int32_t *nmodes_dev,
+                  void *stream);
+
+/* project_vector_sky_to_svd (drift/core/beamtransfer.py:1324-1364) for one m:
+ *   beam_svd c128 [nfreq][svd_len][npol_sky][nl], vec c128 [nfreq][npol_sky][nl][nrhs]
+ *   svnum int32[nfreq], svbounds int32[nfreq+1]; out c128 [svbounds[nfreq]][nrhs]. */
+int dsb_project_sky_to_svd(const void *beam_svd_dev, const void *vec_dev, const int32_t *svnum_host,
+                           const int32_t *svbounds_host, int nfreq, int svd_len, int npol_sky,
+                           int npol_use, int nl, int nrhs, void *out_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRIFTSCAN_B200_H */

@@ -1,0 +1,83 @@
+"""GPU parity: dsb_transfer_units (C ABI) against the CPU oracle on seeded inputs."""
+
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import beam as obeam
+from oracle import healpix as ohp
+from oracle import transfer as otr
+
+pytestmark = pytest.mark.gpu
+
+ZENITH = np.array([np.pi / 2 - np.radians(45.0), 0.0])
+
+
+def _run_units(nside, lside, units_spec, beams, polarised, npol_sky, precision, mmax=None, out="tarray"):
+    from driftscan_b200 import _lib
+
+    ang = ohp.ang_positions(nside)
+    hor = obeam.horizon(ang, ZENITH)
+    plan = _lib.Plan(nside, hor)
+    for s, b in enumerate(beams):
+        plan.upload_beam(s, b)
+    units = np.zeros(len(units_spec), dtype=_lib.UNIT_DTYPE)
+    for i, (uv, bi, bj, lmax) in enumerate(units_spec):
+        units[i]["uvec"] = obeam.uv_vector(ZENITH, np.asarray(uv))
+        units[i]["prefactor"] = 1.0 / np.sqrt(plan.omega[bi] * plan.omega[bj])
+        units[i]["beam_i"], units[i]["beam_j"] = bi, bj
+        units[i]["lmax"] = lmax
+        units[i]["out0"] = i
+    npol_out = 4 if polarised else 1
+    res = np.full((len(units), npol_out, lside + 1, 2 * lside + 1), np.nan + 0j, dtype=np.complex128)
+    plan.transfer_units(
+        units, npol_sky, polarised, lside if mmax is None else mmax, precision, _lib.DSB_OUT_TARRAY_C128,
+        [len(units), npol_out, lside], res.ctypes.data, True,
+    )
+    plan.close()
+    return res, ang, hor
+
+
+def _oracle_units(nside, lside, units_spec, beams, polarised, npol_sky, ang, hor):
+    out = []
+    for uv, bi, bj, lmax in units_spec:
+        if polarised:
+            out.append(otr.transfer_single_pol(ang, hor, beams[bi], beams[bj], ZENITH, np.asarray(uv), lmax,
+                                               lside, npol=npol_sky))
+        else:
+            out.append(otr.transfer_single_unpol(ang, hor, beams[bi], beams[bj], ZENITH, np.asarray(uv), lmax,
+                                                 lside))
+    return np.array(out)
+
+
+def _relerr(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+@pytest.mark.parametrize("nside,lside", [(8, 10), (16, 20), (32, 40)])
+@pytest.mark.parametrize("npol_sky", [4, 3, 1])
+def test_polarised_fp64(nside, lside, npol_sky):
+    rng = np.random.default_rng(nside * 10 + npol_sky)
+    npix = 12 * nside * nside
+    beams = [rng.standard_normal((npix, 2)) for _ in range(2)]
+    spec = [((3.1, 1.7), 0, 1, lside), ((0.0, 2.2), 0, 0, lside - 3), ((5.5, -0.4), 1, 1, lside // 2),
+            ((1.0, 0.0), 1, 0, lside)]
+    res, ang, hor = _run_units(nside, lside, spec, beams, True, npol_sky, 0)
+    ref = _oracle_units(nside, lside, spec, beams, True, npol_sky, ang, hor)
+    assert np.isfinite(res).all()
+    for X in range(4):
+        scale = max(np.abs(ref[:, X]).max(), 1e-300)
+        assert np.abs(res[:, X] - ref[:, X]).max() <= 1e-10 * max(scale, np.abs(ref).max()), X
+    assert _relerr(res, ref) < 1e-11
+
+
+@pytest.mark.parametrize("nside,lside", [(16, 22), (64, 70)])
+def test_unpolarised_fp64(nside, lside):
+    rng = np.random.default_rng(nside)
+    npix = 12 * nside * nside
+    beams = [rng.standard_normal(npix)]
+    spec = [((4.0 + i, 0.5 * i), 0, 0, lside - i) for i in range(5)]
+    res, ang, hor = _run_units(nside, lside, spec, beams, False, 1, 0)
+    ref = _oracle_units(nside, lside, spec, beams, False, 1, ang, hor)
+    assert _relerr(res, ref) < 1e-11
