@@ -73,6 +73,7 @@ def _load():
         "dsb_transfer_units": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, P(i64), vp, i32, vp]),
         "dsb_mmajor_size": (i64, [i32, i32, i32, i32, i32, P(i64)]),
         "dsb_set_workspace_limit": (i32, [ctypes.c_size_t]),
+        "dsb_debug_gemm_tc": (i32, [i32, i32, i32, i32, i32, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -162,7 +162,8 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
         for (int m = 0; m <= std::min(lay.mcap, Lt); ++m)
           for (int p = 0; p < 2; ++p) {
             const int nr = nrows_mp(Lt, m, p);
-            if (nr > 0) items.push_back({2 * m + p, ct, nr, s});
+            for (int r0 = 0; r0 < nr; r0 += 256)
+              items.push_back({2 * m + p, ct, std::min(256, nr - r0), s, r0});
           }
       }
     }

@@ -198,12 +198,17 @@ int launch_ringfft(dsb_plan *plan, const BucketLayout &lay, const UnitDev *units
 struct WorkItem {
   int32_t prob;     // 2*m + p
   int32_t coltile;  // 128-column tile
-  int32_t nrows;    // valid rows (<= NP)
+  int32_t nrows;    // valid rows in this item (<= 256)
   int32_t spin;     // 0 or 2
+  int32_t row0;     // first row (multiple of 16)
 };
 int launch_legendre_f64(dsb_plan *plan, const Tables &t, const BucketLayout &lay,
                         const std::vector<WorkItem> &items, const WorkItem *items_dev, const double *F0,
                         const double *F2, double *C0, double *C2, cudaStream_t stream);
+int launch_legendre_tc_raw(int nprobA, int nprobT, int Kp, int NP, int ncols0, int ncols2, int has2, int nitems,
+                           const WorkItem *items_dev, int max_rows, const __nv_bfloat16 *F0,
+                           const __nv_bfloat16 *F2, const __nv_bfloat16 *T0, const __nv_bfloat16 *T2, float *C0,
+                           float *C2, cudaStream_t stream);
 int launch_legendre_tc(dsb_plan *plan, const Tables &t, const BucketLayout &lay,
                        const std::vector<WorkItem> &items, const WorkItem *items_dev,
                        const __nv_bfloat16 *F0, const __nv_bfloat16 *F2, float *C0, float *C2,

@@ -18,8 +18,8 @@ legendre_f64_kernel(const WorkItem *__restrict__ items, int nitems, const double
   __shared__ double Fs[F64_TK][F64_TC];
   __shared__ double Ts[F64_TK][F64_TR + 1];
   const WorkItem it = items[blockIdx.x];
-  const int r0 = blockIdx.y * F64_TR;
-  if (r0 >= it.nrows) return;
+  const int r0 = it.row0 + blockIdx.y * F64_TR;
+  if (r0 >= it.row0 + it.nrows) return;
   const bool s2 = it.spin == 2;
   const int K = s2 ? 2 * Kp : Kp;
   const int ncols = s2 ? ncols2 : ncols0;

@@ -1,11 +1,423 @@
-// placeholder, replaced below
+// Stage 2, production path: the Legendre contraction on the 5th-generation tensor
+// cores (tcgen05) in error-compensated fp32.
+//
+//   C_s[prob][col][row0 + n] = sum_k F_s[prob][k][col] * T_s[prob][row0 + n][k]
+//
+// Both operands are pre-split into three bf16 planes (x = x1 + x2 + x3, 24 significant
+// bits); the product keeps the six terms of weight >= 2^-16:
+//   a1 b3 + a2 b2 + a3 b1 + a1 b2 + a2 b1 + a1 b1          (fp32 accumulation in TMEM)
+// which is the theta -> l half of healpy.map2alm (drift/core/telescope.py:1189,1300,1310)
+// for 128 operand columns (16 or 32 units) at a time.
+//
+// Mapping onto the MMA:  D[M = 128 operand columns][N = l rows] += A[M x K] B[N x K]^T
+//   A = ring spectra,  MN-major (columns contiguous), 128B swizzle, two 64-column TMA boxes
+//   B = Legendre table, K-major, 64B swizzle, one TMA box of NB rows x 32 k
+// so each output column of the contraction (a unit/pol/+-/re-im series in l) ends up in
+// one TMEM lane and is written out contiguously in l.
+//
+// Warp roles (192 threads):  warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..5 = epilogue (TMEM -> registers -> global).  Persistent over work items with
+// a double-buffered accumulator (2 x 256 TMEM columns).
+#include <cuda.h>
+
 #include "dsb_common.cuh"
+
 namespace dsb {
+
+constexpr int TC_KC = 32;          // k per pipeline stage
+constexpr int TC_M = 128;          // operand columns per tile
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_PLANE = TC_KC * TC_M * 2;  // bytes of one split plane of A per stage (8 KB)
+
+struct TcParams {
+  const WorkItem *items;
+  int nitems;
+  int K0, K2;        // contraction length of the spin-0 / spin-2 blocks
+  int ncols0, ncols2;
+  int NP;            // row pitch of C and of the tables
+  float *C0, *C2;
+  int NB;            // table box rows (TMA box), multiple of 16, <= 256
+  int nstages;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)),
+      "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// Shared-memory matrix descriptor (see cute/arch/mma_sm100_desc.hpp: SmemDescriptor).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+      "%14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA2,
+                   const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB2,
+                   const TcParams P) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // swizzled operand tiles need 1024-byte alignment in the shared address space
+  unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // stage layout: [A: 3 planes x 8 KB][B: 3 planes x NB*64 B]
+  const uint32_t b_plane = (uint32_t)P.NB * 64;
+  const uint32_t stage_bytes = 3 * TC_A_PLANE + ((3 * b_plane + 1023) & ~1023u);
+  unsigned char *stages = smem;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)P.nstages * stage_bytes);
+  uint64_t *full = bars;                       // [nstages]
+  uint64_t *empty = bars + P.nstages;          // [nstages]
+  uint64_t *tfull = bars + 2 * P.nstages;      // [2]
+  uint64_t *tempty = bars + 2 * P.nstages + 2; // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * P.nstages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.nstages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < P.nitems; it += gridDim.x) {
+        const WorkItem wi = P.items[it];
+        const bool s2 = wi.spin == 2;
+        const CUtensorMap *mA = s2 ? &mapA2 : &mapA0;
+        const CUtensorMap *mB = s2 ? &mapB2 : &mapB0;
+        const int nk = (s2 ? P.K2 : P.K0) / TC_KC;
+        const uint32_t tx = 3 * TC_A_PLANE + 3 * b_plane;
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char *sA = stages + (size_t)stage * stage_bytes;
+          unsigned char *sB = sA + 3 * TC_A_PLANE;
+          mbar_expect_tx(&full[stage], tx);
+#pragma unroll
+          for (int pl = 0; pl < 3; ++pl) {
+            tma_load_4d(mA, &full[stage], sA + pl * TC_A_PLANE, wi.coltile * TC_M, kc * TC_KC, wi.prob, pl);
+            tma_load_4d(mA, &full[stage], sA + pl * TC_A_PLANE + TC_A_PLANE / 2, wi.coltile * TC_M + 64,
+                        kc * TC_KC, wi.prob, pl);
+            tma_load_4d(mB, &full[stage], sB + pl * b_plane, kc * TC_KC, wi.row0, wi.prob, pl);
+          }
+          if (++stage == P.nstages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int it = blockIdx.x; it < P.nitems; it += gridDim.x, ++local) {
+        const WorkItem wi = P.items[it];
+        const bool s2 = wi.spin == 2;
+        const int nk = (s2 ? P.K2 : P.K0) / TC_KC;
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        const uint32_t N = (uint32_t)((wi.nrows + 15) & ~15);
+        // instruction descriptor: D=f32, A=B=bf16, A MN-major, B K-major, M=128, N
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((N >> 3) << 17) |
+                               ((uint32_t)(TC_M >> 4) << 24);
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256;
+        uint32_t accum = 0;
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(&full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sA = smem_u32(stages + (size_t)stage * stage_bytes);
+          const uint32_t sB = sA + 3 * TC_A_PLANE;
+#pragma unroll
+          for (int ks = 0; ks < TC_KC / 16; ++ks) {
+            // six split products, smallest first
+            const int pa[6] = {0, 1, 2, 0, 1, 0};
+            const int pb[6] = {2, 1, 0, 1, 0, 0};
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+              // A: MN-major SW128. 64-column box = 32 k-rows x 128 B; LBO = next 64 columns (4096 B),
+              //    SBO = next 8 k-rows (1024 B); one K=16 step = two 8-row atoms = 2048 B.
+              const uint64_t da = make_desc(sA + pa[q] * TC_A_PLANE + ks * 2048, TC_A_PLANE / 2, 1024, 2);
+              // B: K-major SW64. rows of 64 B; 8-row atom = 512 B (SBO); K=16 step = 32 B inside the row.
+              const uint64_t db = make_desc(sB + pb[q] * b_plane + ks * 32, 16, 512, 4);
+              umma_bf16(d_tmem, da, db, idesc, accum);
+              accum = 1;
+            }
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == P.nstages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    int local = 0;
+    for (int it = blockIdx.x; it < P.nitems; it += gridDim.x, ++local) {
+      const WorkItem wi = P.items[it];
+      const bool s2 = wi.spin == 2;
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int N = (wi.nrows + 15) & ~15;
+      const int ncols = s2 ? P.ncols2 : P.ncols0;
+      float *C = (s2 ? P.C2 : P.C0) +
+                 ((size_t)wi.prob * ncols + (size_t)wi.coltile * TC_M + quarter * 32 + lane) * P.NP + wi.row0;
+      mbar_wait(&tfull[acc], acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 256;
+      for (int n0 = 0; n0 < N; n0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + n0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float4 *dst = reinterpret_cast<float4 *>(C + n0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                               __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 4-D bf16 tensor map: dims (d0 contiguous, d1, d2, d3)
+static int encode4(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+                   uint64_t s1, uint64_t s2, uint64_t s3, uint32_t b0, uint32_t b1, CUtensorMapSwizzle sw) {
+  EncodeTiledFn enc = get_encode();
+  DSB_CHECK(enc != nullptr, DSB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {d0, d1, d2, d3};
+  cuuint64_t strides[3] = {s1 * 2, s2 * 2, s3 * 2};  // bytes
+  cuuint32_t box[4] = {b0, b1, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DSB_CHECK(r == CUDA_SUCCESS, DSB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return DSB_OK;
+}
+
+int launch_legendre_tc_raw(int nprobA, int nprobT, int Kp, int NP, int ncols0, int ncols2, int has2, int nitems,
+                           const WorkItem *items_dev, int max_rows, const __nv_bfloat16 *F0,
+                           const __nv_bfloat16 *F2, const __nv_bfloat16 *T0, const __nv_bfloat16 *T2, float *C0,
+                           float *C2, cudaStream_t stream) {
+  if (nitems == 0) return DSB_OK;
+  DSB_CHECK(Kp % TC_KC == 0, DSB_ERR_INVALID, "contraction length must be a multiple of %d", TC_KC);
+  DSB_CHECK(ncols0 % TC_M == 0 && ncols2 % TC_M == 0, DSB_ERR_INVALID, "column counts must be multiples of 128");
+  DSB_CHECK(NP % 16 == 0, DSB_ERR_INVALID, "row pitch must be a multiple of 16");
+  int NB = (int)round_up(std::min(std::max(max_rows, 16), 256), 16);
+  NB = std::min(NB, 256);
+
+  CUtensorMap mA0, mA2, mB0, mB2;
+  const uint64_t K0 = Kp, K2 = 2 * (uint64_t)Kp;
+  DSB_TRY(encode4(&mA0, F0, ncols0, K0, nprobA, 3, ncols0, K0 * ncols0, (uint64_t)nprobA * K0 * ncols0, 64,
+                  TC_KC, CU_TENSOR_MAP_SWIZZLE_128B));
+  DSB_TRY(encode4(&mB0, T0, K0, NP, nprobT, 3, K0, (uint64_t)NP * K0, (uint64_t)nprobT * NP * K0, TC_KC, NB,
+                  CU_TENSOR_MAP_SWIZZLE_64B));
+  if (has2) {
+    DSB_TRY(encode4(&mA2, F2, ncols2, K2, nprobA, 3, ncols2, K2 * ncols2, (uint64_t)nprobA * K2 * ncols2, 64,
+                    TC_KC, CU_TENSOR_MAP_SWIZZLE_128B));
+    DSB_TRY(encode4(&mB2, T2, K2, NP, nprobT, 3, K2, (uint64_t)NP * K2, (uint64_t)nprobT * NP * K2, TC_KC, NB,
+                    CU_TENSOR_MAP_SWIZZLE_64B));
+  } else {
+    mA2 = mA0;
+    mB2 = mB0;
+  }
+
+  TcParams P;
+  P.items = items_dev;
+  P.nitems = nitems;
+  P.K0 = (int)K0;
+  P.K2 = (int)K2;
+  P.ncols0 = ncols0;
+  P.ncols2 = ncols2;
+  P.NP = NP;
+  P.C0 = C0;
+  P.C2 = C2;
+  P.NB = NB;
+  const size_t stage_bytes = 3 * TC_A_PLANE + (((size_t)3 * NB * 64 + 1023) & ~(size_t)1023);
+  int nstages = (int)std::min<size_t>(8, (220 * 1024) / stage_bytes);
+  DSB_CHECK(nstages >= 2, DSB_ERR_UNSUPPORTED, "pipeline does not fit shared memory");
+  P.nstages = nstages;
+  const size_t smem = nstages * stage_bytes + (2 * nstages + 4) * 8 + 16 + 1024;
+  DSB_CUDA(cudaFuncSetAttribute(legendre_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, nsm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = std::min(nitems, nsm);
+  legendre_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mA0, mA2, mB0, mB2, P);
+  DSB_LAUNCH_CHECK();
+  return DSB_OK;
+}
+
 int launch_legendre_tc(dsb_plan *plan, const Tables &t, const BucketLayout &lay,
                        const std::vector<WorkItem> &items, const WorkItem *items_dev,
                        const __nv_bfloat16 *F0, const __nv_bfloat16 *F2, float *C0, float *C2,
                        cudaStream_t stream) {
-  set_error("tensor-core contraction not built yet");
-  return DSB_ERR_UNSUPPORTED;
+  int max_rows = 16;
+  for (const auto &w : items) max_rows = std::max(max_rows, w.nrows);
+  // the tables may cover more m than this bucket needs: separate problem counts
+  const int nprobA = 2 * (lay.mcap + 1);
+  const int nprobT = 2 * (t.mmax + 1);
+  return launch_legendre_tc_raw(nprobA, nprobT, t.Kp, t.NP, lay.ncols0, lay.ncols2, lay.has2, (int)items.size(),
+                                items_dev, max_rows, F0, F2, t.t0_bf, t.t2_bf, C0, C2, stream);
 }
+
 }  // namespace dsb
+
+using namespace dsb;
+
+// Debug / unit-test entry: run the tensor-core contraction on caller-provided split planes
+// (host memory).  F [3][nprob][K][ncols] bf16, T [3][nprob][NP][K] bf16, items int32[nitems][5]
+// (prob, coltile, nrows, spin=0, row0), C out fp32 [nprob][ncols][NP].
+extern "C" int dsb_debug_gemm_tc(int nprob, int K, int NP, int ncols, int nitems, const int32_t *items_host,
+                                 const uint16_t *F_host, const uint16_t *T_host, float *C_host) {
+  const size_t nF = (size_t)3 * nprob * K * ncols, nT = (size_t)3 * nprob * NP * K;
+  const size_t nC = (size_t)nprob * ncols * NP;
+  __nv_bfloat16 *F = nullptr, *T = nullptr;
+  float *C = nullptr;
+  WorkItem *items = nullptr;
+  DSB_CUDA(cudaMalloc(&F, nF * 2));
+  DSB_CUDA(cudaMalloc(&T, nT * 2));
+  DSB_CUDA(cudaMalloc(&C, nC * 4));
+  DSB_CUDA(cudaMalloc(&items, nitems * sizeof(WorkItem)));
+  DSB_CUDA(cudaMemcpy(F, F_host, nF * 2, cudaMemcpyHostToDevice));
+  DSB_CUDA(cudaMemcpy(T, T_host, nT * 2, cudaMemcpyHostToDevice));
+  DSB_CUDA(cudaMemset(C, 0, nC * 4));
+  DSB_CUDA(cudaMemcpy(items, items_host, nitems * sizeof(WorkItem), cudaMemcpyHostToDevice));
+  int max_rows = 16;
+  for (int i = 0; i < nitems; ++i) max_rows = std::max(max_rows, items_host[5 * i + 2]);
+  int rc = launch_legendre_tc_raw(nprob, nprob, K, NP, ncols, ncols, 0, nitems, items, max_rows, F, nullptr, T,
+                                  nullptr, C, nullptr, 0);
+  if (rc == DSB_OK) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      set_error("dsb_debug_gemm_tc: kernel failed: %s", cudaGetErrorString(e));
+      rc = DSB_ERR_CUDA;
+    }
+  }
+  if (rc == DSB_OK) DSB_CUDA(cudaMemcpy(C_host, C, nC * 4, cudaMemcpyDeviceToHost));
+  cudaFree(F);
+  cudaFree(T);
+  cudaFree(C);
+  cudaFree(items);
+  return rc;
+}

@@ -134,6 +134,14 @@ int64_t dsb_mmajor_size(int n_out0, int n_out1, int npol, int lside, int mmax, i
  * output).  Default 24 GiB. */
 int dsb_set_workspace_limit(size_t bytes);
 
+/* Unit-test entry for the tensor-core contraction kernel alone (host buffers):
+ *   C[prob][col][n] = sum_k F[prob][k][col] * T[prob][n][k]
+ * with both operands given as three bf16 planes (x = x1 + x2 + x3).
+ *   F bf16 [3][nprob][K][ncols], T bf16 [3][nprob][NP][K], C fp32 [nprob][ncols][NP]
+ *   items int32 [nitems][5] = (prob, column tile, rows, 0, first row). */
+int dsb_debug_gemm_tc(int nprob, int K, int NP, int ncols, int nitems, const int32_t *items_host,
+                      const uint16_t *F_host, const uint16_t *T_host, float *C_host);
+
 /* ---- per-(m, freq) SVD chain --------------------------------------------
  * Replaces the frequency loop body of BeamTransfer._generate_svdfile_m
  * (drift/core/beamtransfer.py:802-924): noise whitening, matrix_image (:68-104),

@@ -81,3 +81,19 @@ def test_unpolarised_fp64(nside, lside):
     res, ang, hor = _run_units(nside, lside, spec, beams, False, 1, 0)
     ref = _oracle_units(nside, lside, spec, beams, False, 1, ang, hor)
     assert _relerr(res, ref) < 1e-11
+
+
+@pytest.mark.parametrize("nside,lside", [(16, 20), (32, 40), (64, 90)])
+@pytest.mark.parametrize("npol_sky", [4, 1])
+def test_polarised_fp32x3(nside, lside, npol_sky):
+    """Production precision: target <= 1e-6 of max|B| (north_star)."""
+    rng = np.random.default_rng(nside * 10 + npol_sky)
+    npix = 12 * nside * nside
+    beams = [rng.standard_normal((npix, 2)) for _ in range(2)]
+    spec = [((3.1 + 2 * i, 1.7 - i), i % 2, (i // 2) % 2, lside - i) for i in range(6)]
+    res, ang, hor = _run_units(nside, lside, spec, beams, True, npol_sky, 1)
+    ref = _oracle_units(nside, lside, spec, beams, True, npol_sky, ang, hor)
+    assert np.isfinite(res).all()
+    err = _relerr(res, ref)
+    print("fp32x3 relerr", nside, npol_sky, err)
+    assert err < 1e-6
