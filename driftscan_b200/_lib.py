@@ -74,6 +74,8 @@ def _load():
         "dsb_mmajor_size": (i64, [i32, i32, i32, i32, i32, P(i64)]),
         "dsb_set_workspace_limit": (i32, [ctypes.c_size_t]),
         "dsb_debug_gemm_tc": (i32, [i32, i32, i32, i32, i32, vp, vp, vp, vp]),
+        "dsb_svd_chain": (i32, [vp, vp, i32, i32, i32, i32, i32, dbl, dbl, vp, vp, vp, vp, vp, vp]),
+        "dsb_project_sky_to_svd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

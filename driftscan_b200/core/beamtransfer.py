@@ -1,0 +1,461 @@
+"""Generation, storage and application of beam-transfer matrices.
+
+Drop-in mirror of ``drift.core.beamtransfer.BeamTransfer`` (reference
+drift/core/beamtransfer.py:146-1453): same constructor, configuration
+properties, product directory layout (``<dir>/beam_m/<m>/beam.hdf5``,
+``svd.hdf5``, ``svdspectrum.hdf5``, ``telescopeobject.pickle``, the
+``COMPLETED`` marker), dataset names/shapes/dtypes/attributes and accessor /
+projection methods.  The arithmetic runs on the GPU:
+
+* ``_generate_mfiles``  -> ``dsb_transfer_units`` writes compact m-major blocks
+  directly (the frequency-major -> m-major regrouping of the reference's MPI
+  ``transpose_blocks`` is the output layout of the pack kernel; across GPUs it
+  is an NCCL all-to-all, see :mod:`driftscan_b200.parallel`).
+* ``_generate_svdfile_m`` -> ``dsb_svd_chain`` (batched over frequency).
+* ``project_vector_sky_to_svd`` -> ``dsb_project_sky_to_svd``.
+
+torch is used only to own device buffers and for the collective plumbing.
+"""
+
+import logging
+import os
+import pickle
+import time
+
+import numpy as np
+
+from .. import config
+from ..util import h5lite, util
+
+logger = logging.getLogger(__name__)
+
+
+def _find_index_sorted(a, v):
+    """Index of ``v`` in the sorted array ``a`` or None (beamtransfer.py:1998-2002)."""
+    ind = int(np.searchsorted(a, v))
+    return ind if ind < len(a) and a[ind] == v else None
+
+
+def _load_beam_f(path, dset_name, ind=None):
+    """Read (a frequency block of) a dataset (beamtransfer.py:1975-1995)."""
+    ind = slice(None) if ind is None else ind
+    with h5lite.File(path, "r") as fh:
+        if dset_name not in fh:
+            raise RuntimeError(f"Malformed beam file: {path}")
+        return fh[dset_name][ind]
+
+
+class BeamTransfer(config.Reader):
+    """Reads, writes and applies beam-transfer matrices (beamtransfer.py:146-1453)."""
+
+    mem_chunk = config.Property(proptype=float, default=3.0)
+    svcut = config.Property(proptype=float, default=1e-6)
+    polsvcut = config.Property(proptype=float, default=1e-4)
+    truncate = config.Property(proptype=bool, default=False)
+    truncate_rel = config.Property(proptype=float, default=1e-7)
+    truncate_maxl = config.Property(proptype=float, default=1e-8)
+    chunk_cache_size = config.Property(proptype=int, default=128)
+
+    noise_weight = True
+
+    # ---- file names (beamtransfer.py:199-224) ------------------------------------
+    @property
+    def _picklefile(self):
+        return self.directory + "/telescopeobject.pickle"
+
+    def _mdir(self, mi):
+        return (self.directory + "/beam_m/" + util.natpattern(self.telescope.mmax)) % abs(mi)
+
+    def _mfile(self, mi):
+        return self._mdir(mi) + "/beam.hdf5"
+
+    def _svdfile(self, mi):
+        return (self.directory + "/beam_m/" + util.natpattern(self.telescope.mmax) + "/svd.hdf5") % mi
+
+    @property
+    def _telescope_pickle(self):
+        return pickle.dumps(self.telescope)
+
+    def __init__(self, directory, telescope=None):
+        from .. import parallel
+
+        self.directory = directory
+        self.telescope = telescope
+        self.comm = parallel.Comm.current()
+        if self.comm.rank0 and not os.path.exists(directory):
+            os.makedirs(directory)
+        self.comm.barrier()
+        if self.telescope is None:
+            logger.info("Attempting to read telescope from disk...")
+            try:
+                with open(self._picklefile, "rb") as f:
+                    self.telescope = pickle.load(f)
+            except (IOError, pickle.UnpicklingError) as e:
+                raise RuntimeError("Could not load Telescope object from disk.") from e
+
+    # ---- dimensions (beamtransfer.py:1427-1453) -----------------------------------
+    @property
+    def ntel(self):
+        return 2 * self.telescope.npairs
+
+    @property
+    def nsky(self):
+        return (self.telescope.lmax + 1) * self.telescope.num_pol_sky
+
+    @property
+    def nfreq(self):
+        return self.telescope.nfreq
+
+    @property
+    def svd_len(self):
+        return min(self.telescope.lmax + 1, self.ntel)
+
+    @property
+    def ndofmax(self):
+        return self.svd_len * self.nfreq
+
+    def ndof(self, mi):
+        return self._svd_num(mi)[1][-1]
+
+    # ---- readers ---------------------------------------------------------------------
+    @util.cache_last
+    def beam_m(self, mi, fi=None):
+        """Beam-transfer matrix of one m: ``[nfreq, 2, npairs, npol_sky, lmax+1]`` (or
+        without the frequency axis), zero where skipped or l < m (beamtransfer.py:256-308)."""
+        tel = self.telescope
+        ind_list = [np.arange(2), tel.included_baseline, tel.included_pol, np.arange(mi, tel.lmax + 1)]
+        shape = (2, tel.nbase, tel.num_pol_sky, tel.lmax + 1)
+        if fi is None:
+            ind_list = [tel.included_freq] + ind_list
+            shape = (tel.nfreq,) + shape
+        bf = np.zeros(shape, dtype=np.complex128)
+        if fi is not None:
+            fi = _find_index_sorted(tel.included_freq, fi)
+            if fi is None:
+                return bf
+        bf[np.ix_(*ind_list)] = _load_beam_f(self._mfile(mi), "beam_m", fi)
+        return bf
+
+    @util.cache_last
+    def beam_svd(self, mi, fi=None):
+        """SVD beam ``[nfreq, svd_len, npol_sky, lmax+1]`` (beamtransfer.py:364-384)."""
+        return _load_beam_f(self._svdfile(mi), "beam_svd", fi)
+
+    @util.cache_last
+    def invbeam_svd(self, mi, fi=None):
+        """Pseudo-inverse of the SVD beam ``[nfreq, npol_sky, lmax+1, svd_len]``."""
+        return _load_beam_f(self._svdfile(mi), "invbeam_svd", fi)
+
+    @util.cache_last
+    def beam_ut(self, mi, fi=None):
+        """Telescope -> SVD projection ``[nfreq, svd_len, ntel]`` (beamtransfer.py:407-426)."""
+        return _load_beam_f(self._svdfile(mi), "beam_ut", fi)
+
+    @util.cache_last
+    def beam_singularvalues(self, mi):
+        """Singular values ``[nfreq, svd_len]`` (beamtransfer.py:428-441)."""
+        return _load_beam_f(self._svdfile(mi), "singularvalues")
+
+    # ---- generation -------------------------------------------------------------------
+    def generate(self, regen=False, skip_svd=False, skip_svd_inv=False):
+        """Write all beam-transfer products (beamtransfer.py:447-480)."""
+        st = time.time()
+        self._generate_dirs()
+        if self.comm.rank0:
+            with open(self._picklefile, "wb") as f:
+                logger.info("Saving Telescope object.")
+                pickle.dump(self.telescope, f)
+        self._generate_mfiles(regen)
+        if not skip_svd:
+            self._generate_svdfiles(regen, skip_svd_inv)
+        self.comm.barrier()
+        if self.comm.rank0:
+            logger.info(f"Beam generation time: {time.time() - st:f}")
+
+    generate_cache = generate
+
+    def _generate_dirs(self):
+        if self.comm.rank0:
+            os.makedirs(self.directory, exist_ok=True)
+            for mi in range(self.telescope.mmax + 1):
+                os.makedirs(self._mdir(mi), exist_ok=True)
+        self.comm.barrier()
+
+    def _generate_mfiles(self, regen=False):
+        """Compute every (frequency, baseline) unit and store the result m by m
+        (beamtransfer.py:502-676).
+
+        Frequencies are sharded over ranks (one GPU each); each rank produces compact
+        m-major blocks for its frequencies, an all-to-all hands every rank the m range
+        it owns (the ``split_local`` partition of the reference) for all frequencies, and
+        every rank writes only its own m-files.
+        """
+        import torch
+
+        from .. import _lib
+
+        if os.path.exists(self.directory + "/beam_m/COMPLETED") and not regen:
+            if self.comm.rank0:
+                logger.info("m-files already generated")
+            return
+        st = time.time()
+        tel, comm = self.telescope, self.comm
+        freq_inc, bl_inc = tel.included_freq, tel.included_baseline
+        nf_inc, nb_inc, np_inc = len(freq_inc), len(bl_inc), len(tel.included_pol)
+        nl, nm = tel.lmax + 1, tel.mmax + 1
+
+        # m ownership: contiguous ranges, first (nm % size) ranks get one more
+        m_lo, m_hi = comm.split_range(nm)
+        for mi in range(m_lo, m_hi):
+            if os.path.exists(self._mfile(mi)) and not regen:
+                logger.info(f"m index {mi}. File: {self._mfile(mi)} exists. Skipping...")
+                continue
+            with h5lite.File(self._mfile(mi), "w") as f:
+                f.create_dataset("beam_m", (nf_inc, 2, nb_inc, np_inc, nl - mi), dtype=np.complex128)
+                f.attrs["m"] = mi
+                f.attrs["frequencies"] = tel.frequencies
+        comm.barrier()
+
+        # chunk the frequency axis so that one chunk of m-major output is ~mem_chunk GB per rank
+        per_freq = 16 * _lib.mmajor_offsets(1, nb_inc, np_inc, tel.lmax, tel.mmax)[0]
+        nf_chunk = max(1, int(self.mem_chunk * 2**30 / max(per_freq, 1)))
+        f_lo, f_hi = comm.split_range(nf_inc)
+        nf_loc_max = max(hi - lo for lo, hi in comm.all_ranges(nf_inc))
+        nchunks = max(1, -(-nf_loc_max // nf_chunk))
+        if comm.rank0:
+            logger.info(f"Splitting into {nchunks} chunks....")
+
+        dev = torch.device("cuda", torch.cuda.current_device())
+        for ci in range(nchunks):
+            c_lo = min(f_lo + ci * nf_chunk, f_hi)
+            c_hi = min(c_lo + nf_chunk, f_hi)
+            nfc = c_hi - c_lo
+            total, moff = _lib.mmajor_offsets(max(nfc, 1), nb_inc, np_inc, tel.lmax, tel.mmax)
+            buf = torch.zeros(total if nfc else 0, dtype=torch.complex128, device=dev)
+            if nfc:
+                fgrid, bgrid = np.meshgrid(np.arange(c_lo, c_hi), np.arange(nb_inc), indexing="ij")
+                f_ind, b_ind = freq_inc[fgrid.ravel()], bl_inc[bgrid.ravel()]
+                lmax_u, _ = tel.unit_lmax(b_ind, f_ind)
+                tel.engine.transfer_mmajor(
+                    b_ind, f_ind, lmax_u, (fgrid.ravel() - c_lo).astype(np.int32),
+                    bgrid.ravel().astype(np.int32), nfc, nb_inc, tel.lmax, tel.mmax, buf.data_ptr(), False,
+                    stream=torch.cuda.current_stream().cuda_stream,
+                )
+            # regroup: every rank receives, for the m range it owns, the blocks of all
+            # ranks' frequency chunks (frequency-major -> m-major transpose, beamtransfer.py:632)
+            pieces = comm.exchange_mblocks(buf, nfc, moff, nm, f_lo=c_lo)
+            for src, (s_lo, s_hi, blocks) in enumerate(pieces):
+                if s_hi <= s_lo:
+                    continue
+                for mi, block in zip(range(m_lo, m_hi), blocks):
+                    data = block.reshape(s_hi - s_lo, 2, nb_inc, np_inc, nl - mi).cpu().numpy()
+                    with h5lite.File(self._mfile(mi), "r+") as f:
+                        f["beam_m"][s_lo:s_hi] = data
+            del buf, pieces
+
+        comm.barrier()
+        if comm.rank0:
+            open(self.directory + "/beam_m/COMPLETED", "a").close()
+            logger.info(f"=== MPI transpose took {time.time() - st:f} s ===")
+
+    def _generate_svdfiles(self, regen=False, skip_svd_inv=False):
+        """Per-m SVD files (beamtransfer.py:678-728)."""
+        comm = self.comm
+        m_list = []
+        for mi in range(self.telescope.mmax + 1):
+            if os.path.exists(self._svdfile(mi)) and not regen:
+                try:
+                    with h5lite.File(self._svdfile(mi), "r"):
+                        pass
+                    logger.info(f"m index {mi}. Complete file: {self._svdfile(mi)} exists.Skipping...")
+                    continue
+                except Exception:
+                    logger.info(f"m index {mi}. ***INCOMPLETE file: {self._svdfile(mi)} exists. Will regenerate...")
+            m_list.append(mi)
+        if comm.rank0:
+            logger.info(f"m's remaining in beam SVD computation: {m_list}")
+        comm.barrier()
+        lo, hi = comm.split_range(len(m_list))
+        for mi in m_list[lo:hi]:
+            logger.info(f"m index {mi}. Creating SVD file: {self._svdfile(mi)}")
+            self._generate_svdfile_m(mi, skip_svd_inv=skip_svd_inv)
+        comm.barrier()
+        self._collect_svd_spectrum()
+
+    def _svd_chain_device(self, bf_host, noisew_host, skip_svd_inv):
+        """Run dsb_svd_chain on ``bf_host [batch, ntel, npol, nl]``; returns host arrays."""
+        import torch
+
+        from .. import _lib
+
+        batch, ntel, npol, nl = bf_host.shape
+        svd_len = self.svd_len
+        dev = torch.device("cuda", torch.cuda.current_device())
+        bf = torch.from_numpy(np.ascontiguousarray(bf_host)).to(dev)
+        nw = torch.from_numpy(np.ascontiguousarray(noisew_host, dtype=np.float64)).to(dev)
+        bsvd = torch.empty((batch, svd_len, npol, nl), dtype=torch.complex128, device=dev)
+        but = torch.empty((batch, svd_len, ntel), dtype=torch.complex128, device=dev)
+        ibs = None if skip_svd_inv else torch.empty((batch, npol, nl, svd_len), dtype=torch.complex128, device=dev)
+        sv = torch.empty((batch, svd_len), dtype=torch.float64, device=dev)
+        nmodes = torch.empty((batch,), dtype=torch.int32, device=dev)
+        _lib.check(
+            _lib.lib.dsb_svd_chain(
+                bf.data_ptr(), nw.data_ptr(), batch, ntel, npol, nl, svd_len, 1e-10, float(self.polsvcut),
+                bsvd.data_ptr(), but.data_ptr(), 0 if ibs is None else ibs.data_ptr(), sv.data_ptr(),
+                nmodes.data_ptr(), torch.cuda.current_stream().cuda_stream,
+            )
+        )
+        return (bsvd.cpu().numpy(), but.cpu().numpy(), None if ibs is None else ibs.cpu().numpy(),
+                sv.cpu().numpy(), nmodes.cpu().numpy())
+
+    def _generate_svdfile_m(self, mi, skip_svd_inv=False):
+        """SVD products of one m (beamtransfer.py:730-929); written to a dot-prefixed
+        temporary and renamed on success, as ``caput.misc.lock_file`` does."""
+        tel = self.telescope
+        nfreq, npol, nl = tel.nfreq, tel.num_pol_sky, tel.lmax + 1
+        bf = self.beam_m(mi).reshape(nfreq, self.ntel, npol, nl)
+        noisew = tel.noisepower(np.arange(tel.npairs)[np.newaxis, :], np.arange(nfreq)[:, np.newaxis])
+        noisew = noisew.reshape(nfreq, tel.npairs) ** (-0.5)
+        noisew = np.concatenate([noisew, noisew], axis=1)
+        bsvd, but, ibs, sv, nmodes = self._svd_chain_device(bf, noisew, skip_svd_inv)
+
+        final = self._svdfile(mi)
+        tmp = os.path.join(os.path.dirname(final), "." + os.path.basename(final))
+        with h5lite.File(tmp, "w") as fs:
+            fs.create_dataset("beam_svd", data=bsvd)
+            if not skip_svd_inv:
+                fs.create_dataset("invbeam_svd", data=ibs)
+            fs.create_dataset("beam_ut", data=but)
+            fs.create_dataset("singularvalues", data=sv)
+            try:
+                fs.attrs["baselines"] = tel.baselines
+            except ValueError:
+                logger.warning("baselines attribute too large for an HDF5 object header; omitted")
+            fs.attrs["m"] = mi
+            fs.attrs["frequencies"] = tel.frequencies
+        os.replace(tmp, final)
+
+    def _collect_svd_spectrum(self):
+        """Gather all singular values into ``svdspectrum.hdf5`` (beamtransfer.py:931-947)."""
+        self.comm.barrier()
+        if self.comm.rank0:
+            spec = np.zeros((self.telescope.mmax + 1, self.nfreq, self.svd_len), dtype=np.float64)
+            for mi in range(self.telescope.mmax + 1):
+                spec[mi] = _load_beam_f(self._svdfile(mi), "singularvalues")
+            with h5lite.File(self.directory + "/svdspectrum.hdf5", "w") as f:
+                f.create_dataset("singularvalues", data=spec)
+        self.comm.barrier()
+
+    def svd_all(self):
+        """``[mmax+1, nfreq, svd_len]`` singular values (beamtransfer.py:949-964)."""
+        return _load_beam_f(self.directory + "/svdspectrum.hdf5", "singularvalues")
+
+    # ---- projections -------------------------------------------------------------------
+    def _svd_num(self, mi):
+        """Number of modes above ``svcut`` per frequency and the block bounds
+        (beamtransfer.py:1116-1129)."""
+        sv = self.beam_singularvalues(mi)
+        svnum = (sv > sv.max() * self.svcut).sum(axis=1)
+        return svnum, np.cumsum(np.insert(svnum, 0, 0))
+
+    def _svd_freq_iter(self, mi):
+        num = self._svd_num(mi)[0]
+        return [fi for fi in range(self.nfreq) if num[fi] > 0]
+
+    def project_vector_sky_to_svd(self, mi, vec, temponly=False):
+        """Sky vector ``[nfreq, npol, lmax+1, ...]`` -> stacked SVD modes
+        (beamtransfer.py:1324-1364); evaluated on the device."""
+        import torch
+
+        from .. import _lib
+
+        tel = self.telescope
+        npol = 1 if temponly else tel.num_pol_sky
+        svnum, svbounds = self._svd_num(mi)
+        vec = np.asarray(vec)
+        vecf = np.zeros((svbounds[-1],) + vec.shape[3:], dtype=np.complex128)
+        if np.all(vec == 0) or svbounds[-1] == 0:
+            return vecf
+        nrhs = int(np.prod(vec.shape[3:])) if vec.ndim > 3 else 1
+        dev = torch.device("cuda", torch.cuda.current_device())
+        beam = torch.from_numpy(np.ascontiguousarray(self.beam_svd(mi))).to(dev)
+        v = torch.from_numpy(
+            np.ascontiguousarray(vec, dtype=np.complex128).reshape(self.nfreq, tel.num_pol_sky, tel.lmax + 1, nrhs)
+        ).to(dev)
+        out = torch.zeros((int(svbounds[-1]), nrhs), dtype=torch.complex128, device=dev)
+        sn = np.ascontiguousarray(svnum, dtype=np.int32)
+        sb = np.ascontiguousarray(svbounds, dtype=np.int32)
+        _lib.check(
+            _lib.lib.dsb_project_sky_to_svd(
+                beam.data_ptr(), v.data_ptr(), sn.ctypes.data, sb.ctypes.data, self.nfreq, self.svd_len,
+                tel.num_pol_sky, npol, tel.lmax + 1, nrhs, out.data_ptr(),
+                torch.cuda.current_stream().cuda_stream,
+            )
+        )
+        return out.cpu().numpy().reshape(vecf.shape)
+
+    def project_vector_sky_to_telescope(self, mi, vec):
+        """Sky vector ``[nfreq, npol, lmax+1]`` -> visibilities ``[nfreq, ntel]``
+        (beamtransfer.py:970-1010).  Small dense host algebra on the stored product."""
+        tel = self.telescope
+        vecf = np.zeros((self.nfreq, 2, tel.nbase), dtype=np.complex128)
+        ind = np.ix_(tel.included_freq, tel.included_pol, np.arange(mi, tel.lmax + 1))
+        nfreq_trim = len(tel.included_freq)
+        nsky_trim = len(tel.included_pol) * (tel.lmax + 1 - mi)
+        vec = np.asarray(vec)[ind].reshape((nfreq_trim, nsky_trim))
+        if np.all(vec == 0):
+            return vecf.reshape(self.nfreq, self.ntel)
+        with h5lite.File(self._mfile(mi), "r") as mfile:
+            dset = mfile["beam_m"]
+            for file_fi, fi in enumerate(tel.included_freq):
+                beamf = dset[file_fi].reshape(-1, nsky_trim)
+                vecf[fi][:, tel.included_baseline] = np.dot(beamf, vec[file_fi]).reshape(2, -1)
+        return vecf.reshape(self.nfreq, self.ntel)
+
+    project_vector_forward = project_vector_sky_to_telescope
+
+    def project_vector_telescope_to_svd(self, mi, vec):
+        """Telescope vector ``[nfreq, ntel, ...]`` -> SVD modes (beamtransfer.py:1233-1271)."""
+        svnum, svbounds = self._svd_num(mi)
+        vec = np.asarray(vec)
+        vecf = np.zeros((svbounds[-1],) + vec.shape[2:], dtype=np.complex128)
+        if np.all(vec == 0):
+            return vecf
+        beam = self.beam_ut(mi)
+        for fi in self._svd_freq_iter(mi):
+            vecf[svbounds[fi] : svbounds[fi + 1]] = np.dot(beam[fi, : svnum[fi], :], vec[fi, :])
+        return vecf
+
+    def project_vector_svd_to_telescope(self, mi, svec):
+        """SVD modes -> telescope vector ``[nfreq, 2, npairs]`` (beamtransfer.py:1273-1322)."""
+        tel = self.telescope
+        svnum, svbounds = self._svd_num(mi)
+        vecf = np.zeros((self.nfreq, self.ntel), dtype=np.complex128)
+        if np.all(svec == 0):
+            return vecf.reshape(self.nfreq, 2, tel.npairs)
+        beam = self.beam_ut(mi)
+        for fi in self._svd_freq_iter(mi):
+            noise = tel.noisepower(np.arange(tel.npairs), fi).flatten()
+            noise = np.concatenate([noise, noise])
+            lvec = svec[svbounds[fi] : svbounds[fi + 1]]
+            vecf[fi, :] = noise * np.dot(beam[fi, : svnum[fi], :].T.conj(), lvec)
+        return vecf.reshape(self.nfreq, 2, tel.npairs)
+
+    def project_vector_svd_to_sky(self, mi, vec, temponly=False, conj=False):
+        """SVD modes -> sky vector (beamtransfer.py:1366-1421)."""
+        tel = self.telescope
+        npol = 1 if temponly else tel.num_pol_sky
+        svnum, svbounds = self._svd_num(mi)
+        vec = np.asarray(vec)
+        vecf = np.zeros((self.nfreq, tel.num_pol_sky, tel.lmax + 1) + vec.shape[1:], dtype=np.complex128)
+        if np.all(vec == 0):
+            return vecf
+        beam = self.beam_svd(mi) if conj else self.invbeam_svd(mi)
+        for pi in range(npol):
+            for fi in self._svd_freq_iter(mi):
+                if conj:
+                    fbeam = beam[fi, : svnum[fi], pi, :].T.conj()
+                else:
+                    fbeam = beam[fi, pi, :, : svnum[fi]]
+                vecf[fi, pi] += np.dot(fbeam, vec[svbounds[fi] : svbounds[fi + 1]])
+        return vecf

@@ -1,0 +1,588 @@
+"""Transit-telescope model with a B200 beam-transfer engine behind it.
+
+Drop-in mirror of ``drift.core.telescope`` (reference drift/core/telescope.py):
+same class names, configuration properties, baseline bookkeeping and the
+``transfer_matrices`` / ``_transfer_single`` / ``noisepower`` API.  The per-unit
+arithmetic (fringe, Stokes maps, spherical-harmonic transform) is not done
+here: ``transfer_matrices`` batches the requested (baseline, frequency) units
+by HEALPix resolution and hands them to the CUDA library through
+:class:`driftscan_b200.engine.TransferEngine`.
+"""
+
+import abc
+import logging
+from functools import cached_property
+
+import numpy as np
+
+from .. import config
+from ..util import hputil
+from . import visibility
+
+logger = logging.getLogger(__name__)
+
+
+def in_range(arr, lo, hi):
+    """True if ``lo <= arr < hi`` everywhere."""
+    arr = np.asarray(arr)
+    return bool(np.all(arr >= lo) and np.all(arr < hi))
+
+
+def out_of_range(arr, lo, hi):
+    return not in_range(arr, lo, hi)
+
+
+def max_lm(baselines, wavelengths, uwidth, vwidth=0.0):
+    """Largest (l, m) a baseline of finite extent is sensitive to
+    (drift/core/telescope.py:99-122)."""
+    ureach = (np.abs(baselines[:, 0]) + uwidth) / wavelengths
+    vreach = (np.abs(baselines[:, 1]) + vwidth) / wavelengths
+    mmax = np.ceil(2 * np.pi * ureach).astype(np.int64)
+    lmax = np.ceil((mmax**2 + (2 * np.pi * vreach) ** 2) ** 0.5).astype(np.int64)
+    return lmax, mmax
+
+
+def _dense_labels(keys, mask):
+    """Label equal keys (rows of ``keys``) with 0..n-1 in lexicographic key order;
+    masked-out entries get -1.  ``keys`` has shape [..., nkey]."""
+    shape = mask.shape
+    flat = keys.reshape(-1, keys.shape[-1])
+    sel = np.flatnonzero(mask.ravel())
+    labels = np.full(mask.size, -1, dtype=np.int64)
+    if sel.size:
+        _, inv = np.unique(flat[sel], axis=0, return_inverse=True)
+        labels[sel] = np.asarray(inv).ravel()
+    return labels.reshape(shape)
+
+
+def _first_members(labels, mask):
+    """For every label 0..n-1, the (i, j) of its first member in row-major order among
+    the entries selected by ``mask``."""
+    sel = np.flatnonzero(mask.ravel())
+    lab = labels.ravel()[sel]
+    _, first = np.unique(lab, return_index=True)
+    return np.array(np.unravel_index(sel[first], labels.shape)).T.reshape(-1, 2)
+
+
+class TransitTelescope(config.Reader, metaclass=abc.ABCMeta):
+    """Base class of every transit interferometer (reference
+    drift/core/telescope.py:125-1123).  Subclasses provide ``feedpositions``,
+    ``beamclass``, ``u_width``/``v_width`` and the primary beam."""
+
+    freq_lower = config.Property(proptype=float, default=None)
+    freq_upper = config.Property(proptype=float, default=None)
+    freq_start = config.Property(proptype=float, default=800.0)
+    freq_end = config.Property(proptype=float, default=400.0)
+    num_freq = config.Property(proptype=int, default=1024)
+    freq_mode = config.enum(["centre", "centre_nyquist", "edge"], default="centre")
+
+    channel_bin = config.Property(proptype=int, default=1)
+    channel_range = config.Property(proptype=list)
+    channel_list = config.Property(proptype=list)
+
+    tsys_flat = config.Property(proptype=float, default=50.0, key="tsys")
+    ndays = config.Property(proptype=int, default=733)
+
+    accuracy_boost = config.Property(proptype=float, default=1.0)
+    l_boost = config.Property(proptype=float, default=1.0)
+    force_lmax = config.Property(proptype=int, default=None)
+    force_mmax = config.Property(proptype=int, default=None)
+
+    minlength = config.Property(proptype=float, default=0.0)
+    maxlength = config.Property(proptype=float, default=1.0e7)
+    auto_correlations = config.Property(proptype=bool, default=False)
+    local_origin = config.Property(proptype=bool, default=True)
+
+    skip_freq = config.list_type(type_=int, default=[])
+    skip_baselines = config.list_type(type_=int, default=[])
+    beam_cache_size = config.Property(proptype=int, default=200)
+
+    # B200 engine options (not present in the reference)
+    precision = config.enum(["fp32x3", "fp64"], default="fp32x3")
+
+    def __init__(self, latitude=45, longitude=0, **kwargs):
+        # The reference inherits the observer position from caput.time.Observer
+        # (drift/core/telescope.py:245-255); only latitude/longitude are used here.
+        self.latitude = latitude
+        self.longitude = longitude
+        self.altitude = kwargs.get("altitude", 0.0)
+
+    _pickle_keys = []
+
+    def __getstate__(self):
+        # Lazily computed private state is dropped (telescope.py:257-266); configuration
+        # values (stored under ``_prop_*``) are kept.
+        return {
+            k: v
+            for k, v in self.__dict__.items()
+            if not k.startswith("_") or k.startswith("_prop_") or k in self._pickle_keys
+        }
+
+    # ------------------------------------------------------------------ geometry
+    @property
+    def zenith(self):
+        """[theta, phi] of the zenith in spherical polars (telescope.py:268-291)."""
+        theta = np.pi / 2.0 - np.radians(self.latitude)
+        phi = 0.0 if self.local_origin else np.remainder(np.radians(self.longitude), 2 * np.pi)
+        return np.array([theta, phi])
+
+    # ------------------------------------------------------------------ baselines
+    _baselines = None
+    _redundancy = None
+    _uniquepairs = None
+    _feedmap = None
+    _feedmask = None
+    _feedconj = None
+
+    def _ensure_pairs(self):
+        if self._feedmap is None:
+            self.calculate_feedpairs()
+
+    @property
+    def baselines(self):
+        """Unique baseline vectors [nbase, 2] in metres."""
+        self._ensure_pairs()
+        return self._baselines
+
+    @property
+    def redundancy(self):
+        self._ensure_pairs()
+        return self._redundancy
+
+    @property
+    def uniquepairs(self):
+        """[nbase, 2] feed pair representing each unique baseline."""
+        self._ensure_pairs()
+        return self._uniquepairs
+
+    @property
+    def feedmap(self):
+        """[nfeed, nfeed] map from feed pair to unique-baseline index (-1 = excluded)."""
+        self._ensure_pairs()
+        return self._feedmap
+
+    @property
+    def feedmask(self):
+        self._ensure_pairs()
+        return self._feedmask
+
+    @property
+    def feedconj(self):
+        """[nfeed, nfeed] pairs that are the complex conjugate of their unique baseline."""
+        self._ensure_pairs()
+        return self._feedconj
+
+    @property
+    def npairs(self):
+        return self.uniquepairs.shape[0]
+
+    @property
+    def nbase(self):
+        return self.npairs
+
+    _bl_tol = 6  # decimals kept when comparing baselines (telescope.py:554)
+
+    def _baseline_mask(self, sep):
+        """Which feed pairs take part at all (telescope.py:556-576)."""
+        length = np.sum(sep**2, axis=-1) ** 0.5
+        mask = (length >= self.minlength) & (length <= self.maxlength)
+        if not self.auto_correlations:
+            mask &= length > 0.0
+        return mask
+
+    def _beam_pair_mask(self):
+        if self.auto_correlations:
+            return np.ones((self.nfeed, self.nfeed), dtype=bool)
+        return ~np.identity(self.nfeed, dtype=bool)
+
+    def calculate_feedpairs(self):
+        """Identify redundant feed pairs (telescope.py:507-675).
+
+        Two pairs are equivalent when their separations agree to ``_bl_tol`` decimals
+        and their beam classes agree; a pair and its transpose are one baseline and its
+        conjugate.  The unconjugated orientation points East (North if purely N-S); for
+        zero separation it is the one with the smaller (class_i, class_j).  Baselines are
+        ordered by (dx, dy, class_j, class_i) of their first member.
+        """
+        pos = self.feedpositions
+        cls = np.asarray(self.beamclass)
+        nfeed = pos.shape[0]
+        sep = pos[:, np.newaxis, :] - pos[np.newaxis, :, :]
+        mask = self._baseline_mask(sep) & self._beam_pair_mask()
+
+        rsep = np.around(sep[..., 0] + 1.0j * sep[..., 1], self._bl_tol)
+        ci = np.broadcast_to(cls[:, np.newaxis], (nfeed, nfeed))
+        cj = np.broadcast_to(cls[np.newaxis, :], (nfeed, nfeed))
+        keys = np.stack([rsep.real, rsep.imag, ci.astype(np.float64), cj.astype(np.float64)], axis=-1)
+        oriented = _dense_labels(keys, mask)  # labels in lexicographic key order
+
+        # a pair is provisionally "conjugated" when its transpose carries the smaller label
+        conj = oriented > oriented.T
+        merged = np.minimum(oriented, oriented.T)
+        labels = _dense_labels(merged[..., np.newaxis].astype(np.float64), mask)
+
+        # point the unconjugated orientation East / North
+        reps = _first_members(labels, mask & ~conj)
+        rsep_rep = pos[reps[:, 0]] - pos[reps[:, 1]]
+        flip = (rsep_rep[:, 0] < 0.0) | ((rsep_rep[:, 0] == 0.0) & (rsep_rep[:, 1] < 0.0))
+        flip = np.append(flip, False)  # label -1 indexes the extra entry
+        conj = np.logical_xor(conj, flip[labels])
+
+        # order the baselines
+        reps = _first_members(labels, mask & ~conj)
+        fi, fj = reps[:, 0], reps[:, 1]
+        sortkey = np.zeros(fi.size, dtype=np.dtype("f8,f8,i4,i4"))
+        sortkey["f0"] = pos[fi, 0] - pos[fj, 0]
+        sortkey["f1"] = pos[fi, 1] - pos[fj, 1]
+        sortkey["f2"] = cls[fj]
+        sortkey["f3"] = cls[fi]
+        order = np.argsort(sortkey)
+        rank = np.empty_like(order)
+        rank[order] = np.arange(order.size)
+        feedmap = np.where(mask, rank[np.where(mask, labels, 0)], labels)
+
+        self._feedmap = feedmap
+        self._feedmask = mask
+        self._feedconj = conj
+        keep = mask & ~conj
+        self._uniquepairs = _first_members(feedmap, keep)
+        self._redundancy = np.bincount(feedmap[keep])
+        self._baselines = pos[self._uniquepairs[:, 0]] - pos[self._uniquepairs[:, 1]]
+
+    # ------------------------------------------------------------------ frequencies
+    _frequencies = None
+
+    @property
+    def frequencies(self):
+        """Centre of every channel in MHz."""
+        if self._frequencies is None:
+            self.calculate_frequencies()
+        return self._frequencies
+
+    def calculate_frequencies(self):
+        """Channelisation (telescope.py:386-431)."""
+        if self.freq_lower or self.freq_upper:
+            import warnings
+
+            warnings.warn("`freq_lower` and `freq_upper` parameters are deprecated", DeprecationWarning)
+            self.freq_start = self.freq_lower
+            self.freq_end = self.freq_upper
+
+        nf, f0, f1 = self.num_freq, self.freq_start, self.freq_end
+        if self.freq_mode == "centre":
+            freq = np.linspace(f0, f1, nf, endpoint=False)
+        elif self.freq_mode == "centre_nyquist":
+            freq = np.linspace(f0, f1, nf, endpoint=True)
+        else:
+            width = abs(f1 - f0) / nf
+            freq = f0 + width * (np.arange(nf) + 0.5)
+
+        if self.channel_bin > 1:
+            if nf % self.channel_bin != 0:
+                raise ValueError("Channel binning must exactly divide the total number of channels")
+            freq = freq.reshape(-1, self.channel_bin).mean(axis=1)
+
+        if self.channel_list is not None:
+            raise NotImplementedError(
+                "`channel_list` is not yet supported, as sparse channel selections "
+                "may break things downstream."
+            )
+        if self.channel_range is not None:
+            freq = freq[self.channel_range[0] : self.channel_range[1]]
+        self._frequencies = freq
+
+    @property
+    def wavelengths(self):
+        return hputil.C_LIGHT / (1e6 * self.frequencies)
+
+    @property
+    def nfreq(self):
+        return self.frequencies.shape[0]
+
+    # ------------------------------------------------------------------ feeds / pol
+    @property
+    def input_index(self):
+        return np.array(np.arange(self.nfeed), dtype=[("chan_id", "u2")])
+
+    @property
+    def nfeed(self):
+        return self.feedpositions.shape[0]
+
+    @property
+    def num_pol_sky(self):
+        return self._npol_sky_
+
+    # ------------------------------------------------------------------ harmonic reach
+    @property
+    def lmax(self):
+        if self.force_lmax is not None:
+            return self.force_lmax
+        lmax, _ = max_lm(self.baselines, self.wavelengths.min(), self.u_width, self.v_width)
+        return int(np.ceil(lmax.max() * self.l_boost))
+
+    @property
+    def mmax(self):
+        if self.force_mmax is not None:
+            return self.force_mmax
+        _, mmax = max_lm(self.baselines, self.wavelengths.min(), self.u_width, self.v_width)
+        return int(np.ceil(mmax.max() * self.l_boost))
+
+    # ------------------------------------------------------------------ skipping
+    def _skip_freq(self, freq_ind):
+        return freq_ind in self.skip_freq
+
+    def _skip_baseline(self, bl_ind):
+        return bl_ind in self.skip_baselines
+
+    @cached_property
+    def included_freq(self):
+        return np.array([i for i in range(self.nfreq) if not self._skip_freq(i)], dtype=int)
+
+    @cached_property
+    def included_baseline(self):
+        return np.array([i for i in range(self.nbase) if not self._skip_baseline(i)], dtype=int)
+
+    @cached_property
+    def included_pol(self):
+        return np.arange(self.num_pol_sky)
+
+    # ------------------------------------------------------------------ transfer matrices
+    def unit_lmax(self, bl_indices, f_indices):
+        """Per-unit (lmax, mmax) (telescope.py:792-802)."""
+        lm = max_lm(self.baselines[bl_indices], self.wavelengths[f_indices], self.u_width, self.v_width)
+        lmax, mmax = np.ceil(self.l_boost * np.array(lm)).astype(np.int64)
+        return lmax, mmax
+
+    def _unit_nside(self, lmax):
+        """HEALPix resolution used for a unit of the given lmax."""
+        raise NotImplementedError
+
+    _engine = None
+
+    @property
+    def engine(self):
+        """The device engine (created on first use; needs the CUDA library)."""
+        if self._engine is None:
+            from ..engine import TransferEngine
+
+            self._engine = TransferEngine(self)
+        return self._engine
+
+    def transfer_matrices(self, bl_indices, f_indices, global_lmax=True):
+        """Beam-transfer matrices of (baseline, frequency) combinations
+        (telescope.py:755-830).
+
+        Returns a complex128 array of shape ``broadcast(bl, f).shape + (num_pol_sky,
+        lside + 1, 2 * lside + 1)`` with column ``m`` for m >= 0 and ``-|m|`` (python
+        indexing) for m < 0.
+        """
+        bl_indices, f_indices = np.broadcast_arrays(bl_indices, f_indices)
+        if out_of_range(bl_indices, 0, self.npairs):
+            raise ValueError("Baseline indices aren't valid")
+        if out_of_range(f_indices, 0, self.nfreq):
+            raise ValueError("Frequency indices aren't valid")
+
+        lmax, _ = self.unit_lmax(bl_indices, f_indices)
+        lside = self.lmax if global_lmax else int(lmax.max())
+        tshape = bl_indices.shape + (self.num_pol_sky, lside + 1, 2 * lside + 1)
+        logger.info(
+            "Size: %i elements. Memory %f GB." % (np.prod(tshape), 2 * np.prod(tshape) * 8.0 / 2**30)
+        )
+        tarray = np.zeros(tshape, dtype=np.complex128)
+        if bl_indices.size:
+            self.engine.transfer_dense(bl_indices.ravel(), f_indices.ravel(), lmax.ravel(), lside, tarray)
+        return tarray
+
+    def transfer_for_frequency(self, freq):
+        bi = np.arange(self.npairs)
+        return self.transfer_matrices(bi, freq * np.ones_like(bi))
+
+    def transfer_for_baseline(self, baseline):
+        fi = np.arange(self.nfreq)
+        return self.transfer_matrices(baseline * np.ones_like(fi), fi)
+
+    def _transfer_single(self, bl_index, f_index, lmax, lside):
+        """One unit (telescope.py:1095-1119): sequence of ``[lside+1, 2*lside+1]`` arrays,
+        one per sky polarisation."""
+        out = np.zeros((1, self.num_pol_sky, lside + 1, 2 * lside + 1), dtype=np.complex128)
+        self.engine.transfer_dense(
+            np.array([bl_index]), np.array([f_index]), np.array([lmax], dtype=np.int64), lside, out
+        )
+        return out[0]
+
+    # ------------------------------------------------------------------ noise
+    def tsys(self, f_indices=None):
+        freq = self.frequencies if f_indices is None else self.frequencies[f_indices]
+        return np.ones_like(freq) * self.tsys_flat
+
+    def _noise_per_channel(self, f_indices, ndays):
+        ndays = self.ndays if not ndays else ndays
+        bw = np.abs(self.frequencies[1] - self.frequencies[0]) * 1e6
+        delnu = hputil.T_SIDEREAL * bw / (2 * np.pi)
+        return self.tsys(f_indices) ** 2 / (2 * np.pi * delnu * ndays)
+
+    def noisepower(self, bl_indices, f_indices, ndays=None):
+        """Instrumental noise power per (baseline, frequency) (telescope.py:894-926)."""
+        bl_indices, f_indices = np.broadcast_arrays(bl_indices, f_indices)
+        return self._noise_per_channel(f_indices, ndays) / self.redundancy[bl_indices]
+
+    def noisepower_feedpairs(self, fi, fj, f_indices, m, ndays=None):
+        noise = self._noise_per_channel(f_indices, ndays)
+        return np.ones_like(fi) * np.ones_like(fj) * np.ones_like(m) * noise / 2.0
+
+    # ------------------------------------------------------------------ per-nside maps
+    _nside = None
+
+    def _init_trans(self, nside):
+        """Pixel positions and horizon for one resolution (telescope.py:943-952); beam
+        functions read ``self._angpos`` / ``self._nside``."""
+        self._nside = nside
+        self._angpos = hputil.ang_positions(nside)
+        self._horizon = visibility.horizon(self._angpos, self.zenith)
+
+    # ------------------------------------------------------------------ draco helpers
+    @cached_property
+    def prodstack(self):
+        upairs = self.uniquepairs
+        dtype = [("input_a", upairs.dtype), ("input_b", upairs.dtype)]
+        return upairs.ravel().view(dtype)
+
+    @cached_property
+    def index_map_prod(self):
+        tpairs = np.array(np.triu_indices(self.nfeed))
+        dtype = [("input_a", tpairs.dtype), ("input_b", tpairs.dtype)]
+        return tpairs.T.flatten().view(dtype)
+
+    @cached_property
+    def index_map_stack(self):
+        n = self.nfeed
+        upairs = self.uniquepairs
+        smap = np.empty(len(upairs), dtype=[("prod", "<u4"), ("conjugate", "u1")])
+        smap["conjugate"] = upairs[:, 0] > upairs[:, 1]
+        a, b = np.where(smap["conjugate"], upairs[:, ::-1].T, upairs.T)
+        smap["prod"] = (n * (n + 1) // 2) - ((n - a) * (n - a + 1) // 2) + (b - a)
+        return smap
+
+    @cached_property
+    def reverse_map_stack(self):
+        tri = np.triu_indices(self.nfeed)
+        rmap = np.empty(self.nfeed * (self.nfeed + 1) // 2, dtype=[("stack", "<i4"), ("conjugate", "u1")])
+        rmap["stack"] = self.feedmap[tri]
+        rmap["conjugate"] = self.feedconj[tri]
+        return rmap
+
+    # ------------------------------------------------------------------ abstract
+    @property
+    @abc.abstractmethod
+    def feedpositions(self):
+        """[nfeed, 2] feed positions in metres (East, North)."""
+
+    @property
+    @abc.abstractmethod
+    def beamclass(self):
+        """[nfeed] integer label; equal labels have identical primary beams."""
+
+    @property
+    @abc.abstractmethod
+    def u_width(self):
+        """Physical extent of an element in the East-West direction (metres)."""
+
+    @property
+    @abc.abstractmethod
+    def v_width(self):
+        """Physical extent of an element in the North-South direction (metres)."""
+
+
+class UnpolarisedTelescope(TransitTelescope, metaclass=abc.ABCMeta):
+    """Single sky polarisation (telescope.py:1126-1221)."""
+
+    _npol_sky_ = 1
+    _polarised_ = False
+
+    @abc.abstractmethod
+    def beam(self, feed, freq):
+        """HEALPix map (size 12*self._nside**2) of the primary beam of ``feed``."""
+
+    def _unit_nside(self, lmax):
+        return hputil.nside_for_lmax(lmax, accuracy_boost=self.accuracy_boost)
+
+    def noisepower(self, bl_indices, f_indices, ndays=None):
+        base = TransitTelescope.noisepower(self, bl_indices, f_indices, ndays)
+        return base[..., np.newaxis] * 0.5
+
+
+class PolarisedTelescope(TransitTelescope, metaclass=abc.ABCMeta):
+    """Four sky polarisations T, E(Q), B(U), V (telescope.py:1224-1335)."""
+
+    skip_V = config.Property(proptype=bool, default=False)
+    skip_pol = config.Property(proptype=bool, default=False)
+
+    _npol_sky_ = 4
+    _polarised_ = True
+
+    @property
+    def polarisation(self):
+        raise NotImplementedError("`polarisation` must be implemented.")
+
+    def _unit_nside(self, lmax):
+        # NB: the polarised path of the reference ignores accuracy_boost
+        # (telescope.py:1288-1289)
+        return hputil.nside_for_lmax(lmax)
+
+    @cached_property
+    def included_pol(self):
+        npol = 1 if self.skip_pol else (3 if self.skip_V else 4)
+        return np.arange(npol)
+
+
+class SimpleUnpolarisedTelescope(UnpolarisedTelescope, metaclass=abc.ABCMeta):
+    """All feeds share one beam (telescope.py:1340-1364)."""
+
+    @property
+    def beamclass(self):
+        return np.zeros(self._single_feedpositions.shape[0], dtype=np.int64)
+
+    @property
+    @abc.abstractmethod
+    def _single_feedpositions(self):
+        """[nfeed, 2] positions of the feeds."""
+
+    @property
+    def feedpositions(self):
+        return self._single_feedpositions
+
+
+class SimplePolarisedTelescope(PolarisedTelescope, metaclass=abc.ABCMeta):
+    """Dual-polarisation feeds at each position: all X feeds, then all Y feeds
+    (telescope.py:1367-1448)."""
+
+    @property
+    def polarisation(self):
+        return np.asarray(["X" if c % 2 == 0 else "Y" for c in self.beamclass], dtype=str)
+
+    @property
+    def beamclass(self):
+        n = self._single_feedpositions.shape[0]
+        return np.concatenate((np.zeros(n), np.ones(n))).astype(np.int64)
+
+    def beam(self, feed, freq):
+        if self.polarisation[feed] == "X":
+            return self.beamx(feed, freq)
+        return self.beamy(feed, freq)
+
+    @property
+    @abc.abstractmethod
+    def _single_feedpositions(self):
+        """[nfeed, 2] positions of the (dual-polarisation) feeds."""
+
+    @property
+    def feedpositions(self):
+        return np.concatenate((self._single_feedpositions, self._single_feedpositions))
+
+    @abc.abstractmethod
+    def beamx(self, feed, freq):
+        """[npix, 2] (theta-hat, phi-hat) field pattern of the X feed."""
+
+    @abc.abstractmethod
+    def beamy(self, feed, freq):
+        """[npix, 2] (theta-hat, phi-hat) field pattern of the Y feed."""

@@ -1,0 +1,130 @@
+"""Host-side driver of the CUDA beam-transfer path.
+
+Groups (baseline, frequency) units by HEALPix resolution (the reference picks
+nside per unit from that unit's own lmax, drift/core/telescope.py:1179-1184,
+1288-1289), keeps one device plan per nside, uploads the primary-beam maps the
+telescope's (possibly user-defined) ``beam*`` methods return -- what the
+reference caches per (nside, freq, beamclass) in ``_beam``
+(telescope.py:956-974) -- and calls ``dsb_transfer_units``.
+
+There is no CPU path here: importing this module needs ``libdriftb200.so``.
+"""
+
+import logging
+
+import numpy as np
+
+from . import _lib
+from .core import visibility
+
+logger = logging.getLogger(__name__)
+
+
+class TransferEngine:
+    """Per-telescope cache of device plans and beam slots."""
+
+    def __init__(self, telescope, precision=None):
+        self.tel = telescope
+        self.precision = _lib.PRECISIONS[precision or getattr(telescope, "precision", "fp32x3")]
+        self.beam_budget = int(getattr(telescope, "beam_cache_size", 200)) << 25  # bytes on device
+        self._plans = {}  # nside -> Plan
+        self._slots = {}  # nside -> {(freq, beamclass): slot}
+
+    # ---- plans and beams -------------------------------------------------------
+    def close(self):
+        for p in self._plans.values():
+            p.close()
+        self._plans.clear()
+        self._slots.clear()
+
+    def plan(self, nside):
+        if nside not in self._plans:
+            self.tel._init_trans(nside)
+            self._plans[nside] = _lib.Plan(nside, self.tel._horizon)
+            self._slots[nside] = {}
+        return self._plans[nside]
+
+    def drop_beams(self, nside):
+        """Forget the uploaded beams of one resolution (slots are reused)."""
+        self._slots[nside] = {}
+
+    def _beam_slot(self, nside, feed, freq):
+        """Device slot of the beam of ``feed`` at ``freq`` (uploads it on first use)."""
+        tel = self.tel
+        key = (int(freq), int(tel.beamclass[feed]))
+        slots = self._slots[nside]
+        if key not in slots:
+            if tel._nside != nside:
+                tel._init_trans(nside)
+            beam = np.asarray(tel.beam(feed, freq))
+            ncomp = 2 if tel._polarised_ else 1
+            want = (12 * nside * nside, 2) if ncomp == 2 else (12 * nside * nside,)
+            if beam.shape != want:
+                raise ValueError(f"beam() returned shape {beam.shape}, expected {want}")
+            slot = len(slots)
+            self._plans[nside].upload_beam(slot, beam)
+            slots[key] = slot
+        return slots[key]
+
+    # ---- unit tables -----------------------------------------------------------
+    def _npol_compute(self):
+        tel = self.tel
+        if not tel._polarised_:
+            return 1
+        return len(tel.included_pol)
+
+    def _units_for(self, nside, bl, fi, lmax, out0, out1):
+        tel = self.tel
+        plan = self.plan(nside)
+        units = np.zeros(len(bl), dtype=_lib.UNIT_DTYPE)
+        pairs = tel.uniquepairs[bl]
+        # bound the device memory held by cached beams (fp64 + fp32 copy per map)
+        needed = {(int(f), int(c)) for f, c in zip(np.repeat(fi, 2), tel.beamclass[pairs].ravel())}
+        per_slot = 12 * nside * nside * (2 if tel._polarised_ else 1) * 12
+        if len(needed | set(self._slots[nside])) * per_slot > self.beam_budget:
+            self.drop_beams(nside)
+        uv = tel.baselines[bl] / tel.wavelengths[fi][:, np.newaxis]
+        units["uvec"] = visibility.uv_vector(tel.zenith, uv)
+        # upload in frequency order so that the host beam cache of user telescopes is hit
+        for i in np.argsort(fi, kind="stable"):
+            si = self._beam_slot(nside, pairs[i, 0], fi[i])
+            sj = self._beam_slot(nside, pairs[i, 1], fi[i])
+            units["beam_i"][i], units["beam_j"][i] = si, sj
+            units["prefactor"][i] = 1.0 / np.sqrt(plan.omega[si] * plan.omega[sj])
+        units["lmax"] = lmax
+        units["out0"] = out0
+        units["out1"] = out1
+        return plan, units
+
+    def _buckets(self, lmax):
+        nside = np.array([self.tel._unit_nside(int(l)) for l in lmax], dtype=np.int64)
+        # ascending nside == ascending lmax order of the reference's unit loop
+        return [(int(ns), np.flatnonzero(nside == ns)) for ns in np.unique(nside)]
+
+    # ---- dense output (TransitTelescope.transfer_matrices) -----------------------
+    def transfer_dense(self, bl, fi, lmax, lside, tarray):
+        """Fill ``tarray`` (host complex128, flattened leading dims = units) in place."""
+        tel = self.tel
+        flat = tarray.reshape((-1,) + tarray.shape[-3:])
+        assert flat.flags.c_contiguous and flat.shape[0] == len(bl)
+        npol = self._npol_compute()
+        for nside, idx in self._buckets(lmax):
+            plan, units = self._units_for(nside, bl[idx], fi[idx], lmax[idx], idx, 0)
+            plan.transfer_units(
+                units, npol, tel._polarised_, lside, self.precision, _lib.DSB_OUT_TARRAY_C128,
+                [flat.shape[0], flat.shape[1], lside], flat.ctypes.data, True,
+            )
+
+    # ---- m-major output (BeamTransfer._generate_mfiles) ---------------------------
+    def transfer_mmajor(self, bl, fi, lmax, fslot, bslot, nf, nb, lside, mmax, out_ptr, out_is_host,
+                        out_kind=_lib.DSB_OUT_MMAJOR_C128, stream=None):
+        """Write the compact m-major beam_m blocks of the given units into ``out_ptr``
+        (layout documented at DSB_OUT_MMAJOR_* in include/driftscan_b200.h)."""
+        tel = self.tel
+        npol = self._npol_compute()
+        for nside, idx in self._buckets(lmax):
+            plan, units = self._units_for(nside, bl[idx], fi[idx], lmax[idx], fslot[idx], bslot[idx])
+            plan.transfer_units(
+                units, npol, tel._polarised_, mmax, self.precision, out_kind, [nf, nb, npol, lside, mmax],
+                out_ptr, out_is_host, stream,
+            )
