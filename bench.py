@@ -1,0 +1,435 @@
+#!/usr/bin/env python
+"""Benchmark of the beam-transfer hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm
+    python bench.py --impl reference --gpus N --steps K ...   # CPU reference arm
+
+Workload (config.workload): BASELINE.json configs[2], the largest single-GPU
+configuration -- PolarisedCylinder pathfinder scale, 2 cylinders x 64 feeds x
+2 pols (760 unique baselines), 200-250 MHz in 64 channels, lmax 233 / mmax 210,
+units spread over nside 64/128/256.  One "step" = the transfer matrices of all
+760 baselines at `--freqs-per-gpu` frequencies per GPU (weak scaling: each GPU
+owns its own frequencies), i.e. fringe x beam on rings -> ring FFT -> Legendre
+contraction (tcgen05) -> m-major pack, followed for N > 1 by the NCCL all-to-all
+that regroups frequency-major blocks into the m ranges each GPU owns.
+
+metric  = beam-transfer (baseline*freq) units per second, whole job.
+value   = device-resident (beams, tables and unit descriptors already in HBM).
+e2e     = same call through the C ABI with HOST buffers: host beam maps are
+          uploaded and the m-major complex128 product is copied back to pinned
+          host memory inside the timed region.
+"""
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(
+    num_cylinders=2, num_feeds=64, cylinder_width=20.0, feed_spacing=0.3048,
+    freq_start=200.0, freq_end=250.0, num_freq=64, freq_mode="edge",
+)
+WORKLOAD_NAME = "configs[2] PolarisedCylinder pathfinder-scale 2cyl x 64feeds x 2pol, 200-250MHz/64ch, nside<=256"
+
+
+# ---------------------------------------------------------------------------------
+# algorithmic work (SURVEY section 8d definitions)
+# ---------------------------------------------------------------------------------
+
+
+def t_lm(L, M):
+    m = np.arange(0, M + 1)
+    return int(((L - m + 1) * np.where(m == 0, 1, 2)).sum())
+
+
+def unit_work(nside, L, mmax_tel, P=4, c=2):
+    M = min(mmax_tel, L)
+    npix, nring, nfold = 12 * nside * nside, 4 * nside - 1, 2 * nside
+    kappa = {1: 1, 3: 5, 4: 6}[P]
+    s1_bytes = 2 * c * 4 * npix + P * nring * (2 * M + 1) * 8
+    s2_flops = 2 * nfold * kappa * 2 * t_lm(L, M)
+    s3_bytes = 2 * P * t_lm(L, M) * 16
+    return s1_bytes, s2_flops, s3_bytes
+
+
+# ---------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline (oracle port; the reference's own SHT lives in
+# healpy/libsharp which is not installable offline)
+# ---------------------------------------------------------------------------------
+
+_W = {}
+
+
+def _cpu_init(cfg_items):
+    os.environ.setdefault("DSB_ORACLE_CACHE_GB", "6")
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import beam as obeam
+    from oracle import transfer as otr
+
+    _W["obeam"], _W["otr"] = obeam, otr
+    _W["geom"] = {}
+    _W["beams"] = {}
+    _W.update(dict(cfg_items))
+
+
+def _cpu_unit(task):
+    nside, fi, width_wl, uv, lmax, lside, ci, cj = task
+    obeam, otr = _W["obeam"], _W["otr"]
+    zen = _W["zenith"]
+    if nside not in _W["geom"]:
+        from oracle import healpix as ohp
+
+        ang = ohp.ang_positions(nside)
+        _W["geom"][nside] = (ang, obeam.horizon(ang, zen))
+    ang, hor = _W["geom"][nside]
+    key = (nside, fi)
+    if key not in _W["beams"]:
+        fe, fh = _W["fwhm_e"], _W["fwhm_h"]
+        _W["beams"][key] = (obeam.beam_x(ang, zen, width_wl, fe, fh), obeam.beam_y(ang, zen, width_wl, fe, fh))
+    b = _W["beams"][key]
+    otr.transfer_single_pol(ang, hor, b[ci], b[cj], zen, np.asarray(uv), lmax, lside, npol=4)
+    return 1
+
+
+def cpu_sample_tasks(tel, f_list, nsample):
+    """A deterministic sample of the step's units, stratified over the lmax (hence nside)
+    distribution: every k-th unit of the lmax-sorted list."""
+    bl = np.tile(np.arange(tel.nbase), len(f_list))
+    fi = np.repeat(np.asarray(f_list), tel.nbase)
+    lmax, _ = tel.unit_lmax(bl, fi)
+    order = np.argsort(lmax, kind="stable")
+    pick = order[np.linspace(0, len(order) - 1, nsample).astype(int)]
+    tasks = []
+    for i in pick:
+        b, f = int(bl[i]), int(fi[i])
+        pair = tel.uniquepairs[b]
+        tasks.append((tel._unit_nside(int(lmax[i])), f, tel.cylinder_width / tel.wavelengths[f],
+                      tuple(tel.baselines[b] / tel.wavelengths[f]), int(lmax[i]), tel.lmax,
+                      int(tel.beamclass[pair[0]]), int(tel.beamclass[pair[1]])))
+    return tasks
+
+
+def run_cpu(tel, f_list, nsample, cores):
+    import multiprocessing as mp
+
+    tasks = cpu_sample_tasks(tel, f_list, nsample)
+    # group tasks so that each worker sees few distinct (nside, freq) beams
+    tasks.sort(key=lambda t: (t[0], t[1]))
+    cfg = dict(zenith=tel.zenith, fwhm_e=tel.fwhm_e, fwhm_h=tel.fwhm_h)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(list(cfg.items()),)) as pool:
+        # warm the per-worker Legendre tables outside the timed region (the reference's
+        # libsharp also plans once per geometry)
+        warm = [t for t in tasks if t[0] == max(x[0] for x in tasks)][:cores]
+        pool.map(_cpu_unit, warm, chunksize=1)
+        t0 = time.time()
+        pool.map(_cpu_unit, tasks, chunksize=1)
+        dt = time.time() - t0
+    return len(tasks) / dt, dt, len(tasks)
+
+
+# ---------------------------------------------------------------------------------
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--freqs-per-gpu", type=int, default=2)
+    ap.add_argument("--precision", default="fp32x3", choices=["fp32x3", "fp64"])
+    ap.add_argument("--cpu-sample", type=int, default=48)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from driftscan_b200.telescope import cylinder
+
+    tel = cylinder.PolarisedCylinderTelescope.from_config(dict(WORKLOAD, precision=args.precision))
+    F = args.freqs_per_gpu
+    config = {
+        "workload": WORKLOAD_NAME, "nbase": int(tel.nbase), "nfreq_total": int(tel.nfreq),
+        "freqs_per_gpu_per_step": F, "units_per_step_per_gpu": int(tel.nbase * F), "lmax": int(tel.lmax),
+        "mmax": int(tel.mmax), "npol_sky": 4, "precision": args.precision,
+        "l2": "per-step working set (ring spectra + product, several GB) is far larger than the 126 MB L2",
+        "sharding": "frequency per GPU; NCCL all-to-all of m-major blocks when N>1",
+    }
+
+    # ------------------------------------------------------------- reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cores = os.cpu_count() or 1
+        per_step = max(cores, min(args.cpu_sample, 4 * cores))
+        vals = []
+        for _ in range(args.warmup + args.steps):
+            ups, dt, ns = run_cpu(tel, [i * (tel.nfreq // F) for i in range(F)], per_step, cores)
+            vals.append((ups, dt))
+        vals = vals[args.warmup:] or vals
+        ups = float(np.mean([v[0] for v in vals]))
+        ms = float(np.mean([v[1] for v in vals])) * 1e3
+        sample = (f"{per_step} units per step, every k-th unit of the lmax-sorted unit list of {F} frequencies "
+                  f"(all nside buckets), oracle port (numpy fp64 restatement; reference SHT = healpy/libsharp "
+                  f"is not installable offline), {cores} worker processes, Legendre tables warm")
+        line = {
+            "impl": "reference", "metric": "beam-transfer (baseline*freq)/s", "value": ups,
+            "unit": "units/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": ups, "unit": "units/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": ups, "unit": "units/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------- B200 arm
+    import torch
+
+    from driftscan_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    from driftscan_b200 import parallel
+
+    comm = parallel.Comm.current()
+
+    eng = tel.engine
+    nb, np_inc, lside, mmax = tel.nbase, 4, tel.lmax, tel.mmax
+    # frequencies spread over the band so that every step sees the full nside mix
+    f_list = np.array([(i * (tel.nfreq // F) + rank * max(1, tel.nfreq // (F * world))) % tel.nfreq for i in range(F)])
+    fgrid, bgrid = np.meshgrid(np.arange(F), np.arange(nb), indexing="ij")
+    f_ind, b_ind = f_list[fgrid.ravel()], bgrid.ravel()
+    lmax_u, _ = tel.unit_lmax(b_ind, f_ind)
+    fslot, bslot = fgrid.ravel().astype(np.int32), bgrid.ravel().astype(np.int32)
+    total, moff = _lib.mmajor_offsets(F, nb, np_inc, lside, mmax)
+    out_dev = torch.zeros(total, dtype=torch.complex128, device=dev)
+    dims = [F, nb, np_inc, lside, mmax]
+
+    # setup (untimed): plans, host beam maps, tables, unit descriptors
+    buckets = eng._buckets(lmax_u)
+    prepared = []
+    host_beams = {}
+    for nside, idx in buckets:
+        plan, units = eng._units_for(nside, b_ind[idx], f_ind[idx], lmax_u[idx], fslot[idx], bslot[idx])
+        plan.build_tables(int(lmax_u[idx].max()), min(mmax, int(lmax_u[idx].max())), True, eng.precision, stream)
+        prepared.append((nside, plan, units))
+        tel._init_trans(nside)
+        for (fq, cls), slot in eng._slots[nside].items():
+            feed = 0 if cls == 0 else tel.nfeed // 2
+            host_beams[(nside, slot)] = torch.from_numpy(np.ascontiguousarray(tel.beam(feed, fq))).pin_memory().numpy()
+    torch.cuda.synchronize()
+
+    work = np.array([unit_work(tel._unit_nside(int(l)), int(l), mmax) for l in lmax_u], dtype=np.float64)
+    s1_bytes, s2_flops, s3_bytes = work.sum(axis=0)
+    units_per_step = len(lmax_u)
+
+    def step_device():
+        for nside, plan, units in prepared:
+            plan.transfer_units(units, 4, True, mmax, eng.precision, _lib.DSB_OUT_MMAJOR_C128, dims,
+                                out_dev.data_ptr(), False, stream)
+        if world > 1:
+            return comm.exchange_mblocks(out_dev, F, moff, mmax + 1, f_lo=rank * F)
+        return None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident measurement with per-stage event timing and clock sampling
+    sampler = ClockSampler(local_rank)
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    _lib.lib.dsb_set_profiling(1)
+    launches0 = _lib.launch_count()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    launches = _lib.launch_count() - launches0
+    prof_ms = (ctypes.c_double * 3)()
+    prof_n = (ctypes.c_uint64 * 3)()
+    _lib.lib.dsb_get_profile(prof_ms, prof_n)
+    _lib.lib.dsb_set_profiling(0)
+    ms_step = ms_total / args.steps
+    value = world * units_per_step / (ms_step * 1e-3)
+
+    # ---- rooflines (measured peaks written by the driver, else the documented fallback)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as fh:
+            peaks = json.load(fh)
+        hbm_peak, tf_peak, peak_src = peaks["hbm_gbs"], peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]), "measured"
+    else:
+        hbm_peak, tf_peak, peak_src = 6650.0, 1400.0, "fallback"
+    stage_ms = [prof_ms[i] / max(args.steps, 1) for i in range(3)]
+    stage_launch = [int(prof_n[i]) for i in range(3)]
+    ring_gbs = s1_bytes / (stage_ms[0] * 1e-3) / 1e9 if stage_ms[0] > 0 else 0.0
+    leg_tflops = s2_flops / (stage_ms[1] * 1e-3) / 1e12 if stage_ms[1] > 0 else 0.0
+    pack_gbs = s3_bytes / (stage_ms[2] * 1e-3) / 1e9 if stage_ms[2] > 0 else 0.0
+    # executed tensor flops: six bf16 products per algorithmic multiply-add
+    roof_ring = {"kernel": "ringfft_kernel<float>", "bound": "hbm", "achieved": ring_gbs, "peak": hbm_peak,
+                 "unit": "GB/s", "frac": ring_gbs / hbm_peak, "traffic": None, "ms_per_step": stage_ms[0],
+                 "peak_source": peak_src}
+    roof_leg = {"kernel": "legendre_tc_kernel", "bound": "tensor", "achieved": leg_tflops, "peak": tf_peak,
+                "unit": "TFLOP/s", "frac": leg_tflops / tf_peak, "traffic": None, "ms_per_step": stage_ms[1],
+                "executed_tflops_bf16": 6 * leg_tflops, "executed_frac": 6 * leg_tflops / tf_peak,
+                "peak_source": peak_src}
+    roof_pack = {"kernel": "pack_mmajor_kernel", "bound": "hbm", "achieved": pack_gbs, "peak": hbm_peak,
+                 "unit": "GB/s", "frac": pack_gbs / hbm_peak, "traffic": None, "ms_per_step": stage_ms[2],
+                 "peak_source": peak_src}
+    dominant = max((roof_ring, roof_leg, roof_pack), key=lambda r: r["ms_per_step"])
+
+    # ---- end-to-end through the C ABI with host buffers
+    e2e = None
+    if not args.no_e2e:
+        out_host = torch.empty(total, dtype=torch.complex128, pin_memory=True)
+        h2d = sum(b.nbytes for b in host_beams.values()) + sum(u.nbytes for _, _, u in prepared)
+        d2h = out_host.numel() * 16
+
+        def step_e2e():
+            for nside, plan, units in prepared:
+                for (ns, slot), b in host_beams.items():
+                    if ns == nside:
+                        plan.upload_beam(slot, b, stream)
+                plan.transfer_units(units, 4, True, mmax, eng.precision, _lib.DSB_OUT_MMAJOR_C128, dims,
+                                    out_dev.data_ptr(), False, stream)
+            if world > 1:
+                comm.exchange_mblocks(out_dev, F, moff, mmax + 1, f_lo=rank * F)
+            out_host.copy_(out_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        ms_e2e = timed(step_e2e, max(2, args.steps // 2), 1) / max(2, args.steps // 2)
+        e2e = {"value": world * units_per_step / (ms_e2e * 1e-3), "unit": "units/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        ns = max(cores, min(args.cpu_sample, 4 * cores))
+        ups, dt, n = run_cpu(tel, list(f_list), ns, cores)
+        cpu = {"value": ups, "unit": "units/s", "cores": cores, "kind": "port",
+               "sample": f"{n} units (every k-th unit of the lmax-sorted unit list of this step, all nside "
+                         f"buckets) in {dt:.1f} s; numpy fp64 oracle port, {cores} processes, tables warm"}
+
+    if rank == 0:
+        line = {
+            "metric": "beam-transfer (baseline*freq)/s", "value": value, "unit": "units/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3->f32 (fp64 phase)" if args.precision == "fp32x3" else "f64",
+            "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": dominant, "roofline_all": [roof_ring, roof_leg, roof_pack],
+            "stage_launches_per_run": stage_launch, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -73,6 +73,8 @@ def _load():
         "dsb_transfer_units": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, P(i64), vp, i32, vp]),
         "dsb_mmajor_size": (i64, [i32, i32, i32, i32, i32, P(i64)]),
         "dsb_set_workspace_limit": (i32, [ctypes.c_size_t]),
+        "dsb_set_profiling": (i32, [i32]),
+        "dsb_get_profile": (i32, [P(dbl), P(u64)]),
         "dsb_debug_gemm_tc": (i32, [i32, i32, i32, i32, i32, vp, vp, vp, vp]),
         "dsb_svd_chain": (i32, [vp, vp, i32, i32, i32, i32, i32, dbl, dbl, vp, vp, vp, vp, vp, vp]),
         "dsb_project_sky_to_svd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),

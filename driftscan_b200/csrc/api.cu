@@ -22,6 +22,39 @@ extern "C" int64_t dsb_mmajor_size(int n_out0, int n_out1, int npol, int lside, 
 
 namespace {
 
+// Optional per-stage device timing (CUDA events on the launching stream), used by bench.py
+// for the roofline figures.  Stages: 0 ring FFT, 1 Legendre contraction, 2 pack.
+bool g_prof = false;
+double g_prof_ms[3] = {0, 0, 0};
+uint64_t g_prof_n[3] = {0, 0, 0};
+
+struct StageTimer {
+  cudaEvent_t e[4];
+  bool on;
+  cudaStream_t st;
+  explicit StageTimer(cudaStream_t s) : on(g_prof), st(s) {
+    if (on)
+      for (auto &x : e) cudaEventCreate(&x);
+  }
+  void mark(int i) {
+    if (on) cudaEventRecord(e[i], st);
+  }
+  void finish() {
+    if (!on) return;
+    cudaEventSynchronize(e[3]);
+    for (int i = 0; i < 3; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e[i], e[i + 1]);
+      g_prof_ms[i] += ms;
+      g_prof_n[i] += 1;
+    }
+  }
+  ~StageTimer() {
+    if (on)
+      for (auto &x : e) cudaEventDestroy(x);
+  }
+};
+
 struct Carve {
   char *base;
   size_t off = 0;
@@ -36,6 +69,23 @@ struct Carve {
 };
 
 }  // namespace
+
+extern "C" int dsb_set_profiling(int enable) {
+  g_prof = enable != 0;
+  for (int i = 0; i < 3; ++i) {
+    g_prof_ms[i] = 0;
+    g_prof_n[i] = 0;
+  }
+  return DSB_OK;
+}
+
+extern "C" int dsb_get_profile(double *ms3, uint64_t *launches3) {
+  for (int i = 0; i < 3; ++i) {
+    if (ms3) ms3[i] = g_prof_ms[i];
+    if (launches3) launches3[i] = g_prof_n[i];
+  }
+  return DSB_OK;
+}
 
 extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, int nunits, int npol_sky,
                                   int polarised, int mmax, int precision, int out_kind, const int64_t *dims,
@@ -199,11 +249,11 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
     int64_t *moff_dev = cv.take<int64_t>(moff.size());
     char *stage = (tarray && out_is_host) ? cv.take<char>((size_t)nu * plane_out) : nullptr;
 
-    // Rows of the operand that no ring writes (padding of the fold-ring count, columns of
-    // the last partial tile) must be finite: clear whenever the layout leaves such holes.
-    const bool holes = plan->Kp != plan->nfold || lay.ncols0 != nu * lay.cpu0 ||
-                       (lay.has2 && lay.ncols2 != nu * 8);
-    if (holes) {
+    // Padding rows of the operand (fold-ring count rounded up to the k-tile) are written by
+    // no ring and must be finite: clear the operand whenever the layout has such rows.
+    // Columns of the last partial 128-column tile may hold stale (finite or not) data: each
+    // output column depends only on its own operand column and those are never read back.
+    if (plan->Kp != plan->nfold) {
       DSB_CUDA(cudaMemsetAsync(F0, 0, f0_bytes, stream));
       if (f2_bytes) DSB_CUDA(cudaMemsetAsync(F2, 0, f2_bytes, stream));
     }
@@ -215,7 +265,10 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
     DSB_CUDA(cudaMemcpyAsync(moff_dev, moff.data(), moff.size() * sizeof(int64_t), cudaMemcpyHostToDevice,
                              stream));
 
+    StageTimer timer(stream);
+    timer.mark(0);
     if ((rc = launch_ringfft(plan, lay, ud_dev, precision, F0, F2, stream)) != DSB_OK) break;
+    timer.mark(1);
     if (f64)
       rc = launch_legendre_f64(plan, t, lay, items, items_dev, (const double *)F0, (const double *)F2,
                                (double *)C0, (double *)C2, stream);
@@ -223,6 +276,7 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
       rc = launch_legendre_tc(plan, t, lay, items, items_dev, (const __nv_bfloat16 *)F0,
                               (const __nv_bfloat16 *)F2, (float *)C0, (float *)C2, stream);
     if (rc != DSB_OK) break;
+    timer.mark(2);
 
     PackParams pp;
     pp.out_kind = out_kind;
@@ -245,6 +299,8 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
     if ((rc = launch_pack(pp, ud_dev, o0_dev, o1_dev, moff_dev, C0, C2, f64 ? 1 : 0, pack_out, stream)) !=
         DSB_OK)
       break;
+    timer.mark(3);
+    timer.finish();
     if (tarray && out_is_host) {
       for (int i = 0; i < nu; ++i) {
         const dsb_unit &u = units_host[order[c0 + i]];

@@ -95,6 +95,8 @@ struct RingDesc {
   int32_t chirp_off;  // offset into chirp tables (Bluestein only)
   int32_t dhat_off;   // offset into the transformed-chirp table (Bluestein only)
   int32_t shifted;    // 1 if phi0 = pi/nphi (half-pixel shift), 0 if phi0 = 0
+  int32_t vis_north;  // 0 if every pixel of the northern ring is below the horizon
+  int32_t vis_south;  // same for the southern mirror ring
   int32_t pad;
   double cth, sth;    // cos / sin of the northern colatitude
   double ch2, sh2;    // cos / sin of half the northern colatitude
@@ -140,6 +142,8 @@ struct dsb_plan {
   double2 *dhat64 = nullptr;     // FFT(d wrapped)/Nb in DIF (bit-reversed) order
   float2 *dhat32 = nullptr;
   std::vector<dsb::BeamSlot> beams;
+  const void **beam_ptrs32 = nullptr;  // device arrays of per-slot map pointers
+  const void **beam_ptrs64 = nullptr;
   std::vector<dsb::Tables> tables;
   // workspace (grown on demand, capped by dsb_set_workspace_limit)
   void *ws = nullptr;

@@ -47,24 +47,27 @@ int ensure_workspace(dsb_plan *plan, size_t bytes) {
 __global__ void bluestein_prepare_kernel(const RingDesc *rings, int nrings_cap, const double2 *chirp,
                                          double2 *dhat, const double2 *tw, int tw_log2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx<double> *buf = reinterpret_cast<cplx<double> *>(smem_raw);
   const RingDesc rd = rings[blockIdx.x];
   if (!rd.bluestein) return;
   const int n = rd.nphi;
   const int Nb = 1 << rd.log2n;
-  for (int t = threadIdx.x; t < Nb; t += blockDim.x) buf[t] = {0.0, 0.0};
+  cplx<double> *tw_s = reinterpret_cast<cplx<double> *>(smem_raw);
+  cplx<double> *buf = tw_s + (Nb >> 1);
+  load_twiddles<double>(tw_s, rd.log2n, tw, tw_log2);
+  const int pitch = fft_pitch(Nb);
+  for (int t = threadIdx.x; t < pitch; t += blockDim.x) buf[t] = {0.0, 0.0};
   __syncthreads();
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
     double2 c = chirp[rd.chirp_off + t];
     cplx<double> d = {c.x, -c.y};
-    buf[t] = d;
-    if (t > 0) buf[Nb - t] = d;
+    buf[fft_phys(t)] = d;
+    if (t > 0) buf[fft_phys(Nb - t)] = d;
   }
   __syncthreads();
-  fft_dif<double, -1>(buf, rd.log2n, 1, Nb, tw, tw_log2);
+  fft_dif<double, -1>(buf, rd.log2n, 1, pitch, tw_s);
   const double inv = 1.0 / Nb;
   for (int t = threadIdx.x; t < Nb; t += blockDim.x)
-    dhat[rd.dhat_off + t] = make_double2(buf[t].x * inv, buf[t].y * inv);
+    dhat[rd.dhat_off + t] = make_double2(buf[fft_phys(t)].x * inv, buf[fft_phys(t)].y * inv);
 }
 
 __global__ void d2f2_kernel(const double2 *in, float2 *out, size_t n) {
@@ -99,6 +102,8 @@ __global__ void beam_power_partial_kernel(const double *beam, const uint8_t *hor
 }  // namespace dsb
 
 using namespace dsb;
+
+static const int kMaxBeamSlots = 8192;
 
 extern "C" int dsb_version(void) { return 100; }
 extern "C" const char *dsb_last_error(void) { return g_last_error.c_str(); }
@@ -174,6 +179,12 @@ extern "C" int dsb_plan_create(int nside, const uint8_t *horizon_host, dsb_plan 
       dhat_total += 1 << rd.log2n;
     }
     rd.pad = 0;
+    rd.vis_north = 0;
+    rd.vis_south = 0;
+    for (int j = 0; j < n; ++j) {
+      if (horizon_host[rd.startN + j]) rd.vis_north = 1;
+      if (rd.startS >= 0 && horizon_host[rd.startS + j]) rd.vis_south = 1;
+    }
   }
 
   // ---- trig table (cos phi_j, sin phi_j)
@@ -236,7 +247,7 @@ extern "C" int dsb_plan_create(int nside, const uint8_t *horizon_host, dsb_plan 
   DSB_CUDA(cudaMalloc(&plan->dhat64, sizeof(double2) * ndh));
   DSB_CUDA(cudaMalloc(&plan->dhat32, sizeof(float2) * ndh));
   if (dhat_total > 0) {
-    const size_t smem = sizeof(double2) * (size_t)(1 << plan->tw_log2);
+    const size_t smem = sizeof(double2) * ((size_t)(1 << plan->tw_log2) * 3 / 2 + (1 << plan->tw_log2) / 16 + 16);
     DSB_CUDA(cudaFuncSetAttribute(bluestein_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     bluestein_prepare_kernel<<<ncapring, 256, smem>>>(plan->rings, ncapring, plan->chirp64, plan->dhat64,
@@ -245,6 +256,10 @@ extern "C" int dsb_plan_create(int nside, const uint8_t *horizon_host, dsb_plan 
     d2f2_kernel<<<(unsigned)((ndh + 255) / 256), 256>>>(plan->dhat64, plan->dhat32, ndh);
     DSB_LAUNCH_CHECK();
   }
+  DSB_CUDA(cudaMalloc((void **)&plan->beam_ptrs32, sizeof(void *) * kMaxBeamSlots));
+  DSB_CUDA(cudaMalloc((void **)&plan->beam_ptrs64, sizeof(void *) * kMaxBeamSlots));
+  DSB_CUDA(cudaMemset(plan->beam_ptrs32, 0, sizeof(void *) * kMaxBeamSlots));
+  DSB_CUDA(cudaMemset(plan->beam_ptrs64, 0, sizeof(void *) * kMaxBeamSlots));
   DSB_CUDA(cudaDeviceSynchronize());
   *out = plan;
   return DSB_OK;
@@ -270,6 +285,8 @@ extern "C" int dsb_plan_destroy(dsb_plan *plan) {
   cudaFree(plan->chirp32);
   cudaFree(plan->dhat64);
   cudaFree(plan->dhat32);
+  cudaFree((void *)plan->beam_ptrs32);
+  cudaFree((void *)plan->beam_ptrs64);
   for (auto &b : plan->beams) {
     cudaFree(b.d64);
     cudaFree(b.d32);
@@ -293,7 +310,8 @@ extern "C" int dsb_beam_upload(dsb_plan *plan, int slot, const double *beam_host
   DSB_CHECK(ncomp == 1 || ncomp == 2, DSB_ERR_INVALID, "dsb_beam_upload: ncomp must be 1 or 2");
   DSB_CHECK(!is_complex, DSB_ERR_UNSUPPORTED,
             "dsb_beam_upload: complex primary beams are not supported by the device path yet");
-  DSB_CHECK(slot >= 0, DSB_ERR_INVALID, "dsb_beam_upload: negative slot");
+  DSB_CHECK(slot >= 0 && slot < kMaxBeamSlots, DSB_ERR_INVALID, "dsb_beam_upload: slot %d outside [0, %d)", slot,
+            kMaxBeamSlots);
   if ((int)plan->beams.size() <= slot) plan->beams.resize(slot + 1);
   BeamSlot &b = plan->beams[slot];
   const size_t n = (size_t)plan->npix * ncomp;
@@ -305,6 +323,10 @@ extern "C" int dsb_beam_upload(dsb_plan *plan, int slot, const double *beam_host
     DSB_CUDA(cudaMalloc(&b.d64, n * sizeof(double)));
     DSB_CUDA(cudaMalloc(&b.d32, n * sizeof(float)));
     b.ncomp = ncomp;
+    const void *p32 = b.d32, *p64 = b.d64;
+    DSB_CUDA(cudaMemcpyAsync(plan->beam_ptrs32 + slot, &p32, sizeof(void *), cudaMemcpyHostToDevice, stream));
+    DSB_CUDA(cudaMemcpyAsync(plan->beam_ptrs64 + slot, &p64, sizeof(void *), cudaMemcpyHostToDevice, stream));
+    DSB_CUDA(cudaStreamSynchronize(stream));
   }
   DSB_CUDA(cudaMemcpyAsync(b.d64, beam_host, n * sizeof(double), cudaMemcpyHostToDevice, stream));
   const int nblk = 128;

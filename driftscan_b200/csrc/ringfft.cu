@@ -80,24 +80,57 @@ __device__ __forceinline__ void store_vals<float>(void *F, size_t plane, size_t 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) ringfft_kernel(const RingFFTParams<T> P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx<T> *buf = reinterpret_cast<cplx<T> *>(smem_raw);
+__device__ __forceinline__ void store8(void *F, size_t plane, size_t idx, const T (&v)[8]);
 
+template <>
+__device__ __forceinline__ void store8<double>(void *F, size_t plane, size_t idx, const double (&v)[8]) {
+  double2 *p = reinterpret_cast<double2 *>(reinterpret_cast<double *>(F) + idx);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = make_double2(v[2 * i], v[2 * i + 1]);
+}
+
+template <>
+__device__ __forceinline__ void store8<float>(void *F, size_t plane, size_t idx, const float (&v)[8]) {
+  __nv_bfloat16 h[8], m[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split3f(v[i], h[i], m[i], l[i]);
+  __nv_bfloat16 *p = reinterpret_cast<__nv_bfloat16 *>(F) + idx;
+  *reinterpret_cast<uint4 *>(p) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+  *reinterpret_cast<uint4 *>(p + plane) =
+      make_uint4(pack2(m[0], m[1]), pack2(m[2], m[3]), pack2(m[4], m[5]), pack2(m[6], m[7]));
+  *reinterpret_cast<uint4 *>(p + 2 * plane) =
+      make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) ringfft_kernel(const RingFFTParams<T> P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int k = P.nfold - 1 - (int)blockIdx.x;  // long (equatorial) rings first
   const RingDesc rd = P.rings[k];
   const int n = rd.nphi;
   const int log2L = rd.log2n;
   const int L = 1 << log2L;
-  const bool has_south = rd.startS >= 0;
-  const int nring = has_south ? 2 : 1;
+  // shared memory: [twiddles L/2][sequences ...]
+  cplx<T> *tw_s = reinterpret_cast<cplx<T> *>(smem_raw);
+  cplx<T> *buf = tw_s + (L >> 1);
+  const int pitch = fft_pitch(L);
+  load_twiddles<T>(tw_s, log2L, P.tw, P.tw_log2);
+
+  const bool equator = rd.startS < 0;
+  // rings entirely below the horizon contribute nothing: skip their transforms
+  const bool liveN = rd.vis_north != 0;
+  const bool liveS = !equator && rd.vis_south != 0;
+  const int nlive = (liveN ? 1 : 0) + (liveS ? 1 : 0);
   const int npol = P.npol_sky;  // number of Stokes maps to transform: 1, 3 or 4
-  int npp = P.seq_capacity / (2 * L);
+  int npp = nlive ? (P.seq_capacity - (L >> 1)) / (nlive * pitch) : npol;
   if (npp > npol) npp = npol;
   if (npp == 3) npp = 2;  // keep passes balanced: (I,Q) (U,V)
+  // sequence slot of a ring inside a pol group: live rings are packed first
+  const int slotS = liveN ? 1 : 0;
 
   const int u0 = blockIdx.y * P.units_per_cta;
   const int u1 = min(u0 + P.units_per_cta, P.nunits);
+  __syncthreads();
 
   for (int u = u0; u < u1; ++u) {
     const UnitDev ud = P.units[u];
@@ -108,8 +141,9 @@ __global__ void __launch_bounds__(256) ringfft_kernel(const RingFFTParams<T> P) 
     for (int pol0 = 0; pol0 < npol; pol0 += npp) {
       const int npass = min(npp, npol - pol0);
       // ---- fill: Stokes response of the ring pair ------------------------------------
-      for (int idx = threadIdx.x; idx < nring * L; idx += blockDim.x) {
-        const int ring = idx >> log2L;
+      for (int idx = threadIdx.x; idx < nlive * L; idx += blockDim.x) {
+        const int lr = idx >> log2L;  // live-ring slot
+        const int ring = (liveN && lr == 0) ? 0 : 1;
         const int j = idx & (L - 1);
         cplx<T> vals[4];
 #pragma unroll
@@ -139,9 +173,9 @@ __global__ void __launch_bounds__(256) ringfft_kernel(const RingFFTParams<T> P) 
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const int pol = pol0 + q;
               if (q < npass) {
-                const T a = pref * prod[pol];
+                const int pol = pol0 + q;
+                const T a = pref * (pol == 0 ? prod[0] : pol == 1 ? prod[1] : pol == 2 ? prod[2] : prod[3]);
                 cplx<T> v = {a * fc, a * fs};
                 if (pol == 3) v = {-v.y, v.x};
                 vals[q] = v;
@@ -158,60 +192,46 @@ __global__ void __launch_bounds__(256) ringfft_kernel(const RingFFTParams<T> P) 
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (q < npass) buf[((q * 2 + ring) << log2L) + j] = vals[q];
+          if (q < npass) buf[(q * nlive + lr) * pitch + fft_phys(j)] = vals[q];
       }
       __syncthreads();
 
-      // ---- ring FFT -----------------------------------------------------------------
-      // sequences are laid out [q][ring][L]; when there is no southern ring only the
-      // ring-0 slots are live but transforming the dead ones is harmless and keeps the
-      // indexing uniform, so zero them first.
-      if (!has_south) {
-        for (int idx = threadIdx.x; idx < npass * L; idx += blockDim.x) {
-          const int q = idx >> log2L, j = idx & (L - 1);
-          buf[((q * 2 + 1) << log2L) + j] = {T(0), T(0)};
+      // ---- ring FFT (sequences laid out [q][live ring][L]) ---------------------------
+      const int nseq = npass * nlive;
+      if (nseq > 0) {
+        if (!rd.bluestein) {
+          fft_dif<T, +1>(buf, log2L, nseq, pitch, tw_s);
+        } else {
+          fft_dif<T, -1>(buf, log2L, nseq, pitch, tw_s);
+          for (int idx = threadIdx.x; idx < nseq * L; idx += blockDim.x) {
+            const int j = idx & (L - 1);
+            const int sq = idx >> log2L;
+            const typename TwPtr<T>::type d = P.dhat[rd.dhat_off + j];
+            const cplx<T> dd = {d.x, d.y};
+            cplx<T> *e = buf + sq * pitch + fft_phys(j);
+            *e = cmul(*e, dd);
+          }
+          __syncthreads();
+          fft_dit<T, +1>(buf, log2L, nseq, pitch, tw_s);
         }
-        __syncthreads();
-      }
-      const int nseq = npass * 2;
-      if (!rd.bluestein) {
-        fft_dif<T, +1>(buf, log2L, nseq, L, P.tw, P.tw_log2);
-      } else {
-        fft_dif<T, -1>(buf, log2L, nseq, L, P.tw, P.tw_log2);
-        for (int idx = threadIdx.x; idx < nseq * L; idx += blockDim.x) {
-          const int j = idx & (L - 1);
-          const typename TwPtr<T>::type d = P.dhat[rd.dhat_off + j];
-          const cplx<T> dd = {d.x, d.y};
-          buf[idx] = cmul(buf[idx], dd);
-        }
-        __syncthreads();
-        fft_dit<T, +1>(buf, log2L, nseq, L, P.tw, P.tw_log2);
       }
 
-      // ---- gather bins, apply e^{i m phi0}, fold, emit --------------------------------
-      for (int idx = threadIdx.x; idx < (Mu + 1) * npass; idx += blockDim.x) {
-        const int q = idx / (Mu + 1);
-        const int m = idx - q * (Mu + 1);
-        const int pol = pol0 + q;
+      // ---- gather bins, apply e^{i m phi0}, fold, emit: one thread per m ---------------
+      for (int m = threadIdx.x; m <= Mu; m += blockDim.x) {
         const int kp = m % n;
         const int km = kp ? n - kp : 0;
-        cplx<T> yNp, yNm, ySp, ySm;
-        const cplx<T> *bN = buf + ((q * 2 + 0) << log2L);
-        const cplx<T> *bS = buf + ((q * 2 + 1) << log2L);
+        int ip, im;
+        cplx<T> cp = {T(1), T(0)}, cm = {T(1), T(0)};
         if (!rd.bluestein) {
-          const int ip = bitrev(kp, log2L), im = bitrev(km, log2L);
-          yNp = bN[ip];
-          yNm = bN[im];
-          ySp = bS[ip];
-          ySm = bS[im];
+          ip = fft_phys(digitrev(kp, log2L));
+          im = fft_phys(digitrev(km, log2L));
         } else {
+          ip = fft_phys(kp);
+          im = fft_phys(km);
           const typename TwPtr<T>::type c1 = P.chirp[rd.chirp_off + kp];
           const typename TwPtr<T>::type c2 = P.chirp[rd.chirp_off + km];
-          const cplx<T> cp = {c1.x, c1.y}, cm = {c2.x, c2.y};
-          yNp = cmul(bN[kp], cp);
-          yNm = cmul(bN[km], cm);
-          ySp = cmul(bS[kp], cp);
-          ySm = cmul(bS[km], cm);
+          cp = {c1.x, c1.y};
+          cm = {c2.x, c2.y};
         }
         cplx<T> ph = {T(1), T(0)};
         if (rd.shifted) {
@@ -219,43 +239,89 @@ __global__ void __launch_bounds__(256) ringfft_kernel(const RingFFTParams<T> P) 
           sincospi((double)(m % (2 * n)) / (double)n, &s, &c);
           ph = {(T)c, (T)s};
         }
-        const cplx<T> fNp = cmul(ph, yNp), fNm = cmul(ph, cconj(yNm));
-        const cplx<T> fSp = cmul(ph, ySp), fSm = cmul(ph, cconj(ySm));
-        // [parity][+-]
-        const cplx<T> ev_p = cadd(fNp, fSp), ev_m = cadd(fNm, fSm);
-        cplx<T> od_p = csub(fNp, fSp), od_m = csub(fNm, fSm);
-        if (!has_south) {  // the equator is its own mirror: it only feeds the even fold
-          od_p = {T(0), T(0)};
-          od_m = {T(0), T(0)};
-        }
-
-        if (pol == 0 || pol == 3) {
-          const int slot = pol == 0 ? 0 : 1;
-          const size_t col = (size_t)u * P.cpu0 + slot * 4;
-          const size_t i0 = ((size_t)(2 * m + 0) * P.Kp + k) * P.ncols0 + col;
-          const size_t i1 = ((size_t)(2 * m + 1) * P.Kp + k) * P.ncols0 + col;
-          store_vals<T>(P.F0, P.plane0, i0, ev_p.x, ev_p.y, ev_m.x, ev_m.y);
-          store_vals<T>(P.F0, P.plane0, i1, od_p.x, od_p.y, od_m.x, od_m.y);
-        } else {
-          const size_t K2 = 2 * (size_t)P.Kp;
-          const size_t colE = (size_t)u * 8, colB = (size_t)u * 8 + 4;
-          const size_t w0 = ((size_t)(2 * m + 0) * K2 + k) * P.ncols2;        // W part, parity 0
-          const size_t w1 = ((size_t)(2 * m + 1) * K2 + k) * P.ncols2;        // W part, parity 1
-          const size_t x0 = ((size_t)(2 * m + 0) * K2 + P.Kp + k) * P.ncols2;  // X part, parity 0
-          const size_t x1 = ((size_t)(2 * m + 1) * K2 + P.Kp + k) * P.ncols2;  // X part, parity 1
-          if (pol == 1) {
-            // Q: W part feeds E with the same fold parity; X part feeds B with +i F[Q] of the
-            // opposite fold parity.
-            store_vals<T>(P.F2, P.plane2, w0 + colE, ev_p.x, ev_p.y, ev_m.x, ev_m.y);
-            store_vals<T>(P.F2, P.plane2, w1 + colE, od_p.x, od_p.y, od_m.x, od_m.y);
-            store_vals<T>(P.F2, P.plane2, x0 + colB, -od_p.y, od_p.x, -od_m.y, od_m.x);
-            store_vals<T>(P.F2, P.plane2, x1 + colB, -ev_p.y, ev_p.x, -ev_m.y, ev_m.x);
+        // per pol of the pass: even / odd fold as (+re, +im, -re, -im)
+        T ev[4][4], od[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q < npass) {
+            cplx<T> fNp = {T(0), T(0)}, fNm = fNp, fSp = fNp, fSm = fNp;
+            if (liveN) {
+              const cplx<T> *b = buf + (q * nlive + 0) * pitch;
+              fNp = cmul(ph, cmul(b[ip], cp));
+              fNm = cmul(ph, cconj(cmul(b[im], cm)));
+            }
+            if (liveS) {
+              const cplx<T> *b = buf + (q * nlive + slotS) * pitch;
+              fSp = cmul(ph, cmul(b[ip], cp));
+              fSm = cmul(ph, cconj(cmul(b[im], cm)));
+            }
+            const cplx<T> e_p = cadd(fNp, fSp), e_m = cadd(fNm, fSm);
+            cplx<T> o_p = csub(fNp, fSp), o_m = csub(fNm, fSm);
+            if (equator) {  // the equator is its own mirror: it only feeds the even fold
+              o_p = {T(0), T(0)};
+              o_m = {T(0), T(0)};
+            }
+            ev[q][0] = e_p.x, ev[q][1] = e_p.y, ev[q][2] = e_m.x, ev[q][3] = e_m.y;
+            od[q][0] = o_p.x, od[q][1] = o_p.y, od[q][2] = o_m.x, od[q][3] = o_m.y;
           } else {
-            // U: W part feeds B; X part feeds E with -i F[U] of the opposite fold parity.
-            store_vals<T>(P.F2, P.plane2, w0 + colB, ev_p.x, ev_p.y, ev_m.x, ev_m.y);
-            store_vals<T>(P.F2, P.plane2, w1 + colB, od_p.x, od_p.y, od_m.x, od_m.y);
-            store_vals<T>(P.F2, P.plane2, x0 + colE, od_p.y, -od_p.x, od_m.y, -od_m.x);
-            store_vals<T>(P.F2, P.plane2, x1 + colE, ev_p.y, -ev_p.x, ev_m.y, -ev_m.x);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) ev[q][c] = od[q][c] = T(0);
+          }
+        }
+        // which pols does this pass hold?  (q index of pol p is p - pol0)
+        const bool hasI = pol0 == 0;
+        const bool hasQ = pol0 <= 1 && pol0 + npass > 1;
+        const bool hasU = pol0 <= 2 && pol0 + npass > 2;
+        const bool hasV = pol0 <= 3 && pol0 + npass > 3;
+        const size_t r0 = ((size_t)(2 * m + 0) * P.Kp + k) * P.ncols0 + (size_t)u * P.cpu0;
+        const size_t r1 = ((size_t)(2 * m + 1) * P.Kp + k) * P.ncols0 + (size_t)u * P.cpu0;
+        if (hasI && hasV) {  // single pass over (I, Q, U, V): q = pol
+          const T a[8] = {ev[0][0], ev[0][1], ev[0][2], ev[0][3], ev[3][0], ev[3][1], ev[3][2], ev[3][3]};
+          const T b[8] = {od[0][0], od[0][1], od[0][2], od[0][3], od[3][0], od[3][1], od[3][2], od[3][3]};
+          store8<T>(P.F0, P.plane0, r0, a);
+          store8<T>(P.F0, P.plane0, r1, b);
+        } else {
+          if (hasI) {
+            store_vals<T>(P.F0, P.plane0, r0, ev[0][0], ev[0][1], ev[0][2], ev[0][3]);
+            store_vals<T>(P.F0, P.plane0, r1, od[0][0], od[0][1], od[0][2], od[0][3]);
+          }
+          if (hasV) {
+            const int qV = 3 - pol0;
+            store_vals<T>(P.F0, P.plane0, r0 + 4, ev[qV][0], ev[qV][1], ev[qV][2], ev[qV][3]);
+            store_vals<T>(P.F0, P.plane0, r1 + 4, od[qV][0], od[qV][1], od[qV][2], od[qV][3]);
+          }
+        }
+        if (hasQ || hasU) {
+          const size_t K2 = 2 * (size_t)P.Kp;
+          const size_t cu = (size_t)u * 8;
+          const size_t w0 = ((size_t)(2 * m + 0) * K2 + k) * P.ncols2 + cu;         // W part, parity 0
+          const size_t w1 = ((size_t)(2 * m + 1) * K2 + k) * P.ncols2 + cu;         // W part, parity 1
+          const size_t x0 = ((size_t)(2 * m + 0) * K2 + P.Kp + k) * P.ncols2 + cu;  // X part, parity 0
+          const size_t x1 = ((size_t)(2 * m + 1) * K2 + P.Kp + k) * P.ncols2 + cu;  // X part, parity 1
+          const int qQ = 1 - pol0, qU = 2 - pol0;
+          // W part: E columns <- F[Q], B columns <- F[U], same fold parity.
+          // X part: E columns <- -i F[U], B columns <- +i F[Q], opposite fold parity.
+          if (hasQ && hasU) {
+            const T wa[8] = {ev[qQ][0], ev[qQ][1], ev[qQ][2], ev[qQ][3], ev[qU][0], ev[qU][1], ev[qU][2], ev[qU][3]};
+            const T wb[8] = {od[qQ][0], od[qQ][1], od[qQ][2], od[qQ][3], od[qU][0], od[qU][1], od[qU][2], od[qU][3]};
+            const T xa[8] = {od[qU][1], -od[qU][0], od[qU][3], -od[qU][2],
+                             -od[qQ][1], od[qQ][0], -od[qQ][3], od[qQ][2]};
+            const T xb[8] = {ev[qU][1], -ev[qU][0], ev[qU][3], -ev[qU][2],
+                             -ev[qQ][1], ev[qQ][0], -ev[qQ][3], ev[qQ][2]};
+            store8<T>(P.F2, P.plane2, w0, wa);
+            store8<T>(P.F2, P.plane2, w1, wb);
+            store8<T>(P.F2, P.plane2, x0, xa);
+            store8<T>(P.F2, P.plane2, x1, xb);
+          } else if (hasQ) {
+            store_vals<T>(P.F2, P.plane2, w0, ev[qQ][0], ev[qQ][1], ev[qQ][2], ev[qQ][3]);
+            store_vals<T>(P.F2, P.plane2, w1, od[qQ][0], od[qQ][1], od[qQ][2], od[qQ][3]);
+            store_vals<T>(P.F2, P.plane2, x0 + 4, -od[qQ][1], od[qQ][0], -od[qQ][3], od[qQ][2]);
+            store_vals<T>(P.F2, P.plane2, x1 + 4, -ev[qQ][1], ev[qQ][0], -ev[qQ][3], ev[qQ][2]);
+          } else {
+            store_vals<T>(P.F2, P.plane2, w0 + 4, ev[qU][0], ev[qU][1], ev[qU][2], ev[qU][3]);
+            store_vals<T>(P.F2, P.plane2, w1 + 4, od[qU][0], od[qU][1], od[qU][2], od[qU][3]);
+            store_vals<T>(P.F2, P.plane2, x0, od[qU][1], -od[qU][0], od[qU][3], -od[qU][2]);
+            store_vals<T>(P.F2, P.plane2, x1, ev[qU][1], -ev[qU][0], ev[qU][3], -ev[qU][2]);
           }
         }
       }
@@ -303,13 +369,14 @@ static int launch_t(dsb_plan *plan, const BucketLayout &lay, const UnitDev *unit
   int Lmax = 4 * plan->nside;
   for (const auto &rd : plan->rings_h) Lmax = std::max(Lmax, 1 << rd.log2n);
   // shared memory: as many (pol, ring) sequences as fit in ~200 KB, at least one pol pair
-  const size_t per_seq = (size_t)Lmax * sizeof(cplx<T>);
-  int nseq = (int)std::min<size_t>(8, (200 * 1024) / per_seq);
+  const size_t per_seq = (size_t)fft_pitch(Lmax) * sizeof(cplx<T>);
+  const size_t tw_bytes = (size_t)(Lmax / 2) * sizeof(cplx<T>);
+  int nseq = (int)std::min<size_t>(8, (200 * 1024 - tw_bytes) / per_seq);
   nseq = std::max(2, nseq & ~1);
-  const size_t smem = nseq * per_seq;
+  const size_t smem = nseq * per_seq + tw_bytes;
   DSB_CHECK(smem <= 227 * 1024, DSB_ERR_UNSUPPORTED, "ring FFT of length %d does not fit shared memory",
             Lmax);
-  P.seq_capacity = nseq * Lmax;
+  P.seq_capacity = nseq * fft_pitch(Lmax) + Lmax / 2;
   DSB_CUDA(cudaFuncSetAttribute(ringfft_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
   // units per CTA: enough CTAs to fill the machine, but amortise the per-ring setup
@@ -317,7 +384,9 @@ static int launch_t(dsb_plan *plan, const BucketLayout &lay, const UnitDev *unit
   while (upc > 1 && (long)plan->nfold * ((lay.nunits + upc - 1) / upc) < 4 * 148) upc >>= 1;
   P.units_per_cta = upc;
   dim3 grid(plan->nfold, (lay.nunits + upc - 1) / upc);
-  ringfft_kernel<T><<<grid, 256, smem, stream>>>(P);
+  // a block that owns most of an SM's shared memory runs with more warps
+  const int threads = smem > 100 * 1024 ? 512 : 256;
+  ringfft_kernel<T><<<grid, threads, smem, stream>>>(P);
   DSB_LAUNCH_CHECK();
   return DSB_OK;
 }
@@ -327,22 +396,11 @@ int launch_ringfft(dsb_plan *plan, const BucketLayout &lay, const UnitDev *units
   const size_t nprob = 2 * ((size_t)lay.mcap + 1);
   const size_t plane0 = nprob * lay.Kp * lay.ncols0;
   const size_t plane2 = nprob * 2 * lay.Kp * lay.ncols2;
-  const int nslots = (int)plan->beams.size();
-  std::vector<const void *> ptrs(nslots > 0 ? nslots : 1, nullptr);
-  for (int i = 0; i < nslots; ++i)
-    ptrs[i] = precision == DSB_PREC_FP64 ? (const void *)plan->beams[i].d64 : (const void *)plan->beams[i].d32;
-  const void **ptrs_dev = nullptr;
-  DSB_CUDA(cudaMallocAsync((void **)&ptrs_dev, ptrs.size() * sizeof(void *), stream));
-  DSB_CUDA(cudaMemcpyAsync(ptrs_dev, ptrs.data(), ptrs.size() * sizeof(void *), cudaMemcpyHostToDevice, stream));
-  int rc;
   if (precision == DSB_PREC_FP64)
-    rc = launch_t<double>(plan, lay, units_dev, F0, F2, plane0, plane2, (const double *const *)ptrs_dev, stream);
-  else
-    rc = launch_t<float>(plan, lay, units_dev, F0, F2, plane0, plane2, (const float *const *)ptrs_dev, stream);
-  // ptrs must stay alive until the copy has been consumed
-  DSB_CUDA(cudaStreamSynchronize(stream));
-  DSB_CUDA(cudaFreeAsync(ptrs_dev, stream));
-  return rc;
+    return launch_t<double>(plan, lay, units_dev, F0, F2, plane0, plane2,
+                            (const double *const *)plan->beam_ptrs64, stream);
+  return launch_t<float>(plan, lay, units_dev, F0, F2, plane0, plane2, (const float *const *)plan->beam_ptrs32,
+                         stream);
 }
 
 }  // namespace dsb

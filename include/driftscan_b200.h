@@ -70,14 +70,6 @@ int dsb_beam_upload(dsb_plan *plan, int slot, const double *beam_host, int ncomp
                     int is_complex, double *omega_out, void *stream);
 int dsb_beam_slots(dsb_plan *plan, int nslots); /* reserve `nslots` beam slots */
 
-/* Evaluate the analytic cylinder beam of drift/telescope/cylbeam.py:101-212 on
- * the device into `slot` (pol = 0: beam_x, 1: beam_y, -1: unpolarised beam_amp).
- * `pattern_k/pattern_f` is the host-computed 1-D Fraunhofer pattern of
- * cylbeam.fraunhofer_cylinder (:52-95) as natural-cubic-spline knots. */
-int dsb_beam_cylinder(dsb_plan *plan, int slot, int pol, const double *zenith,
-                      const double *pattern_k, const double *pattern_f, const double *pattern_m2,
-                      int npattern, double fwhm_ns, double *omega_out, void *stream);
-
 /* Legendre / spin-2 tables for l <= lmax, m <= mmax (the part of
  * healpy.map2alm that the reference reaches through cora.util.hputil,
  * drift/core/telescope.py:1189,1300,1310). */
@@ -133,6 +125,12 @@ int64_t dsb_mmajor_size(int n_out0, int n_out1, int npol, int lside, int mmax, i
 /* Workspace cap (bytes) for the library-owned scratch (ring spectra, GEMM
  * output).  Default 24 GiB. */
 int dsb_set_workspace_limit(size_t bytes);
+
+/* Per-stage device timing of dsb_transfer_units (CUDA events on the launching stream):
+ * accumulated milliseconds and launch counts of {ring FFT, Legendre contraction, pack}
+ * since profiling was last enabled.  Used by bench.py for the roofline figures. */
+int dsb_set_profiling(int enable);
+int dsb_get_profile(double *ms3, uint64_t *launches3);
 
 /* Unit-test entry for the tensor-core contraction kernel alone (host buffers):
  *   C[prob][col][n] = sum_k F[prob][k][col] * T[prob][n][k]

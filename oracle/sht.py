@@ -126,21 +126,27 @@ def pol_tables(m, lmax, theta):
 
 _table_cache = {}
 _table_cache_bytes = [0]
-_TABLE_CACHE_LIMIT = 1 << 30
+_TABLE_CACHE_LIMIT = int(float(__import__("os").environ.get("DSB_ORACLE_CACHE_GB", "1")) * (1 << 30))
 
 
 def _cached_tables(nside, lmax, m, kind, theta):
-    """Memoise the per-(nside, lmax, m) Legendre tables (pure speed-up)."""
-    key = (nside, lmax, m, kind)
-    if key not in _table_cache:
-        val = lambda_lm(m, lmax, theta) if kind == 0 else pol_tables(m, lmax, theta)
+    """Memoise the per-(nside, m) Legendre tables (pure speed-up).  A table computed up to
+    a larger lmax serves smaller ones (the recurrence in l does not depend on lmax)."""
+    key = (nside, m, kind)
+    ent = _table_cache.get(key)
+    if ent is None or ent[0] < lmax:
+        lcap = (lmax // 32 + 1) * 32
+        val = lambda_lm(m, lcap, theta) if kind == 0 else pol_tables(m, lcap, theta)
         nbytes = val.nbytes if kind == 0 else val[0].nbytes * 2
         if _table_cache_bytes[0] + nbytes > _TABLE_CACHE_LIMIT:
             _table_cache.clear()
             _table_cache_bytes[0] = 0
-        _table_cache[key] = val
+        _table_cache[key] = ent = (lcap, val)
         _table_cache_bytes[0] += nbytes
-    return _table_cache[key]
+    val = ent[1]
+    if kind == 0:
+        return val[: lmax + 1]
+    return val[0][: lmax + 1], val[1][: lmax + 1]
 
 
 # ---------------------------------------------------------------------------
