@@ -4,6 +4,7 @@
 // +-m packing of BeamTransfer._generate_mfiles (drift/core/beamtransfer.py:610-624).
 #include <algorithm>
 #include <numeric>
+#include <map>
 
 #include "dsb_common.cuh"
 
@@ -87,6 +88,91 @@ extern "C" int dsb_get_profile(double *ms3, uint64_t *launches3) {
   return DSB_OK;
 }
 
+namespace {
+
+// Looks up / builds the pair-weight maps of every unit.  Maps live in plan->wbuf (grown on
+// demand); an entry is valid while both beam slots keep the generation it was built from.
+int pair_weights_for_units(dsb_plan *plan, const dsb_unit *units, int nunits, int polarised, int precision,
+                           std::vector<int> &unit_pair, const void ***wptr_dev_out, cudaStream_t stream) {
+  const bool f64 = precision == DSB_PREC_FP64;
+  const size_t wplane_bytes = (size_t)(polarised ? 4 : 1) * plan->npix * (f64 ? 8 : 4);
+  if (plan->w_precision != precision || plan->w_polarised != polarised) {
+    plan->pair_cache.clear();
+    plan->w_precision = precision;
+    plan->w_polarised = polarised;
+  }
+  auto valid = [&](const dsb_plan::PairEntry &e) {
+    return plan->beams[e.slot_i].gen == e.gen_i && plan->beams[e.slot_j].gen == e.gen_j;
+  };
+  // distinct pairs of this call
+  std::map<std::pair<int, int>, int> need;
+  for (int i = 0; i < nunits; ++i) need.emplace(std::make_pair(units[i].beam_i, units[i].beam_j), -1);
+  // drop stale entries; if the call's pairs do not all fit next to the live ones, start over
+  std::vector<dsb_plan::PairEntry> keep;
+  for (const auto &e : plan->pair_cache)
+    if (valid(e)) keep.push_back(e);
+  size_t missing = 0;
+  for (auto &kv : need) {
+    bool found = false;
+    for (const auto &e : keep) found = found || (e.slot_i == kv.first.first && e.slot_j == kv.first.second);
+    if (!found) ++missing;
+  }
+  size_t cap_pairs = plan->wbuf_bytes / wplane_bytes;
+  bool rebuild_all = keep.size() != plan->pair_cache.size();  // compact after invalidation
+  if (keep.size() + missing > cap_pairs) {
+    size_t free_b = 0, total_b = 0;
+    DSB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t want = std::max(need.size(), keep.size() + missing);
+    DSB_CHECK(want * wplane_bytes < (free_b + plan->wbuf_bytes) / 2, DSB_ERR_NOMEM,
+              "dsb_transfer_units: %zu beam pairs need %zu bytes of weight maps; pass fewer frequencies per call",
+              want, want * wplane_bytes);
+    DSB_CUDA(cudaStreamSynchronize(stream));
+    if (plan->wbuf) DSB_CUDA(cudaFree(plan->wbuf));
+    if (plan->wptr_dev) DSB_CUDA(cudaFree((void *)plan->wptr_dev));
+    plan->wbuf = nullptr;
+    plan->wptr_dev = nullptr;
+    plan->wbuf_bytes = 0;
+    DSB_CUDA(cudaMalloc((void **)&plan->wbuf, want * wplane_bytes));
+    DSB_CUDA(cudaMalloc((void **)&plan->wptr_dev, want * sizeof(void *)));
+    plan->wbuf_bytes = want * wplane_bytes;
+    keep.clear();
+    rebuild_all = true;
+  }
+  if (rebuild_all) {
+    // entries are re-laid out from scratch: keep only what this call needs
+    plan->pair_cache.clear();
+    keep.clear();
+  }
+  bool changed = rebuild_all;
+  for (auto &kv : need) {
+    int idx = -1;
+    for (size_t e = 0; e < plan->pair_cache.size(); ++e)
+      if (plan->pair_cache[e].slot_i == kv.first.first && plan->pair_cache[e].slot_j == kv.first.second) idx = (int)e;
+    if (idx < 0) {
+      idx = (int)plan->pair_cache.size();
+      dsb_plan::PairEntry e{kv.first.first, kv.first.second, plan->beams[kv.first.first].gen,
+                            plan->beams[kv.first.second].gen};
+      plan->pair_cache.push_back(e);
+      DSB_TRY(launch_pair_weights(plan, precision, e.slot_i, e.slot_j, polarised,
+                                  plan->wbuf + (size_t)idx * wplane_bytes, stream));
+      changed = true;
+    }
+    kv.second = idx;
+  }
+  if (changed) {
+    std::vector<const void *> wptr(plan->pair_cache.size());
+    for (size_t i = 0; i < wptr.size(); ++i) wptr[i] = plan->wbuf + i * wplane_bytes;
+    DSB_CUDA(cudaMemcpyAsync(plan->wptr_dev, wptr.data(), wptr.size() * sizeof(void *), cudaMemcpyHostToDevice,
+                             stream));
+    DSB_CUDA(cudaStreamSynchronize(stream));
+  }
+  for (int i = 0; i < nunits; ++i) unit_pair[i] = need[std::make_pair(units[i].beam_i, units[i].beam_j)];
+  *wptr_dev_out = plan->wptr_dev;
+  return DSB_OK;
+}
+
+}  // namespace
+
 extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, int nunits, int npol_sky,
                                   int polarised, int mmax, int precision, int out_kind, const int64_t *dims,
                                   void *out, int out_is_host, void *stream_) {
@@ -129,10 +215,24 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
               "dsb_transfer_units: unit %d output index out of range", i);
     lmax_b = std::max(lmax_b, u.lmax);
   }
+  // ---- pair weights: one set of Stokes weight maps per distinct (beam_i, beam_j), cached in
+  // the plan until one of the two beam slots is uploaded again
+  const bool f64 = precision == DSB_PREC_FP64;
+  std::vector<int> unit_pair(nunits);
+  const void **wptr_dev = nullptr;
+  DSB_TRY(pair_weights_for_units(plan, units_host, nunits, polarised, precision, unit_pair, &wptr_dev, stream));
+
   std::vector<int> order(nunits);
   std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(),
-                   [&](int a, int b) { return units_host[a].lmax > units_host[b].lmax; });
+  // Descending lmax in steps of 8, units of one beam pair together inside a step: a CTA of the
+  // ring kernel then re-reads the same weight rows for consecutive units (L1 hits), and a
+  // 128-column tile of the contraction still spans few distinct row counts.
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    const int la = units_host[a].lmax >> 3, lb = units_host[b].lmax >> 3;
+    if (la != lb) return la > lb;
+    if (unit_pair[a] != unit_pair[b]) return unit_pair[a] < unit_pair[b];
+    return units_host[a].lmax > units_host[b].lmax;
+  });
 
   BucketLayout lay;
   lay.npol_sky = npol_sky;
@@ -154,7 +254,6 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
   const Tables &t = *tab;
 
   // ---- chunk size from the workspace budget
-  const bool f64 = precision == DSB_PREC_FP64;
   const size_t nprob = 2 * ((size_t)lay.mcap + 1);
   const size_t es = f64 ? 8 : 6, cs = f64 ? 8 : 4;
   const size_t per_unit = nprob * lay.Kp * lay.cpu0 * es + (lay.has2 ? nprob * 2 * lay.Kp * 8 * es : 0) +
@@ -199,8 +298,8 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
     std::vector<int32_t> o0(nu), o1(nu);
     for (int i = 0; i < nu; ++i) {
       const dsb_unit &u = units_host[order[c0 + i]];
-      ud[i] = {u.uvec[0], u.uvec[1], u.uvec[2], u.prefactor, u.beam_i, u.beam_j, u.lmax,
-               std::min(u.lmax, lay.mcap)};
+      ud[i] = {u.uvec[0], u.uvec[1], u.uvec[2], u.prefactor, unit_pair[order[c0 + i]],
+               (polarised && u.beam_i == u.beam_j) ? 1 : 0, u.lmax, std::min(u.lmax, lay.mcap)};
       o0[i] = (tarray && out_is_host) ? i : u.out0;
       o1[i] = u.out1;
     }
@@ -208,7 +307,8 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
       const int cpu = s == 0 ? lay.cpu0 : 8;
       const int upt = 128 / cpu;
       for (int ct = 0; ct * upt < nu; ++ct) {
-        const int Lt = ud[ct * upt].lmax;  // units are sorted by descending lmax
+        int Lt = 0;  // rows computed for the tile: its largest unit lmax
+        for (int i = ct * upt; i < std::min(nu, (ct + 1) * upt); ++i) Lt = std::max(Lt, ud[i].lmax);
         for (int m = 0; m <= std::min(lay.mcap, Lt); ++m)
           for (int p = 0; p < 2; ++p) {
             const int nr = nrows_mp(Lt, m, p);
@@ -267,7 +367,7 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
 
     StageTimer timer(stream);
     timer.mark(0);
-    if ((rc = launch_ringfft(plan, lay, ud_dev, precision, F0, F2, stream)) != DSB_OK) break;
+    if ((rc = launch_ringfft(plan, lay, ud_dev, precision, wptr_dev, F0, F2, stream)) != DSB_OK) break;
     timer.mark(1);
     if (f64)
       rc = launch_legendre_f64(plan, t, lay, items, items_dev, (const double *)F0, (const double *)F2,

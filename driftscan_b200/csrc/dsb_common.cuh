@@ -109,6 +109,7 @@ struct BeamSlot {
   int ncomp = 0;
   double omega = 0.0;
   bool valid = false;
+  uint64_t gen = 0;  // bumped by every upload (invalidates cached pair weights)
 };
 
 // Legendre tables of one (lmax, mmax, spin2, precision) request.
@@ -134,16 +135,39 @@ struct dsb_plan {
   dsb::RingDesc *rings = nullptr;
   uint8_t *horizon = nullptr;
   double2 *trig = nullptr;       // (cos phi_j, sin phi_j) per distinct ring pattern
-  int tw_log2 = 0;               // twiddle table size = 2^tw_log2
-  double2 *tw64 = nullptr;       // e^{+2 pi i j / Ntw}, j < Ntw/2
-  float2 *tw32 = nullptr;
+  // twiddle tables of fft16.cuh, one block per transform length 2^a (a = 5 .. max)
+  int tw16_off[16] = {0};        // offset of length 2^a's block
+  int *tw16_off_dev = nullptr;
+  double2 *tw16_64 = nullptr;
+  float2 *tw16_32 = nullptr;
+  // fold rings grouped by transform length: one ring-kernel launch per class
+  struct RingClass {
+    int kind = 0;      // 0 power-of-two ring, 1 Bluestein, 2 direct sum (<= 16 pixels)
+    int log2L = 5;     // transform length
+    int first = 0;     // offset into ring_list
+    int count = 0;
+    int max_n = 0;     // longest ring
+    int max_live = 1;  // 2 if a ring pair of the class has both rings above the horizon
+  };
+  std::vector<RingClass> ring_classes;  // sorted by decreasing work
+  int *ring_list_dev = nullptr;
+  cudaStream_t side_stream = nullptr;   // short-ring classes run beside the long ones
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   double2 *chirp64 = nullptr;    // c_j = e^{+i pi j^2 / n} per Bluestein ring
   float2 *chirp32 = nullptr;
-  double2 *dhat64 = nullptr;     // FFT(d wrapped)/Nb in DIF (bit-reversed) order
+  double2 *dhat64 = nullptr;     // FFT(d wrapped)/L in the DIF position order of fft16.cuh
   float2 *dhat32 = nullptr;
   std::vector<dsb::BeamSlot> beams;
-  const void **beam_ptrs32 = nullptr;  // device arrays of per-slot map pointers
-  const void **beam_ptrs64 = nullptr;
+  // Stokes weight maps per (beam_i, beam_j) pair, [pair][nplane][npix] in the working precision
+  struct PairEntry {
+    int slot_i, slot_j;
+    uint64_t gen_i, gen_j;
+  };
+  std::vector<PairEntry> pair_cache;
+  char *wbuf = nullptr;
+  size_t wbuf_bytes = 0;
+  const void **wptr_dev = nullptr;
+  int w_precision = -1, w_polarised = -1;
   std::vector<dsb::Tables> tables;
   // workspace (grown on demand, capped by dsb_set_workspace_limit)
   void *ws = nullptr;
@@ -185,7 +209,7 @@ struct BucketLayout {
 struct UnitDev {
   double ax, ay, az;  // uvec
   double pref;
-  int32_t beam_i, beam_j;
+  int32_t beam_i, beam_j;  // on the device: pair-weight index, "Stokes V is zero" flag
   int32_t lmax;
   int32_t mmax;  // min(lmax, mcap)
 };
@@ -193,8 +217,13 @@ struct UnitDev {
 // ringfft.cu -- fused fringe x beam -> ring FFT -> north/south fold -> spectra
 // F planes: spin-0 [nprob][Kp][ncols0], spin-2 [nprob][2*Kp][ncols2]; element type double
 // (precision fp64, 1 plane) or bf16 (3 planes, plane stride = nprob*K*ncols).
+// units_dev[u].beam_i = index into wplanes_dev (pair weights), .beam_j = 1 if Stokes V of the pair is
+// identically zero.  wplanes_dev[pair] -> [nplane][npix] in the working precision.
 int launch_ringfft(dsb_plan *plan, const BucketLayout &lay, const UnitDev *units_dev, int precision,
-                   void *F0, void *F2, cudaStream_t stream);
+                   const void *const *wplanes_dev, void *F0, void *F2, cudaStream_t stream);
+int launch_pair_weights(dsb_plan *plan, int precision, int slot_i, int slot_j, int polarised, void *w,
+                        cudaStream_t stream);
+int launch_bluestein_prepare16(dsb_plan *plan);
 
 // legendre_f64.cu / legendre_tc.cu -- grouped contraction
 //   C_s[prob][col][n] = sum_k F_s[prob][k][col] * T_s[prob][n][k]

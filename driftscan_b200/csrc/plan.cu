@@ -4,9 +4,10 @@
 #include <cmath>
 #include <cstdarg>
 #include <atomic>
+#include <algorithm>
 
 #include "dsb_common.cuh"
-#include "fft.cuh"
+#include "fft16.cuh"
 
 namespace dsb {
 
@@ -39,35 +40,6 @@ int ensure_workspace(dsb_plan *plan, size_t bytes) {
   DSB_CUDA(cudaMemset(plan->ws, 0, bytes));
   plan->ws_bytes = bytes;
   return DSB_OK;
-}
-
-// Transformed Bluestein chirp, one block per non-power-of-two ring length.
-//   d_t = exp(-i pi t^2 / n);  D[t] = d_t (t < n), D[Nb - t] = d_t (0 < t < n), else 0
-//   dhat = DFT_-(D) / Nb, left in fft_dif (bit-reversed) order.
-__global__ void bluestein_prepare_kernel(const RingDesc *rings, int nrings_cap, const double2 *chirp,
-                                         double2 *dhat, const double2 *tw, int tw_log2) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const RingDesc rd = rings[blockIdx.x];
-  if (!rd.bluestein) return;
-  const int n = rd.nphi;
-  const int Nb = 1 << rd.log2n;
-  cplx<double> *tw_s = reinterpret_cast<cplx<double> *>(smem_raw);
-  cplx<double> *buf = tw_s + (Nb >> 1);
-  load_twiddles<double>(tw_s, rd.log2n, tw, tw_log2);
-  const int pitch = fft_pitch(Nb);
-  for (int t = threadIdx.x; t < pitch; t += blockDim.x) buf[t] = {0.0, 0.0};
-  __syncthreads();
-  for (int t = threadIdx.x; t < n; t += blockDim.x) {
-    double2 c = chirp[rd.chirp_off + t];
-    cplx<double> d = {c.x, -c.y};
-    buf[fft_phys(t)] = d;
-    if (t > 0) buf[fft_phys(Nb - t)] = d;
-  }
-  __syncthreads();
-  fft_dif<double, -1>(buf, rd.log2n, 1, pitch, tw_s);
-  const double inv = 1.0 / Nb;
-  for (int t = threadIdx.x; t < Nb; t += blockDim.x)
-    dhat[rd.dhat_off + t] = make_double2(buf[fft_phys(t)].x * inv, buf[fft_phys(t)].y * inv);
 }
 
 __global__ void d2f2_kernel(const double2 *in, float2 *out, size_t n) {
@@ -133,7 +105,6 @@ extern "C" int dsb_plan_create(int nside, const uint8_t *horizon_host, dsb_plan 
   const int nfold = plan->nfold;
   const int ncapring = nside - 1;  // fold rings 0 .. nside-2 are polar-cap rings
   const long captotal = 2L * (nside - 1) * nside;
-  plan->tw_log2 = ilog2_ceil(8 * nside < 8 ? 8 : 8 * nside);
 
   // ---- ring descriptors
   plan->rings_h.resize(nfold);
@@ -171,10 +142,12 @@ extern "C" int dsb_plan_create(int nside, const uint8_t *horizon_host, dsb_plan 
     const int n = rd.nphi;
     const bool pow2 = (n & (n - 1)) == 0;
     rd.bluestein = pow2 ? 0 : 1;
+    // rings of <= 16 pixels are summed directly (no transform)
     rd.log2n = pow2 ? ilog2_ceil(n) : ilog2_ceil(2 * n - 1);
+    if (n <= 16) rd.bluestein = 0;
     rd.chirp_off = chirp_total;
     rd.dhat_off = dhat_total;
-    if (!pow2) {
+    if (rd.bluestein) {
       chirp_total += n;
       dhat_total += 1 << rd.log2n;
     }
@@ -205,12 +178,58 @@ extern "C" int dsb_plan_create(int nside, const uint8_t *horizon_host, dsb_plan 
     trig[captotal + 4 * nside + j] = make_double2((double)cosl(a0), (double)sinl(a0));
   }
 
-  // ---- FFT twiddles
-  const int Ntw = 1 << plan->tw_log2;
-  std::vector<double2> tw(Ntw / 2);
-  for (int j = 0; j < Ntw / 2; ++j) {
-    long double ang = 2.0L * M_PIl * j / Ntw;
-    tw[j] = make_double2((double)cosl(ang), (double)sinl(ang));
+  // ---- FFT twiddles (fft16.cuh), one block per transform length
+  int maxlog = 5;
+  for (const auto &rd : plan->rings_h)
+    if (rd.nphi > 16) maxlog = std::max(maxlog, rd.log2n);
+  DSB_CHECK(maxlog <= 15, DSB_ERR_UNSUPPORTED, "dsb_plan_create: transform length 2^%d unsupported", maxlog);
+  std::vector<double2> tw;
+  for (int a = 5; a <= maxlog; ++a) {
+    std::vector<double2> blk;
+    fft16_twiddles_host(a, blk);
+    plan->tw16_off[a] = (int)tw.size();
+    tw.insert(tw.end(), blk.begin(), blk.end());
+    if (tw.size() & 1) tw.push_back(make_double2(1.0, 0.0));
+  }
+
+  // ---- ring classes: one launch per (kind, transform length), most work first
+  {
+    std::map<std::pair<int, int>, std::vector<int>> by_len;
+    for (int k = 0; k < nfold; ++k) {
+      const RingDesc &rd = plan->rings_h[k];
+      const int kind = rd.nphi <= 16 ? 2 : rd.bluestein ? 1 : 0;
+      by_len[std::make_pair(kind, kind == 2 ? 5 : rd.log2n)].push_back(k);
+    }
+    std::vector<dsb_plan::RingClass> classes;
+    for (auto &kv : by_len) {
+      dsb_plan::RingClass rc;
+      rc.kind = kv.first.first;
+      rc.log2L = kv.first.second;
+      rc.count = (int)kv.second.size();
+      for (int r : kv.second) {
+        const RingDesc &rd = plan->rings_h[r];
+        rc.max_n = std::max(rc.max_n, rd.nphi);
+        if (rd.vis_north && rd.vis_south && rd.startS >= 0) rc.max_live = 2;
+      }
+      classes.push_back(rc);
+    }
+    auto work = [](const dsb_plan::RingClass &c) {
+      return (double)c.count * (1 << c.log2L) * c.log2L * (c.kind == 1 ? 2.2 : 1.0);
+    };
+    std::sort(classes.begin(), classes.end(),
+              [&](const dsb_plan::RingClass &a, const dsb_plan::RingClass &b) { return work(a) > work(b); });
+    std::vector<int> list;
+    for (auto &rc : classes) {
+      rc.first = (int)list.size();
+      const auto &v = by_len[std::make_pair(rc.kind, rc.log2L)];
+      list.insert(list.end(), v.rbegin(), v.rend());
+    }
+    plan->ring_classes = classes;
+    DSB_CUDA(cudaMalloc(&plan->ring_list_dev, sizeof(int) * list.size()));
+    DSB_CUDA(cudaMemcpy(plan->ring_list_dev, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice));
+    DSB_CUDA(cudaStreamCreateWithFlags(&plan->side_stream, cudaStreamNonBlocking));
+    DSB_CUDA(cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming));
+    DSB_CUDA(cudaEventCreateWithFlags(&plan->ev_join, cudaEventDisableTiming));
   }
 
   // ---- Bluestein chirps c_j = exp(+i pi j^2 / n) with exact phase reduction
@@ -232,11 +251,13 @@ extern "C" int dsb_plan_create(int nside, const uint8_t *horizon_host, dsb_plan 
   DSB_CUDA(cudaMemcpy(plan->horizon, horizon_host, plan->npix, cudaMemcpyHostToDevice));
   DSB_CUDA(cudaMalloc(&plan->trig, sizeof(double2) * ntrig));
   DSB_CUDA(cudaMemcpy(plan->trig, trig.data(), sizeof(double2) * ntrig, cudaMemcpyHostToDevice));
-  DSB_CUDA(cudaMalloc(&plan->tw64, sizeof(double2) * (Ntw / 2)));
-  DSB_CUDA(cudaMemcpy(plan->tw64, tw.data(), sizeof(double2) * (Ntw / 2), cudaMemcpyHostToDevice));
-  DSB_CUDA(cudaMalloc(&plan->tw32, sizeof(float2) * (Ntw / 2)));
-  d2f2_kernel<<<(Ntw / 2 + 255) / 256, 256>>>(plan->tw64, plan->tw32, Ntw / 2);
+  DSB_CUDA(cudaMalloc(&plan->tw16_64, sizeof(double2) * tw.size()));
+  DSB_CUDA(cudaMemcpy(plan->tw16_64, tw.data(), sizeof(double2) * tw.size(), cudaMemcpyHostToDevice));
+  DSB_CUDA(cudaMalloc(&plan->tw16_32, sizeof(float2) * tw.size()));
+  d2f2_kernel<<<(unsigned)((tw.size() + 255) / 256), 256>>>(plan->tw16_64, plan->tw16_32, tw.size());
   DSB_LAUNCH_CHECK();
+  DSB_CUDA(cudaMalloc(&plan->tw16_off_dev, sizeof(plan->tw16_off)));
+  DSB_CUDA(cudaMemcpy(plan->tw16_off_dev, plan->tw16_off, sizeof(plan->tw16_off), cudaMemcpyHostToDevice));
   const size_t nch = chirp.size();
   DSB_CUDA(cudaMalloc(&plan->chirp64, sizeof(double2) * nch));
   DSB_CUDA(cudaMemcpy(plan->chirp64, chirp.data(), sizeof(double2) * nch, cudaMemcpyHostToDevice));
@@ -247,19 +268,10 @@ extern "C" int dsb_plan_create(int nside, const uint8_t *horizon_host, dsb_plan 
   DSB_CUDA(cudaMalloc(&plan->dhat64, sizeof(double2) * ndh));
   DSB_CUDA(cudaMalloc(&plan->dhat32, sizeof(float2) * ndh));
   if (dhat_total > 0) {
-    const size_t smem = sizeof(double2) * ((size_t)(1 << plan->tw_log2) * 3 / 2 + (1 << plan->tw_log2) / 16 + 16);
-    DSB_CUDA(cudaFuncSetAttribute(bluestein_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    bluestein_prepare_kernel<<<ncapring, 256, smem>>>(plan->rings, ncapring, plan->chirp64, plan->dhat64,
-                                                      plan->tw64, plan->tw_log2);
-    DSB_LAUNCH_CHECK();
+    DSB_TRY(launch_bluestein_prepare16(plan));
     d2f2_kernel<<<(unsigned)((ndh + 255) / 256), 256>>>(plan->dhat64, plan->dhat32, ndh);
     DSB_LAUNCH_CHECK();
   }
-  DSB_CUDA(cudaMalloc((void **)&plan->beam_ptrs32, sizeof(void *) * kMaxBeamSlots));
-  DSB_CUDA(cudaMalloc((void **)&plan->beam_ptrs64, sizeof(void *) * kMaxBeamSlots));
-  DSB_CUDA(cudaMemset(plan->beam_ptrs32, 0, sizeof(void *) * kMaxBeamSlots));
-  DSB_CUDA(cudaMemset(plan->beam_ptrs64, 0, sizeof(void *) * kMaxBeamSlots));
   DSB_CUDA(cudaDeviceSynchronize());
   *out = plan;
   return DSB_OK;
@@ -279,14 +291,19 @@ extern "C" int dsb_plan_destroy(dsb_plan *plan) {
   cudaFree(plan->rings);
   cudaFree(plan->horizon);
   cudaFree(plan->trig);
-  cudaFree(plan->tw64);
-  cudaFree(plan->tw32);
+  cudaFree(plan->tw16_64);
+  cudaFree(plan->tw16_32);
+  cudaFree(plan->tw16_off_dev);
+  cudaFree(plan->ring_list_dev);
+  if (plan->side_stream) cudaStreamDestroy(plan->side_stream);
+  if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+  if (plan->ev_join) cudaEventDestroy(plan->ev_join);
+  cudaFree(plan->wbuf);
+  cudaFree((void *)plan->wptr_dev);
   cudaFree(plan->chirp64);
   cudaFree(plan->chirp32);
   cudaFree(plan->dhat64);
   cudaFree(plan->dhat32);
-  cudaFree((void *)plan->beam_ptrs32);
-  cudaFree((void *)plan->beam_ptrs64);
   for (auto &b : plan->beams) {
     cudaFree(b.d64);
     cudaFree(b.d32);
@@ -323,10 +340,6 @@ extern "C" int dsb_beam_upload(dsb_plan *plan, int slot, const double *beam_host
     DSB_CUDA(cudaMalloc(&b.d64, n * sizeof(double)));
     DSB_CUDA(cudaMalloc(&b.d32, n * sizeof(float)));
     b.ncomp = ncomp;
-    const void *p32 = b.d32, *p64 = b.d64;
-    DSB_CUDA(cudaMemcpyAsync(plan->beam_ptrs32 + slot, &p32, sizeof(void *), cudaMemcpyHostToDevice, stream));
-    DSB_CUDA(cudaMemcpyAsync(plan->beam_ptrs64 + slot, &p64, sizeof(void *), cudaMemcpyHostToDevice, stream));
-    DSB_CUDA(cudaStreamSynchronize(stream));
   }
   DSB_CUDA(cudaMemcpyAsync(b.d64, beam_host, n * sizeof(double), cudaMemcpyHostToDevice, stream));
   const int nblk = 128;
@@ -343,6 +356,7 @@ extern "C" int dsb_beam_upload(dsb_plan *plan, int slot, const double *beam_host
   for (int i = 0; i < nblk; ++i) tot += hp[i];
   b.omega = tot * 4.0 * M_PI / plan->npix;
   b.valid = true;
+  b.gen += 1;
   if (omega_out) *omega_out = b.omega;
   return DSB_OK;
 }

@@ -4,9 +4,18 @@
 //   - _construct_pol_real          (drift/util/_fast_tools.pyx:96-164)
 //   - UnpolarisedTelescope._beam_map_single (drift/core/telescope.py:1156-1176)
 //   - the phi -> m ring FFT inside healpy.map2alm (called from telescope.py:1189,1300,1310)
-// and never writes the pixel maps to HBM: a CTA owns one ring pair (north ring +
-// its southern mirror) for a group of units, builds the Stokes response of the
-// ring in shared memory, transforms it and emits the folded spectra
+// and never writes the pixel maps to HBM.
+//
+// The Stokes response of a unit is  M^X_p = pref * fringe_p * w^X_p  with real weights
+// w^X = H * (beam_i (x) beam_j combination) that depend only on the pair of beam maps;
+// pair_weights_kernel builds them once per (frequency, class pair) and they stay in L2.
+//
+// A CTA owns one ring pair (north ring + its southern mirror) for a range of units.  Per
+// group of units it (A) evaluates the fringe of every pixel of the pair into shared
+// memory (fp64 phase reduced to a fraction of a turn, then sincospi in working precision),
+// (B) runs the ring transforms with the register-blocked FFT of fft16.cuh -- the first
+// pass forms fringe x weight on the fly -- and (C) gathers bins +-m, applies e^{i m phi0},
+// folds north/south and emits
 //   F+_m(k) = e^{i m phi0} sum_j M_j e^{+2 pi i m j / n},  F-_m(k) = same for conj(M)
 //   even = north + south, odd = north - south
 // laid out as the A operand of the Legendre contraction (legendre_*.cu):
@@ -14,29 +23,45 @@
 //   spin-2  F2[2m+p][k or Kp+k][unit*8 + eb*4 + pm*2 + reim]
 // with the (Q,U)->(E,B) combination folded into the operand roles:
 //   E = sum_k (-W)(F[Q]) + (-X)(-i F[U]),   B = sum_k (-W)(F[U]) + (-X)(+i F[Q]).
+//
+// Ring lengths are 4, 8, ..., 4*nside.  Power-of-two rings >= 32 run one forward
+// transform; other lengths go through Bluestein's chirp-z identity (forward transform,
+// multiplication by the pre-transformed chirp and inverse transform, the innermost pass
+// pair fused in registers); rings of <= 16 pixels are summed directly.  Rings entirely
+// below the horizon are skipped, as is Stokes V of a pair of identical real beams
+// (identically zero, _fast_tools.pyx:158-162).
 #include "dsb_common.cuh"
-#include "fft.cuh"
+#include "fft16.cuh"
 
 namespace dsb {
+
+constexpr int kMaxGroup = 16;  // units processed together by a CTA (short rings)
+#ifndef DSB_RING_MINBLOCKS
+#define DSB_RING_MINBLOCKS 3
+#endif
 
 template <typename T>
 struct RingFFTParams {
   const RingDesc *rings;
-  const uint8_t *horizon;
+  const int *ring_list;  // fold rings handled by this launch
   const double2 *trig;
-  const typename TwPtr<T>::type *tw;
-  const typename TwPtr<T>::type *chirp;
-  const typename TwPtr<T>::type *dhat;
-  int tw_log2;
+  const cplx<T> *tw16;   // twiddle tables of all lengths
+  int tw16_off[16];      // offset per log2 L
+  const cplx<T> *chirp;
+  const cplx<T> *dhat;
   const UnitDev *units;
   int nunits;
-  const T *const *beams;
+  const T *const *wplanes;  // per pair: [nplane][npix]
+  int npix;
   int polarised, npol_sky, nsp0, has2;
   int cpu0, cpu2, ncols0, ncols2, Kp, nfold;
+  int mcap;
   void *F0, *F2;
   size_t plane0, plane2;
   int units_per_cta;
-  int seq_capacity;  // complex elements of dynamic shared memory
+  int npp;                                   // Stokes maps transformed per pass (1, 2 or 4)
+  int tw_cap, ch_cap, ph_cap, fr_cap, seq_cap;  // shared-memory carve, complex elements
+  int tw_global;                                // twiddles are read from global memory
 };
 
 __device__ __forceinline__ void sincospi_t(float x, float *s, float *c) { sincospif(x, s, c); }
@@ -102,254 +127,582 @@ __device__ __forceinline__ void store8<float>(void *F, size_t plane, size_t idx,
       make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
 }
 
+// ---- pair weights -------------------------------------------------------------------
+// w[X][pix] = H * {I: it jt + ip jp, Q: it jt - ip jp, U: it jp + ip jt, V: it jp - ip jt}
+// (_fast_tools.pyx:141-162); unpolarised: H * b_i * b_j (telescope.py:1170-1174).
 template <typename T>
-__global__ void __launch_bounds__(512) ringfft_kernel(const RingFFTParams<T> P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int k = P.nfold - 1 - (int)blockIdx.x;  // long (equatorial) rings first
-  const RingDesc rd = P.rings[k];
-  const int n = rd.nphi;
-  const int log2L = rd.log2n;
-  const int L = 1 << log2L;
-  // shared memory: [twiddles L/2][sequences ...]
-  cplx<T> *tw_s = reinterpret_cast<cplx<T> *>(smem_raw);
-  cplx<T> *buf = tw_s + (L >> 1);
-  const int pitch = fft_pitch(L);
-  load_twiddles<T>(tw_s, log2L, P.tw, P.tw_log2);
+__global__ void pair_weights_kernel(const T *__restrict__ bi, const T *__restrict__ bj,
+                                    const uint8_t *__restrict__ horizon, int npix, int polarised, T *__restrict__ w) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+    const T h = horizon[p] ? T(1) : T(0);
+    if (polarised) {
+      const T it = bi[2 * (size_t)p], ip = bi[2 * (size_t)p + 1];
+      const T jt = bj[2 * (size_t)p], jp = bj[2 * (size_t)p + 1];
+      w[p] = h * (it * jt + ip * jp);
+      w[(size_t)npix + p] = h * (it * jt - ip * jp);
+      w[2 * (size_t)npix + p] = h * (it * jp + ip * jt);
+      w[3 * (size_t)npix + p] = h * (it * jp - ip * jt);
+    } else {
+      w[p] = h * (bi[p] * bj[p]);
+    }
+  }
+}
 
-  const bool equator = rd.startS < 0;
-  // rings entirely below the horizon contribute nothing: skip their transforms
-  const bool liveN = rd.vis_north != 0;
-  const bool liveS = !equator && rd.vis_south != 0;
-  const int nlive = (liveN ? 1 : 0) + (liveS ? 1 : 0);
-  const int npol = P.npol_sky;  // number of Stokes maps to transform: 1, 3 or 4
-  int npp = nlive ? (P.seq_capacity - (L >> 1)) / (nlive * pitch) : npol;
-  if (npp > npol) npp = npol;
-  if (npp == 3) npp = 2;  // keep passes balanced: (I,Q) (U,V)
-  // sequence slot of a ring inside a pol group: live rings are packed first
-  const int slotS = liveN ? 1 : 0;
+int launch_pair_weights(dsb_plan *plan, int precision, int slot_i, int slot_j, int polarised, void *w,
+                        cudaStream_t stream) {
+  const int nblk = std::min(4 * 148, (plan->npix + 255) / 256);
+  if (precision == DSB_PREC_FP64)
+    pair_weights_kernel<double><<<nblk, 256, 0, stream>>>(plan->beams[slot_i].d64, plan->beams[slot_j].d64,
+                                                          plan->horizon, plan->npix, polarised, (double *)w);
+  else
+    pair_weights_kernel<float><<<nblk, 256, 0, stream>>>(plan->beams[slot_i].d32, plan->beams[slot_j].d32,
+                                                         plan->horizon, plan->npix, polarised, (float *)w);
+  DSB_LAUNCH_CHECK();
+  return DSB_OK;
+}
+
+// ---- Bluestein chirp transform --------------------------------------------------------
+//   d_t = exp(-i pi t^2 / n);  D[t] = d_t (t < n), D[L - t] = d_t (0 < t < n), else 0
+//   dhat = DFT_-(D) / L, left in the position order of the DIF passes of fft16.cuh.
+template <typename F, int P>
+__device__ __forceinline__ void prepare_passes(cplx<double> *buf, const cplx<double> *tw) {
+  for (int t = threadIdx.x; t < (F::L >> 4); t += blockDim.x) dif_pass<double, F, P, -1>(buf, tw, t);
+  __syncthreads();
+  if constexpr (P + 1 < F::NPASS) prepare_passes<F, P + 1>(buf, tw);
+}
+
+template <int LOG2L>
+__global__ void bluestein_prepare16_kernel(const RingDesc *rings, const int *ring_list, const double2 *chirp,
+                                           double2 *dhat, const double2 *tw16) {
+  using F = Fft16<LOG2L>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const RingDesc rd = rings[ring_list[blockIdx.x]];
+  const int n = rd.nphi;
+  cplx<double> *buf = reinterpret_cast<cplx<double> *>(smem_raw);
+  const cplx<double> *tw = reinterpret_cast<const cplx<double> *>(tw16);
+  for (int t = threadIdx.x; t < F::PITCH; t += blockDim.x) buf[t] = {0.0, 0.0};
+  __syncthreads();
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    const double2 c = chirp[rd.chirp_off + t];
+    const cplx<double> d = {c.x, -c.y};
+    buf[F::phys(t)] = d;
+    if (t > 0) buf[F::phys(F::L - t)] = d;
+  }
+  __syncthreads();
+  prepare_passes<F, 0>(buf, tw);
+  const double inv = 1.0 / F::L;
+  for (int t = threadIdx.x; t < F::L; t += blockDim.x) {
+    const cplx<double> v = buf[F::phys(t)];
+    dhat[rd.dhat_off + t] = make_double2(v.x * inv, v.y * inv);
+  }
+}
+
+template <int LOG2L>
+static int prepare_class(dsb_plan *plan, const dsb_plan::RingClass &cls) {
+  using F = Fft16<LOG2L>;
+  const size_t smem = sizeof(double2) * (size_t)F::PITCH;
+  DSB_CHECK(smem <= 227 * 1024, DSB_ERR_UNSUPPORTED, "Bluestein length 2^%d does not fit shared memory", LOG2L);
+  DSB_CUDA(cudaFuncSetAttribute(bluestein_prepare16_kernel<LOG2L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  bluestein_prepare16_kernel<LOG2L><<<cls.count, 256, smem>>>(plan->rings, plan->ring_list_dev + cls.first,
+                                                              plan->chirp64, plan->dhat64,
+                                                              plan->tw16_64 + plan->tw16_off[LOG2L]);
+  DSB_LAUNCH_CHECK();
+  return DSB_OK;
+}
+
+int launch_bluestein_prepare16(dsb_plan *plan) {
+  for (const auto &cls : plan->ring_classes) {
+    if (cls.kind != 1 || cls.count == 0) continue;
+    switch (cls.log2L) {
+      case 6: DSB_TRY(prepare_class<6>(plan, cls)); break;
+      case 7: DSB_TRY(prepare_class<7>(plan, cls)); break;
+      case 8: DSB_TRY(prepare_class<8>(plan, cls)); break;
+      case 9: DSB_TRY(prepare_class<9>(plan, cls)); break;
+      case 10: DSB_TRY(prepare_class<10>(plan, cls)); break;
+      case 11: DSB_TRY(prepare_class<11>(plan, cls)); break;
+      case 12: DSB_TRY(prepare_class<12>(plan, cls)); break;
+      case 13: DSB_TRY(prepare_class<13>(plan, cls)); break;
+      default:
+        set_error("Bluestein transform length 2^%d unsupported", cls.log2L);
+        return DSB_ERR_UNSUPPORTED;
+    }
+  }
+  return DSB_OK;
+}
+
+// ---- the ring kernel ---------------------------------------------------------------------
+struct GroupUnit {
+  double axs, ays, az;  // uvec x sin(theta) (x, y), uvec z
+  double pref;
+  int pair;
+  int mmax;
+  int deadV;
+  int pad;
+};
+
+// Stokes maps handled by one pass: spin-0 group {I[,V]} or spin-2 group {Q,U}, whole or
+// one map at a time (when shared memory only holds one map's sequences).
+enum PassMode { MODE_I = 0, MODE_V = 1, MODE_IV = 2, MODE_Q = 3, MODE_U = 4, MODE_QU = 5 };
+__host__ __device__ constexpr int mode_npol(int mode) { return (mode == MODE_IV || mode == MODE_QU) ? 2 : 1; }
+__host__ __device__ constexpr int mode_pol(int mode, int q) {
+  return mode == MODE_I ? 0 : mode == MODE_V ? 3 : mode == MODE_IV ? (q ? 3 : 0) : mode == MODE_Q ? 1
+         : mode == MODE_U ? 2 : (q ? 2 : 1);
+}
+// pi-th pass of a unit group, -1 when there is none
+__device__ __forceinline__ int pass_mode(int npp, int npol, int pi) {
+  if (npp >= 2) {
+    if (pi == 0) return npol == 4 ? MODE_IV : MODE_I;
+    if (pi == 1 && npol >= 3) return MODE_QU;
+    return -1;
+  }
+  if (pi == 0) return MODE_I;
+  if (npol == 1) return -1;
+  if (npol == 3) return pi == 1 ? MODE_Q : pi == 2 ? MODE_U : -1;
+  return pi == 1 ? MODE_V : pi == 2 ? MODE_Q : MODE_U;
+}
+
+enum RingKind { KIND_POW2 = 0, KIND_BLUESTEIN = 1, KIND_DIRECT = 2 };
+
+template <typename T>
+struct RingCtx {
+  const RingFFTParams<T> *P;
+  RingDesc rd;
+  const GroupUnit *us;
+  const cplx<T> *tw, *ch_s, *ph_s, *fr_s;
+  cplx<T> *seq_s;
+  const cplx<T> *dh;
+  int k, n, pitch, nlive, slotS, ug, Gn;
+  bool liveN, liveS, equator;
+};
+
+// ---- B: ring transforms of one pass ---------------------------------------------------------
+// sequences: index s = (gi * NQ + q) * nlive + lr; a sequence of Stokes V of two identical beams
+// is identically zero and is not transformed
+template <typename T, typename F, int P, int SIGN>
+__device__ __forceinline__ void middle_passes(const RingCtx<T> &c, int mode, int ntask) {
+  if constexpr (P + 1 < F::NPASS) {
+    const int nq = mode_npol(mode);
+    for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+      const int s = task >> F::LTQ;
+      const int gq = c.nlive == 2 ? s >> 1 : s;
+      const int q = nq == 2 ? gq & 1 : 0, gi = nq == 2 ? gq >> 1 : gq;
+      if (mode_pol(mode, q) == 3 && c.us[gi].deadV) continue;
+      if (SIGN < 0)
+        dif_pass<T, F, P, -1>(c.seq_s + s * F::PITCH, c.tw, task & ((1 << F::LTQ) - 1));
+      else
+        dit_pass<T, F, P, +1>(c.seq_s + s * F::PITCH, c.tw, task & ((1 << F::LTQ) - 1));
+    }
+    __syncthreads();
+    if constexpr (SIGN < 0) {
+      if constexpr (P + 2 < F::NPASS) middle_passes<T, F, P + 1, SIGN>(c, mode, ntask);
+    } else {
+      if constexpr (P > 0) middle_passes<T, F, P - 1, SIGN>(c, mode, ntask);
+    }
+  }
+}
+
+template <typename T, typename F, int KIND>
+__device__ __forceinline__ void transform_pass(const RingCtx<T> &c, int mode) {
+  const RingFFTParams<T> &P = *c.P;
+  const int nq = mode_npol(mode);
+  const int ntask = (c.Gn * nq * c.nlive) << F::LTQ;
+  const int n = c.n;
+  // pass 0: x_i = fringe_i * w_i formed in registers (Bluestein: elements >= L/2 are zero padding)
+  for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+    const int s = task >> F::LTQ, t = task & ((1 << F::LTQ) - 1);
+    const int lr = c.nlive == 2 ? s & 1 : 0, gq = c.nlive == 2 ? s >> 1 : s;
+    const int q = nq == 2 ? gq & 1 : 0, gi = nq == 2 ? gq >> 1 : gq;
+    const int pol = mode_pol(mode, q);
+    if (pol == 3 && c.us[gi].deadV) continue;
+    const int ring = (c.liveN && lr == 0) ? 0 : 1;
+    const T *__restrict__ w = P.wplanes[c.us[gi].pair] + (size_t)pol * P.npix + (ring ? c.rd.startS : c.rd.startN) + t;
+    const cplx<T> *__restrict__ f = c.fr_s + (gi * c.nlive + lr) * n + t;
+    constexpr int S0 = 1 << F::lS(0);
+    constexpr int NR = KIND == KIND_BLUESTEIN ? 8 : 16;
+    cplx<T> v[16];
+    T wv[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) wv[r] = (KIND == KIND_POW2 || t + r * S0 < n) ? w[r * S0] : T(0);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      cplx<T> x = {T(0), T(0)};
+      if (KIND == KIND_POW2 || t + r * S0 < n) {
+        const cplx<T> fv = f[r * S0];
+        x = {fv.x * wv[r], fv.y * wv[r]};
+      }
+      v[r] = x;
+    }
+#pragma unroll
+    for (int r = NR; r < 16; ++r) v[r] = {T(0), T(0)};
+    if (pol == 3) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) v[r] = {-v[r].y, v[r].x};
+    }
+    const PassAddr<F, 0> a = pass_addr<F, 0>(t);
+    dft16<T, -1, KIND == KIND_BLUESTEIN>(v);
+    pass_twiddle<T, F, 0, -1>(c.tw, a, v);
+    pass_store<T, F, 0>(c.seq_s + s * F::PITCH, a, v);
+  }
+  __syncthreads();
+  if constexpr (F::NPASS > 2) middle_passes<T, F, 1, -1>(c, mode, ntask);
+  {
+    constexpr int PL = F::NPASS - 1;
+    constexpr int LR = F::lR(PL);
+    for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+      const int s = task >> F::LTQ, t = task & ((1 << F::LTQ) - 1);
+      const int gq = c.nlive == 2 ? s >> 1 : s;
+      const int q = nq == 2 ? gq & 1 : 0, gi = nq == 2 ? gq >> 1 : gq;
+      if (mode_pol(mode, q) == 3 && c.us[gi].deadV) continue;
+      cplx<T> *seq = c.seq_s + s * F::PITCH;
+      cplx<T> v[16];
+      const PassAddr<F, PL> a = pass_addr<F, PL>(t);
+      pass_load<T, F, PL>(seq, a, v);
+      dif_pass_regs<T, F, PL, -1>(c.tw, a, v);
+      if (KIND == KIND_BLUESTEIN) {
+#pragma unroll
+        for (int b = 0; b < (16 >> LR); ++b)
+#pragma unroll
+          for (int qq = 0; qq < (1 << LR); ++qq) v[(b << LR) + qq] = cmul(v[(b << LR) + qq], c.dh[a.base[b] + qq]);
+        dit_pass_regs<T, F, PL, +1>(c.tw, a, v);
+      }
+      pass_store<T, F, PL>(seq, a, v);
+    }
+    __syncthreads();
+  }
+  if constexpr (KIND == KIND_BLUESTEIN) middle_passes<T, F, F::NPASS - 2, +1>(c, mode, ntask);
+}
+
+// ---- C: gather bins, apply e^{i m phi0}, fold, emit: one thread per (unit, m) ---------------
+template <typename T, typename F, int KIND, int MODE>
+__device__ __forceinline__ void gather_emit(const RingCtx<T> &c) {
+  constexpr int NQ = mode_npol(MODE);
+  const RingFFTParams<T> &P = *c.P;
+  const RingDesc &rd = c.rd;
+  const int n = c.n;
+  const int Mc = P.mcap + 1;
+  const int lG = 31 - __clz(c.Gn);
+  const bool gpow2 = (c.Gn & (c.Gn - 1)) == 0;
+  for (int task = threadIdx.x; task < c.Gn * Mc; task += blockDim.x) {
+    int gi, m;
+    if (gpow2) {
+      gi = task & (c.Gn - 1);
+      m = task >> lG;
+    } else {
+      m = task / c.Gn;
+      gi = task - m * c.Gn;
+    }
+    if (m > c.us[gi].mmax) continue;
+    const int u = c.ug + gi;
+    int kp = m;
+    if (KIND == KIND_POW2)
+      kp = m & (n - 1);
+    else if (m >= n)
+      kp = m % n;
+    const int km = kp ? n - kp : 0;
+    // X+[k] = sum_j x_j e^{+2 pi i j k / n}
+    int ip = 0, im = 0;  // positions of X+[kp], X+[km]
+    cplx<T> cp = {T(1), T(0)}, cm = {T(1), T(0)};
+    if (KIND == KIND_POW2) {  // the transform run is X-[k] = X+[n-k]
+      ip = F::phys(F::binpos(km));
+      im = F::phys(F::binpos(kp));
+    } else if (KIND == KIND_BLUESTEIN) {
+      ip = F::phys(kp);
+      im = F::phys(km);
+      cp = c.ch_s[kp];
+      cm = c.ch_s[km];
+    }
+    const cplx<T> ph = c.ph_s[m];
+    const bool deadV = c.us[gi].deadV != 0;
+    // per map of the pass: even / odd fold as (+re, +im, -re, -im)
+    T ev[NQ][4], od[NQ][4];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      constexpr int polq[2] = {mode_pol(MODE, 0), mode_pol(MODE, 1)};
+      const int pol = polq[q];
+      cplx<T> fNp = {T(0), T(0)}, fNm = fNp, fSp = fNp, fSm = fNp;
+      if (!(pol == 3 && deadV)) {
+#pragma unroll
+        for (int ring = 0; ring < 2; ++ring) {
+          if (ring == 0 ? !c.liveN : !c.liveS) continue;
+          const int lr = ring == 0 ? 0 : c.slotS;
+          cplx<T> xp, xm;
+          if (KIND == KIND_DIRECT) {
+            const T *__restrict__ w =
+                P.wplanes[c.us[gi].pair] + (size_t)pol * P.npix + (ring ? rd.startS : rd.startN);
+            const cplx<T> *f = c.fr_s + (gi * c.nlive + lr) * n;
+            xp = {T(0), T(0)};
+            xm = xp;
+            int ep = 0, em = 0;
+            for (int j = 0; j < n; ++j) {
+              const T wv = w[j];
+              cplx<T> x = {f[j].x * wv, f[j].y * wv};
+              if (pol == 3) x = {-x.y, x.x};
+              xp = cadd(xp, cmul(x, c.tw[ep]));
+              xm = cadd(xm, cmul(x, c.tw[em]));
+              ep += kp;
+              if (ep >= n) ep -= n;
+              em += km;
+              if (em >= n) em -= n;
+            }
+          } else {
+            const cplx<T> *b = c.seq_s + ((gi * NQ + q) * c.nlive + lr) * c.pitch;
+            xp = cmul(b[ip], cp);
+            xm = cmul(b[im], cm);
+          }
+          const cplx<T> fp = cmul(ph, xp), fm = cmul(ph, cconj(xm));
+          if (ring == 0) {
+            fNp = fp;
+            fNm = fm;
+          } else {
+            fSp = fp;
+            fSm = fm;
+          }
+        }
+      }
+      const cplx<T> e_p = cadd(fNp, fSp), e_m = cadd(fNm, fSm);
+      cplx<T> o_p = csub(fNp, fSp), o_m = csub(fNm, fSm);
+      if (c.equator) {  // the equator is its own mirror: it only feeds the even fold
+        o_p = {T(0), T(0)};
+        o_m = {T(0), T(0)};
+      }
+      ev[q][0] = e_p.x, ev[q][1] = e_p.y, ev[q][2] = e_m.x, ev[q][3] = e_m.y;
+      od[q][0] = o_p.x, od[q][1] = o_p.y, od[q][2] = o_m.x, od[q][3] = o_m.y;
+    }
+    if (MODE == MODE_I || MODE == MODE_V || MODE == MODE_IV) {
+      const size_t r0 = ((size_t)(2 * m + 0) * P.Kp + c.k) * P.ncols0 + (size_t)u * P.cpu0;
+      const size_t r1 = ((size_t)(2 * m + 1) * P.Kp + c.k) * P.ncols0 + (size_t)u * P.cpu0;
+      if (MODE == MODE_IV) {
+        const T a[8] = {ev[0][0], ev[0][1], ev[0][2], ev[0][3], ev[NQ - 1][0], ev[NQ - 1][1], ev[NQ - 1][2], ev[NQ - 1][3]};
+        const T b[8] = {od[0][0], od[0][1], od[0][2], od[0][3], od[NQ - 1][0], od[NQ - 1][1], od[NQ - 1][2], od[NQ - 1][3]};
+        store8<T>(P.F0, P.plane0, r0, a);
+        store8<T>(P.F0, P.plane0, r1, b);
+      } else {
+        const int off = MODE == MODE_V ? 4 : 0;
+        store_vals<T>(P.F0, P.plane0, r0 + off, ev[0][0], ev[0][1], ev[0][2], ev[0][3]);
+        store_vals<T>(P.F0, P.plane0, r1 + off, od[0][0], od[0][1], od[0][2], od[0][3]);
+      }
+    } else {
+      const size_t K2 = 2 * (size_t)P.Kp;
+      const size_t cu = (size_t)u * 8;
+      const size_t w0 = ((size_t)(2 * m + 0) * K2 + c.k) * P.ncols2 + cu;         // W part, parity 0
+      const size_t w1 = ((size_t)(2 * m + 1) * K2 + c.k) * P.ncols2 + cu;         // W part, parity 1
+      const size_t x0 = ((size_t)(2 * m + 0) * K2 + P.Kp + c.k) * P.ncols2 + cu;  // X part, parity 0
+      const size_t x1 = ((size_t)(2 * m + 1) * K2 + P.Kp + c.k) * P.ncols2 + cu;  // X part, parity 1
+      // W part: E columns <- F[Q], B columns <- F[U], same fold parity.
+      // X part: E columns <- -i F[U], B columns <- +i F[Q], opposite fold parity.
+      if (MODE == MODE_QU) {
+        constexpr int qQ = 0, qU = NQ - 1;
+        const T wa[8] = {ev[qQ][0], ev[qQ][1], ev[qQ][2], ev[qQ][3], ev[qU][0], ev[qU][1], ev[qU][2], ev[qU][3]};
+        const T wb[8] = {od[qQ][0], od[qQ][1], od[qQ][2], od[qQ][3], od[qU][0], od[qU][1], od[qU][2], od[qU][3]};
+        const T xa[8] = {od[qU][1], -od[qU][0], od[qU][3], -od[qU][2], -od[qQ][1], od[qQ][0], -od[qQ][3], od[qQ][2]};
+        const T xb[8] = {ev[qU][1], -ev[qU][0], ev[qU][3], -ev[qU][2], -ev[qQ][1], ev[qQ][0], -ev[qQ][3], ev[qQ][2]};
+        store8<T>(P.F2, P.plane2, w0, wa);
+        store8<T>(P.F2, P.plane2, w1, wb);
+        store8<T>(P.F2, P.plane2, x0, xa);
+        store8<T>(P.F2, P.plane2, x1, xb);
+      } else if (MODE == MODE_Q) {
+        store_vals<T>(P.F2, P.plane2, w0, ev[0][0], ev[0][1], ev[0][2], ev[0][3]);
+        store_vals<T>(P.F2, P.plane2, w1, od[0][0], od[0][1], od[0][2], od[0][3]);
+        store_vals<T>(P.F2, P.plane2, x0 + 4, -od[0][1], od[0][0], -od[0][3], od[0][2]);
+        store_vals<T>(P.F2, P.plane2, x1 + 4, -ev[0][1], ev[0][0], -ev[0][3], ev[0][2]);
+      } else {
+        store_vals<T>(P.F2, P.plane2, w0 + 4, ev[0][0], ev[0][1], ev[0][2], ev[0][3]);
+        store_vals<T>(P.F2, P.plane2, w1 + 4, od[0][0], od[0][1], od[0][2], od[0][3]);
+        store_vals<T>(P.F2, P.plane2, x0, od[0][1], -od[0][0], od[0][3], -od[0][2]);
+        store_vals<T>(P.F2, P.plane2, x1, ev[0][1], -ev[0][0], ev[0][3], -ev[0][2]);
+      }
+    }
+  }
+}
+
+template <typename T, int LOG2L, int KIND>
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? DSB_RING_MINBLOCKS : 1)
+    ringfft_kernel(const RingFFTParams<T> P) {
+  using F = Fft16<LOG2L>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ GroupUnit us[kMaxGroup];
+  RingCtx<T> c;
+  c.P = &P;
+  c.k = P.ring_list[blockIdx.x];
+  c.rd = P.rings[c.k];
+  const RingDesc &rd = c.rd;
+  const int n = c.n = rd.nphi;
+  const int pitch = c.pitch = KIND == KIND_DIRECT ? n : F::PITCH;
+  const int tid = threadIdx.x;
+
+  // shared memory carve
+  cplx<T> *tw_s = reinterpret_cast<cplx<T> *>(smem_raw);
+  cplx<T> *ch_s = tw_s + P.tw_cap;
+  cplx<T> *ph_s = ch_s + P.ch_cap;
+  cplx<T> *fr_s = ph_s + P.ph_cap;
+  cplx<T> *seq_s = fr_s + P.fr_cap;
+  const cplx<T> *__restrict__ twg = P.tw16 + P.tw16_off[LOG2L];
+  c.tw = twg;
+  if (KIND == KIND_DIRECT) {
+    // e^{+2 pi i j / n}
+    for (int j = tid; j < n; j += blockDim.x) {
+      double sn, cs;
+      sincospi(2.0 * j / n, &sn, &cs);
+      tw_s[j] = {(T)cs, (T)sn};
+    }
+    c.tw = tw_s;
+  } else if (!P.tw_global) {
+    for (int j = tid; j < F::twtotal(); j += blockDim.x) tw_s[j] = twg[j];
+    c.tw = tw_s;
+  }
+  if (KIND == KIND_BLUESTEIN)
+    for (int j = tid; j < n; j += blockDim.x) ch_s[j] = P.chirp[rd.chirp_off + j];
+  // e^{i m phi0}
+  for (int m = tid; m <= P.mcap; m += blockDim.x) {
+    cplx<T> ph = {T(1), T(0)};
+    if (rd.shifted) {
+      double sn, cs;
+      sincospi((double)(m % (2 * n)) / (double)n, &sn, &cs);
+      ph = {(T)cs, (T)sn};
+    }
+    ph_s[m] = ph;
+  }
+
+  c.equator = rd.startS < 0;
+  const bool liveN = c.liveN = rd.vis_north != 0;
+  const bool liveS = c.liveS = !c.equator && rd.vis_south != 0;
+  const int nlive = c.nlive = (liveN ? 1 : 0) + (liveS ? 1 : 0);
+  c.slotS = liveN ? 1 : 0;
+  c.us = us;
+  c.ch_s = ch_s;
+  c.ph_s = ph_s;
+  c.fr_s = fr_s;
+  c.seq_s = seq_s;
+  c.dh = P.dhat + rd.dhat_off;
+  const int npol = P.npol_sky;
+  const int npp = P.npp;
+  int G = kMaxGroup;
+  if (nlive) {
+    G = min(G, P.seq_cap / (npp * nlive * pitch));
+    G = min(G, P.fr_cap / (nlive * n));
+  }
+  G = max(1, min(G, P.units_per_cta));
+  const double2 *__restrict__ trig = P.trig + rd.trig_off;
+  // idx / n by multiplication: exact for idx * n < 2^32
+  const unsigned nmagic = 0xFFFFFFFFu / (unsigned)n + 1u;
 
   const int u0 = blockIdx.y * P.units_per_cta;
   const int u1 = min(u0 + P.units_per_cta, P.nunits);
-  __syncthreads();
 
-  for (int u = u0; u < u1; ++u) {
-    const UnitDev ud = P.units[u];
-    const T *__restrict__ bi = P.beams[ud.beam_i];
-    const T *__restrict__ bj = P.beams[ud.beam_j];
-    const int Mu = ud.mmax;
+  for (int ug = u0; ug < u1; ug += G) {
+    const int Gn = min(G, u1 - ug);
+    c.ug = ug;
+    c.Gn = Gn;
+    __syncthreads();  // previous group fully emitted; tables loaded
+    if (tid < Gn) {
+      const UnitDev ud = P.units[ug + tid];
+      GroupUnit x;
+      x.axs = ud.ax * rd.sth;
+      x.ays = ud.ay * rd.sth;
+      x.az = ud.az;
+      x.pref = ud.pref;
+      x.pair = ud.beam_i;
+      x.mmax = ud.mmax;
+      x.deadV = ud.beam_j;
+      x.pad = 0;
+      us[tid] = x;
+    }
+    __syncthreads();
 
-    for (int pol0 = 0; pol0 < npol; pol0 += npp) {
-      const int npass = min(npp, npol - pol0);
-      // ---- fill: Stokes response of the ring pair ------------------------------------
-      for (int idx = threadIdx.x; idx < nlive * L; idx += blockDim.x) {
-        const int lr = idx >> log2L;  // live-ring slot
-        const int ring = (liveN && lr == 0) ? 0 : 1;
-        const int j = idx & (L - 1);
-        cplx<T> vals[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) vals[q] = {T(0), T(0)};
-        if (j < n) {
-          const int pix = (ring ? rd.startS : rd.startN) + j;
-          if (P.horizon[pix]) {
-            const double2 tr = P.trig[rd.trig_off + j];
-            const double zc = ring ? -rd.cth : rd.cth;
-            // n . (u uhat + v vhat) in wavelengths, reduced to a fraction of a turn in fp64
-            double du = ud.ax * (rd.sth * tr.x) + ud.ay * (rd.sth * tr.y) + ud.az * zc;
-            du -= rint(du);
-            T fs, fc;
-            sincospi_t((T)(2.0 * du), &fs, &fc);
-            const T pref = (T)ud.pref;
-            T prod[4];
-            if (P.polarised) {
-              const T it = bi[2 * (size_t)pix], ip = bi[2 * (size_t)pix + 1];
-              const T jt = bj[2 * (size_t)pix], jp = bj[2 * (size_t)pix + 1];
-              prod[0] = it * jt + ip * jp;  // I
-              prod[1] = it * jt - ip * jp;  // Q
-              prod[2] = it * jp + ip * jt;  // U
-              prod[3] = it * jp - ip * jt;  // V (times i below)
-            } else {
-              prod[0] = bi[pix] * bj[pix];
-              prod[1] = prod[2] = prod[3] = T(0);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (q < npass) {
-                const int pol = pol0 + q;
-                const T a = pref * (pol == 0 ? prod[0] : pol == 1 ? prod[1] : pol == 2 ? prod[2] : prod[3]);
-                cplx<T> v = {a * fc, a * fs};
-                if (pol == 3) v = {-v.y, v.x};
-                vals[q] = v;
-              }
-            }
-            if (rd.bluestein) {
-              const typename TwPtr<T>::type c = P.chirp[rd.chirp_off + j];
-              const cplx<T> cc = {c.x, c.y};
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (q < npass) vals[q] = cmul(vals[q], cc);
-            }
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (q < npass) buf[(q * nlive + lr) * pitch + fft_phys(j)] = vals[q];
-      }
-      __syncthreads();
+    // ---- A: fringe of every pixel of the live rings ------------------------------------
+    for (int idx = tid; idx < Gn * nlive * n; idx += blockDim.x) {
+      const int sq = (int)__umulhi((unsigned)idx, nmagic), j = idx - sq * n;
+      const int gi = nlive == 2 ? sq >> 1 : sq, lr = nlive == 2 ? sq & 1 : 0;
+      const int ring = (liveN && lr == 0) ? 0 : 1;
+      const double2 tr = trig[j];
+      const double zc = ring ? -rd.cth : rd.cth;
+      // n . (u uhat + v vhat) in wavelengths, reduced to a fraction of a turn in fp64
+      double du = us[gi].axs * tr.x + us[gi].ays * tr.y + us[gi].az * zc;
+      du -= rint(du);
+      T fs, fc;
+      sincospi_t((T)(2.0 * du), &fs, &fc);
+      const T pref = (T)us[gi].pref;
+      cplx<T> v = {pref * fc, pref * fs};
+      if (KIND == KIND_BLUESTEIN) v = cmul(v, ch_s[j]);
+      fr_s[idx] = v;
+    }
+    __syncthreads();
 
-      // ---- ring FFT (sequences laid out [q][live ring][L]) ---------------------------
-      const int nseq = npass * nlive;
-      if (nseq > 0) {
-        if (!rd.bluestein) {
-          fft_dif<T, +1>(buf, log2L, nseq, pitch, tw_s);
-        } else {
-          fft_dif<T, -1>(buf, log2L, nseq, pitch, tw_s);
-          for (int idx = threadIdx.x; idx < nseq * L; idx += blockDim.x) {
-            const int j = idx & (L - 1);
-            const int sq = idx >> log2L;
-            const typename TwPtr<T>::type d = P.dhat[rd.dhat_off + j];
-            const cplx<T> dd = {d.x, d.y};
-            cplx<T> *e = buf + sq * pitch + fft_phys(j);
-            *e = cmul(*e, dd);
-          }
-          __syncthreads();
-          fft_dit<T, +1>(buf, log2L, nseq, pitch, tw_s);
-        }
-      }
-
-      // ---- gather bins, apply e^{i m phi0}, fold, emit: one thread per m ---------------
-      for (int m = threadIdx.x; m <= Mu; m += blockDim.x) {
-        const int kp = m % n;
-        const int km = kp ? n - kp : 0;
-        int ip, im;
-        cplx<T> cp = {T(1), T(0)}, cm = {T(1), T(0)};
-        if (!rd.bluestein) {
-          ip = fft_phys(digitrev(kp, log2L));
-          im = fft_phys(digitrev(km, log2L));
-        } else {
-          ip = fft_phys(kp);
-          im = fft_phys(km);
-          const typename TwPtr<T>::type c1 = P.chirp[rd.chirp_off + kp];
-          const typename TwPtr<T>::type c2 = P.chirp[rd.chirp_off + km];
-          cp = {c1.x, c1.y};
-          cm = {c2.x, c2.y};
-        }
-        cplx<T> ph = {T(1), T(0)};
-        if (rd.shifted) {
-          double s, c;
-          sincospi((double)(m % (2 * n)) / (double)n, &s, &c);
-          ph = {(T)c, (T)s};
-        }
-        // per pol of the pass: even / odd fold as (+re, +im, -re, -im)
-        T ev[4][4], od[4][4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (q < npass) {
-            cplx<T> fNp = {T(0), T(0)}, fNm = fNp, fSp = fNp, fSm = fNp;
-            if (liveN) {
-              const cplx<T> *b = buf + (q * nlive + 0) * pitch;
-              fNp = cmul(ph, cmul(b[ip], cp));
-              fNm = cmul(ph, cconj(cmul(b[im], cm)));
-            }
-            if (liveS) {
-              const cplx<T> *b = buf + (q * nlive + slotS) * pitch;
-              fSp = cmul(ph, cmul(b[ip], cp));
-              fSm = cmul(ph, cconj(cmul(b[im], cm)));
-            }
-            const cplx<T> e_p = cadd(fNp, fSp), e_m = cadd(fNm, fSm);
-            cplx<T> o_p = csub(fNp, fSp), o_m = csub(fNm, fSm);
-            if (equator) {  // the equator is its own mirror: it only feeds the even fold
-              o_p = {T(0), T(0)};
-              o_m = {T(0), T(0)};
-            }
-            ev[q][0] = e_p.x, ev[q][1] = e_p.y, ev[q][2] = e_m.x, ev[q][3] = e_m.y;
-            od[q][0] = o_p.x, od[q][1] = o_p.y, od[q][2] = o_m.x, od[q][3] = o_m.y;
-          } else {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) ev[q][c] = od[q][c] = T(0);
-          }
-        }
-        // which pols does this pass hold?  (q index of pol p is p - pol0)
-        const bool hasI = pol0 == 0;
-        const bool hasQ = pol0 <= 1 && pol0 + npass > 1;
-        const bool hasU = pol0 <= 2 && pol0 + npass > 2;
-        const bool hasV = pol0 <= 3 && pol0 + npass > 3;
-        const size_t r0 = ((size_t)(2 * m + 0) * P.Kp + k) * P.ncols0 + (size_t)u * P.cpu0;
-        const size_t r1 = ((size_t)(2 * m + 1) * P.Kp + k) * P.ncols0 + (size_t)u * P.cpu0;
-        if (hasI && hasV) {  // single pass over (I, Q, U, V): q = pol
-          const T a[8] = {ev[0][0], ev[0][1], ev[0][2], ev[0][3], ev[3][0], ev[3][1], ev[3][2], ev[3][3]};
-          const T b[8] = {od[0][0], od[0][1], od[0][2], od[0][3], od[3][0], od[3][1], od[3][2], od[3][3]};
-          store8<T>(P.F0, P.plane0, r0, a);
-          store8<T>(P.F0, P.plane0, r1, b);
-        } else {
-          if (hasI) {
-            store_vals<T>(P.F0, P.plane0, r0, ev[0][0], ev[0][1], ev[0][2], ev[0][3]);
-            store_vals<T>(P.F0, P.plane0, r1, od[0][0], od[0][1], od[0][2], od[0][3]);
-          }
-          if (hasV) {
-            const int qV = 3 - pol0;
-            store_vals<T>(P.F0, P.plane0, r0 + 4, ev[qV][0], ev[qV][1], ev[qV][2], ev[qV][3]);
-            store_vals<T>(P.F0, P.plane0, r1 + 4, od[qV][0], od[qV][1], od[qV][2], od[qV][3]);
-          }
-        }
-        if (hasQ || hasU) {
-          const size_t K2 = 2 * (size_t)P.Kp;
-          const size_t cu = (size_t)u * 8;
-          const size_t w0 = ((size_t)(2 * m + 0) * K2 + k) * P.ncols2 + cu;         // W part, parity 0
-          const size_t w1 = ((size_t)(2 * m + 1) * K2 + k) * P.ncols2 + cu;         // W part, parity 1
-          const size_t x0 = ((size_t)(2 * m + 0) * K2 + P.Kp + k) * P.ncols2 + cu;  // X part, parity 0
-          const size_t x1 = ((size_t)(2 * m + 1) * K2 + P.Kp + k) * P.ncols2 + cu;  // X part, parity 1
-          const int qQ = 1 - pol0, qU = 2 - pol0;
-          // W part: E columns <- F[Q], B columns <- F[U], same fold parity.
-          // X part: E columns <- -i F[U], B columns <- +i F[Q], opposite fold parity.
-          if (hasQ && hasU) {
-            const T wa[8] = {ev[qQ][0], ev[qQ][1], ev[qQ][2], ev[qQ][3], ev[qU][0], ev[qU][1], ev[qU][2], ev[qU][3]};
-            const T wb[8] = {od[qQ][0], od[qQ][1], od[qQ][2], od[qQ][3], od[qU][0], od[qU][1], od[qU][2], od[qU][3]};
-            const T xa[8] = {od[qU][1], -od[qU][0], od[qU][3], -od[qU][2],
-                             -od[qQ][1], od[qQ][0], -od[qQ][3], od[qQ][2]};
-            const T xb[8] = {ev[qU][1], -ev[qU][0], ev[qU][3], -ev[qU][2],
-                             -ev[qQ][1], ev[qQ][0], -ev[qQ][3], ev[qQ][2]};
-            store8<T>(P.F2, P.plane2, w0, wa);
-            store8<T>(P.F2, P.plane2, w1, wb);
-            store8<T>(P.F2, P.plane2, x0, xa);
-            store8<T>(P.F2, P.plane2, x1, xb);
-          } else if (hasQ) {
-            store_vals<T>(P.F2, P.plane2, w0, ev[qQ][0], ev[qQ][1], ev[qQ][2], ev[qQ][3]);
-            store_vals<T>(P.F2, P.plane2, w1, od[qQ][0], od[qQ][1], od[qQ][2], od[qQ][3]);
-            store_vals<T>(P.F2, P.plane2, x0 + 4, -od[qQ][1], od[qQ][0], -od[qQ][3], od[qQ][2]);
-            store_vals<T>(P.F2, P.plane2, x1 + 4, -ev[qQ][1], ev[qQ][0], -ev[qQ][3], ev[qQ][2]);
-          } else {
-            store_vals<T>(P.F2, P.plane2, w0 + 4, ev[qU][0], ev[qU][1], ev[qU][2], ev[qU][3]);
-            store_vals<T>(P.F2, P.plane2, w1 + 4, od[qU][0], od[qU][1], od[qU][2], od[qU][3]);
-            store_vals<T>(P.F2, P.plane2, x0, od[qU][1], -od[qU][0], od[qU][3], -od[qU][2]);
-            store_vals<T>(P.F2, P.plane2, x1, ev[qU][1], -ev[qU][0], ev[qU][3], -ev[qU][2]);
-          }
-        }
+    for (int pi = 0; pi < 4; ++pi) {
+      const int mode = pass_mode(npp, npol, pi);
+      if (mode < 0) break;
+      if (KIND != KIND_DIRECT && nlive > 0) transform_pass<T, F, KIND>(c, mode);
+      switch (mode) {
+        case MODE_I: gather_emit<T, F, KIND, MODE_I>(c); break;
+        case MODE_V: gather_emit<T, F, KIND, MODE_V>(c); break;
+        case MODE_IV: gather_emit<T, F, KIND, MODE_IV>(c); break;
+        case MODE_Q: gather_emit<T, F, KIND, MODE_Q>(c); break;
+        case MODE_U: gather_emit<T, F, KIND, MODE_U>(c); break;
+        default: gather_emit<T, F, KIND, MODE_QU>(c); break;
       }
       __syncthreads();
     }
   }
 }
 
+template <typename T, int LOG2L, int KIND>
+static int launch_class(const dsb_plan::RingClass &cls, RingFFTParams<T> &P, const BucketLayout &lay,
+                        cudaStream_t stream) {
+  using F = Fft16<LOG2L>;
+  const size_t cs = sizeof(cplx<T>);
+  const int pitch = KIND == KIND_DIRECT ? 16 : F::PITCH;
+  P.ph_cap = (lay.mcap + 2) & ~1;
+  P.ch_cap = KIND == KIND_BLUESTEIN ? ((cls.max_n + 1) & ~1) : 0;
+  int npp = lay.npol_sky >= 2 ? 2 : 1;
+  int tw_cap = KIND == KIND_DIRECT ? 16 : ((F::twtotal() + 1) & ~1);
+  const size_t budget = 200 * 1024;
+  auto need = [&](int npp_, int twc, int G) {
+    return cs * ((size_t)twc + P.ch_cap + P.ph_cap + (size_t)G * cls.max_live * cls.max_n + (size_t)G * npp_ * cls.max_live * pitch);
+  };
+  P.tw_global = 0;
+  if (need(npp, tw_cap, 1) > budget) {  // twiddles stay in global memory (L1/L2)
+    tw_cap = 0;
+    P.tw_global = 1;
+  }
+  if (need(npp, tw_cap, 1) > budget) npp = 1;
+  DSB_CHECK(need(npp, tw_cap, 1) <= budget, DSB_ERR_UNSUPPORTED,
+            "ring transform of length %d does not fit shared memory", F::L);
+  // units per group: fill ~64 KB with sequences, more only helps the short rings
+  int G = 1;
+  while (G < kMaxGroup && need(npp, tw_cap, 2 * G) <= 64 * 1024) G *= 2;
+  P.npp = npp;
+  P.tw_cap = tw_cap;
+  P.fr_cap = G * cls.max_live * cls.max_n;
+  P.seq_cap = G * npp * cls.max_live * pitch;
+  const size_t smem = need(npp, tw_cap, G);
+  // units per CTA: amortise the per-ring setup, but keep enough CTAs to fill the machine
+  int upc = std::max(8, G);
+  while (upc > G && (long)cls.count * ((lay.nunits + upc - 1) / upc) < 4 * 148) upc >>= 1;
+  P.units_per_cta = upc;
+  auto kern = ringfft_kernel<T, LOG2L, KIND>;
+  DSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(cls.count, (lay.nunits + upc - 1) / upc);
+  kern<<<grid, 256, smem, stream>>>(P);
+  DSB_LAUNCH_CHECK();
+  return DSB_OK;
+}
+
 template <typename T>
 static int launch_t(dsb_plan *plan, const BucketLayout &lay, const UnitDev *units_dev, void *F0, void *F2,
-                    size_t plane0, size_t plane2, const T *const *beams_dev, cudaStream_t stream) {
+                    size_t plane0, size_t plane2, const T *const *wplanes_dev, cudaStream_t stream) {
   RingFFTParams<T> P;
   P.rings = plan->rings;
-  P.horizon = plan->horizon;
   P.trig = plan->trig;
-  if (sizeof(T) == 4) {
-    P.tw = reinterpret_cast<const typename TwPtr<T>::type *>(plan->tw32);
-    P.chirp = reinterpret_cast<const typename TwPtr<T>::type *>(plan->chirp32);
-    P.dhat = reinterpret_cast<const typename TwPtr<T>::type *>(plan->dhat32);
-  } else {
-    P.tw = reinterpret_cast<const typename TwPtr<T>::type *>(plan->tw64);
-    P.chirp = reinterpret_cast<const typename TwPtr<T>::type *>(plan->chirp64);
-    P.dhat = reinterpret_cast<const typename TwPtr<T>::type *>(plan->dhat64);
-  }
-  P.tw_log2 = plan->tw_log2;
+  const bool f32 = sizeof(T) == 4;
+  P.tw16 = reinterpret_cast<const cplx<T> *>(f32 ? (const void *)plan->tw16_32 : (const void *)plan->tw16_64);
+  for (int i = 0; i < 16; ++i) P.tw16_off[i] = plan->tw16_off[i];
+  P.chirp = reinterpret_cast<const cplx<T> *>(f32 ? (const void *)plan->chirp32 : (const void *)plan->chirp64);
+  P.dhat = reinterpret_cast<const cplx<T> *>(f32 ? (const void *)plan->dhat32 : (const void *)plan->dhat64);
   P.units = units_dev;
   P.nunits = lay.nunits;
-  P.beams = beams_dev;
+  P.wplanes = wplanes_dev;
+  P.npix = plan->npix;
   P.polarised = lay.polarised;
   P.npol_sky = lay.npol_sky;
   P.nsp0 = lay.nsp0;
@@ -360,47 +713,64 @@ static int launch_t(dsb_plan *plan, const BucketLayout &lay, const UnitDev *unit
   P.ncols2 = lay.ncols2;
   P.Kp = lay.Kp;
   P.nfold = plan->nfold;
+  P.mcap = lay.mcap;
   P.F0 = F0;
   P.F2 = F2;
   P.plane0 = plane0;
   P.plane2 = plane2;
 
-  // Largest FFT length in this plan: Bluestein rings need 2^tw_log2, otherwise 4*nside.
-  int Lmax = 4 * plan->nside;
-  for (const auto &rd : plan->rings_h) Lmax = std::max(Lmax, 1 << rd.log2n);
-  // shared memory: as many (pol, ring) sequences as fit in ~200 KB, at least one pol pair
-  const size_t per_seq = (size_t)fft_pitch(Lmax) * sizeof(cplx<T>);
-  const size_t tw_bytes = (size_t)(Lmax / 2) * sizeof(cplx<T>);
-  int nseq = (int)std::min<size_t>(8, (200 * 1024 - tw_bytes) / per_seq);
-  nseq = std::max(2, nseq & ~1);
-  const size_t smem = nseq * per_seq + tw_bytes;
-  DSB_CHECK(smem <= 227 * 1024, DSB_ERR_UNSUPPORTED, "ring FFT of length %d does not fit shared memory",
-            Lmax);
-  P.seq_capacity = nseq * fft_pitch(Lmax) + Lmax / 2;
-  DSB_CUDA(cudaFuncSetAttribute(ringfft_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-
-  // units per CTA: enough CTAs to fill the machine, but amortise the per-ring setup
-  int upc = 8;
-  while (upc > 1 && (long)plan->nfold * ((lay.nunits + upc - 1) / upc) < 4 * 148) upc >>= 1;
-  P.units_per_cta = upc;
-  dim3 grid(plan->nfold, (lay.nunits + upc - 1) / upc);
-  // a block that owns most of an SM's shared memory runs with more warps
-  const int threads = smem > 100 * 1024 ? 512 : 256;
-  ringfft_kernel<T><<<grid, threads, smem, stream>>>(P);
-  DSB_LAUNCH_CHECK();
+  // One launch per (transform kind, length): shared memory, hence occupancy, follows the
+  // ring length and every index in the kernel is a compile-time constant.  The three
+  // largest classes run back to back on the caller's stream, the many short-ring classes
+  // concurrently on the plan's side stream.
+  DSB_CUDA(cudaEventRecord(plan->ev_fork, stream));
+  DSB_CUDA(cudaStreamWaitEvent(plan->side_stream, plan->ev_fork, 0));
+  int nmain = 0;
+  for (const auto &cls : plan->ring_classes) {
+    if (cls.count == 0) continue;
+    P.ring_list = plan->ring_list_dev + cls.first;
+    cudaStream_t st = (nmain < 3) ? stream : plan->side_stream;
+    ++nmain;
+    int rc = DSB_ERR_UNSUPPORTED;
+#define DSB_RING_CASE(K, A) \
+  case (K) * 16 + (A): rc = launch_class<T, A, K>(cls, P, lay, st); break;
+    switch (cls.kind * 16 + cls.log2L) {
+      DSB_RING_CASE(KIND_POW2, 5)
+      DSB_RING_CASE(KIND_POW2, 6)
+      DSB_RING_CASE(KIND_POW2, 7)
+      DSB_RING_CASE(KIND_POW2, 8)
+      DSB_RING_CASE(KIND_POW2, 9)
+      DSB_RING_CASE(KIND_POW2, 10)
+      DSB_RING_CASE(KIND_POW2, 11)
+      DSB_RING_CASE(KIND_POW2, 12)
+      DSB_RING_CASE(KIND_BLUESTEIN, 6)
+      DSB_RING_CASE(KIND_BLUESTEIN, 7)
+      DSB_RING_CASE(KIND_BLUESTEIN, 8)
+      DSB_RING_CASE(KIND_BLUESTEIN, 9)
+      DSB_RING_CASE(KIND_BLUESTEIN, 10)
+      DSB_RING_CASE(KIND_BLUESTEIN, 11)
+      DSB_RING_CASE(KIND_BLUESTEIN, 12)
+      DSB_RING_CASE(KIND_BLUESTEIN, 13)
+      DSB_RING_CASE(KIND_DIRECT, 5)
+      default:
+        set_error("ring class (kind %d, length 2^%d) unsupported", cls.kind, cls.log2L);
+    }
+#undef DSB_RING_CASE
+    if (rc != DSB_OK) return rc;
+  }
+  DSB_CUDA(cudaEventRecord(plan->ev_join, plan->side_stream));
+  DSB_CUDA(cudaStreamWaitEvent(stream, plan->ev_join, 0));
   return DSB_OK;
 }
 
 int launch_ringfft(dsb_plan *plan, const BucketLayout &lay, const UnitDev *units_dev, int precision,
-                   void *F0, void *F2, cudaStream_t stream) {
+                   const void *const *wplanes_dev, void *F0, void *F2, cudaStream_t stream) {
   const size_t nprob = 2 * ((size_t)lay.mcap + 1);
   const size_t plane0 = nprob * lay.Kp * lay.ncols0;
   const size_t plane2 = nprob * 2 * lay.Kp * lay.ncols2;
   if (precision == DSB_PREC_FP64)
-    return launch_t<double>(plan, lay, units_dev, F0, F2, plane0, plane2,
-                            (const double *const *)plan->beam_ptrs64, stream);
-  return launch_t<float>(plan, lay, units_dev, F0, F2, plane0, plane2, (const float *const *)plan->beam_ptrs32,
-                         stream);
+    return launch_t<double>(plan, lay, units_dev, F0, F2, plane0, plane2, (const double *const *)wplanes_dev, stream);
+  return launch_t<float>(plan, lay, units_dev, F0, F2, plane0, plane2, (const float *const *)wplanes_dev, stream);
 }
 
 }  // namespace dsb
