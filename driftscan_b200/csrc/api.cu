@@ -255,8 +255,10 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
 
   // ---- chunk size from the workspace budget
   const size_t nprob = 2 * ((size_t)lay.mcap + 1);
-  const size_t es = f64 ? 8 : 6, cs = f64 ? 8 : 4;
-  const size_t per_unit = nprob * lay.Kp * lay.cpu0 * es + (lay.has2 ? nprob * 2 * lay.Kp * 8 * es : 0) +
+  // ring spectra: fp64 with the spin-2 block in both operand roles, or fp32 stored once
+  const size_t es = f64 ? 8 : 4, cs = f64 ? 8 : 4;
+  const size_t k2mul = f64 ? 2 : 1;
+  const size_t per_unit = nprob * lay.Kp * lay.cpu0 * es + (lay.has2 ? nprob * k2mul * lay.Kp * 8 * es : 0) +
                           nprob * t.NP * (lay.cpu0 + (lay.has2 ? 8 : 0)) * cs;
   const size_t plane_out = (size_t)npol_out * (lside + 1) * (2 * lside + 1) * 16;
   const size_t per_unit_tot = per_unit + ((tarray && out_is_host) ? plane_out : 0);
@@ -323,7 +325,7 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
     {
       Carve cv(nullptr);
       cv.take<char>(nprob * lay.Kp * lay.ncols0 * es);
-      cv.take<char>(lay.has2 ? nprob * 2 * lay.Kp * lay.ncols2 * es : 0);
+      cv.take<char>(lay.has2 ? nprob * k2mul * lay.Kp * lay.ncols2 * es : 0);
       cv.take<char>(nprob * lay.ncols0 * t.NP * cs);
       cv.take<char>(lay.has2 ? nprob * lay.ncols2 * t.NP * cs : 0);
       cv.take<UnitDev>(nu);
@@ -337,7 +339,7 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
     if ((rc = ensure_workspace(plan, need)) != DSB_OK) break;
     Carve cv(plan->ws);
     const size_t f0_bytes = nprob * lay.Kp * lay.ncols0 * es;
-    const size_t f2_bytes = lay.has2 ? nprob * 2 * lay.Kp * lay.ncols2 * es : 0;
+    const size_t f2_bytes = lay.has2 ? nprob * k2mul * lay.Kp * lay.ncols2 * es : 0;
     char *F0 = cv.take<char>(f0_bytes);
     char *F2 = cv.take<char>(f2_bytes);
     char *C0 = cv.take<char>(nprob * lay.ncols0 * t.NP * cs);
@@ -373,8 +375,8 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
       rc = launch_legendre_f64(plan, t, lay, items, items_dev, (const double *)F0, (const double *)F2,
                                (double *)C0, (double *)C2, stream);
     else
-      rc = launch_legendre_tc(plan, t, lay, items, items_dev, (const __nv_bfloat16 *)F0,
-                              (const __nv_bfloat16 *)F2, (float *)C0, (float *)C2, stream);
+      rc = launch_legendre_tc(plan, t, lay, items, items_dev, (const float *)F0, (const float *)F2, (float *)C0,
+                              (float *)C2, stream);
     if (rc != DSB_OK) break;
     timer.mark(2);
 

@@ -215,8 +215,8 @@ struct UnitDev {
 };
 
 // ringfft.cu -- fused fringe x beam -> ring FFT -> north/south fold -> spectra
-// F planes: spin-0 [nprob][Kp][ncols0], spin-2 [nprob][2*Kp][ncols2]; element type double
-// (precision fp64, 1 plane) or bf16 (3 planes, plane stride = nprob*K*ncols).
+// F: spin-0 [nprob][Kp][ncols0]; spin-2 [nprob][2*Kp][ncols2] double (fp64: both operand roles)
+// or [nprob][Kp][ncols2] float (fp32: stored once, roles derived by the tensor-core kernel).
 // units_dev[u].beam_i = index into wplanes_dev (pair weights), .beam_j = 1 if Stokes V of the pair is
 // identically zero.  wplanes_dev[pair] -> [nplane][npix] in the working precision.
 int launch_ringfft(dsb_plan *plan, const BucketLayout &lay, const UnitDev *units_dev, int precision,
@@ -239,13 +239,12 @@ int launch_legendre_f64(dsb_plan *plan, const Tables &t, const BucketLayout &lay
                         const std::vector<WorkItem> &items, const WorkItem *items_dev, const double *F0,
                         const double *F2, double *C0, double *C2, cudaStream_t stream);
 int launch_legendre_tc_raw(int nprobA, int nprobT, int Kp, int NP, int ncols0, int ncols2, int has2, int nitems,
-                           const WorkItem *items_dev, int max_rows, const __nv_bfloat16 *F0,
-                           const __nv_bfloat16 *F2, const __nv_bfloat16 *T0, const __nv_bfloat16 *T2, float *C0,
-                           float *C2, cudaStream_t stream);
+                           const WorkItem *items_dev, int max_rows, const float *F0, const float *F2,
+                           const __nv_bfloat16 *T0, const __nv_bfloat16 *T2, float *C0, float *C2,
+                           cudaStream_t stream);
 int launch_legendre_tc(dsb_plan *plan, const Tables &t, const BucketLayout &lay,
-                       const std::vector<WorkItem> &items, const WorkItem *items_dev,
-                       const __nv_bfloat16 *F0, const __nv_bfloat16 *F2, float *C0, float *C2,
-                       cudaStream_t stream);
+                       const std::vector<WorkItem> &items, const WorkItem *items_dev, const float *F0,
+                       const float *F2, float *C0, float *C2, cudaStream_t stream);
 
 // pack.cu
 struct PackParams {

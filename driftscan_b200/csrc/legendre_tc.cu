@@ -3,21 +3,30 @@
 //
 //   C_s[prob][col][row0 + n] = sum_k F_s[prob][k][col] * T_s[prob][row0 + n][k]
 //
-// Both operands are pre-split into three bf16 planes (x = x1 + x2 + x3, 24 significant
-// bits); the product keeps the six terms of weight >= 2^-16:
+// Both operands are used as three bf16 planes (x = x1 + x2 + x3, 24 significant bits);
+// the product keeps the six terms of weight >= 2^-16:
 //   a1 b3 + a2 b2 + a3 b1 + a1 b2 + a2 b1 + a1 b1          (fp32 accumulation in TMEM)
 // which is the theta -> l half of healpy.map2alm (drift/core/telescope.py:1189,1300,1310)
-// for 128 operand columns (16 or 32 units) at a time.
+// for 128 operand columns (16 units) at a time.
+//
+// The ring spectra F arrive in HBM as plain fp32 (one 32-byte sector per unit, fold ring
+// and map group): TMA brings a [32 k][128 column] fp32 tile into a staging buffer and
+// converter warps split it into the three bf16 planes directly in the swizzled layout the
+// MMA reads.  The tables are pre-split (they are reused by every unit).  For the spin-2
+// block the same fp32 data is used in two roles,
+//   E = sum_k (-W)(F[Q]) + (-X)(-i F[U]),   B = sum_k (-W)(F[U]) + (-X)(+i F[Q]),
+// the X role with the opposite fold parity: the converter applies the (+-i, Q<->U)
+// permutation while splitting, so the spectra are stored once.
 //
 // Mapping onto the MMA:  D[M = 128 operand columns][N = l rows] += A[M x K] B[N x K]^T
-//   A = ring spectra,  MN-major (columns contiguous), 128B swizzle, two 64-column TMA boxes
+//   A = ring spectra,  MN-major (columns contiguous), 128B swizzle, two 64-column boxes
 //   B = Legendre table, K-major, 64B swizzle, one TMA box of NB rows x 32 k
 // so each output column of the contraction (a unit/pol/+-/re-im series in l) ends up in
 // one TMEM lane and is written out contiguously in l.
 //
-// Warp roles (192 threads):  warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2..5 = epilogue (TMEM -> registers -> global).  Persistent over work items with
-// a double-buffered accumulator (2 x 256 TMEM columns).
+// Warp roles:  warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 =
+// epilogue (TMEM -> registers -> global), warps 6.. = converters.  Persistent over work
+// items with a double-buffered accumulator (2 x 256 TMEM columns).
 #include <cuda.h>
 
 #include "dsb_common.cuh"
@@ -26,8 +35,10 @@ namespace dsb {
 
 constexpr int TC_KC = 32;          // k per pipeline stage
 constexpr int TC_M = 128;          // operand columns per tile
-constexpr int TC_THREADS = 192;
+constexpr int TC_NCONV = 4;        // converter warps
+constexpr int TC_THREADS = 192 + 32 * TC_NCONV;
 constexpr int TC_A_PLANE = TC_KC * TC_M * 2;  // bytes of one split plane of A per stage (8 KB)
+constexpr int TC_A_RAW = TC_KC * TC_M * 4;    // bytes of the fp32 staging tile per stage (16 KB)
 
 struct TcParams {
   const WorkItem *items;
@@ -63,6 +74,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "DONE:\n\t"
       "}" ::"r"(smem_u32(bar)),
       "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)),
+      "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 
@@ -114,6 +134,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
 }
 
+__device__ __forceinline__ void split3_bf16(float v, uint32_t &h, uint32_t &m, uint32_t &l) {
+  const __nv_bfloat16 bh = __float2bfloat16_rn(v);
+  float r = v - __bfloat162float(bh);
+  const __nv_bfloat16 bm = __float2bfloat16_rn(r);
+  r -= __bfloat162float(bm);
+  const __nv_bfloat16 bl = __float2bfloat16_rn(r);
+  h = __bfloat16_as_ushort(bh);
+  m = __bfloat16_as_ushort(bm);
+  l = __bfloat16_as_ushort(bl);
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA2,
                    const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB2,
@@ -121,16 +152,17 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // swizzled operand tiles need 1024-byte alignment in the shared address space
   unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  // stage layout: [A: 3 planes x 8 KB][B: 3 planes x NB*64 B]
+  // stage layout: [A split: 3 planes x 8 KB][A fp32 staging: 16 KB][B: 3 planes x NB*64 B]
   const uint32_t b_plane = (uint32_t)P.NB * 64;
-  const uint32_t stage_bytes = 3 * TC_A_PLANE + ((3 * b_plane + 1023) & ~1023u);
+  const uint32_t stage_bytes = 3 * TC_A_PLANE + TC_A_RAW + ((3 * b_plane + 1023) & ~1023u);
   unsigned char *stages = smem;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)P.nstages * stage_bytes);
-  uint64_t *full = bars;                       // [nstages]
-  uint64_t *empty = bars + P.nstages;          // [nstages]
-  uint64_t *tfull = bars + 2 * P.nstages;      // [2]
-  uint64_t *tempty = bars + 2 * P.nstages + 2; // [2]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * P.nstages + 4);
+  uint64_t *full = bars;                        // [nstages] TMA landed (fp32 A tile + B planes)
+  uint64_t *empty = bars + P.nstages;           // [nstages] MMAs reading the stage retired
+  uint64_t *conv = bars + 2 * P.nstages;        // [nstages] A planes written by the converters
+  uint64_t *tfull = bars + 3 * P.nstages;       // [2]
+  uint64_t *tempty = bars + 3 * P.nstages + 2;  // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * P.nstages + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -139,6 +171,7 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
     for (int s = 0; s < P.nstages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+      mbar_init(&conv[s], TC_NCONV);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
@@ -167,20 +200,22 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         const bool s2 = wi.spin == 2;
         const CUtensorMap *mA = s2 ? &mapA2 : &mapA0;
         const CUtensorMap *mB = s2 ? &mapB2 : &mapB0;
-        const int nk = (s2 ? P.K2 : P.K0) / TC_KC;
-        const uint32_t tx = 3 * TC_A_PLANE + 3 * b_plane;
+        const int nkA = P.K0 / TC_KC;            // stages per role
+        const int nk = s2 ? 2 * nkA : nkA;       // spin 2: W role then X role
+        const uint32_t tx = TC_A_RAW + 3 * b_plane;
         for (int kc = 0; kc < nk; ++kc) {
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char *sA = stages + (size_t)stage * stage_bytes;
-          unsigned char *sB = sA + 3 * TC_A_PLANE;
+          unsigned char *sR = sA + 3 * TC_A_PLANE;
+          unsigned char *sB = sR + TC_A_RAW;
           mbar_expect_tx(&full[stage], tx);
+          // X role reads the spectra of the opposite fold parity
+          const bool xrole = kc >= nkA;
+          tma_load_3d(mA, &full[stage], sR, wi.coltile * TC_M, (xrole ? kc - nkA : kc) * TC_KC,
+                      xrole ? (wi.prob ^ 1) : wi.prob);
 #pragma unroll
-          for (int pl = 0; pl < 3; ++pl) {
-            tma_load_4d(mA, &full[stage], sA + pl * TC_A_PLANE, wi.coltile * TC_M, kc * TC_KC, wi.prob, pl);
-            tma_load_4d(mA, &full[stage], sA + pl * TC_A_PLANE + TC_A_PLANE / 2, wi.coltile * TC_M + 64,
-                        kc * TC_KC, wi.prob, pl);
+          for (int pl = 0; pl < 3; ++pl)
             tma_load_4d(mB, &full[stage], sB + pl * b_plane, kc * TC_KC, wi.row0, wi.prob, pl);
-          }
           if (++stage == P.nstages) {
             stage = 0;
             phase ^= 1;
@@ -198,7 +233,7 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       for (int it = blockIdx.x; it < P.nitems; it += gridDim.x, ++local) {
         const WorkItem wi = P.items[it];
         const bool s2 = wi.spin == 2;
-        const int nk = (s2 ? P.K2 : P.K0) / TC_KC;
+        const int nk = (s2 ? 2 : 1) * (P.K0 / TC_KC);
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         const uint32_t N = (uint32_t)((wi.nrows + 15) & ~15);
@@ -210,10 +245,11 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256;
         uint32_t accum = 0;
         for (int kc = 0; kc < nk; ++kc) {
-          mbar_wait(&full[stage], phase);
+          mbar_wait(&full[stage], phase);  // B planes (TMA)
+          mbar_wait(&conv[stage], phase);  // A planes (converters)
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sA = smem_u32(stages + (size_t)stage * stage_bytes);
-          const uint32_t sB = sA + 3 * TC_A_PLANE;
+          const uint32_t sB = sA + 3 * TC_A_PLANE + TC_A_RAW;
 #pragma unroll
           for (int ks = 0; ks < TC_KC / 16; ++ks) {
             // six split products, smallest first
@@ -240,7 +276,7 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < 6) {
     // ===================== epilogue =====================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
     int local = 0;
@@ -269,6 +305,58 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  } else {
+    // ===================== converters: fp32 tile -> three swizzled bf16 planes =====================
+    const int ct = threadIdx.x - 192;  // 0 .. 32*TC_NCONV-1
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = blockIdx.x; it < P.nitems; it += gridDim.x) {
+      const WorkItem wi = P.items[it];
+      const bool s2 = wi.spin == 2;
+      const int nkA = P.K0 / TC_KC;
+      const int nk = s2 ? 2 * nkA : nkA;
+      for (int kc = 0; kc < nk; ++kc) {
+        const bool xrole = kc >= nkA;
+        mbar_wait(&full[stage], phase);
+        unsigned char *sA = stages + (size_t)stage * stage_bytes;
+        const float4 *sR = reinterpret_cast<const float4 *>(sA + 3 * TC_A_PLANE);
+        // one (k row, 8-column group) per thread and step: 32 rows x 16 groups
+#pragma unroll
+        for (int e = ct; e < TC_KC * 16; e += 32 * TC_NCONV) {
+          const int k = e >> 4, grp = e & 15;
+          const float4 lo = sR[k * 32 + grp * 2], hi = sR[k * 32 + grp * 2 + 1];
+          float v[8];
+          if (!xrole) {
+            v[0] = lo.x, v[1] = lo.y, v[2] = lo.z, v[3] = lo.w;
+            v[4] = hi.x, v[5] = hi.y, v[6] = hi.z, v[7] = hi.w;
+          } else {
+            // columns (Q: a0..a3 | U: b0..b3) -> (-i U | +i Q) = (b1, -b0, b3, -b2 | -a1, a0, -a3, a2)
+            v[0] = hi.y, v[1] = -hi.x, v[2] = hi.w, v[3] = -hi.z;
+            v[4] = -lo.y, v[5] = lo.x, v[6] = -lo.w, v[7] = lo.z;
+          }
+          uint32_t h[8], m[8], l[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) split3_bf16(v[i], h[i], m[i], l[i]);
+          // MN-major SW128: box (64 columns) -> k row of 128 B -> 16-byte chunk ^ (k & 7)
+          const uint32_t off = (uint32_t)(grp >> 3) * (TC_A_PLANE / 2) + (uint32_t)k * 128 +
+                               ((uint32_t)((grp & 7) ^ (k & 7)) << 4);
+          *reinterpret_cast<uint4 *>(sA + off) =
+              make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+          *reinterpret_cast<uint4 *>(sA + TC_A_PLANE + off) =
+              make_uint4(m[0] | (m[1] << 16), m[2] | (m[3] << 16), m[4] | (m[5] << 16), m[6] | (m[7] << 16));
+          *reinterpret_cast<uint4 *>(sA + 2 * TC_A_PLANE + off) =
+              make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+        }
+        // make the generic-proxy writes visible to the tensor core (async proxy), then signal
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv[stage]);
+        if (++stage == P.nstages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
     }
   }
 
@@ -299,6 +387,22 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// 3-D fp32 tensor map (ring spectra): dims (columns contiguous, k, prob), box 128 x TC_KC x 1, no swizzle
+static int encode3_f32(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
+                       uint32_t b1) {
+  EncodeTiledFn enc = get_encode();
+  DSB_CHECK(enc != nullptr, DSB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0 * 4, d0 * d1 * 4};  // bytes
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DSB_CHECK(r == CUDA_SUCCESS, DSB_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r);
+  return DSB_OK;
+}
+
 // 4-D bf16 tensor map: dims (d0 contiguous, d1, d2, d3)
 static int encode4(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
                    uint64_t s1, uint64_t s2, uint64_t s3, uint32_t b0, uint32_t b1, CUtensorMapSwizzle sw) {
@@ -316,9 +420,9 @@ static int encode4(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1,
 }
 
 int launch_legendre_tc_raw(int nprobA, int nprobT, int Kp, int NP, int ncols0, int ncols2, int has2, int nitems,
-                           const WorkItem *items_dev, int max_rows, const __nv_bfloat16 *F0,
-                           const __nv_bfloat16 *F2, const __nv_bfloat16 *T0, const __nv_bfloat16 *T2, float *C0,
-                           float *C2, cudaStream_t stream) {
+                           const WorkItem *items_dev, int max_rows, const float *F0, const float *F2,
+                           const __nv_bfloat16 *T0, const __nv_bfloat16 *T2, float *C0, float *C2,
+                           cudaStream_t stream) {
   if (nitems == 0) return DSB_OK;
   DSB_CHECK(Kp % TC_KC == 0, DSB_ERR_INVALID, "contraction length must be a multiple of %d", TC_KC);
   DSB_CHECK(ncols0 % TC_M == 0 && ncols2 % TC_M == 0, DSB_ERR_INVALID, "column counts must be multiples of 128");
@@ -328,13 +432,12 @@ int launch_legendre_tc_raw(int nprobA, int nprobT, int Kp, int NP, int ncols0, i
 
   CUtensorMap mA0, mA2, mB0, mB2;
   const uint64_t K0 = Kp, K2 = 2 * (uint64_t)Kp;
-  DSB_TRY(encode4(&mA0, F0, ncols0, K0, nprobA, 3, ncols0, K0 * ncols0, (uint64_t)nprobA * K0 * ncols0, 64,
-                  TC_KC, CU_TENSOR_MAP_SWIZZLE_128B));
+  DSB_TRY(encode3_f32(&mA0, F0, ncols0, K0, nprobA, TC_M, TC_KC));
   DSB_TRY(encode4(&mB0, T0, K0, NP, nprobT, 3, K0, (uint64_t)NP * K0, (uint64_t)nprobT * NP * K0, TC_KC, NB,
                   CU_TENSOR_MAP_SWIZZLE_64B));
   if (has2) {
-    DSB_TRY(encode4(&mA2, F2, ncols2, K2, nprobA, 3, ncols2, K2 * ncols2, (uint64_t)nprobA * K2 * ncols2, 64,
-                    TC_KC, CU_TENSOR_MAP_SWIZZLE_128B));
+    DSB_CHECK(nprobA % 2 == 0, DSB_ERR_INVALID, "spin-2 problems come in fold-parity pairs");
+    DSB_TRY(encode3_f32(&mA2, F2, ncols2, K0, nprobA, TC_M, TC_KC));
     DSB_TRY(encode4(&mB2, T2, K2, NP, nprobT, 3, K2, (uint64_t)NP * K2, (uint64_t)nprobT * NP * K2, TC_KC, NB,
                     CU_TENSOR_MAP_SWIZZLE_64B));
   } else {
@@ -353,11 +456,11 @@ int launch_legendre_tc_raw(int nprobA, int nprobT, int Kp, int NP, int ncols0, i
   P.C0 = C0;
   P.C2 = C2;
   P.NB = NB;
-  const size_t stage_bytes = 3 * TC_A_PLANE + (((size_t)3 * NB * 64 + 1023) & ~(size_t)1023);
+  const size_t stage_bytes = 3 * TC_A_PLANE + TC_A_RAW + (((size_t)3 * NB * 64 + 1023) & ~(size_t)1023);
   int nstages = (int)std::min<size_t>(8, (220 * 1024) / stage_bytes);
   DSB_CHECK(nstages >= 2, DSB_ERR_UNSUPPORTED, "pipeline does not fit shared memory");
   P.nstages = nstages;
-  const size_t smem = nstages * stage_bytes + (2 * nstages + 4) * 8 + 16 + 1024;
+  const size_t smem = nstages * stage_bytes + (3 * nstages + 4) * 8 + 16 + 1024;
   DSB_CUDA(cudaFuncSetAttribute(legendre_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);
@@ -369,9 +472,8 @@ int launch_legendre_tc_raw(int nprobA, int nprobT, int Kp, int NP, int ncols0, i
 }
 
 int launch_legendre_tc(dsb_plan *plan, const Tables &t, const BucketLayout &lay,
-                       const std::vector<WorkItem> &items, const WorkItem *items_dev,
-                       const __nv_bfloat16 *F0, const __nv_bfloat16 *F2, float *C0, float *C2,
-                       cudaStream_t stream) {
+                       const std::vector<WorkItem> &items, const WorkItem *items_dev, const float *F0,
+                       const float *F2, float *C0, float *C2, cudaStream_t stream) {
   int max_rows = 16;
   for (const auto &w : items) max_rows = std::max(max_rows, w.nrows);
   // the tables may cover more m than this bucket needs: separate problem counts
@@ -386,20 +488,20 @@ int launch_legendre_tc(dsb_plan *plan, const Tables &t, const BucketLayout &lay,
 using namespace dsb;
 
 // Debug / unit-test entry: run the tensor-core contraction on caller-provided split planes
-// (host memory).  F [3][nprob][K][ncols] bf16, T [3][nprob][NP][K] bf16, items int32[nitems][5]
+// (host memory).  F [nprob][K][ncols] fp32, T [3][nprob][NP][K] bf16, items int32[nitems][5]
 // (prob, coltile, nrows, spin=0, row0), C out fp32 [nprob][ncols][NP].
 extern "C" int dsb_debug_gemm_tc(int nprob, int K, int NP, int ncols, int nitems, const int32_t *items_host,
-                                 const uint16_t *F_host, const uint16_t *T_host, float *C_host) {
-  const size_t nF = (size_t)3 * nprob * K * ncols, nT = (size_t)3 * nprob * NP * K;
+                                 const float *F_host, const uint16_t *T_host, float *C_host) {
+  const size_t nF = (size_t)nprob * K * ncols, nT = (size_t)3 * nprob * NP * K;
   const size_t nC = (size_t)nprob * ncols * NP;
-  __nv_bfloat16 *F = nullptr, *T = nullptr;
-  float *C = nullptr;
+  __nv_bfloat16 *T = nullptr;
+  float *F = nullptr, *C = nullptr;
   WorkItem *items = nullptr;
-  DSB_CUDA(cudaMalloc(&F, nF * 2));
+  DSB_CUDA(cudaMalloc(&F, nF * 4));
   DSB_CUDA(cudaMalloc(&T, nT * 2));
   DSB_CUDA(cudaMalloc(&C, nC * 4));
   DSB_CUDA(cudaMalloc(&items, nitems * sizeof(WorkItem)));
-  DSB_CUDA(cudaMemcpy(F, F_host, nF * 2, cudaMemcpyHostToDevice));
+  DSB_CUDA(cudaMemcpy(F, F_host, nF * 4, cudaMemcpyHostToDevice));
   DSB_CUDA(cudaMemcpy(T, T_host, nT * 2, cudaMemcpyHostToDevice));
   DSB_CUDA(cudaMemset(C, 0, nC * 4));
   DSB_CUDA(cudaMemcpy(items, items_host, nitems * sizeof(WorkItem), cudaMemcpyHostToDevice));

@@ -18,11 +18,14 @@
 // folds north/south and emits
 //   F+_m(k) = e^{i m phi0} sum_j M_j e^{+2 pi i m j / n},  F-_m(k) = same for conj(M)
 //   even = north + south, odd = north - south
-// laid out as the A operand of the Legendre contraction (legendre_*.cu):
-//   spin-0  F0[2m+p][k][unit*cpu0 + slot*4 + pm*2 + reim]
-//   spin-2  F2[2m+p][k or Kp+k][unit*8 + eb*4 + pm*2 + reim]
-// with the (Q,U)->(E,B) combination folded into the operand roles:
-//   E = sum_k (-W)(F[Q]) + (-X)(-i F[U]),   B = sum_k (-W)(F[U]) + (-X)(+i F[Q]).
+// laid out as the A operand of the Legendre contraction (legendre_*.cu).  Production
+// (fp32) layout, one 32-byte sector per (m, fold parity, fold ring, unit, map group):
+//   spin-0  F0[2m+fold][k][unit*cpu0 + (I|V)*4 + pm*2 + reim]
+//   spin-2  F2[2m+fold][k][unit*8    + (Q|U)*4 + pm*2 + reim]
+// The fp64 validation layout stores the spin-2 block in its two operand roles,
+//   F2[2m+p][k or Kp+k][unit*8 + eb*4 + pm*2 + reim]
+//   E = sum_k (-W)(F[Q]) + (-X)(-i F[U]),   B = sum_k (-W)(F[U]) + (-X)(+i F[Q]),
+// which the tensor-core kernel derives from the fp32 data on the fly.
 //
 // Ring lengths are 4, 8, ..., 4*nside.  Power-of-two rings >= 32 run one forward
 // transform; other lengths go through Bluestein's chirp-z identity (forward transform,
@@ -78,32 +81,6 @@ __device__ __forceinline__ void store_vals<double>(void *F, size_t plane, size_t
   reinterpret_cast<double2 *>(p)[1] = make_double2(c, d);
 }
 
-__device__ __forceinline__ void split3f(float v, __nv_bfloat16 &h, __nv_bfloat16 &m, __nv_bfloat16 &l) {
-  h = __float2bfloat16_rn(v);
-  float r = v - __bfloat162float(h);
-  m = __float2bfloat16_rn(r);
-  r -= __bfloat162float(m);
-  l = __float2bfloat16_rn(r);
-}
-
-__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-}
-
-template <>
-__device__ __forceinline__ void store_vals<float>(void *F, size_t plane, size_t idx, float a, float b,
-                                                  float c, float d) {
-  __nv_bfloat16 h[4], m[4], l[4];
-  split3f(a, h[0], m[0], l[0]);
-  split3f(b, h[1], m[1], l[1]);
-  split3f(c, h[2], m[2], l[2]);
-  split3f(d, h[3], m[3], l[3]);
-  __nv_bfloat16 *p = reinterpret_cast<__nv_bfloat16 *>(F) + idx;
-  *reinterpret_cast<uint2 *>(p) = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
-  *reinterpret_cast<uint2 *>(p + plane) = make_uint2(pack2(m[0], m[1]), pack2(m[2], m[3]));
-  *reinterpret_cast<uint2 *>(p + 2 * plane) = make_uint2(pack2(l[0], l[1]), pack2(l[2], l[3]));
-}
-
 template <typename T>
 __device__ __forceinline__ void store8(void *F, size_t plane, size_t idx, const T (&v)[8]);
 
@@ -112,19 +89,6 @@ __device__ __forceinline__ void store8<double>(void *F, size_t plane, size_t idx
   double2 *p = reinterpret_cast<double2 *>(reinterpret_cast<double *>(F) + idx);
 #pragma unroll
   for (int i = 0; i < 4; ++i) p[i] = make_double2(v[2 * i], v[2 * i + 1]);
-}
-
-template <>
-__device__ __forceinline__ void store8<float>(void *F, size_t plane, size_t idx, const float (&v)[8]) {
-  __nv_bfloat16 h[8], m[8], l[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) split3f(v[i], h[i], m[i], l[i]);
-  __nv_bfloat16 *p = reinterpret_cast<__nv_bfloat16 *>(F) + idx;
-  *reinterpret_cast<uint4 *>(p) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-  *reinterpret_cast<uint4 *>(p + plane) =
-      make_uint4(pack2(m[0], m[1]), pack2(m[2], m[3]), pack2(m[4], m[5]), pack2(m[6], m[7]));
-  *reinterpret_cast<uint4 *>(p + 2 * plane) =
-      make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
 }
 
 // ---- pair weights -------------------------------------------------------------------
@@ -469,7 +433,21 @@ __device__ __forceinline__ void gather_emit(const RingCtx<T> &c) {
       ev[q][0] = e_p.x, ev[q][1] = e_p.y, ev[q][2] = e_m.x, ev[q][3] = e_m.y;
       od[q][0] = o_p.x, od[q][1] = o_p.y, od[q][2] = o_m.x, od[q][3] = o_m.y;
     }
-    if (MODE == MODE_I || MODE == MODE_V || MODE == MODE_IV) {
+    if constexpr (sizeof(T) == 4) {
+      // fp32 spectra, stored once: fold parity 0 = even (N + S), 1 = odd (N - S); the Legendre
+      // kernel splits them into bf16 planes and applies the spin-2 role permutation itself
+      float *F = reinterpret_cast<float *>((MODE == MODE_I || MODE == MODE_V || MODE == MODE_IV) ? P.F0 : P.F2);
+      const int ncols = (MODE == MODE_I || MODE == MODE_V || MODE == MODE_IV) ? P.ncols0 : P.ncols2;
+      const int cpu = (MODE == MODE_I || MODE == MODE_V || MODE == MODE_IV) ? P.cpu0 : 8;
+      const int coff = (MODE == MODE_V || MODE == MODE_U) ? 4 : 0;
+      float4 *d0 = reinterpret_cast<float4 *>(F + ((size_t)(2 * m + 0) * P.Kp + c.k) * ncols + (size_t)u * cpu + coff);
+      float4 *d1 = reinterpret_cast<float4 *>(F + ((size_t)(2 * m + 1) * P.Kp + c.k) * ncols + (size_t)u * cpu + coff);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        d0[q] = make_float4(ev[q][0], ev[q][1], ev[q][2], ev[q][3]);
+        d1[q] = make_float4(od[q][0], od[q][1], od[q][2], od[q][3]);
+      }
+    } else if (MODE == MODE_I || MODE == MODE_V || MODE == MODE_IV) {
       const size_t r0 = ((size_t)(2 * m + 0) * P.Kp + c.k) * P.ncols0 + (size_t)u * P.cpu0;
       const size_t r1 = ((size_t)(2 * m + 1) * P.Kp + c.k) * P.ncols0 + (size_t)u * P.cpu0;
       if (MODE == MODE_IV) {
@@ -766,7 +744,7 @@ static int launch_t(dsb_plan *plan, const BucketLayout &lay, const UnitDev *unit
 int launch_ringfft(dsb_plan *plan, const BucketLayout &lay, const UnitDev *units_dev, int precision,
                    const void *const *wplanes_dev, void *F0, void *F2, cudaStream_t stream) {
   const size_t nprob = 2 * ((size_t)lay.mcap + 1);
-  const size_t plane0 = nprob * lay.Kp * lay.ncols0;
+  const size_t plane0 = nprob * lay.Kp * lay.ncols0;  // fp64 layout only
   const size_t plane2 = nprob * 2 * lay.Kp * lay.ncols2;
   if (precision == DSB_PREC_FP64)
     return launch_t<double>(plan, lay, units_dev, F0, F2, plane0, plane2, (const double *const *)wplanes_dev, stream);

@@ -134,11 +134,12 @@ int dsb_get_profile(double *ms3, uint64_t *launches3);
 
 /* Unit-test entry for the tensor-core contraction kernel alone (host buffers):
  *   C[prob][col][n] = sum_k F[prob][k][col] * T[prob][n][k]
- * with both operands given as three bf16 planes (x = x1 + x2 + x3).
- *   F bf16 [3][nprob][K][ncols], T bf16 [3][nprob][NP][K], C fp32 [nprob][ncols][NP]
+ * F is plain fp32 (split into three bf16 planes inside the kernel), T is given as three
+ * bf16 planes (x = x1 + x2 + x3).
+ *   F fp32 [nprob][K][ncols], T bf16 [3][nprob][NP][K], C fp32 [nprob][ncols][NP]
  *   items int32 [nitems][5] = (prob, column tile, rows, 0, first row). */
 int dsb_debug_gemm_tc(int nprob, int K, int NP, int ncols, int nitems, const int32_t *items_host,
-                      const uint16_t *F_host, const uint16_t *T_host, float *C_host);
+                      const float *F_host, const uint16_t *T_host, float *C_host);
 
 /* ---- per-(m, freq) SVD chain --------------------------------------------
  * Replaces the frequency loop body of BeamTransfer._generate_svdfile_m

@@ -41,9 +41,9 @@ def test_gemm_tc(nprob, K, NP, ncols, rows):
     T = rng.standard_normal((nprob, NP, K))
     for p in range(nprob):
         T[p, rows[p]:] = 0.0
-    Fp = split3(F)
+    F32 = np.ascontiguousarray(F, dtype=np.float32)
     Tp = split3(T)
-    Fs = from_bf16(Fp).sum(0)
+    Fs = F32.astype(np.float64)
     Ts = from_bf16(Tp).sum(0)
     items = []
     for p in range(nprob):
@@ -53,7 +53,7 @@ def test_gemm_tc(nprob, K, NP, ncols, rows):
     items = np.array(items, dtype=np.int32)
     C = np.zeros((nprob, ncols, NP), dtype=np.float32)
     rc = _lib.lib.dsb_debug_gemm_tc(
-        nprob, K, NP, ncols, len(items), items.ctypes.data, np.ascontiguousarray(Fp).ctypes.data,
+        nprob, K, NP, ncols, len(items), items.ctypes.data, F32.ctypes.data,
         np.ascontiguousarray(Tp).ctypes.data, C.ctypes.data,
     )
     _lib.check(rc)
