@@ -29,32 +29,42 @@ bool g_prof = false;
 double g_prof_ms[3] = {0, 0, 0};
 uint64_t g_prof_n[3] = {0, 0, 0};
 
-struct StageTimer {
+struct StageEvents {
   cudaEvent_t e[4];
+};
+std::vector<StageEvents> g_prof_pending;  // recorded, not yet read back
+
+// Records four events around the three stages; the times are collected by dsb_get_profile so
+// that profiling never blocks the launching thread.
+struct StageTimer {
+  StageEvents ev;
   bool on;
   cudaStream_t st;
   explicit StageTimer(cudaStream_t s) : on(g_prof), st(s) {
     if (on)
-      for (auto &x : e) cudaEventCreate(&x);
+      for (auto &x : ev.e) cudaEventCreate(&x);
   }
   void mark(int i) {
-    if (on) cudaEventRecord(e[i], st);
+    if (on) cudaEventRecord(ev.e[i], st);
   }
   void finish() {
-    if (!on) return;
-    cudaEventSynchronize(e[3]);
+    if (on) g_prof_pending.push_back(ev);
+  }
+};
+
+void collect_profile() {
+  for (auto &ev : g_prof_pending) {
+    cudaEventSynchronize(ev.e[3]);
     for (int i = 0; i < 3; ++i) {
       float ms = 0.f;
-      cudaEventElapsedTime(&ms, e[i], e[i + 1]);
+      cudaEventElapsedTime(&ms, ev.e[i], ev.e[i + 1]);
       g_prof_ms[i] += ms;
       g_prof_n[i] += 1;
     }
+    for (auto &x : ev.e) cudaEventDestroy(x);
   }
-  ~StageTimer() {
-    if (on)
-      for (auto &x : e) cudaEventDestroy(x);
-  }
-};
+  g_prof_pending.clear();
+}
 
 struct Carve {
   char *base;
@@ -72,6 +82,7 @@ struct Carve {
 }  // namespace
 
 extern "C" int dsb_set_profiling(int enable) {
+  collect_profile();
   g_prof = enable != 0;
   for (int i = 0; i < 3; ++i) {
     g_prof_ms[i] = 0;
@@ -81,6 +92,7 @@ extern "C" int dsb_set_profiling(int enable) {
 }
 
 extern "C" int dsb_get_profile(double *ms3, uint64_t *launches3) {
+  collect_profile();
   for (int i = 0; i < 3; ++i) {
     if (ms3) ms3[i] = g_prof_ms[i];
     if (launches3) launches3[i] = g_prof_n[i];
@@ -305,19 +317,22 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
       o0[i] = (tarray && out_is_host) ? i : u.out0;
       o1[i] = u.out1;
     }
+    // Work items in (m, parity)-major order: the column tiles of one (m, parity) run on
+    // neighbouring CTAs at the same time, so the table tile they share -- and, for spin 2, the
+    // spectra tile that (m, 0) and (m, 1) both read (W and X roles) -- are served from L2.
     for (int s = 0; s <= (lay.has2 ? 2 : 0); s += 2) {
       const int cpu = s == 0 ? lay.cpu0 : 8;
       const int upt = 128 / cpu;
-      for (int ct = 0; ct * upt < nu; ++ct) {
-        int Lt = 0;  // rows computed for the tile: its largest unit lmax
-        for (int i = ct * upt; i < std::min(nu, (ct + 1) * upt); ++i) Lt = std::max(Lt, ud[i].lmax);
-        for (int m = 0; m <= std::min(lay.mcap, Lt); ++m)
-          for (int p = 0; p < 2; ++p) {
-            const int nr = nrows_mp(Lt, m, p);
-            for (int r0 = 0; r0 < nr; r0 += 256)
-              items.push_back({2 * m + p, ct, std::min(256, nr - r0), s, r0});
+      const int ntile = (nu + upt - 1) / upt;
+      std::vector<int> Lt(ntile, 0);  // rows computed for a tile: its largest unit lmax
+      for (int i = 0; i < nu; ++i) Lt[i / upt] = std::max(Lt[i / upt], ud[i].lmax);
+      for (int m = 0; m <= lay.mcap; ++m)
+        for (int p = 0; p < 2; ++p)
+          for (int ct = 0; ct < ntile; ++ct) {
+            if (m > Lt[ct]) continue;
+            const int nr = nrows_mp(Lt[ct], m, p);
+            for (int r0 = 0; r0 < nr; r0 += 256) items.push_back({2 * m + p, ct, std::min(256, nr - r0), s, r0});
           }
-      }
     }
 
     // carve the workspace
@@ -411,8 +426,8 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
       }
     }
     // host-side vectors (ud, items, ...) are consumed by async copies from pageable memory,
-    // which the runtime stages synchronously; chunk buffers are reused, so drain the stream.
-    DSB_CUDA(cudaStreamSynchronize(stream));
+    // which the runtime stages before returning; the device buffers reused by the next chunk
+    // (or the next call) are protected by stream order, so nothing blocks here.
   }
 
   if (!tarray && out_is_host) {

@@ -55,7 +55,7 @@ void count_launch(int n = 1);
 
 // ---- small device helpers ----------------------------------------------------
 template <typename T>
-struct cplx {
+struct alignas(2 * sizeof(T)) cplx {  // one 64-/128-bit load or store
   T x, y;
 };
 template <typename T>
@@ -147,7 +147,7 @@ struct dsb_plan {
     int first = 0;     // offset into ring_list
     int count = 0;
     int max_n = 0;     // longest ring
-    int max_live = 1;  // 2 if a ring pair of the class has both rings above the horizon
+    int max_live = 1;  // 2: both rings of every pair of the class are above the horizon
   };
   std::vector<RingClass> ring_classes;  // sorted by decreasing work
   int *ring_list_dev = nullptr;

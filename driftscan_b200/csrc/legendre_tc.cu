@@ -35,7 +35,7 @@ namespace dsb {
 
 constexpr int TC_KC = 32;          // k per pipeline stage
 constexpr int TC_M = 128;          // operand columns per tile
-constexpr int TC_NCONV = 4;        // converter warps
+constexpr int TC_NCONV = 8;        // converter warps
 constexpr int TC_THREADS = 192 + 32 * TC_NCONV;
 constexpr int TC_A_PLANE = TC_KC * TC_M * 2;  // bytes of one split plane of A per stage (8 KB)
 constexpr int TC_A_RAW = TC_KC * TC_M * 4;    // bytes of the fp32 staging tile per stage (16 KB)
@@ -134,16 +134,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
 }
 
-__device__ __forceinline__ void split3_bf16(float v, uint32_t &h, uint32_t &m, uint32_t &l) {
-  const __nv_bfloat16 bh = __float2bfloat16_rn(v);
-  float r = v - __bfloat162float(bh);
-  const __nv_bfloat16 bm = __float2bfloat16_rn(r);
-  r -= __bfloat162float(bm);
-  const __nv_bfloat16 bl = __float2bfloat16_rn(r);
-  h = __bfloat16_as_ushort(bh);
-  m = __bfloat16_as_ushort(bm);
-  l = __bfloat16_as_ushort(bl);
+// v = h + m + l with h, m, l representable in bf16 (8 significant bits each, round to nearest,
+// ties away): integer rounding on the fp32 bit pattern, no conversion instructions.  The
+// results are the fp32 bit patterns whose upper halves are the bf16 planes.
+__device__ __forceinline__ void split3_bits(float v, uint32_t &h, uint32_t &m, uint32_t &l) {
+  h = (__float_as_uint(v) + 0x8000u) & 0xFFFF0000u;
+  float r = v - __uint_as_float(h);
+  m = (__float_as_uint(r) + 0x8000u) & 0xFFFF0000u;
+  r -= __uint_as_float(m);
+  l = __float_as_uint(r) + 0x8000u;
 }
+// (upper half of a, upper half of b) -> one 32-bit word, a in the low half
+__device__ __forceinline__ uint32_t hi2(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA2,
@@ -337,16 +339,16 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
           }
           uint32_t h[8], m[8], l[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) split3_bf16(v[i], h[i], m[i], l[i]);
+          for (int i = 0; i < 8; ++i) split3_bits(v[i], h[i], m[i], l[i]);
           // MN-major SW128: box (64 columns) -> k row of 128 B -> 16-byte chunk ^ (k & 7)
           const uint32_t off = (uint32_t)(grp >> 3) * (TC_A_PLANE / 2) + (uint32_t)k * 128 +
                                ((uint32_t)((grp & 7) ^ (k & 7)) << 4);
           *reinterpret_cast<uint4 *>(sA + off) =
-              make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+              make_uint4(hi2(h[0], h[1]), hi2(h[2], h[3]), hi2(h[4], h[5]), hi2(h[6], h[7]));
           *reinterpret_cast<uint4 *>(sA + TC_A_PLANE + off) =
-              make_uint4(m[0] | (m[1] << 16), m[2] | (m[3] << 16), m[4] | (m[5] << 16), m[6] | (m[7] << 16));
+              make_uint4(hi2(m[0], m[1]), hi2(m[2], m[3]), hi2(m[4], m[5]), hi2(m[6], m[7]));
           *reinterpret_cast<uint4 *>(sA + 2 * TC_A_PLANE + off) =
-              make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+              make_uint4(hi2(l[0], l[1]), hi2(l[2], l[3]), hi2(l[4], l[5]), hi2(l[6], l[7]));
         }
         // make the generic-proxy writes visible to the tensor core (async proxy), then signal
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

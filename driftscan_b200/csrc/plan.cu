@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <atomic>
 #include <algorithm>
+#include <tuple>
 
 #include "dsb_common.cuh"
 #include "fft16.cuh"
@@ -194,34 +195,33 @@ extern "C" int dsb_plan_create(int nside, const uint8_t *horizon_host, dsb_plan 
 
   // ---- ring classes: one launch per (kind, transform length), most work first
   {
-    std::map<std::pair<int, int>, std::vector<int>> by_len;
+    // key: (kind, log2 L, both rings of the pair live) -- shared memory is sized per class
+    std::map<std::tuple<int, int, int>, std::vector<int>> by_len;
     for (int k = 0; k < nfold; ++k) {
       const RingDesc &rd = plan->rings_h[k];
       const int kind = rd.nphi <= 16 ? 2 : rd.bluestein ? 1 : 0;
-      by_len[std::make_pair(kind, kind == 2 ? 5 : rd.log2n)].push_back(k);
+      const int both = (rd.vis_north && rd.vis_south && rd.startS >= 0) ? 1 : 0;
+      by_len[std::make_tuple(kind, kind == 2 ? 5 : rd.log2n, both)].push_back(k);
     }
     std::vector<dsb_plan::RingClass> classes;
     for (auto &kv : by_len) {
       dsb_plan::RingClass rc;
-      rc.kind = kv.first.first;
-      rc.log2L = kv.first.second;
+      rc.kind = std::get<0>(kv.first);
+      rc.log2L = std::get<1>(kv.first);
+      rc.max_live = std::get<2>(kv.first) ? 2 : 1;
       rc.count = (int)kv.second.size();
-      for (int r : kv.second) {
-        const RingDesc &rd = plan->rings_h[r];
-        rc.max_n = std::max(rc.max_n, rd.nphi);
-        if (rd.vis_north && rd.vis_south && rd.startS >= 0) rc.max_live = 2;
-      }
+      for (int r : kv.second) rc.max_n = std::max(rc.max_n, plan->rings_h[r].nphi);
       classes.push_back(rc);
     }
     auto work = [](const dsb_plan::RingClass &c) {
-      return (double)c.count * (1 << c.log2L) * c.log2L * (c.kind == 1 ? 2.2 : 1.0);
+      return (double)c.count * c.max_live * (1 << c.log2L) * c.log2L * (c.kind == 1 ? 2.2 : 1.0);
     };
     std::sort(classes.begin(), classes.end(),
               [&](const dsb_plan::RingClass &a, const dsb_plan::RingClass &b) { return work(a) > work(b); });
     std::vector<int> list;
     for (auto &rc : classes) {
       rc.first = (int)list.size();
-      const auto &v = by_len[std::make_pair(rc.kind, rc.log2L)];
+      const auto &v = by_len[std::make_tuple(rc.kind, rc.log2L, rc.max_live == 2 ? 1 : 0)];
       list.insert(list.end(), v.rbegin(), v.rend());
     }
     plan->ring_classes = classes;

@@ -64,7 +64,6 @@ struct RingFFTParams {
   int units_per_cta;
   int npp;                                   // Stokes maps transformed per pass (1, 2 or 4)
   int tw_cap, ch_cap, ph_cap, fr_cap, seq_cap;  // shared-memory carve, complex elements
-  int tw_global;                                // twiddles are read from global memory
 };
 
 __device__ __forceinline__ void sincospi_t(float x, float *s, float *c) { sincospif(x, s, c); }
@@ -240,6 +239,19 @@ struct RingCtx {
   bool liveN, liveS, equator;
 };
 
+// Barrier among the L/16 threads that own one sequence (the passes of different sequences are
+// independent): a warp-level sync up to 32 threads, a named barrier up to 128, the CTA above.
+template <int LTQ>
+__device__ __forceinline__ void seq_group_sync() {
+  if constexpr (LTQ <= 5) {
+    __syncwarp();
+  } else if constexpr (LTQ < 8) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> LTQ)), "r"(1 << LTQ) : "memory");
+  } else {
+    __syncthreads();
+  }
+}
+
 // ---- B: ring transforms of one pass ---------------------------------------------------------
 // sequences: index s = (gi * NQ + q) * nlive + lr; a sequence of Stokes V of two identical beams
 // is identically zero and is not transformed
@@ -257,7 +269,10 @@ __device__ __forceinline__ void middle_passes(const RingCtx<T> &c, int mode, int
       else
         dit_pass<T, F, P, +1>(c.seq_s + s * F::PITCH, c.tw, task & ((1 << F::LTQ) - 1));
     }
-    __syncthreads();
+    if (SIGN > 0 && P == 0)
+      __syncthreads();  // last pass of the pair: the gather reads every sequence
+    else
+      seq_group_sync<F::LTQ>();
     if constexpr (SIGN < 0) {
       if constexpr (P + 2 < F::NPASS) middle_passes<T, F, P + 1, SIGN>(c, mode, ntask);
     } else {
@@ -308,7 +323,7 @@ __device__ __forceinline__ void transform_pass(const RingCtx<T> &c, int mode) {
     pass_twiddle<T, F, 0, -1>(c.tw, a, v);
     pass_store<T, F, 0>(c.seq_s + s * F::PITCH, a, v);
   }
-  __syncthreads();
+  seq_group_sync<F::LTQ>();
   if constexpr (F::NPASS > 2) middle_passes<T, F, 1, -1>(c, mode, ntask);
   {
     constexpr int PL = F::NPASS - 1;
@@ -332,7 +347,10 @@ __device__ __forceinline__ void transform_pass(const RingCtx<T> &c, int mode) {
       }
       pass_store<T, F, PL>(seq, a, v);
     }
-    __syncthreads();
+    if (KIND == KIND_BLUESTEIN)
+      seq_group_sync<F::LTQ>();
+    else
+      __syncthreads();  // the gather reads every sequence
   }
   if constexpr (KIND == KIND_BLUESTEIN) middle_passes<T, F, F::NPASS - 2, +1>(c, mode, ntask);
 }
@@ -525,7 +543,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? DSB_RING_MINBLOCKS : 1)
       tw_s[j] = {(T)cs, (T)sn};
     }
     c.tw = tw_s;
-  } else if (!P.tw_global) {
+  } else if (sizeof(T) == 4) {  // fp64 (validation) reads its twiddles from global memory
     for (int j = tid; j < F::twtotal(); j += blockDim.x) tw_s[j] = twg[j];
     c.tw = tw_s;
   }
@@ -638,11 +656,7 @@ static int launch_class(const dsb_plan::RingClass &cls, RingFFTParams<T> &P, con
   auto need = [&](int npp_, int twc, int G) {
     return cs * ((size_t)twc + P.ch_cap + P.ph_cap + (size_t)G * cls.max_live * cls.max_n + (size_t)G * npp_ * cls.max_live * pitch);
   };
-  P.tw_global = 0;
-  if (need(npp, tw_cap, 1) > budget) {  // twiddles stay in global memory (L1/L2)
-    tw_cap = 0;
-    P.tw_global = 1;
-  }
+  if (sizeof(T) == 8 && KIND != KIND_DIRECT) tw_cap = 0;  // fp64: twiddles stay in global memory (L1/L2)
   if (need(npp, tw_cap, 1) > budget) npp = 1;
   DSB_CHECK(need(npp, tw_cap, 1) <= budget, DSB_ERR_UNSUPPORTED,
             "ring transform of length %d does not fit shared memory", F::L);
