@@ -115,79 +115,76 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------
-# CPU reference arm / cpu_baseline (oracle port; the reference's own SHT lives in
-# healpy/libsharp which is not installable offline)
+# CPU reference arm / cpu_baseline.  The reference's own SHT lives in healpy/libsharp and
+# cannot be installed offline, so the CPU arm times the oracle's C restatement of the unit
+# (oracle/csht.c: fringe, Stokes maps, ring FFT, Legendre recurrences, fp64), one unit per
+# thread on all host cores -- the reference parallelises the same way (one unit per MPI
+# rank, drift/core/beamtransfer.py:584-607).
 # ---------------------------------------------------------------------------------
-
-_W = {}
-
-
-def _cpu_init(cfg_items):
-    os.environ.setdefault("DSB_ORACLE_CACHE_GB", "6")
-    os.environ["OMP_NUM_THREADS"] = "1"
-    from oracle import beam as obeam
-    from oracle import transfer as otr
-
-    _W["obeam"], _W["otr"] = obeam, otr
-    _W["geom"] = {}
-    _W["beams"] = {}
-    _W.update(dict(cfg_items))
-
-
-def _cpu_unit(task):
-    nside, fi, width_wl, uv, lmax, lside, ci, cj = task
-    obeam, otr = _W["obeam"], _W["otr"]
-    zen = _W["zenith"]
-    if nside not in _W["geom"]:
-        from oracle import healpix as ohp
-
-        ang = ohp.ang_positions(nside)
-        _W["geom"][nside] = (ang, obeam.horizon(ang, zen))
-    ang, hor = _W["geom"][nside]
-    key = (nside, fi)
-    if key not in _W["beams"]:
-        fe, fh = _W["fwhm_e"], _W["fwhm_h"]
-        _W["beams"][key] = (obeam.beam_x(ang, zen, width_wl, fe, fh), obeam.beam_y(ang, zen, width_wl, fe, fh))
-    b = _W["beams"][key]
-    otr.transfer_single_pol(ang, hor, b[ci], b[cj], zen, np.asarray(uv), lmax, lside, npol=4)
-    return 1
 
 
 def cpu_sample_tasks(tel, f_list, nsample):
     """A deterministic sample of the step's units, stratified over the lmax (hence nside)
-    distribution: every k-th unit of the lmax-sorted list."""
+    distribution: every k-th unit of the lmax-sorted list, in an order whose every prefix is
+    itself spread over the whole range (bit-reversed positions)."""
     bl = np.tile(np.arange(tel.nbase), len(f_list))
     fi = np.repeat(np.asarray(f_list), tel.nbase)
     lmax, _ = tel.unit_lmax(bl, fi)
     order = np.argsort(lmax, kind="stable")
+    nsample = min(nsample, len(order))
     pick = order[np.linspace(0, len(order) - 1, nsample).astype(int)]
+    nbits = max(1, int(np.ceil(np.log2(nsample))))
+    rev = sorted(range(nsample), key=lambda i: int(format(i, f"0{nbits}b")[::-1], 2))
     tasks = []
-    for i in pick:
+    for i in pick[rev]:
         b, f = int(bl[i]), int(fi[i])
         pair = tel.uniquepairs[b]
-        tasks.append((tel._unit_nside(int(lmax[i])), f, tel.cylinder_width / tel.wavelengths[f],
-                      tuple(tel.baselines[b] / tel.wavelengths[f]), int(lmax[i]), tel.lmax,
+        tasks.append((tel._unit_nside(int(lmax[i])), f, tuple(tel.baselines[b] / tel.wavelengths[f]), int(lmax[i]),
                       int(tel.beamclass[pair[0]]), int(tel.beamclass[pair[1]])))
     return tasks
 
 
-def run_cpu(tel, f_list, nsample, cores):
-    import multiprocessing as mp
+class CpuArm:
+    """Beams and horizon masks per (nside, frequency), computed once outside the timed region
+    (the reference caches them per (nside, freq, beamclass) too, telescope.py:956-974)."""
 
-    tasks = cpu_sample_tasks(tel, f_list, nsample)
-    # group tasks so that each worker sees few distinct (nside, freq) beams
-    tasks.sort(key=lambda t: (t[0], t[1]))
-    cfg = dict(zenith=tel.zenith, fwhm_e=tel.fwhm_e, fwhm_h=tel.fwhm_h)
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_cpu_init, initargs=(list(cfg.items()),)) as pool:
-        # warm the per-worker Legendre tables outside the timed region (the reference's
-        # libsharp also plans once per geometry)
-        warm = [t for t in tasks if t[0] == max(x[0] for x in tasks)][:cores]
-        pool.map(_cpu_unit, warm, chunksize=1)
-        t0 = time.time()
-        pool.map(_cpu_unit, tasks, chunksize=1)
-        dt = time.time() - t0
-    return len(tasks) / dt, dt, len(tasks)
+    def __init__(self, tel, tasks):
+        from oracle import beam as obeam
+        from oracle import cbuild
+        from oracle import healpix as ohp
+
+        cbuild.lib()
+        self.tel, self.cbuild = tel, cbuild
+        self.geom, self.beams = {}, {}
+        for nside, f, _, _, _, _ in tasks:
+            if nside not in self.geom:
+                ang = ohp.ang_positions(nside)
+                self.geom[nside] = (ang, obeam.horizon(ang, tel.zenith).astype(np.uint8))
+            if (nside, f) not in self.beams:
+                ang = self.geom[nside][0]
+                w = tel.cylinder_width / tel.wavelengths[f]
+                self.beams[(nside, f)] = (obeam.beam_x(ang, tel.zenith, w, tel.fwhm_e, tel.fwhm_h),
+                                          obeam.beam_y(ang, tel.zenith, w, tel.fwhm_e, tel.fwhm_h))
+
+    def unit(self, task):
+        nside, f, uv, lmax, ci, cj = task
+        b = self.beams[(nside, f)]
+        self.cbuild.transfer_unit(nside, b[ci], b[cj], self.geom[nside][1], self.tel.zenith, uv, lmax, self.tel.lmax)
+        return 1
+
+    def run(self, tasks, cores):
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(cores) as ex:
+            t0 = time.time()
+            n = sum(ex.map(self.unit, tasks))
+            dt = time.time() - t0
+        return n / dt, dt, n
+
+
+CPU_SAMPLE_NOTE = ("units = every k-th unit of the lmax-sorted unit list of the step's frequencies (all nside "
+                   "buckets); C restatement of the reference unit (oracle/csht.c, fp64; the reference's SHT is "
+                   "healpy/libsharp, not installable offline), one unit per thread, beams precomputed")
 
 
 # ---------------------------------------------------------------------------------
@@ -201,7 +198,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--freqs-per-gpu", type=int, default=2)
     ap.add_argument("--precision", default="fp32x3", choices=["fp32x3", "fp64"])
-    ap.add_argument("--cpu-sample", type=int, default=48)
+    ap.add_argument("--cpu-sample", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -227,17 +224,17 @@ def main():
         if rank != 0:
             return 0
         cores = os.cpu_count() or 1
-        per_step = max(cores, min(args.cpu_sample, 4 * cores))
+        per_step = max(cores, args.cpu_sample)
+        f_list = [i * (tel.nfreq // F) for i in range(F)]
+        tasks = cpu_sample_tasks(tel, f_list, per_step)
+        arm = CpuArm(tel, tasks)
         vals = []
         for _ in range(args.warmup + args.steps):
-            ups, dt, ns = run_cpu(tel, [i * (tel.nfreq // F) for i in range(F)], per_step, cores)
-            vals.append((ups, dt))
+            vals.append(arm.run(tasks, cores)[:2])
         vals = vals[args.warmup:] or vals
         ups = float(np.mean([v[0] for v in vals]))
         ms = float(np.mean([v[1] for v in vals])) * 1e3
-        sample = (f"{per_step} units per step, every k-th unit of the lmax-sorted unit list of {F} frequencies "
-                  f"(all nside buckets), oracle port (numpy fp64 restatement; reference SHT = healpy/libsharp "
-                  f"is not installable offline), {cores} worker processes, Legendre tables warm")
+        sample = f"{len(tasks)} units per step; " + CPU_SAMPLE_NOTE
         line = {
             "impl": "reference", "metric": "beam-transfer (baseline*freq)/s", "value": ups,
             "unit": "units/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -410,11 +407,12 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        ns = max(cores, min(args.cpu_sample, 4 * cores))
-        ups, dt, n = run_cpu(tel, list(f_list), ns, cores)
+        tasks = cpu_sample_tasks(tel, list(f_list), max(cores, args.cpu_sample))
+        arm = CpuArm(tel, tasks)
+        arm.run(tasks[:cores], cores)  # warm: page in the beams, build the C contexts
+        ups, dt, n = arm.run(tasks, cores)
         cpu = {"value": ups, "unit": "units/s", "cores": cores, "kind": "port",
-               "sample": f"{n} units (every k-th unit of the lmax-sorted unit list of this step, all nside "
-                         f"buckets) in {dt:.1f} s; numpy fp64 oracle port, {cores} processes, tables warm"}
+               "sample": f"{n} units in {dt:.1f} s; " + CPU_SAMPLE_NOTE}
 
     if rank == 0:
         line = {

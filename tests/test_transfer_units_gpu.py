@@ -97,3 +97,44 @@ def test_polarised_fp32x3(nside, lside, npol_sky):
     err = _relerr(res, ref)
     print("fp32x3 relerr", nside, npol_sky, err)
     assert err < 1e-6
+
+
+def _cylinder_beams(nside, width_wl):
+    ang = ohp.ang_positions(nside)
+    fw = 2.0 * np.pi / 3.0
+    return [obeam.beam_x(ang, ZENITH, width_wl, fw * 0.7, fw), obeam.beam_y(ang, ZENITH, width_wl, fw * 0.7, fw)]
+
+
+@pytest.mark.parametrize("nside,lside,nunits,precision,tol",
+                         [(128, 190, 20, 1, 1e-6), (256, 233, 20, 1, 1e-6), (256, 233, 5, 0, 1e-10),
+                          (512, 468, 3, 1, 1e-6)])
+def test_full_size_units_against_c_oracle(nside, lside, nunits, precision, tol):
+    """BASELINE-size units (configs[2] reaches nside 256 / lmax 233, configs[3] nside 512 / lmax 468)
+    with the analytic cylinder beams, checked against the C restatement (the numpy oracle needs
+    minutes per unit at these sizes).  Covers every transform length class, several column tiles
+    and unit groups, identical-beam pairs (Stokes V identically zero) and mixed lmax."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import cbuild
+
+    beams = _cylinder_beams(nside, 20.0 / 1.4)
+    rng = np.random.default_rng(nside + nunits)
+    spec = []
+    for i in range(nunits):
+        lmax = lside - int(rng.integers(0, 25))
+        # |u| bounded by mmax/(2 pi), |v| so that the fringe is resolved at this lmax
+        u = rng.uniform(-0.9, 0.9) * lmax / (2 * np.pi)
+        v = rng.uniform(-0.9, 0.9) * np.sqrt(max(lmax**2 - (2 * np.pi * u) ** 2, 0.0)) / (2 * np.pi)
+        spec.append(((u, v), i % 2, (i // 2) % 2, lmax))
+    res, ang, hor = _run_units(nside, lside, spec, beams, True, 4, precision)
+    with ThreadPoolExecutor(8) as ex:
+        ref = np.array(list(ex.map(
+            lambda s: cbuild.transfer_unit(nside, beams[s[1]], beams[s[2]], hor, ZENITH, s[0], s[3], lside), spec)))
+    assert np.isfinite(res).all()
+    for i in range(nunits):
+        err = np.abs(res[i] - ref[i]).max() / np.abs(ref[i]).max()
+        assert err < tol, (i, spec[i], err)
+    # identical beams: V is exactly zero in the reference too (_fast_tools.pyx:158-162)
+    for i, s in enumerate(spec):
+        if s[1] == s[2]:
+            assert not res[i, 3].any() and np.abs(ref[i, 3]).max() == 0.0
