@@ -331,7 +331,7 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
           for (int ct = 0; ct < ntile; ++ct) {
             if (m > Lt[ct]) continue;
             const int nr = nrows_mp(Lt[ct], m, p);
-            for (int r0 = 0; r0 < nr; r0 += 256) items.push_back({2 * m + p, ct, std::min(256, nr - r0), s, r0});
+            for (int r0 = 0; r0 < nr; r0 += 128) items.push_back({2 * m + p, ct, std::min(128, nr - r0), s, r0});
           }
     }
 

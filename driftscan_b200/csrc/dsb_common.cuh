@@ -231,7 +231,7 @@ int launch_bluestein_prepare16(dsb_plan *plan);
 struct WorkItem {
   int32_t prob;     // 2*m + p
   int32_t coltile;  // 128-column tile
-  int32_t nrows;    // valid rows in this item (<= 256)
+  int32_t nrows;    // valid rows in this item (<= 128)
   int32_t spin;     // 0 or 2
   int32_t row0;     // first row (multiple of 16)
 };

@@ -24,9 +24,18 @@
 // so each output column of the contraction (a unit/pol/+-/re-im series in l) ends up in
 // one TMEM lane and is written out contiguously in l.
 //
-// Warp roles:  warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 =
-// epilogue (TMEM -> registers -> global), warps 6.. = converters.  Persistent over work
-// items with a double-buffered accumulator (2 x 256 TMEM columns).
+// Accumulation.  The tensor core adds each K=16 partial product into the fp32 TMEM
+// accumulator with truncation, a bias of ~2^-24 of the accumulator per MMA that grows
+// linearly with the number of chained MMAs (measured: 6e-6 of max|B| at nside 256, where a
+// series chains 192 of them).  So the leading product a1 b1 never accumulates across pipeline
+// stages: each stage (K = 32, two MMAs) writes a fresh TMEM chunk that the epilogue warps
+// drain and add to fp32 register sums (round to nearest); the five correction products, 2^-8
+// and smaller, accumulate in their own TMEM block, where the same truncation is harmless.
+//
+// Warp roles:  warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 =
+// epilogue (two per TMEM lane quarter, 64 rows each), warps 10.. = converters.  Persistent
+// over work items of <= 128 rows; TMEM: 2 x 128 columns of leading-product chunks (ping-pong
+// per stage) + 2 x 128 columns of correction accumulators (ping-pong per item).
 #include <cuda.h>
 
 #include "dsb_common.cuh"
@@ -35,8 +44,11 @@ namespace dsb {
 
 constexpr int TC_KC = 32;          // k per pipeline stage
 constexpr int TC_M = 128;          // operand columns per tile
-constexpr int TC_NCONV = 8;        // converter warps
-constexpr int TC_THREADS = 192 + 32 * TC_NCONV;
+constexpr int TC_NCONV = 6;        // converter warps
+constexpr int TC_NEPI = 8;         // epilogue warps
+constexpr int TC_CONV0 = 64 + 32 * TC_NEPI;  // first converter thread
+constexpr int TC_THREADS = TC_CONV0 + 32 * TC_NCONV;
+constexpr int TC_MAXROWS = 128;    // rows per work item
 constexpr int TC_A_PLANE = TC_KC * TC_M * 2;  // bytes of one split plane of A per stage (8 KB)
 constexpr int TC_A_RAW = TC_KC * TC_M * 4;    // bytes of the fp32 staging tile per stage (16 KB)
 
@@ -162,9 +174,11 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
   uint64_t *full = bars;                        // [nstages] TMA landed (fp32 A tile + B planes)
   uint64_t *empty = bars + P.nstages;           // [nstages] MMAs reading the stage retired
   uint64_t *conv = bars + 2 * P.nstages;        // [nstages] A planes written by the converters
-  uint64_t *tfull = bars + 3 * P.nstages;       // [2]
-  uint64_t *tempty = bars + 3 * P.nstages + 2;  // [2]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * P.nstages + 4);
+  uint64_t *mfull = bars + 3 * P.nstages;       // [2] leading-product chunk written
+  uint64_t *mfree = bars + 3 * P.nstages + 2;   // [2] chunk drained by the epilogue
+  uint64_t *cfull = bars + 3 * P.nstages + 4;   // [2] correction accumulator of an item complete
+  uint64_t *cfree = bars + 3 * P.nstages + 6;   // [2] correction accumulator read out
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * P.nstages + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -176,8 +190,10 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       mbar_init(&conv[s], TC_NCONV);
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&mfull[a], 1);
+      mbar_init(&mfree[a], TC_NEPI);
+      mbar_init(&cfull[a], 1);
+      mbar_init(&cfree[a], TC_NEPI);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -232,85 +248,125 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
+      uint32_t chunk = 0;  // leading-product chunks issued so far (one per pipeline stage)
       for (int it = blockIdx.x; it < P.nitems; it += gridDim.x, ++local) {
         const WorkItem wi = P.items[it];
         const bool s2 = wi.spin == 2;
         const int nk = (s2 ? 2 : 1) * (P.K0 / TC_KC);
-        const int acc = local & 1;
-        const uint32_t acc_phase = (local >> 1) & 1;
+        const int cb = local & 1;
+        const uint32_t cb_phase = (local >> 1) & 1;
         const uint32_t N = (uint32_t)((wi.nrows + 15) & ~15);
         // instruction descriptor: D=f32, A=B=bf16, A MN-major, B K-major, M=128, N
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((N >> 3) << 17) |
                                ((uint32_t)(TC_M >> 4) << 24);
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        mbar_wait(&cfree[cb], cb_phase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256;
-        uint32_t accum = 0;
-        for (int kc = 0; kc < nk; ++kc) {
+        const uint32_t d_corr = tmem_base + 256 + (uint32_t)cb * 128;
+        uint32_t accum_c = 0;
+        for (int kc = 0; kc < nk; ++kc, ++chunk) {
+          const uint32_t mb = chunk & 1;
           mbar_wait(&full[stage], phase);  // B planes (TMA)
           mbar_wait(&conv[stage], phase);  // A planes (converters)
+          mbar_wait(&mfree[mb], ((chunk >> 1) & 1) ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sA = smem_u32(stages + (size_t)stage * stage_bytes);
           const uint32_t sB = sA + 3 * TC_A_PLANE + TC_A_RAW;
+          const uint32_t d_main = tmem_base + mb * 128;
 #pragma unroll
           for (int ks = 0; ks < TC_KC / 16; ++ks) {
-            // six split products, smallest first
-            const int pa[6] = {0, 1, 2, 0, 1, 0};
-            const int pb[6] = {2, 1, 0, 1, 0, 0};
+            // A: MN-major SW128. 64-column box = 32 k-rows x 128 B; LBO = next 64 columns (4096 B),
+            //    SBO = next 8 k-rows (1024 B); one K=16 step = two 8-row atoms = 2048 B.
+            // B: K-major SW64. rows of 64 B; 8-row atom = 512 B (SBO); K=16 step = 32 B inside the row.
+            // five correction products, smallest first, into the correction accumulator
+            const int pa[5] = {0, 1, 2, 0, 1};
+            const int pb[5] = {2, 1, 0, 1, 0};
 #pragma unroll
-            for (int q = 0; q < 6; ++q) {
-              // A: MN-major SW128. 64-column box = 32 k-rows x 128 B; LBO = next 64 columns (4096 B),
-              //    SBO = next 8 k-rows (1024 B); one K=16 step = two 8-row atoms = 2048 B.
+            for (int q = 0; q < 5; ++q) {
               const uint64_t da = make_desc(sA + pa[q] * TC_A_PLANE + ks * 2048, TC_A_PLANE / 2, 1024, 2);
-              // B: K-major SW64. rows of 64 B; 8-row atom = 512 B (SBO); K=16 step = 32 B inside the row.
               const uint64_t db = make_desc(sB + pb[q] * b_plane + ks * 32, 16, 512, 4);
-              umma_bf16(d_tmem, da, db, idesc, accum);
-              accum = 1;
+              umma_bf16(d_corr, da, db, idesc, accum_c);
+              accum_c = 1;
             }
+            // leading product a1 b1 into this stage's fresh chunk
+            const uint64_t da = make_desc(sA + ks * 2048, TC_A_PLANE / 2, 1024, 2);
+            const uint64_t db = make_desc(sB + ks * 32, 16, 512, 4);
+            umma_bf16(d_main, da, db, idesc, ks > 0 ? 1u : 0u);
           }
           umma_commit(&empty[stage]);
+          umma_commit(&mfull[mb]);
           if (++stage == P.nstages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);
+        umma_commit(&cfull[cb]);
       }
     }
     __syncwarp();
-  } else if (warp < 6) {
-    // ===================== epilogue =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+  } else if (warp < 2 + TC_NEPI) {
+    // ===================== epilogue: drain chunks, sum in registers, store =====================
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;      // rows [64 half, 64 half + 64)
     int local = 0;
+    uint32_t chunk = 0;
     for (int it = blockIdx.x; it < P.nitems; it += gridDim.x, ++local) {
       const WorkItem wi = P.items[it];
       const bool s2 = wi.spin == 2;
-      const int acc = local & 1;
-      const uint32_t acc_phase = (local >> 1) & 1;
+      const int nk = (s2 ? 2 : 1) * (P.K0 / TC_KC);
+      const int cb = local & 1;
+      const uint32_t cb_phase = (local >> 1) & 1;
       const int N = (wi.nrows + 15) & ~15;
       const int ncols = s2 ? P.ncols2 : P.ncols0;
-      float *C = (s2 ? P.C2 : P.C0) +
-                 ((size_t)wi.prob * ncols + (size_t)wi.coltile * TC_M + quarter * 32 + lane) * P.NP + wi.row0;
-      mbar_wait(&tfull[acc], acc_phase);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 256;
-      for (int n0 = 0; n0 < N; n0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + n0, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float4 *dst = reinterpret_cast<float4 *>(C + n0);
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)half * 64;
+      float sums[64];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                               __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+      for (int i = 0; i < 64; ++i) sums[i] = 0.f;
+      for (int kc = 0; kc < nk; ++kc, ++chunk) {
+        const uint32_t mb = chunk & 1;
+        mbar_wait(&mfull[mb], (chunk >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (half * 64 + g * 16 < N) {
+            uint32_t v[16];
+            tmem_ld16(lane_base + mb * 128 + g * 16, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sums[g * 16 + i] += __uint_as_float(v[i]);
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mfree[mb]);
+      }
+      // corrections, then store this thread's operand column contiguously in l
+      mbar_wait(&cfull[cb], cb_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float *C = (s2 ? P.C2 : P.C0) +
+                 ((size_t)wi.prob * ncols + (size_t)wi.coltile * TC_M + quarter * 32 + lane) * P.NP + wi.row0 +
+                 half * 64;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (half * 64 + g * 16 < N) {
+          uint32_t v[16];
+          tmem_ld16(lane_base + 256 + (uint32_t)cb * 128 + g * 16, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float4 *dst = reinterpret_cast<float4 *>(C + g * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dst[q] = make_float4(sums[g * 16 + 4 * q] + __uint_as_float(v[4 * q]),
+                                 sums[g * 16 + 4 * q + 1] + __uint_as_float(v[4 * q + 1]),
+                                 sums[g * 16 + 4 * q + 2] + __uint_as_float(v[4 * q + 2]),
+                                 sums[g * 16 + 4 * q + 3] + __uint_as_float(v[4 * q + 3]));
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) mbar_arrive(&cfree[cb]);
     }
   } else {
     // ===================== converters: fp32 tile -> three swizzled bf16 planes =====================
-    const int ct = threadIdx.x - 192;  // 0 .. 32*TC_NCONV-1
+    const int ct = threadIdx.x - TC_CONV0;  // 0 .. 32*TC_NCONV-1
     int stage = 0;
     uint32_t phase = 0;
     for (int it = blockIdx.x; it < P.nitems; it += gridDim.x) {
@@ -429,8 +485,8 @@ int launch_legendre_tc_raw(int nprobA, int nprobT, int Kp, int NP, int ncols0, i
   DSB_CHECK(Kp % TC_KC == 0, DSB_ERR_INVALID, "contraction length must be a multiple of %d", TC_KC);
   DSB_CHECK(ncols0 % TC_M == 0 && ncols2 % TC_M == 0, DSB_ERR_INVALID, "column counts must be multiples of 128");
   DSB_CHECK(NP % 16 == 0, DSB_ERR_INVALID, "row pitch must be a multiple of 16");
-  int NB = (int)round_up(std::min(std::max(max_rows, 16), 256), 16);
-  NB = std::min(NB, 256);
+  DSB_CHECK(max_rows <= TC_MAXROWS, DSB_ERR_INVALID, "work items hold at most %d rows", TC_MAXROWS);
+  int NB = (int)round_up(std::min(std::max(max_rows, 16), TC_MAXROWS), 16);
 
   CUtensorMap mA0, mA2, mB0, mB2;
   const uint64_t K0 = Kp, K2 = 2 * (uint64_t)Kp;
@@ -462,7 +518,7 @@ int launch_legendre_tc_raw(int nprobA, int nprobT, int Kp, int NP, int ncols0, i
   int nstages = (int)std::min<size_t>(8, (220 * 1024) / stage_bytes);
   DSB_CHECK(nstages >= 2, DSB_ERR_UNSUPPORTED, "pipeline does not fit shared memory");
   P.nstages = nstages;
-  const size_t smem = nstages * stage_bytes + (3 * nstages + 4) * 8 + 16 + 1024;
+  const size_t smem = nstages * stage_bytes + (3 * nstages + 8) * 8 + 16 + 1024;
   DSB_CUDA(cudaFuncSetAttribute(legendre_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);

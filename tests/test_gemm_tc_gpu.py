@@ -31,14 +31,19 @@ def split3(x):
 @pytest.mark.parametrize(
     "nprob,K,NP,ncols,rows",
     [(2, 32, 16, 128, [16, 9]), (3, 96, 48, 256, [48, 33, 17]), (2, 256, 128, 128, [128, 100]),
-     (1, 64, 272, 128, [272])],
+     (1, 64, 272, 128, [272]), (2, 1024, 64, 128, [64, 40])],
 )
-def test_gemm_tc(nprob, K, NP, ncols, rows):
+@pytest.mark.parametrize("coherent", [False, True])
+def test_gemm_tc(nprob, K, NP, ncols, rows, coherent):
     from driftscan_b200 import _lib
 
     rng = np.random.default_rng(nprob * 1000 + K)
     F = rng.standard_normal((nprob, K, ncols)) * np.exp(rng.uniform(-3, 3, (nprob, K, 1)))
     T = rng.standard_normal((nprob, NP, K))
+    if coherent:
+        # same-sign terms: a sum that grows monotonically exposes any truncation bias in the
+        # accumulation (the tensor core truncates when it adds into its fp32 accumulator)
+        F, T = np.abs(F), np.abs(T)
     for p in range(nprob):
         T[p, rows[p]:] = 0.0
     F32 = np.ascontiguousarray(F, dtype=np.float32)
@@ -48,8 +53,8 @@ def test_gemm_tc(nprob, K, NP, ncols, rows):
     items = []
     for p in range(nprob):
         for ct in range(ncols // 128):
-            for r0 in range(0, rows[p], 256):
-                items.append((p, ct, min(256, rows[p] - r0), 0, r0))
+            for r0 in range(0, rows[p], 128):
+                items.append((p, ct, min(128, rows[p] - r0), 0, r0))
     items = np.array(items, dtype=np.int32)
     C = np.zeros((nprob, ncols, NP), dtype=np.float32)
     rc = _lib.lib.dsb_debug_gemm_tc(
@@ -63,4 +68,4 @@ def test_gemm_tc(nprob, K, NP, ncols, rows):
         got = C[p, :, :n]
         want = ref[p, :, :n]
         err = np.abs(got - want).max() / np.abs(want).max()
-        assert err < 5e-6, (p, err)
+        assert err < 4e-7, (p, err)
