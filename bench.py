@@ -354,6 +354,17 @@ def main():
     ms_step = ms_total / args.steps
     value = world * units_per_step / (ms_step * 1e-3)
 
+    # ---- the frequency-major -> m-major exchange alone (N > 1): bytes each rank sends over NVLink
+    exchange = None
+    if world > 1:
+        ex_steps = max(3, args.steps)
+        ms_ex = timed(lambda: comm.exchange_mblocks(out_dev, F, moff, mmax + 1, f_lo=rank * F), ex_steps, 2) / ex_steps
+        _, mlo, mhi = parallel.split_counts(mmax + 1, world)
+        sent = int(total - (moff[mhi[rank]] - moff[mlo[rank]])) * 16  # everything but this rank's own m range
+        exchange = {"ms": ms_ex, "bytes_sent_per_gpu": sent, "gbs_per_gpu": sent / (ms_ex * 1e-3) / 1e9,
+                    "nvlink_peak_gbs": 900.0, "frac": sent / (ms_ex * 1e-3) / 1e9 / 900.0,
+                    "collective": "torch.distributed.all_to_all_single (NCCL)"}
+
     # ---- rooflines (measured peaks written by the driver, else the documented fallback)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -421,7 +432,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3->f32 (fp64 phase)" if args.precision == "fp32x3" else "f64",
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": dominant, "roofline_all": [roof_ring, roof_leg, roof_pack],
-            "stage_launches_per_run": stage_launch, "cpu_baseline": cpu,
+            "stage_launches_per_run": stage_launch, "cpu_baseline": cpu, "exchange": exchange,
         }
         print(json.dumps(line))
     if world > 1:

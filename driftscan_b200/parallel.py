@@ -88,14 +88,21 @@ class Comm:
             blocks = [buf[moff[m] : moff[m + 1]] for m in range(nm)]
             return [(0 if f_lo is None else f_lo, (0 if f_lo is None else f_lo) + nfc, blocks)]
 
-        info = self.allgather_ints([nfc, -1 if f_lo is None else f_lo])
+        # layout metadata of every rank (small host-side all-gathers): identical for every chunk of
+        # a run, so it is exchanged once per distinct layout and cached -- the data path then has
+        # no host synchronisation besides the collective itself
+        key = (int(nfc), -1 if f_lo is None else int(f_lo), int(nm), moff[: nm + 1].tobytes())
+        cache = self.__dict__.setdefault("_layout_cache", {})
+        if key not in cache:
+            info = self.allgather_ints([nfc, -1 if f_lo is None else f_lo])
+            # elements per (m, unit frequency): identical on every rank
+            per_m = np.zeros(nm, dtype=np.int64)
+            if nfc > 0:
+                per_m = (moff[1 : nm + 1] - moff[:nm]) // nfc
+            per_m_all = self.allgather_ints(per_m)
+            cache[key] = (info, per_m_all.max(axis=0))
+        info, per_m = cache[key]
         nfc_all = info[:, 0]
-        # elements per (m, unit frequency): identical on every rank
-        per_m = np.zeros(nm, dtype=np.int64)
-        if nfc > 0:
-            per_m = (moff[1 : nm + 1] - moff[:nm]) // nfc
-        per_m_all = self.allgather_ints(per_m)
-        per_m = per_m_all.max(axis=0)
 
         my_lo, my_hi = int(m_lo[self.rank]), int(m_hi[self.rank])
         own = per_m[my_lo:my_hi].sum()
