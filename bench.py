@@ -201,6 +201,10 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--force-scatter", action="store_true", help="use the scatter output path at N = 1 too (diagnostic)")
+    ap.add_argument("--no-fence", action="store_true", help="skip the per-step fence collective (diagnostic only)")
+    ap.add_argument("--nccl-exchange", action="store_true",
+                    help="N > 1: regroup with an NCCL all-to-all after the pack kernel instead of the fused NVLink scatter")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -225,7 +229,10 @@ def main():
             return 0
         cores = os.cpu_count() or 1
         per_step = max(cores, args.cpu_sample)
-        f_list = [i * (tel.nfreq // F) for i in range(F)]
+        f_list = []
+        for j in range((F + 1) // 2):
+            f_list += [j % (tel.nfreq // 2), tel.nfreq - 1 - j % (tel.nfreq // 2)]
+        f_list = f_list[:F]
         tasks = cpu_sample_tasks(tel, f_list, per_step)
         arm = CpuArm(tel, tasks)
         vals = []
@@ -268,8 +275,16 @@ def main():
 
     eng = tel.engine
     nb, np_inc, lside, mmax = tel.nbase, 4, tel.lmax, tel.mmax
-    # frequencies spread over the band so that every step sees the full nside mix
-    f_list = np.array([(i * (tel.nfreq // F) + rank * max(1, tel.nfreq // (F * world))) % tel.nfreq for i in range(F)])
+    # Frequencies of this rank.  The cost of a unit grows with frequency (larger lmax, finer
+    # nside), so the shards are balanced the way a production run interleaves channels: rank r
+    # takes mirrored pairs (a, nfreq-1-a) around the band centre, a = r + j*world, so that
+    # every rank -- and the single GPU of the N = 1 run, which is rank 0 of this scheme -- sees
+    # the same mix of nside buckets per step (weak scaling: work per GPU fixed).
+    f_list = []
+    for j in range((F + 1) // 2):
+        a = (rank + j * world) % (tel.nfreq // 2)
+        f_list += [a, tel.nfreq - 1 - a]
+    f_list = np.array(f_list[:F])
     fgrid, bgrid = np.meshgrid(np.arange(F), np.arange(nb), indexing="ij")
     f_ind, b_ind = f_list[fgrid.ravel()], bgrid.ravel()
     lmax_u, _ = tel.unit_lmax(b_ind, f_ind)
@@ -296,7 +311,30 @@ def main():
     s1_bytes, s2_flops, s3_bytes = work.sum(axis=0)
     units_per_step = len(lmax_u)
 
+    # N > 1: every rank owns an m range for all world*F frequencies; the pack kernels of all ranks
+    # store into the owners' blocks over NVLink (fused exchange), a tiny all-reduce fences the step
+    scatter = None
+    if (world > 1 or args.force_scatter) and not args.nccl_exchange:
+        # CUDA IPC must work on every rank (PeerScatter raises on all of them otherwise): fall back
+        # to the NCCL all-to-all in that case
+        try:
+            scatter = parallel.PeerScatter(comm, world * F, nb, np_inc, lside, mmax)
+        except Exception as exc:  # noqa: BLE001
+            sys.stderr.write(f"[bench] rank {rank}: peer scatter unavailable ({exc}); using the NCCL exchange\n")
+            scatter = None
+        if scatter is not None:
+            gdims = [world * F, nb, np_inc, lside, mmax]
+            for _, _, units in prepared:
+                units["out0"] += rank * F
+
     def step_device():
+        if scatter is not None:
+            for nside, plan, units in prepared:
+                plan.transfer_units_scatter(units, 4, True, mmax, eng.precision, _lib.DSB_OUT_MMAJOR_C128, gdims,
+                                            scatter.block_ptrs, stream)
+            if not args.no_fence:
+                scatter.fence()
+            return None
         for nside, plan, units in prepared:
             plan.transfer_units(units, 4, True, mmax, eng.precision, _lib.DSB_OUT_MMAJOR_C128, dims,
                                 out_dev.data_ptr(), False, stream)
@@ -354,9 +392,18 @@ def main():
     ms_step = ms_total / args.steps
     value = world * units_per_step / (ms_step * 1e-3)
 
+    stage_ms_pack = prof_ms[2] / max(args.steps, 1)
     # ---- the frequency-major -> m-major exchange alone (N > 1): bytes each rank sends over NVLink
     exchange = None
-    if world > 1:
+    if scatter is not None:
+        _, mlo, mhi = parallel.split_counts(mmax + 1, world)
+        own_local = int((moff[mhi[rank]] - moff[mlo[rank]])) * 16
+        sent = int(total * 16 - own_local)
+        exchange = {"mode": "fused: pack kernel stores m-blocks into the owner's memory over NVLink (CUDA IPC)",
+                    "bytes_sent_per_gpu_per_step": sent, "pack_ms_per_step": stage_ms_pack,
+                    "gbs_per_gpu_during_pack": sent / (stage_ms_pack * 1e-3) / 1e9 if stage_ms_pack > 0 else None,
+                    "nvlink_peak_gbs": 900.0}
+    elif world > 1:
         ex_steps = max(3, args.steps)
         ms_ex = timed(lambda: comm.exchange_mblocks(out_dev, F, moff, mmax + 1, f_lo=rank * F), ex_steps, 2) / ex_steps
         _, mlo, mhi = parallel.split_counts(mmax + 1, world)
@@ -394,7 +441,7 @@ def main():
     # ---- end-to-end through the C ABI with host buffers
     e2e = None
     if not args.no_e2e:
-        out_host = torch.empty(total, dtype=torch.complex128, pin_memory=True)
+        out_host = torch.empty(total if scatter is None else 1, dtype=torch.complex128, pin_memory=True)
         h2d = sum(b.nbytes for b in host_beams.values()) + sum(u.nbytes for _, _, u in prepared)
         d2h = out_host.numel() * 16
 
@@ -409,6 +456,24 @@ def main():
                 comm.exchange_mblocks(out_dev, F, moff, mmax + 1, f_lo=rank * F)
             out_host.copy_(out_dev, non_blocking=True)
             torch.cuda.current_stream().synchronize()
+
+        if scatter is not None:
+            # the product a rank brings back to its host is the m range it owns, all frequencies
+            own_host = torch.empty(scatter.own_bytes // 16, dtype=torch.complex128, pin_memory=True)
+            d2h = own_host.numel() * 16
+            cudart = ctypes.CDLL("libcudart.so")
+
+            def step_e2e():  # noqa: F811
+                for nside, plan, units in prepared:
+                    for (ns, slot), b in host_beams.items():
+                        if ns == nside:
+                            plan.upload_beam(slot, b, stream)
+                    plan.transfer_units_scatter(units, 4, True, mmax, eng.precision, _lib.DSB_OUT_MMAJOR_C128, gdims,
+                                                scatter.block_ptrs, stream)
+                scatter.fence()
+                cudart.cudaMemcpyAsync(ctypes.c_void_p(own_host.data_ptr()), ctypes.c_void_p(scatter.own_ptr),
+                                       ctypes.c_size_t(d2h), 2, ctypes.c_void_p(stream))
+                torch.cuda.current_stream().synchronize()
 
         ms_e2e = timed(step_e2e, max(2, args.steps // 2), 1) / max(2, args.steps // 2)
         e2e = {"value": world * units_per_step / (ms_e2e * 1e-3), "unit": "units/s",

@@ -71,6 +71,11 @@ def _load():
         "dsb_beam_slots": (i32, [vp, i32]),
         "dsb_plan_build_tables": (i32, [vp, i32, i32, i32, i32, vp]),
         "dsb_transfer_units": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, P(i64), vp, i32, vp]),
+        "dsb_transfer_units_scatter": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, P(i64), vp, vp]),
+        "dsb_peer_alloc": (i32, [ctypes.c_size_t, P(vp), vp]),
+        "dsb_peer_open": (i32, [vp, P(vp)]),
+        "dsb_peer_close": (i32, [vp]),
+        "dsb_peer_free": (i32, [vp]),
         "dsb_mmajor_size": (i64, [i32, i32, i32, i32, i32, P(i64)]),
         "dsb_set_workspace_limit": (i32, [ctypes.c_size_t]),
         "dsb_set_profiling": (i32, [i32]),
@@ -150,6 +155,20 @@ class Plan:
 
     def build_tables(self, lmax, mmax, spin2, precision, stream=None):
         check(lib.dsb_plan_build_tables(self._h, lmax, mmax, int(spin2), precision, ctypes.c_void_p(stream or 0)))
+
+    def transfer_units_scatter(self, units, npol_sky, polarised, mmax, precision, out_kind, dims, block_ptrs,
+                               stream=None):
+        """m-major output with block m written at device address ``block_ptrs[m]`` (uint64 array,
+        possibly peer memory): the pack kernel does the frequency -> m regrouping itself."""
+        units = np.ascontiguousarray(units, dtype=UNIT_DTYPE)
+        d = (ctypes.c_int64 * len(dims))(*[int(x) for x in dims])
+        bp = np.ascontiguousarray(block_ptrs, dtype=np.uint64)
+        check(
+            lib.dsb_transfer_units_scatter(
+                self._h, units.ctypes.data_as(ctypes.c_void_p), len(units), npol_sky, int(polarised), mmax,
+                precision, out_kind, d, bp.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(stream or 0),
+            )
+        )
 
     def transfer_units(self, units, npol_sky, polarised, mmax, precision, out_kind, dims, out_ptr,
                        out_is_host, stream=None):

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <numeric>
 #include <map>
+#include <cstring>
 
 #include "dsb_common.cuh"
 
@@ -185,11 +186,16 @@ int pair_weights_for_units(dsb_plan *plan, const dsb_unit *units, int nunits, in
 
 }  // namespace
 
-extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, int nunits, int npol_sky,
-                                  int polarised, int mmax, int precision, int out_kind, const int64_t *dims,
-                                  void *out, int out_is_host, void *stream_) {
+// block_ptrs_host != NULL: scatter mode -- m-major block m is written at device address
+// block_ptrs_host[m] (local or peer memory) instead of out + offset(m).
+static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int nunits, int npol_sky, int polarised,
+                               int mmax, int precision, int out_kind, const int64_t *dims, void *out,
+                               int out_is_host, const uint64_t *block_ptrs_host, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  DSB_CHECK(plan && units_host && dims && out, DSB_ERR_INVALID, "dsb_transfer_units: NULL argument");
+  DSB_CHECK(plan && units_host && dims && (out || block_ptrs_host), DSB_ERR_INVALID,
+            "dsb_transfer_units: NULL argument");
+  DSB_CHECK(!block_ptrs_host || (out_kind != DSB_OUT_TARRAY_C128 && !out_is_host), DSB_ERR_INVALID,
+            "dsb_transfer_units_scatter: scatter mode writes m-major blocks in device memory");
   DSB_CHECK(nunits >= 0, DSB_ERR_INVALID, "dsb_transfer_units: negative unit count");
   DSB_CHECK(npol_sky == 1 || npol_sky == 3 || npol_sky == 4, DSB_ERR_INVALID,
             "dsb_transfer_units: npol_sky must be 1, 3 or 4 (got %d)", npol_sky);
@@ -293,6 +299,8 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
   int64_t mm_total = 0;
   if (!tarray) {
     mm_total = dsb_mmajor_size((int)d0, (int)d1, npol_out, lside, mmax_out, moff.data());
+    if (block_ptrs_host)
+      for (int m = 0; m <= mmax_out; ++m) moff[m] = (int64_t)block_ptrs_host[m];
     if (out_is_host) {
       DSB_CUDA(cudaMallocAsync(&out_dev, (size_t)mm_total * out_elem, stream));
       DSB_CUDA(cudaMemcpyAsync(out_dev, out, (size_t)mm_total * out_elem, cudaMemcpyHostToDevice, stream));
@@ -412,6 +420,7 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
     pp.d1 = d1;
     pp.npol_out = npol_out;
     pp.mmax_out = mmax_out;
+    pp.abs_ptrs = block_ptrs_host ? 1 : 0;
     void *pack_out = (tarray && out_is_host) ? (void *)stage : out_dev;
     if ((rc = launch_pack(pp, ud_dev, o0_dev, o1_dev, moff_dev, C0, C2, f64 ? 1 : 0, pack_out, stream)) !=
         DSB_OK)
@@ -438,4 +447,48 @@ extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, in
   }
   if (rc == DSB_OK && out_is_host) DSB_CUDA(cudaStreamSynchronize(stream));
   return rc;
+}
+
+extern "C" int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, int nunits, int npol_sky,
+                                  int polarised, int mmax, int precision, int out_kind, const int64_t *dims,
+                                  void *out, int out_is_host, void *stream_) {
+  return transfer_units_impl(plan, units_host, nunits, npol_sky, polarised, mmax, precision, out_kind, dims, out,
+                             out_is_host, nullptr, stream_);
+}
+
+extern "C" int dsb_transfer_units_scatter(dsb_plan *plan, const dsb_unit *units_host, int nunits, int npol_sky,
+                                          int polarised, int mmax, int precision, int out_kind,
+                                          const int64_t *dims, const uint64_t *block_ptrs_host, void *stream_) {
+  DSB_CHECK(block_ptrs_host != nullptr, DSB_ERR_INVALID, "dsb_transfer_units_scatter: block_ptrs is NULL");
+  return transfer_units_impl(plan, units_host, nunits, npol_sky, polarised, mmax, precision, out_kind, dims,
+                             nullptr, 0, block_ptrs_host, stream_);
+}
+
+// ---- peer (NVLink) buffers --------------------------------------------------------------
+// The m-range a rank owns is filled directly by every rank's pack kernel: the owner allocates
+// the buffer, publishes its CUDA IPC handle, the others map it and store through NVLink.
+extern "C" int dsb_peer_alloc(size_t bytes, void **dev_ptr, unsigned char *handle64) {
+  DSB_CHECK(dev_ptr && handle64, DSB_ERR_INVALID, "dsb_peer_alloc: NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  DSB_CUDA(cudaMalloc(dev_ptr, bytes ? bytes : 256));
+  DSB_CUDA(cudaMemset(*dev_ptr, 0, bytes ? bytes : 256));
+  cudaIpcMemHandle_t h;
+  DSB_CUDA(cudaIpcGetMemHandle(&h, *dev_ptr));
+  memcpy(handle64, &h, 64);
+  return DSB_OK;
+}
+extern "C" int dsb_peer_open(const unsigned char *handle64, void **dev_ptr) {
+  DSB_CHECK(dev_ptr && handle64, DSB_ERR_INVALID, "dsb_peer_open: NULL argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  DSB_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return DSB_OK;
+}
+extern "C" int dsb_peer_close(void *dev_ptr) {
+  if (dev_ptr) DSB_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return DSB_OK;
+}
+extern "C" int dsb_peer_free(void *dev_ptr) {
+  if (dev_ptr) DSB_CUDA(cudaFree(dev_ptr));
+  return DSB_OK;
 }

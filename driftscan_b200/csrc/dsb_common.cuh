@@ -258,6 +258,7 @@ struct PackParams {
   int64_t d0, d1;     // n_out0, n_out1
   int npol_out;
   int mmax_out;       // m-major: number of m blocks - 1
+  int abs_ptrs;       // m-major: moff[m] is the device address of block m (scatter to peers)
 };
 int launch_pack(const PackParams &pp, const UnitDev *units_dev, const int32_t *out0_dev,
                 const int32_t *out1_dev, const int64_t *moff_dev, const void *C0, const void *C2,

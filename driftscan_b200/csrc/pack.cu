@@ -69,7 +69,9 @@ __global__ void pack_mmajor_kernel(const PackParams pp, const UnitDev *__restric
   if (nl <= 0) return;
   const size_t per_unit = (size_t)2 * pp.npol_out * nl;
   const size_t total = per_unit * pp.nunits;
-  OT *o = out + moff[m];
+  // block m lives at out + moff[m], or (scatter mode) at the absolute device address moff[m],
+  // which may be a peer GPU's memory reached over NVLink
+  OT *o = pp.abs_ptrs ? reinterpret_cast<OT *>(moff[m]) : out + moff[m];
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     const int u = (int)(idx / per_unit);
@@ -86,8 +88,10 @@ __global__ void pack_mmajor_kernel(const PackParams pp, const UnitDev *__restric
       im = 0.0;
     }
     const size_t oi = ((((size_t)out0[u] * 2 + pm) * pp.d1 + out1[u]) * pp.npol_out + X) * nl + dl;
-    o[oi].x = re;
-    o[oi].y = im;
+    OT val;
+    val.x = re;
+    val.y = im;
+    o[oi] = val;  // one 16-byte (c128) / 8-byte (c64) store
   }
 }
 

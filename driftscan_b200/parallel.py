@@ -128,3 +128,120 @@ class Comm:
             lo = int(info[s, 1]) if info[s, 1] >= 0 else 0
             out.append((lo, lo + int(nfc_all[s]), blocks))
         return out
+
+
+class PeerScatter:
+    """Frequency-major -> m-major regrouping without a separate collective.
+
+    Every rank owns the m range ``split_counts(mmax + 1, size)`` gives it (the partition of
+    ``mpiutil.split_local``, drift/core/beamtransfer.py:547) and allocates the m-blocks of that
+    range for ALL frequencies, ``[m][freq][+-][baseline][pol][l - m]`` -- the layout of the
+    m-files it will write.  The buffers are published through CUDA IPC handles, so the pack
+    kernel of any rank stores its frequencies straight into the owner's block over NVLink
+    (``dsb_transfer_units_scatter``): the exchange of ``mpiutil.transpose_blocks``
+    (beamtransfer.py:632) is fused into the kernel that produces the data.  :meth:`fence` orders
+    the stores of all ranks before anyone reads its blocks.
+    """
+
+    def __init__(self, comm, nf_global, nb, npol, lside, mmax, elem_bytes=16):
+        import ctypes
+
+        from . import _lib
+
+        self.comm, self._lib = comm, _lib
+        self.nf, self.nb, self.npol, self.lside, self.mmax, self.elem = nf_global, nb, npol, lside, mmax, elem_bytes
+        _, m_lo, m_hi = split_counts(mmax + 1, comm.size)
+        self.m_lo, self.m_hi = m_lo, m_hi
+        per_m = np.array([nf_global * 2 * nb * npol * max(lside + 1 - m, 0) for m in range(mmax + 1)], dtype=np.int64)
+        self.per_m = per_m
+        own = int(per_m[m_lo[comm.rank] : m_hi[comm.rank]].sum()) * elem_bytes
+        self.own_bytes = own
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.check(_lib.lib.dsb_peer_alloc(own, ctypes.byref(ptr), handle))
+        self.own_ptr = ptr.value
+        handles = self._allgather_bytes(bytes(handle))
+        self._opened = []
+        base = []
+        err = None
+        for r in range(comm.size):
+            if r == comm.rank:
+                base.append(self.own_ptr)
+                continue
+            p = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+            try:
+                _lib.check(_lib.lib.dsb_peer_open(buf, ctypes.byref(p)))
+            except Exception as exc:  # noqa: BLE001 -- reported after the collective below
+                err = exc
+                base.append(0)
+                continue
+            self._opened.append(p.value)
+            base.append(p.value)
+        # every rank learns whether every mapping succeeded (this collective also orders the
+        # zero-fill of the buffers before the first store); failure is raised on all ranks
+        oks = comm.allgather_ints([0 if err else 1])
+        if not oks.all():
+            self.close()
+            raise RuntimeError(f"CUDA IPC mapping of the peer m-block buffers failed on rank(s) "
+                               f"{np.flatnonzero(oks[:, 0] == 0).tolist()}: {err}")
+        self.block_ptrs = np.zeros(mmax + 1, dtype=np.uint64)
+        for r in range(comm.size):
+            off = 0
+            for m in range(m_lo[r], m_hi[r]):
+                self.block_ptrs[m] = base[r] + off
+                off += int(per_m[m]) * elem_bytes
+
+    def _allgather_bytes(self, payload):
+        import torch
+
+        comm = self.comm
+        if comm.size == 1:
+            return [payload]
+        backend = comm._dist.get_backend()
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
+        out = [torch.empty_like(mine) for _ in range(comm.size)]
+        comm._dist.all_gather(out, mine)
+        return [bytes(o.cpu().numpy().tobytes()) for o in out]
+
+    def fence(self):
+        """All stores issued by every rank before this call are complete when the (stream-ordered)
+        collective behind it completes on the local stream."""
+        if self.comm.size > 1:
+            import torch
+
+            t = self.__dict__.get("_token")
+            if t is None:
+                t = self._token = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+            self.comm._dist.all_reduce(t)
+
+    def own_block_offset(self, m):
+        """Byte offset of block ``m`` (owned by this rank) inside the local buffer."""
+        lo = int(self.m_lo[self.comm.rank])
+        return int(self.per_m[lo:m].sum()) * self.elem
+
+    def read_own(self, m):
+        """Host copy of an owned block: complex ``[nf, 2, nb, npol, lside + 1 - m]``."""
+        import ctypes
+
+        import torch
+
+        n = int(self.per_m[m])
+        dt = np.complex128 if self.elem == 16 else np.complex64
+        out = np.empty(n, dtype=dt)
+        torch.cuda.synchronize()
+        rc = ctypes.CDLL("libcudart.so").cudaMemcpy(
+            ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(self.own_ptr + self.own_block_offset(m)),
+            ctypes.c_size_t(out.nbytes), 2)
+        if rc != 0:
+            raise RuntimeError(f"cudaMemcpy failed ({rc})")
+        return out.reshape(self.nf, 2, self.nb, self.npol, self.lside + 1 - m)
+
+    def close(self):
+        for p in self._opened:
+            self._lib.lib.dsb_peer_close(p)
+        self._opened = []
+        if self.own_ptr:
+            self._lib.lib.dsb_peer_free(self.own_ptr)
+            self.own_ptr = None

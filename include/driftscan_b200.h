@@ -118,6 +118,23 @@ int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, int nunits, i
                        int polarised, int mmax, int precision, int out_kind, const int64_t *dims,
                        void *out, int out_is_host, void *stream);
 
+/* Same computation, m-major output scattered to per-m destinations: block m (layout as
+ * DSB_OUT_MMAJOR_*, dims = {n_out0, n_out1, npol_out, lside, mmax}) is written at the device
+ * address block_ptrs_host[m] (mmax+1 entries), which may lie in a peer GPU's memory mapped
+ * with dsb_peer_open.  This is the frequency-major -> m-major regrouping of
+ * mpiutil.transpose_blocks (drift/core/beamtransfer.py:632) fused into the pack kernel: every
+ * rank stores its frequencies straight into the m-blocks their owner will write to disk. */
+int dsb_transfer_units_scatter(dsb_plan *plan, const dsb_unit *units_host, int nunits, int npol_sky,
+                               int polarised, int mmax, int precision, int out_kind, const int64_t *dims,
+                               const uint64_t *block_ptrs_host, void *stream);
+
+/* Peer buffers for the scatter above: the owner allocates (zero-filled) device memory and gets
+ * a 64-byte CUDA IPC handle to publish; the other ranks of the node map it. */
+int dsb_peer_alloc(size_t bytes, void **dev_ptr, unsigned char *handle64);
+int dsb_peer_open(const unsigned char *handle64, void **dev_ptr);
+int dsb_peer_close(void *dev_ptr);
+int dsb_peer_free(void *dev_ptr);
+
 /* Size in elements (complex numbers) of an m-major buffer and the per-m block
  * offsets (mmax+2 entries, last = total). */
 int64_t dsb_mmajor_size(int n_out0, int n_out1, int npol, int lside, int mmax, int64_t *offsets);
