@@ -325,14 +325,22 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         const uint32_t mb = chunk & 1;
         mbar_wait(&mfull[mb], (chunk >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // two TMEM loads in flight per wait: the drain of a chunk must stay shorter than the two
+        // MMAs that fill the other chunk buffer
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (half * 64 + g * 16 < N) {
-            uint32_t v[16];
-            tmem_ld16(lane_base + mb * 128 + g * 16, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int g = 0; g < 4; g += 2) {
+          const bool a0 = half * 64 + g * 16 < N, a1 = half * 64 + (g + 1) * 16 < N;
+          uint32_t v0[16], v1[16];
+          if (a0) tmem_ld16(lane_base + mb * 128 + g * 16, v0);
+          if (a1) tmem_ld16(lane_base + mb * 128 + (g + 1) * 16, v1);
+          if (a0) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (a0) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sums[g * 16 + i] += __uint_as_float(v[i]);
+            for (int i = 0; i < 16; ++i) sums[g * 16 + i] += __uint_as_float(v0[i]);
+          }
+          if (a1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sums[(g + 1) * 16 + i] += __uint_as_float(v1[i]);
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

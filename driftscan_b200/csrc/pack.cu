@@ -59,39 +59,52 @@ __global__ void pack_tarray_kernel(const PackParams pp, const UnitDev *__restric
   }
 }
 
+// One warp per output row (unit, +-m slot, polarisation) of block m: the row is contiguous in
+// l both in the product and -- two interleaved parity series -- in the contraction output, so
+// all index arithmetic is per row and the stores are full 512-byte warp transactions (local
+// HBM, or a peer GPU's memory over NVLink in scatter mode).
 template <typename CT, typename OT>
-__global__ void pack_mmajor_kernel(const PackParams pp, const UnitDev *__restrict__ units,
-                                   const int32_t *__restrict__ out0, const int32_t *__restrict__ out1,
-                                   const int64_t *__restrict__ moff, const CT *__restrict__ C0,
-                                   const CT *__restrict__ C2, OT *__restrict__ out) {
+__global__ void __launch_bounds__(256)
+pack_mmajor_kernel(const PackParams pp, const UnitDev *__restrict__ units, const int32_t *__restrict__ out0,
+                   const int32_t *__restrict__ out1, const int64_t *__restrict__ moff, const CT *__restrict__ C0,
+                   const CT *__restrict__ C2, OT *__restrict__ out) {
   const int m = blockIdx.y;
   const int nl = pp.lside + 1 - m;
   if (nl <= 0) return;
-  const size_t per_unit = (size_t)2 * pp.npol_out * nl;
-  const size_t total = per_unit * pp.nunits;
   // block m lives at out + moff[m], or (scatter mode) at the absolute device address moff[m],
   // which may be a peer GPU's memory reached over NVLink
   OT *o = pp.abs_ptrs ? reinterpret_cast<OT *>(moff[m]) : out + moff[m];
-  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const int u = (int)(idx / per_unit);
-    size_t r = idx % per_unit;
-    const int pm = (int)(r / ((size_t)pp.npol_out * nl));
-    r %= (size_t)pp.npol_out * nl;
-    const int X = (int)(r / nl);
-    const int dl = (int)(r % nl);
+  const int lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int nrows = pp.nunits * 2 * pp.npol_out;
+  for (int row = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); row < nrows; row += gridDim.x * warps_per_cta) {
+    const int X = row % pp.npol_out;
+    const int pm = (row / pp.npol_out) & 1;
+    const int u = row / (2 * pp.npol_out);
     const UnitDev ud = units[u];
-    double re, im;
-    fetch<CT>(pp, ud, u, X, pm, m + dl, m, C0, C2, re, im);
-    if (m == 0 && pm == 1) {  // the negative-m slot of m = 0 is left zero (beamtransfer.py:624)
-      re = 0.0;
-      im = 0.0;
+    OT *orow = o + ((((size_t)out0[u] * 2 + pm) * pp.d1 + out1[u]) * pp.npol_out + X) * nl;
+    // zero rows: polarisation not computed, m beyond the unit's range, or the negative-m slot of
+    // m = 0 (left zero by the reference, beamtransfer.py:624)
+    const bool live = X < pp.npol_sky && m <= ud.mmax && !(m == 0 && pm == 1);
+    const bool spin0 = (X == 0 || X == 3);
+    const CT *C = spin0 ? C0 : C2;
+    const size_t ncols = spin0 ? pp.ncols0 : pp.ncols2;
+    const size_t col = spin0 ? (size_t)u * pp.cpu0 + (X == 0 ? 0 : 4) + pm * 2 : (size_t)u * 8 + (X == 1 ? 0 : 4) + pm * 2;
+    const CT *c_even = C + ((size_t)(2 * m) * ncols + col) * pp.NP;      // l - m even
+    const CT *c_odd = C + ((size_t)(2 * m + 1) * ncols + col) * pp.NP;   // l - m odd
+    const int lcut = ud.lmax - m;  // rows above the unit's lmax are zero (telescope.py:792-802)
+    for (int dl = lane; dl < nl; dl += 32) {
+      OT val;
+      val.x = 0;
+      val.y = 0;
+      if (live && dl <= lcut) {
+        const CT *c = (dl & 1) ? c_odd : c_even;
+        const int n = dl >> 1;
+        val.x = c[n];
+        val.y = c[n + pp.NP];
+      }
+      orow[dl] = val;
     }
-    const size_t oi = ((((size_t)out0[u] * 2 + pm) * pp.d1 + out1[u]) * pp.npol_out + X) * nl + dl;
-    OT val;
-    val.x = re;
-    val.y = im;
-    o[oi] = val;  // one 16-byte (c128) / 8-byte (c64) store
   }
 }
 
@@ -109,8 +122,8 @@ int launch_pack(const PackParams &pp, const UnitDev *units_dev, const int32_t *o
       pack_tarray_kernel<float><<<grid, 256, 0, stream>>>(pp, units_dev, out0_dev, (const float *)C0,
                                                           (const float *)C2, (double2 *)out);
   } else {
-    const size_t per_m = (size_t)2 * pp.npol_out * (pp.lside + 1) * pp.nunits;
-    dim3 grid((unsigned)std::min<size_t>((per_m + 255) / 256, 2048), pp.mmax_out + 1);
+    const size_t rows = (size_t)2 * pp.npol_out * pp.nunits;
+    dim3 grid((unsigned)std::min<size_t>((rows + 7) / 8, 1024), pp.mmax_out + 1);
     const bool c128 = pp.out_kind == DSB_OUT_MMAJOR_C128;
     if (c_is_f64 && c128)
       pack_mmajor_kernel<double, double2><<<grid, 256, 0, stream>>>(
