@@ -420,6 +420,12 @@ def main():
         hbm_peak, tf_peak, peak_src = peaks["hbm_gbs"], peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]), "measured"
     else:
         hbm_peak, tf_peak, peak_src = 6650.0, 1400.0, "fallback"
+    # measured DRAM traffic per step of each stage (ncu launch list of this same command, committed)
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and F == 2 and args.precision == "fp32x3":
+        with open(tpath) as fh:
+            traffic = {k: v.get("dram_bytes_per_step") for k, v in json.load(fh).items() if isinstance(v, dict)}
     stage_ms = [prof_ms[i] / max(args.steps, 1) for i in range(3)]
     stage_launch = [int(prof_n[i]) for i in range(3)]
     ring_gbs = s1_bytes / (stage_ms[0] * 1e-3) / 1e9 if stage_ms[0] > 0 else 0.0
@@ -427,14 +433,17 @@ def main():
     pack_gbs = s3_bytes / (stage_ms[2] * 1e-3) / 1e9 if stage_ms[2] > 0 else 0.0
     # executed tensor flops: six bf16 products per algorithmic multiply-add
     roof_ring = {"kernel": "ringfft_kernel<float>", "bound": "hbm", "achieved": ring_gbs, "peak": hbm_peak,
-                 "unit": "GB/s", "frac": ring_gbs / hbm_peak, "traffic": None, "ms_per_step": stage_ms[0],
+                 "unit": "GB/s", "frac": ring_gbs / hbm_peak, "traffic": traffic.get("ringfft_kernel"), "ms_per_step": stage_ms[0],
+                 "algorithmic_bytes_per_step": float(s1_bytes),
                  "peak_source": peak_src}
     roof_leg = {"kernel": "legendre_tc_kernel", "bound": "tensor", "achieved": leg_tflops, "peak": tf_peak,
-                "unit": "TFLOP/s", "frac": leg_tflops / tf_peak, "traffic": None, "ms_per_step": stage_ms[1],
+                "unit": "TFLOP/s", "frac": leg_tflops / tf_peak, "traffic": traffic.get("legendre_tc_kernel"),
+                "ms_per_step": stage_ms[1], "algorithmic_flops_per_step": float(s2_flops),
                 "executed_tflops_bf16": 6 * leg_tflops, "executed_frac": 6 * leg_tflops / tf_peak,
                 "peak_source": peak_src}
     roof_pack = {"kernel": "pack_mmajor_kernel", "bound": "hbm", "achieved": pack_gbs, "peak": hbm_peak,
-                 "unit": "GB/s", "frac": pack_gbs / hbm_peak, "traffic": None, "ms_per_step": stage_ms[2],
+                 "unit": "GB/s", "frac": pack_gbs / hbm_peak, "traffic": traffic.get("pack_mmajor_kernel"),
+                 "ms_per_step": stage_ms[2], "algorithmic_bytes_per_step": float(s3_bytes),
                  "peak_source": peak_src}
     dominant = max((roof_ring, roof_leg, roof_pack), key=lambda r: r["ms_per_step"])
 

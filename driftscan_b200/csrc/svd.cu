@@ -33,103 +33,206 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// R: [batch][ldr rows][ncols] ; idx: [batch][ldr] active row list ; nact: [batch]
-__global__ void __launch_bounds__(512)
-jacobi_rows_kernel(zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
-                   const int32_t *__restrict__ nact_all, int ip0, int ip1, int max_sweeps, double tol,
-                   int32_t *__restrict__ sweeps_out) {
-  const int b = blockIdx.x;
-  zc *R = Rall + (size_t)b * ldr * ncols;
-  const int32_t *idx = idx_all + (size_t)b * ldr;
+// ---------------------------------------------------------------------------------------------
+// One-sided Jacobi pass, one launch per round-robin step.
+//   R: [batch][ldr rows][ncols] ; idx: [batch][ldr] active row list ; nact: [batch]
+// All row pairs of one tournament step are disjoint, so a step is one launch with one CTA per
+// (pair, matrix): the whole GPU works on every matrix of the batch at once (the first version ran
+// a matrix on a single CTA and took 48 s for one 1520 x 936 block).  A pair is read once for
+// the three inner products and once more (L1/L2) for the rotation.  Row norms over the
+// inner-product columns are cached per sweep: a pair with a numerically zero row (the null rows
+// of a rank-deficient block, i.e. most rows of a beam-transfer block after the first sweep)
+// is dropped after two 8-byte loads instead of two row reads.
+// ---------------------------------------------------------------------------------------------
+
+// nrm2[b][r] = |row idx[r]|^2 over columns [ip0, ip1); amax[b] = max_r (only when set_max)
+__global__ void __launch_bounds__(256)
+row_norms_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
+                 const int32_t *__restrict__ nact_all, int ip0, int ip1, double *__restrict__ nrm2_all,
+                 unsigned long long *__restrict__ amax_all, int set_max, const int32_t *__restrict__ done_all) {
+  const int b = blockIdx.y;
+  if (done_all[b]) return;
   const int n = nact_all[b];
-  __shared__ int s_rot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  if (n < 2 || ip1 <= ip0) {
-    if (threadIdx.x == 0 && sweeps_out) sweeps_out[b] = 0;
-    return;
+  const int r = blockIdx.x * nwarps + warp;
+  if (r >= n) return;
+  const zc *x = Rall + ((size_t)b * ldr + idx_all[(size_t)b * ldr + r]) * ncols;
+  double a = 0.0;
+  for (int c = ip0 + lane; c < ip1; c += 32) a += x[c].x * x[c].x + x[c].y * x[c].y;
+  a = warp_sum(a);
+  if (lane == 0) {
+    nrm2_all[(size_t)b * ldr + r] = a;
+    if (set_max) atomicMax(&amax_all[b], (unsigned long long)__double_as_longlong(a));
   }
-  if (tol <= 0.0) tol = 2e-15 * sqrt((double)(ip1 - ip0));  // rounding level of the inner product
+}
+
+constexpr int kPairThreads = 128;
+
+__global__ void __launch_bounds__(kPairThreads)
+jacobi_pair_kernel(zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
+                   const int32_t *__restrict__ nact_all, int ip0, int ip1, int step, double tol,
+                   double *__restrict__ nrm2_all, const unsigned long long *__restrict__ amax_all,
+                   int32_t *__restrict__ rot_all, const int32_t *__restrict__ done_all) {
+  const int b = blockIdx.y;
+  if (done_all[b]) return;
+  const int n = nact_all[b];
+  if (n < 2) return;
   const int P = (n + 1) & ~1;  // players of the round-robin tournament (one dummy if n is odd)
+  const int k = blockIdx.x;
+  if (step >= P - 1 || k >= P / 2) return;
+  int pa, pb;
+  if (k == 0) {
+    pa = P - 1;
+    pb = step;
+  } else {
+    pa = (step + k) % (P - 1);
+    pb = (step - k + (P - 1)) % (P - 1);
+  }
+  if (pa >= n || pb >= n) return;
+  if (pa > pb) {
+    const int t = pa;
+    pa = pb;
+    pb = t;
+  }
+  double *nrm2 = nrm2_all + (size_t)b * ldr;
   // Rows whose norm is at the rounding level of the largest row are numerically zero: a
   // pair involving such a row is not rotated (its angle to anything is noise and would
   // never settle); singular values below 1e-14 of the largest are noise in any case.
-  __shared__ unsigned long long s_amax;
-  if (threadIdx.x == 0) s_amax = 0ull;
-  __syncthreads();
-  for (int r = warp; r < n; r += nwarps) {
-    const zc *x = R + (size_t)idx[r] * ncols;
-    double a = 0.0;
-    for (int c = ip0 + lane; c < ip1; c += 32) a += x[c].x * x[c].x + x[c].y * x[c].y;
-    a = warp_sum(a);
-    if (lane == 0) atomicMax(&s_amax, (unsigned long long)__double_as_longlong(a));
+  const double floor2 = 1e-28 * __longlong_as_double((long long)amax_all[b]);
+  if (nrm2[pa] < floor2 || nrm2[pb] < floor2) return;
+  const int32_t *idx = idx_all + (size_t)b * ldr;
+  zc *x = Rall + ((size_t)b * ldr + idx[pa]) * ncols;
+  zc *y = Rall + ((size_t)b * ldr + idx[pb]) * ncols;
+  double a = 0.0, bb = 0.0, cr = 0.0, ci = 0.0;
+  for (int c = ip0 + threadIdx.x; c < ip1; c += kPairThreads) {
+    const zc xv = x[c], yv = y[c];
+    a += xv.x * xv.x + xv.y * xv.y;
+    bb += yv.x * yv.x + yv.y * yv.y;
+    // <x, y> = sum x conj(y)
+    cr += xv.x * yv.x + xv.y * yv.y;
+    ci += xv.y * yv.x - xv.x * yv.y;
+  }
+  a = warp_sum(a);
+  bb = warp_sum(bb);
+  cr = warp_sum(cr);
+  ci = warp_sum(ci);
+  __shared__ double s_red[kPairThreads / 32][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    s_red[warp][0] = a;
+    s_red[warp][1] = bb;
+    s_red[warp][2] = cr;
+    s_red[warp][3] = ci;
   }
   __syncthreads();
-  const double floor2 = 1e-28 * __longlong_as_double((long long)s_amax);
-  int sweep = 0;
-  for (; sweep < max_sweeps; ++sweep) {
-    if (threadIdx.x == 0) s_rot = 0;
-    __syncthreads();
-    for (int step = 0; step < P - 1; ++step) {
-      for (int k = warp; k < P / 2; k += nwarps) {
-        int pa, pb;
-        if (k == 0) {
-          pa = P - 1;
-          pb = step;
-        } else {
-          pa = (step + k) % (P - 1);
-          pb = (step - k + (P - 1)) % (P - 1);
-        }
-        if (pa >= n || pb >= n) continue;
-        if (pa > pb) {
-          const int t = pa;
-          pa = pb;
-          pb = t;
-        }
-        zc *x = R + (size_t)idx[pa] * ncols;
-        zc *y = R + (size_t)idx[pb] * ncols;
-        double a = 0.0, bb = 0.0, cr = 0.0, ci = 0.0;
-        for (int c = ip0 + lane; c < ip1; c += 32) {
-          const zc xv = x[c], yv = y[c];
-          a += xv.x * xv.x + xv.y * xv.y;
-          bb += yv.x * yv.x + yv.y * yv.y;
-          // <x, y> = sum x conj(y)
-          cr += xv.x * yv.x + xv.y * yv.y;
-          ci += xv.y * yv.x - xv.x * yv.y;
-        }
-        a = warp_sum(a);
-        bb = warp_sum(bb);
-        cr = warp_sum(cr);
-        ci = warp_sum(ci);
-        const double cabs2 = cr * cr + ci * ci;
-        if (cabs2 <= tol * tol * a * bb || cabs2 == 0.0) continue;
-        if (a < floor2 || bb < floor2) continue;
-        const double cabs = sqrt(cabs2);
-        const double zeta = (bb - a) / (2.0 * cabs);
-        const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double cs = rsqrt(1.0 + t * t);
-        const double sn = cs * t;
-        // e^{i phi} = c / |c|
-        const double er = cr / cabs, ei = ci / cabs;
-        // x' = cs x - sn e^{i phi} y ;  y' = sn e^{-i phi} x + cs y
-        for (int c = lane; c < ncols; c += 32) {
-          const zc xv = x[c], yv = y[c];
-          zc xn, yn;
-          xn.x = cs * xv.x - sn * (er * yv.x - ei * yv.y);
-          xn.y = cs * xv.y - sn * (er * yv.y + ei * yv.x);
-          yn.x = sn * (er * xv.x + ei * xv.y) + cs * yv.x;
-          yn.y = sn * (er * xv.y - ei * xv.x) + cs * yv.y;
-          x[c] = xn;
-          y[c] = yn;
-        }
-        if (lane == 0) s_rot = 1;
-      }
-      __syncthreads();
+  a = bb = cr = ci = 0.0;
+#pragma unroll
+  for (int w = 0; w < kPairThreads / 32; ++w) {
+    a += s_red[w][0];
+    bb += s_red[w][1];
+    cr += s_red[w][2];
+    ci += s_red[w][3];
+  }
+  if (tol <= 0.0) tol = 2e-15 * sqrt((double)(ip1 - ip0));  // rounding level of the inner product
+  const double cabs2 = cr * cr + ci * ci;
+  if (cabs2 <= tol * tol * a * bb || cabs2 == 0.0 || a < floor2 || bb < floor2) {
+    if (threadIdx.x == 0) {
+      nrm2[pa] = a;
+      nrm2[pb] = bb;
     }
-    const int rotated = s_rot;
-    __syncthreads();
-    if (!rotated) break;
+    return;
   }
-  if (threadIdx.x == 0 && sweeps_out) sweeps_out[b] = sweep;
+  const double cabs = sqrt(cabs2);
+  const double zeta = (bb - a) / (2.0 * cabs);
+  const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  const double cs = rsqrt(1.0 + t * t);
+  const double sn = cs * t;
+  // e^{i phi} = c / |c|
+  const double er = cr / cabs, ei = ci / cabs;
+  // x' = cs x - sn e^{i phi} y ;  y' = sn e^{-i phi} x + cs y
+  for (int c = threadIdx.x; c < ncols; c += kPairThreads) {
+    const zc xv = x[c], yv = y[c];
+    zc xn, yn;
+    xn.x = cs * xv.x - sn * (er * yv.x - ei * yv.y);
+    xn.y = cs * xv.y - sn * (er * yv.y + ei * yv.x);
+    yn.x = sn * (er * xv.x + ei * xv.y) + cs * yv.x;
+    yn.y = sn * (er * xv.y - ei * xv.x) + cs * yv.y;
+    x[c] = xn;
+    y[c] = yn;
+  }
+  if (threadIdx.x == 0) {
+    nrm2[pa] = a - t * cabs;  // exact for the rotation; refreshed from the data every sweep
+    nrm2[pb] = bb + t * cabs;
+    atomicAdd(&rot_all[b], 1);
+  }
+}
+
+// end of a sweep: a matrix that saw no rotation is converged
+__global__ void sweep_end_kernel(int batch, int32_t *__restrict__ rot, int32_t *__restrict__ done,
+                                 int32_t *__restrict__ sweeps, int32_t *__restrict__ nleft) {
+  int left = 0;
+  for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+    if (!done[b]) {
+      sweeps[b] += 1;
+      if (rot[b] == 0) done[b] = 1;
+      else left += 1;
+    }
+    rot[b] = 0;
+  }
+  if (left) atomicAdd(nleft, left);
+}
+
+__global__ void max_nact_kernel(int batch, const int32_t *__restrict__ nact, int32_t *__restrict__ out) {
+  int mx = 0;
+  for (int b = threadIdx.x; b < batch; b += blockDim.x) mx = max(mx, nact[b]);
+  atomicMax(out, mx);
+}
+
+struct JacobiScratch {
+  double *nrm2 = nullptr;             // [batch][ldr]
+  unsigned long long *amax = nullptr;  // [batch]
+  int32_t *rot = nullptr, *done = nullptr, *flag = nullptr;  // [batch], [batch], [2]
+  int32_t *h_flag = nullptr;          // pinned [2]
+};
+
+// One Jacobi pass over the active rows of every matrix; sweeps[b] receives the sweep count.
+// `nmax` = upper bound of nact (-1: read it back from the device).
+static int jacobi_pass(zc *R, int ldr, int ncols, const int32_t *idx, const int32_t *nact, int batch, int ip0, int ip1,
+                       int nmax, int max_sweeps, double tol, int32_t *sweeps, JacobiScratch &js, cudaStream_t stream) {
+  DSB_CUDA(cudaMemsetAsync(sweeps, 0, sizeof(int32_t) * batch, stream));
+  if (ip1 <= ip0) return DSB_OK;
+  if (nmax < 0) {
+    DSB_CUDA(cudaMemsetAsync(js.flag + 1, 0, sizeof(int32_t), stream));
+    max_nact_kernel<<<1, 256, 0, stream>>>(batch, nact, js.flag + 1);
+    DSB_LAUNCH_CHECK();
+    DSB_CUDA(cudaMemcpyAsync(js.h_flag + 1, js.flag + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    DSB_CUDA(cudaStreamSynchronize(stream));
+    nmax = js.h_flag[1];
+  }
+  if (nmax < 2) return DSB_OK;
+  const int P = (nmax + 1) & ~1;
+  DSB_CUDA(cudaMemsetAsync(js.amax, 0, sizeof(unsigned long long) * batch, stream));
+  DSB_CUDA(cudaMemsetAsync(js.rot, 0, sizeof(int32_t) * batch, stream));
+  DSB_CUDA(cudaMemsetAsync(js.done, 0, sizeof(int32_t) * batch, stream));
+  const dim3 gnorm((nmax + 7) / 8, batch), gpair(P / 2, batch);
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    row_norms_kernel<<<gnorm, 256, 0, stream>>>(R, ldr, ncols, idx, nact, ip0, ip1, js.nrm2, js.amax, sweep == 0,
+                                                js.done);
+    DSB_LAUNCH_CHECK();
+    for (int step = 0; step < P - 1; ++step) {
+      jacobi_pair_kernel<<<gpair, kPairThreads, 0, stream>>>(R, ldr, ncols, idx, nact, ip0, ip1, step, tol, js.nrm2,
+                                                             js.amax, js.rot, js.done);
+    }
+    count_launch(P - 2);
+    DSB_LAUNCH_CHECK();
+    DSB_CUDA(cudaMemsetAsync(js.flag, 0, sizeof(int32_t), stream));
+    sweep_end_kernel<<<1, 256, 0, stream>>>(batch, js.rot, js.done, sweeps, js.flag);
+    DSB_LAUNCH_CHECK();
+    DSB_CUDA(cudaMemcpyAsync(js.h_flag, js.flag, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    DSB_CUDA(cudaStreamSynchronize(stream));
+    if (js.h_flag[0] == 0) break;
+  }
+  return DSB_OK;
 }
 
 // Row norms over the inner-product columns, descending order, and the rank decision that
@@ -404,6 +507,14 @@ extern "C" int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int b
     DSB_CUDA(cudaMallocAsync((void **)&snact, sizeof(int32_t) * batch, stream));
   }
 
+  JacobiScratch js;
+  DSB_CUDA(cudaMallocAsync((void **)&js.nrm2, sizeof(double) * (size_t)batch * ntel, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&js.amax, sizeof(unsigned long long) * batch, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&js.rot, sizeof(int32_t) * batch, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&js.done, sizeof(int32_t) * batch, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&js.flag, sizeof(int32_t) * 2, stream));
+  DSB_CUDA(cudaMallocHost((void **)&js.h_flag, sizeof(int32_t) * 2));
+
   const int max_sweeps = 60;
   const double tol = 0.0;  // derive from the inner-product length
   dim3 gprep(64, batch);
@@ -411,24 +522,20 @@ extern "C" int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int b
   DSB_LAUNCH_CHECK();
   if (npol > 1) {
     // SVD 1: image of the whole whitened matrix
-    jacobi_rows_kernel<<<batch, 512, 0, stream>>>(R, ntel, ncols, idx, nact, 0, nsky, max_sweeps, tol, sweeps);
-    DSB_LAUNCH_CHECK();
+    DSB_TRY(jacobi_pass(R, ntel, ncols, idx, nact, batch, 0, nsky, ntel, max_sweeps, tol, sweeps, js, stream));
     rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, 0, nsky, 0, rtol1, ntel, sig, tmp,
                                                   nullptr, 0);
     DSB_LAUNCH_CHECK();
     // SVD 2: null space of the polarised columns
-    jacobi_rows_kernel<<<batch, 512, 0, stream>>>(R, ntel, ncols, idx, nact, nl, nsky, max_sweeps, tol,
-                                                  sweeps + batch);
-    DSB_LAUNCH_CHECK();
+    DSB_TRY(jacobi_pass(R, ntel, ncols, idx, nact, batch, nl, nsky, -1, max_sweeps, tol, sweeps + batch, js, stream));
     rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, nl, nsky, 1, polsvcut, nsky - nl,
                                                   sig, tmp, nullptr, 0);
     DSB_LAUNCH_CHECK();
   }
   // SVD 3: temperature columns of the surviving rows
   DSB_CUDA(cudaMemsetAsync(sv_dev, 0, sizeof(double) * (size_t)batch * svd_len, stream));
-  jacobi_rows_kernel<<<batch, 512, 0, stream>>>(R, ntel, ncols, idx, nact, 0, nl, max_sweeps, tol,
-                                                sweeps + 2 * batch);
-  DSB_LAUNCH_CHECK();
+  DSB_TRY(jacobi_pass(R, ntel, ncols, idx, nact, batch, 0, nl, npol > 1 ? -1 : ntel, max_sweeps, tol,
+                      sweeps + 2 * batch, js, stream));
   rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, 0, nl, 2, 0.0, nl, sig, tmp, sv_dev,
                                                 svd_len);
   DSB_LAUNCH_CHECK();
@@ -437,9 +544,8 @@ extern "C" int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int b
                                              (zc *)beam_ut_dev, S, sidx, snact, nmodes_dev);
   DSB_LAUNCH_CHECK();
   if (want_inv) {
-    jacobi_rows_kernel<<<batch, 512, 0, stream>>>(S, svd_len, scols, sidx, snact, 0, nsky, max_sweeps, tol,
-                                                  sweeps + 3 * batch);
-    DSB_LAUNCH_CHECK();
+    DSB_TRY(jacobi_pass(S, svd_len, scols, sidx, snact, batch, 0, nsky, -1, max_sweeps, tol, sweeps + 3 * batch, js,
+                        stream));
     dim3 gp(32, batch);
     svd_pinv_kernel<<<gp, 256, sizeof(double) * svd_len, stream>>>(S, snact, nsky, svd_len, (zc *)invbeam_dev);
     DSB_LAUNCH_CHECK();
@@ -454,6 +560,12 @@ extern "C" int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int b
   cudaFreeAsync(sig, stream);
   cudaFreeAsync(nact, stream);
   cudaFreeAsync(sweeps, stream);
+  cudaFreeAsync(js.nrm2, stream);
+  cudaFreeAsync(js.amax, stream);
+  cudaFreeAsync(js.rot, stream);
+  cudaFreeAsync(js.done, stream);
+  cudaFreeAsync(js.flag, stream);
+  cudaFreeHost(js.h_flag);
   if (want_inv) {
     cudaFreeAsync(S, stream);
     cudaFreeAsync(sidx, stream);
