@@ -83,6 +83,14 @@ def _load():
         "dsb_debug_gemm_tc": (i32, [i32, i32, i32, i32, i32, vp, vp, vp, vp]),
         "dsb_svd_chain": (i32, [vp, vp, i32, i32, i32, i32, i32, dbl, dbl, vp, vp, vp, vp, vp, vp]),
         "dsb_project_sky_to_svd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+        "dsb_project_matrix_sky_to_svd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
+        "dsb_project_matrix_diagonal_telescope_to_svd": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp]),
+        "dsb_eigh_gen": (i32, [vp, vp, i32, vp, vp, P(ctypes.c_int32), vp]),
+        "dsb_eigvalsh": (i32, [vp, i32, vp, vp]),
+        "dsb_add_diagonal": (i32, [vp, i32, dbl, vp]),
+        "dsb_herm_congruence": (i32, [vp, vp, i32, i32, vp, vp, vp]),
+        "dsb_zgemm": (i32, [vp, vp, i32, i32, i32, vp, vp]),
+        "dsb_pinv_batched": (i32, [vp, i32, i32, i32, dbl, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

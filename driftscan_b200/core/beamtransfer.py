@@ -394,6 +394,85 @@ class BeamTransfer(config.Reader):
         )
         return out.cpu().numpy().reshape(vecf.shape)
 
+    def project_matrix_sky_to_svd(self, mi, mat, temponly=False):
+        """Sky covariance ``[pol, pol, l, freq, freq]`` -> ``[ndof, ndof]`` in the SVD basis
+        (beamtransfer.py:1135-1188); evaluated on the device."""
+        import torch
+
+        from .. import _lib
+
+        tel = self.telescope
+        npol = 1 if temponly else tel.num_pol_sky
+        svnum, svbounds = self._svd_num(mi)
+        ndof = int(svbounds[-1])
+        matf = np.zeros((ndof, ndof), dtype=np.complex128)
+        if ndof == 0:
+            return matf
+        mat = np.asarray(mat)
+        if np.iscomplexobj(mat):
+            raise NotImplementedError("project_matrix_sky_to_svd: complex sky covariances are not supported")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        beam = torch.from_numpy(np.ascontiguousarray(self.beam_svd(mi))).to(dev)
+        matd = torch.from_numpy(np.ascontiguousarray(mat, dtype=np.float64)).to(dev)
+        out = torch.empty((ndof, ndof), dtype=torch.complex128, device=dev)
+        nz = np.ascontiguousarray(np.any(mat != 0, axis=(2, 3, 4)), dtype=np.uint8)
+        sn = np.ascontiguousarray(svnum, dtype=np.int32)
+        sb = np.ascontiguousarray(svbounds, dtype=np.int32)
+        _lib.check(
+            _lib.lib.dsb_project_matrix_sky_to_svd(
+                beam.data_ptr(), matd.data_ptr(), nz.ctypes.data, sn.ctypes.data, sb.ctypes.data, self.nfreq,
+                self.svd_len, tel.num_pol_sky, npol, tel.lmax + 1, out.data_ptr(),
+                torch.cuda.current_stream().cuda_stream,
+            )
+        )
+        return out.cpu().numpy()
+
+    def project_matrix_diagonal_telescope_to_svd(self, mi, dmat):
+        """Diagonal telescope covariance ``[nfreq, ntel]`` -> block-diagonal ``[ndof, ndof]`` in
+        the SVD basis (beamtransfer.py:1190-1231); evaluated on the device."""
+        import torch
+
+        from .. import _lib
+
+        svnum, svbounds = self._svd_num(mi)
+        ndof = int(svbounds[-1])
+        matf = np.zeros((ndof, ndof), dtype=np.complex128)
+        if ndof == 0:
+            return matf
+        dev = torch.device("cuda", torch.cuda.current_device())
+        beam = torch.from_numpy(np.ascontiguousarray(self.beam_ut(mi))).to(dev)
+        dm = torch.from_numpy(np.ascontiguousarray(dmat, dtype=np.float64).reshape(self.nfreq, self.ntel)).to(dev)
+        out = torch.empty((ndof, ndof), dtype=torch.complex128, device=dev)
+        sn = np.ascontiguousarray(svnum, dtype=np.int32)
+        sb = np.ascontiguousarray(svbounds, dtype=np.int32)
+        _lib.check(
+            _lib.lib.dsb_project_matrix_diagonal_telescope_to_svd(
+                beam.data_ptr(), dm.data_ptr(), sn.ctypes.data, sb.ctypes.data, self.nfreq, self.svd_len, self.ntel,
+                out.data_ptr(), torch.cuda.current_stream().cuda_stream,
+            )
+        )
+        return out.cpu().numpy()
+
+    @util.cache_last
+    def invbeam_m(self, mi):
+        """Pseudo-inverse of the beam transfer of one m, ``[nfreq, npol_sky, lmax+1, ntel]``
+        (beamtransfer.py:316-358): ``blockla.pinv_dm`` with rcond 1e-6 of the noise-weighted
+        blocks, batched over frequency on the device.  As in the reference, the weights are
+        those of frequency 0."""
+        from ..util import blockla
+
+        tel = self.telescope
+        beam = self.beam_m(mi)
+        if self.noise_weight:
+            noisew = tel.noisepower(np.arange(tel.npairs), 0).flatten() ** (-0.5)
+            beam = beam * noisew[:, np.newaxis, np.newaxis]
+        beam = beam.reshape((self.nfreq, self.ntel, self.nsky))
+        ibeam = blockla.pinv_dm(beam, rcond=1e-6)
+        if self.noise_weight:
+            ibeam = ibeam.reshape((-1, tel.npairs))
+            ibeam = ibeam * noisew
+        return ibeam.reshape((self.nfreq, tel.num_pol_sky, tel.lmax + 1, self.ntel))
+
     def project_vector_sky_to_telescope(self, mi, vec):
         """Sky vector ``[nfreq, npol, lmax+1]`` -> visibilities ``[nfreq, ntel]``
         (beamtransfer.py:970-1010).  Small dense host algebra on the stored product."""

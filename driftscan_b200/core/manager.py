@@ -20,9 +20,11 @@ import yaml
 
 from .. import parallel
 from ..telescope import cylinder
-from . import beamtransfer
+from . import beamtransfer, doublekl, kltransform
 
 logger = logging.getLogger(__name__)
+
+kltype_dict = {"KLTransform": kltransform.KLTransform, "DoubleKL": doublekl.DoubleKL}
 
 teltype_dict = {
     "UnpolarisedCylinder": cylinder.UnpolarisedCylinderTelescope,
@@ -111,11 +113,15 @@ class ProductManager(object):
         self.skip_svd = bool(conf.get("skip_svd"))
         self.gen_kl = bool(conf.get("kltransform"))
         self.gen_ps = bool(conf.get("psfisher"))
+        # KL transforms (manager.py:232-246)
         self.kltransforms = {}
+        for klentry in yconf.get("kltransform", []) or []:
+            klclass = _resolve_class(klentry["type"], kltype_dict, "KL filter")
+            self.kltransforms[klentry["name"]] = klclass.from_config(klentry, self.beamtransfer,
+                                                                      subdir=klentry["name"])
         self.psestimators = {}
-        for section in ("kltransform", "psfisher"):
-            if section in yconf:
-                warnings.warn(f"`{section}` entries are accepted but not generated by driftscan_b200")
+        if "psfisher" in yconf:
+            warnings.warn("`psfisher` entries are accepted but not generated by driftscan_b200")
 
     def generate(self):
         os.makedirs(self.directory, exist_ok=True)
@@ -124,6 +130,9 @@ class ProductManager(object):
                 yaml.dump(self.config, fh)
         if self.gen_beams:
             self.beamtransfer.generate(skip_svd=self.skip_svd)
-        if self.gen_kl or self.gen_ps:
-            logger.warning("KL transform / power-spectrum stages are outside the scope of this build; skipped")
+        if self.gen_kl:
+            for klname, klobj in self.kltransforms.items():
+                klobj.generate()
+        if self.gen_ps:
+            logger.warning("power-spectrum estimation is outside the scope of this build; skipped")
         logger.info("DONE GENERATING PRODUCTS")

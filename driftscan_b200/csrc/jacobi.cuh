@@ -1,0 +1,27 @@
+// Batched block one-sided Jacobi (svd.cu), shared by the SVD chain and the KL eigensolver.
+#pragma once
+#include "dsb_common.cuh"
+
+namespace dsb {
+
+typedef cplx<double> zc;
+
+struct JacobiScratch {
+  unsigned long long *amax = nullptr;                        // [batch]
+  int32_t *rot = nullptr, *done = nullptr, *flag = nullptr;  // [batch], [batch], [2]
+  int32_t *skip = nullptr;                                   // [batch][npairs_ld]
+  zc *W = nullptr;                                           // [batch][npairs_ld][32 * 32]
+  int npairs_ld = 0;
+  int32_t *h_flag = nullptr;  // pinned [2]
+  int alloc(int batch, int nrows_max, cudaStream_t stream);
+  void release(cudaStream_t stream);
+};
+
+// One Jacobi pass over the active rows idx[b][0..nact[b]) of every matrix R[b] (ldr x ncols, row
+// major): the rows become mutually orthogonal with respect to columns [ip0, ip1); every column
+// is carried along.  sweeps[b] (device) receives the sweep count; `nmax` = upper bound of nact
+// (-1: read it back from the device).
+int jacobi_pass(zc *R, int ldr, int ncols, const int32_t *idx, const int32_t *nact, int batch, int ip0, int ip1,
+                int nmax, int max_sweeps, double tol, int32_t *sweeps, JacobiScratch &js, cudaStream_t stream);
+
+}  // namespace dsb

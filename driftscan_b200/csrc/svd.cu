@@ -21,11 +21,12 @@
 // cannot be reproduced through B B^H in fp64).
 // One CTA owns one matrix; a warp owns one row pair of the round-robin schedule and
 // uses shuffle reductions for the three inner products.
-#include "dsb_common.cuh"
+#include "jacobi.cuh"
+
+#include <algorithm>
+#include <cstdlib>
 
 namespace dsb {
-
-typedef cplx<double> zc;
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -34,24 +35,30 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// One-sided Jacobi pass, one launch per round-robin step.
+// Block one-sided Jacobi pass.
 //   R: [batch][ldr rows][ncols] ; idx: [batch][ldr] active row list ; nact: [batch]
-// All row pairs of one tournament step are disjoint, so a step is one launch with one CTA per
-// (pair, matrix): the whole GPU works on every matrix of the batch at once (the first version ran
-// a matrix on a single CTA and took 48 s for one 1520 x 936 block).  A pair is read once for
-// the three inner products and once more (L1/L2) for the rotation.  Row norms over the
-// inner-product columns are cached per sweep: a pair with a numerically zero row (the null rows
-// of a rank-deficient block, i.e. most rows of a beam-transfer block after the first sweep)
-// is dropped after two 8-byte loads instead of two row reads.
+// The active rows are cut into blocks of kJB rows; blocks meet pairwise in a round-robin
+// tournament, one launch pair per tournament step with one CTA per (block pair, matrix):
+//   bj_gram_eig_kernel   G = X X^H over the inner-product columns for the 2 kJB rows of the pair
+//                        (fp64, register-blocked from shared-memory tiles), convergence test on the
+//                        true inner products, then a cyclic two-sided Jacobi diagonalisation of the
+//                        small Hermitian G in shared memory that accumulates the unitary W;
+//   bj_apply_kernel      X <- W X over ALL columns (the U^H accumulator included), a tiled GEMM.
+// Compared with rotating row pairs one at a time this moves each row through memory once per
+// block pair instead of once per partner row (kJB x less traffic) and turns the arithmetic
+// into small GEMMs.  Accuracy is that of one-sided Jacobi: every outer step recomputes G from
+// the data, W is a product of exact plane rotations, and convergence is declared on the fresh
+// inner products |<x_i, x_j>| <= tol |x_i| |x_j| only.  The rows of a pair leave sorted by
+// norm, so the null rows of a rank-deficient block sink into the last blocks, whose pairs then
+// cost one Gram evaluation and no update.
 // ---------------------------------------------------------------------------------------------
 
-// nrm2[b][r] = |row idx[r]|^2 over columns [ip0, ip1); amax[b] = max_r (only when set_max)
+// amax[b] = max_r |row idx[r]|^2 over columns [ip0, ip1)
 __global__ void __launch_bounds__(256)
-row_norms_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
-                 const int32_t *__restrict__ nact_all, int ip0, int ip1, double *__restrict__ nrm2_all,
-                 unsigned long long *__restrict__ amax_all, int set_max, const int32_t *__restrict__ done_all) {
+row_norm_max_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
+                    const int32_t *__restrict__ nact_all, int ip0, int ip1,
+                    unsigned long long *__restrict__ amax_all) {
   const int b = blockIdx.y;
-  if (done_all[b]) return;
   const int n = nact_all[b];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int r = blockIdx.x * nwarps + warp;
@@ -60,110 +67,333 @@ row_norms_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32_t 
   double a = 0.0;
   for (int c = ip0 + lane; c < ip1; c += 32) a += x[c].x * x[c].x + x[c].y * x[c].y;
   a = warp_sum(a);
-  if (lane == 0) {
-    nrm2_all[(size_t)b * ldr + r] = a;
-    if (set_max) atomicMax(&amax_all[b], (unsigned long long)__double_as_longlong(a));
-  }
+  if (lane == 0) atomicMax(&amax_all[b], (unsigned long long)__double_as_longlong(a));
 }
 
-constexpr int kPairThreads = 128;
+constexpr int kJB = 16;       // rows per block
+constexpr int kJ2 = 2 * kJB;  // rows per block pair
+constexpr int kGT = 32;       // Gram: columns per shared-memory tile
+constexpr int kAT = 128;      // apply: columns per CTA
 
-__global__ void __launch_bounds__(kPairThreads)
-jacobi_pair_kernel(zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
-                   const int32_t *__restrict__ nact_all, int ip0, int ip1, int step, double tol,
-                   double *__restrict__ nrm2_all, const unsigned long long *__restrict__ amax_all,
-                   int32_t *__restrict__ rot_all, const int32_t *__restrict__ done_all) {
-  const int b = blockIdx.y;
-  if (done_all[b]) return;
-  const int n = nact_all[b];
-  if (n < 2) return;
-  const int P = (n + 1) & ~1;  // players of the round-robin tournament (one dummy if n is odd)
-  const int k = blockIdx.x;
-  if (step >= P - 1 || k >= P / 2) return;
-  int pa, pb;
+// slots of a block pair: the kJ2 row positions (lower block first) and how many are real rows
+__device__ __forceinline__ bool bj_pair_slots(int n, int step, int k, int &pos_a, int &pos_b, int &nvalid) {
+  const int nblk = (n + kJB - 1) / kJB;
+  const int P = max(2, (nblk + 1) & ~1);
+  if (step >= P - 1 || k >= P / 2) return false;
+  int ta, tb;
   if (k == 0) {
-    pa = P - 1;
-    pb = step;
+    ta = P - 1;
+    tb = step;
   } else {
-    pa = (step + k) % (P - 1);
-    pb = (step - k + (P - 1)) % (P - 1);
+    ta = (step + k) % (P - 1);
+    tb = (step - k + (P - 1)) % (P - 1);
   }
-  if (pa >= n || pb >= n) return;
-  if (pa > pb) {
-    const int t = pa;
-    pa = pb;
-    pb = t;
+  if (ta > tb) {
+    const int t = ta;
+    ta = tb;
+    tb = t;
   }
-  double *nrm2 = nrm2_all + (size_t)b * ldr;
+  if (ta >= nblk) return false;  // both blocks are dummies
+  pos_a = ta * kJB;
+  pos_b = tb * kJB;  // may lie beyond n (dummy block)
+  const int na = min(kJB, n - pos_a);
+  const int nb = tb < nblk ? min(kJB, n - pos_b) : 0;
+  // only the last block can be short, and it is never the lower one unless the upper is a dummy
+  nvalid = na + nb;
+  return true;
+}
+__device__ __forceinline__ int bj_slot_pos(int s, int pos_a, int pos_b) {
+  return s < kJB ? pos_a + s : pos_b + (s - kJB);
+}
+
+__global__ void __launch_bounds__(256, 2)
+bj_gram_eig_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
+                   const int32_t *__restrict__ nact_all, int ip0, int ip1, int step, double tol,
+                   const unsigned long long *__restrict__ amax_all, zc *__restrict__ Wall,
+                   int32_t *__restrict__ skip_all, int32_t *__restrict__ rot_all,
+                   const int32_t *__restrict__ done_all, int npairs_ld, int do_sort, int inner_sweeps) {
+  const int b = blockIdx.y, k = blockIdx.x, tid = threadIdx.x;
+  int32_t *skip = skip_all + (size_t)b * npairs_ld + k;
+  if (done_all[b]) {
+    if (tid == 0) *skip = 1;
+    return;
+  }
+  const int n = nact_all[b];
+  int pos_a, pos_b, nvalid;
+  if (n < 2 || !bj_pair_slots(n, step, k, pos_a, pos_b, nvalid)) {
+    if (tid == 0) *skip = 1;
+    return;
+  }
+  static_assert(kGT == kJ2, "the Gram tile is reused for W");
+  __shared__ zc s_tile[kGT][kJ2 + 1];  // [column][slot]; dead after the Gram loop
+  __shared__ zc s_G[kJ2][kJ2 + 1];
+  zc(*s_W)[kJ2 + 1] = s_tile;
+  __shared__ const zc *s_row[kJ2];
+  __shared__ double s_rot[kJB][4];  // cs, sn*er, sn*ei, active
+  __shared__ int s_rank[kJ2];
+  __shared__ int s_flag;
+  if (tid < kJ2) {
+    const int pos = bj_slot_pos(tid, pos_a, pos_b);
+    s_row[tid] = (tid < nvalid) ? Rall + ((size_t)b * ldr + idx_all[(size_t)b * ldr + pos]) * ncols : nullptr;
+  }
+  // ---- Gram matrix: thread (ti, tj) of column slice w owns rows {ti + 8 i} x {tj + 8 j}
+  // (interleaved, so that the shared-memory reads of a quarter-warp are contiguous)
+  const int w = tid >> 6, t64 = tid & 63, ti = t64 >> 3, tj = t64 & 7;
+  double ar[4][4], ai[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ar[i][j] = ai[i][j] = 0.0;
+  __syncthreads();
+  // 32 slots x 32 columns per tile: thread -> slot tid/8, columns (tid%8)*4 .. +3; the next tile
+  // is fetched into registers while the current one is multiplied
+  const int ld_sl = tid >> 3, ld_cc = (tid & 7) * 4;
+  const zc *ld_row = s_row[ld_sl];
+  zc pre[4];
+  auto fetch = [&](int c0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = c0 + ld_cc + q;
+      pre[q] = {0.0, 0.0};
+      if (ld_row && c < ip1) pre[q] = ld_row[c];
+    }
+  };
+  fetch(ip0);
+  for (int c0 = ip0; c0 < ip1; c0 += kGT) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s_tile[ld_cc + q][ld_sl] = pre[q];
+    __syncthreads();
+    if (c0 + kGT < ip1) fetch(c0 + kGT);
+    {
+#pragma unroll
+      for (int cq = 0; cq < kGT / 4; ++cq) {
+        const int c = cq * 4 + w;
+        zc xv[4], yv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xv[i] = s_tile[c][ti + 8 * i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) yv[j] = s_tile[c][tj + 8 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            // x conj(y)
+            ar[i][j] += xv[i].x * yv[j].x + xv[i].y * yv[j].y;
+            ai[i][j] += xv[i].y * yv[j].x - xv[i].x * yv[j].y;
+          }
+      }
+    }
+    __syncthreads();
+  }
+  for (int ws = 0; ws < 4; ++ws) {
+    if (w == ws) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          zc &g = s_G[ti + 8 * i][tj + 8 * j];
+          if (ws == 0) g = {ar[i][j], ai[i][j]};
+          else g = {g.x + ar[i][j], g.y + ai[i][j]};
+        }
+    }
+    __syncthreads();
+  }
+  // W = I
+  for (int e = tid; e < kJ2 * kJ2; e += 256) {
+    const int i = e / kJ2, j = e % kJ2;
+    if (j == i) s_G[i][i].y = 0.0;
+    s_W[i][j] = {i == j ? 1.0 : 0.0, 0.0};
+  }
+  if (tid == 0) s_flag = 0;
+  __syncthreads();
   // Rows whose norm is at the rounding level of the largest row are numerically zero: a
   // pair involving such a row is not rotated (its angle to anything is noise and would
   // never settle); singular values below 1e-14 of the largest are noise in any case.
   const double floor2 = 1e-28 * __longlong_as_double((long long)amax_all[b]);
-  if (nrm2[pa] < floor2 || nrm2[pb] < floor2) return;
-  const int32_t *idx = idx_all + (size_t)b * ldr;
-  zc *x = Rall + ((size_t)b * ldr + idx[pa]) * ncols;
-  zc *y = Rall + ((size_t)b * ldr + idx[pb]) * ncols;
-  double a = 0.0, bb = 0.0, cr = 0.0, ci = 0.0;
-  for (int c = ip0 + threadIdx.x; c < ip1; c += kPairThreads) {
-    const zc xv = x[c], yv = y[c];
-    a += xv.x * xv.x + xv.y * xv.y;
-    bb += yv.x * yv.x + yv.y * yv.y;
-    // <x, y> = sum x conj(y)
-    cr += xv.x * yv.x + xv.y * yv.y;
-    ci += xv.y * yv.x - xv.x * yv.y;
-  }
-  a = warp_sum(a);
-  bb = warp_sum(bb);
-  cr = warp_sum(cr);
-  ci = warp_sum(ci);
-  __shared__ double s_red[kPairThreads / 32][4];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) {
-    s_red[warp][0] = a;
-    s_red[warp][1] = bb;
-    s_red[warp][2] = cr;
-    s_red[warp][3] = ci;
+  if (tol <= 0.0) tol = 2e-15 * sqrt((double)(ip1 - ip0));  // rounding level of the inner product
+  const double tol2 = tol * tol;
+  // The small problem is solved well below the convergence threshold: G is only updated, not
+  // recomputed, inside this kernel, and pairs left hovering at the threshold would be pushed
+  // over it again by the rounding noise of later rotations (observed: no convergence).
+  const double tol2_in = tol2 / 64.0;
+  {
+    int need = 0;
+    for (int e = tid; e < kJ2 * kJ2; e += 256) {
+      const int i = e / kJ2, j = e % kJ2;
+      if (j < i && i < nvalid) {
+        const double a = s_G[i][i].x, bb = s_G[j][j].x;
+        const zc c = s_G[i][j];
+        const double c2 = c.x * c.x + c.y * c.y;
+        if (a >= floor2 && bb >= floor2 && c2 > tol2 * a * bb && c2 != 0.0) need = 1;
+      }
+    }
+    if (need) s_flag = 1;
   }
   __syncthreads();
-  a = bb = cr = ci = 0.0;
-#pragma unroll
-  for (int w = 0; w < kPairThreads / 32; ++w) {
-    a += s_red[w][0];
-    bb += s_red[w][1];
-    cr += s_red[w][2];
-    ci += s_red[w][3];
-  }
-  if (tol <= 0.0) tol = 2e-15 * sqrt((double)(ip1 - ip0));  // rounding level of the inner product
-  const double cabs2 = cr * cr + ci * ci;
-  if (cabs2 <= tol * tol * a * bb || cabs2 == 0.0 || a < floor2 || bb < floor2) {
-    if (threadIdx.x == 0) {
-      nrm2[pa] = a;
-      nrm2[pb] = bb;
-    }
+  if (!s_flag) {
+    if (tid == 0) *skip = 1;
     return;
   }
-  const double cabs = sqrt(cabs2);
-  const double zeta = (bb - a) / (2.0 * cabs);
-  const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-  const double cs = rsqrt(1.0 + t * t);
-  const double sn = cs * t;
-  // e^{i phi} = c / |c|
-  const double er = cr / cabs, ei = ci / cabs;
-  // x' = cs x - sn e^{i phi} y ;  y' = sn e^{-i phi} x + cs y
-  for (int c = threadIdx.x; c < ncols; c += kPairThreads) {
-    const zc xv = x[c], yv = y[c];
-    zc xn, yn;
-    xn.x = cs * xv.x - sn * (er * yv.x - ei * yv.y);
-    xn.y = cs * xv.y - sn * (er * yv.y + ei * yv.x);
-    yn.x = sn * (er * xv.x + ei * xv.y) + cs * yv.x;
-    yn.y = sn * (er * xv.y - ei * xv.x) + cs * yv.y;
-    x[c] = xn;
-    y[c] = yn;
+  // ---- cyclic two-sided Jacobi on G (parallel ordering: 16 disjoint pairs per step).
+  // Thread (a, b) owns the 2 x 2 block rows {p_a, q_a} x columns {p_b, q_b} of G, which the step
+  // maps to T_a block T_b^H, and two columns of the rows {p_a, q_a} of W (W <- T_a W).
+  const int pa = tid >> 4, pb = tid & 15;
+  auto rr_pair = [](int k, int st, int &p, int &q) {
+    if (k == 0) {
+      p = kJ2 - 1;
+      q = st;
+    } else {
+      p = (st + k) % (kJ2 - 1);
+      q = (st - k + (kJ2 - 1)) % (kJ2 - 1);
+    }
+    if (p > q) {
+      const int t = p;
+      p = q;
+      q = t;
+    }
+  };
+  for (int isweep = 0; isweep < inner_sweeps; ++isweep) {
+    __syncthreads();
+    if (tid == 0) s_flag = 0;
+    for (int st = 0; st < kJ2 - 1; ++st) {
+      int p1, q1, p2, q2;
+      rr_pair(pa, st, p1, q1);
+      rr_pair(pb, st, p2, q2);
+      __syncthreads();
+      if (pb == 0) {
+        const double a = s_G[p1][p1].x, bb = s_G[q1][q1].x;
+        const zc c = s_G[p1][q1];  // <x_p, x_q>
+        const double c2 = c.x * c.x + c.y * c.y;
+        double cs = 1.0, sr = 0.0, si = 0.0, act = 0.0;
+        if (q1 < nvalid && a >= floor2 && bb >= floor2 && c2 > tol2_in * a * bb && c2 != 0.0) {
+          // tan = sign(d) |c| / (|d| + sqrt(d^2 + |c|^2)), d = (b - a) / 2  (the smaller rotation)
+          const double d = 0.5 * (bb - a);
+          const double wq = (d >= 0.0 ? 1.0 : -1.0) / (fabs(d) + sqrt(d * d + c2));
+          cs = rsqrt(1.0 + c2 * wq * wq);
+          sr = cs * wq * c.x;  // sin e^{i phi}
+          si = cs * wq * c.y;
+          act = 1.0;
+          s_flag = 1;
+        }
+        s_rot[pa][0] = cs;
+        s_rot[pa][1] = sr;
+        s_rot[pa][2] = si;
+        s_rot[pa][3] = act;
+      }
+      __syncthreads();
+      const double ca = s_rot[pa][0], ar_ = s_rot[pa][1], ai_ = s_rot[pa][2];
+      const double cb = s_rot[pb][0], br_ = s_rot[pb][1], bi_ = s_rot[pb][2];
+      const bool acta = s_rot[pa][3] != 0.0, actb = s_rot[pb][3] != 0.0;
+      if (acta || actb) {
+        zc g00 = s_G[p1][p2], g01 = s_G[p1][q2], g10 = s_G[q1][p2], g11 = s_G[q1][q2];
+        // rows:  x_p' = cs x_p - s x_q ;  x_q' = conj(s) x_p + cs x_q ,  s = ar_ + i ai_
+        zc r00 = {ca * g00.x - (ar_ * g10.x - ai_ * g10.y), ca * g00.y - (ar_ * g10.y + ai_ * g10.x)};
+        zc r01 = {ca * g01.x - (ar_ * g11.x - ai_ * g11.y), ca * g01.y - (ar_ * g11.y + ai_ * g11.x)};
+        zc r10 = {(ar_ * g00.x + ai_ * g00.y) + ca * g10.x, (ar_ * g00.y - ai_ * g00.x) + ca * g10.y};
+        zc r11 = {(ar_ * g01.x + ai_ * g01.y) + ca * g11.x, (ar_ * g01.y - ai_ * g01.x) + ca * g11.y};
+        // columns: g_ip' = cs g_ip - conj(s) g_iq ;  g_iq' = s g_ip + cs g_iq ,  s = br_ + i bi_
+        s_G[p1][p2] = {cb * r00.x - (br_ * r01.x + bi_ * r01.y), cb * r00.y - (br_ * r01.y - bi_ * r01.x)};
+        s_G[p1][q2] = {(br_ * r00.x - bi_ * r00.y) + cb * r01.x, (br_ * r00.y + bi_ * r00.x) + cb * r01.y};
+        s_G[q1][p2] = {cb * r10.x - (br_ * r11.x + bi_ * r11.y), cb * r10.y - (br_ * r11.y - bi_ * r11.x)};
+        s_G[q1][q2] = {(br_ * r10.x - bi_ * r10.y) + cb * r11.x, (br_ * r10.y + bi_ * r10.x) + cb * r11.y};
+      }
+      if (acta) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = 2 * pb + h;
+          const zc gp = s_W[p1][j], gq = s_W[q1][j];
+          s_W[p1][j] = {ca * gp.x - (ar_ * gq.x - ai_ * gq.y), ca * gp.y - (ar_ * gq.y + ai_ * gq.x)};
+          s_W[q1][j] = {(ar_ * gp.x + ai_ * gp.y) + ca * gq.x, (ar_ * gp.y - ai_ * gp.x) + ca * gq.y};
+        }
+      }
+    }
+    __syncthreads();
+    if (!s_flag) break;
   }
-  if (threadIdx.x == 0) {
-    nrm2[pa] = a - t * cabs;  // exact for the rotation; refreshed from the data every sweep
-    nrm2[pb] = bb + t * cabs;
+  __syncthreads();
+  // ---- leave the rows sorted by norm (descending), real rows first
+  if (tid < kJ2) {
+    const double d = tid < nvalid ? s_G[tid][tid].x : -1.0;
+    int rank = 0;
+    for (int j = 0; j < kJ2; ++j) {
+      const double dj = j < nvalid ? s_G[j][j].x : -1.0;
+      rank += (dj > d) || (dj == d && j < tid);
+    }
+    s_rank[tid] = do_sort ? rank : tid;
+  }
+  __syncthreads();
+  zc *W = Wall + ((size_t)b * npairs_ld + k) * (kJ2 * kJ2);
+  for (int e = tid; e < kJ2 * kJ2; e += 256) {
+    const int i = e / kJ2, j = e % kJ2;
+    W[s_rank[i] * kJ2 + j] = s_W[i][j];
+  }
+  if (tid == 0) {
+    *skip = 0;
     atomicAdd(&rot_all[b], 1);
+  }
+}
+
+// X[slot s] <- sum_j W[s][j] X[slot j] over a tile of kAT columns
+__global__ void __launch_bounds__(256, 2)
+bj_apply_kernel(zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
+                const int32_t *__restrict__ nact_all, int step, const zc *__restrict__ Wall,
+                const int32_t *__restrict__ skip_all, int npairs_ld) {
+  const int b = blockIdx.z, k = blockIdx.y, tid = threadIdx.x;
+  if (skip_all[(size_t)b * npairs_ld + k]) return;
+  const int n = nact_all[b];
+  int pos_a, pos_b, nvalid;
+  if (!bj_pair_slots(n, step, k, pos_a, pos_b, nvalid)) return;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  zc(*s_X)[kAT] = reinterpret_cast<zc(*)[kAT]>(s_raw);                          // [slot][column]
+  zc(*s_W)[kJ2] = reinterpret_cast<zc(*)[kJ2]>(s_raw + sizeof(zc) * kJ2 * kAT);  // [j][s] (transposed)
+  __shared__ zc *s_row[kJ2];
+  if (tid < kJ2) {
+    const int pos = bj_slot_pos(tid, pos_a, pos_b);
+    s_row[tid] = (tid < nvalid) ? Rall + ((size_t)b * ldr + idx_all[(size_t)b * ldr + pos]) * ncols : nullptr;
+  }
+  const zc *W = Wall + ((size_t)b * npairs_ld + k) * (kJ2 * kJ2);
+  for (int e = tid; e < kJ2 * kJ2; e += 256) s_W[e % kJ2][e / kJ2] = W[e];
+  __syncthreads();
+  const int c0 = blockIdx.x * kAT;
+  for (int e = tid; e < kJ2 * kAT; e += 256) {
+    const int sl = e / kAT, c = e % kAT;
+    zc v = {0.0, 0.0};
+    const zc *row = s_row[sl];
+    if (row && c0 + c < ncols) v = row[c0 + c];
+    s_X[sl][c] = v;
+  }
+  __syncthreads();
+  // thread: 4 slots (tid / 32) x 4 columns (lane + 32 q)
+  const int sg = (tid >> 5) * 4, cg = tid & 31;
+  double or_[4][4], oi[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) or_[i][j] = oi[i][j] = 0.0;
+#pragma unroll 4
+  for (int j = 0; j < kJ2; ++j) {
+    zc wv[4], xv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) wv[i] = s_W[j][sg + i];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) xv[q] = s_X[j][cg + 32 * q];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        or_[i][q] += wv[i].x * xv[q].x - wv[i].y * xv[q].y;
+        oi[i][q] += wv[i].x * xv[q].y + wv[i].y * xv[q].x;
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    zc *row = s_row[sg + i];
+    if (!row) continue;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = c0 + cg + 32 * q;
+      if (c < ncols) row[c] = {or_[i][q], oi[i][q]};
+    }
   }
 }
 
@@ -188,16 +418,31 @@ __global__ void max_nact_kernel(int batch, const int32_t *__restrict__ nact, int
   atomicMax(out, mx);
 }
 
-struct JacobiScratch {
-  double *nrm2 = nullptr;             // [batch][ldr]
-  unsigned long long *amax = nullptr;  // [batch]
-  int32_t *rot = nullptr, *done = nullptr, *flag = nullptr;  // [batch], [batch], [2]
-  int32_t *h_flag = nullptr;          // pinned [2]
-};
+int JacobiScratch::alloc(int batch, int nrows_max, cudaStream_t stream) {
+  const int nblk = (nrows_max + kJB - 1) / kJB;
+  npairs_ld = std::max(2, (nblk + 1) & ~1) / 2;
+  DSB_CUDA(cudaMallocAsync((void **)&amax, sizeof(unsigned long long) * batch, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&rot, sizeof(int32_t) * batch, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&done, sizeof(int32_t) * batch, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&flag, sizeof(int32_t) * 2, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&skip, sizeof(int32_t) * (size_t)batch * npairs_ld, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&W, sizeof(zc) * (size_t)batch * npairs_ld * kJ2 * kJ2, stream));
+  DSB_CUDA(cudaMallocHost((void **)&h_flag, sizeof(int32_t) * 2));
+  return DSB_OK;
+}
+void JacobiScratch::release(cudaStream_t stream) {
+  cudaFreeAsync(amax, stream);
+  cudaFreeAsync(rot, stream);
+  cudaFreeAsync(done, stream);
+  cudaFreeAsync(flag, stream);
+  cudaFreeAsync(skip, stream);
+  cudaFreeAsync(W, stream);
+  if (h_flag) cudaFreeHost(h_flag);
+}
 
 // One Jacobi pass over the active rows of every matrix; sweeps[b] receives the sweep count.
 // `nmax` = upper bound of nact (-1: read it back from the device).
-static int jacobi_pass(zc *R, int ldr, int ncols, const int32_t *idx, const int32_t *nact, int batch, int ip0, int ip1,
+int jacobi_pass(zc *R, int ldr, int ncols, const int32_t *idx, const int32_t *nact, int batch, int ip0, int ip1,
                        int nmax, int max_sweeps, double tol, int32_t *sweeps, JacobiScratch &js, cudaStream_t stream) {
   DSB_CUDA(cudaMemsetAsync(sweeps, 0, sizeof(int32_t) * batch, stream));
   if (ip1 <= ip0) return DSB_OK;
@@ -210,26 +455,39 @@ static int jacobi_pass(zc *R, int ldr, int ncols, const int32_t *idx, const int3
     nmax = js.h_flag[1];
   }
   if (nmax < 2) return DSB_OK;
-  const int P = (nmax + 1) & ~1;
+  const int nblk = (nmax + kJB - 1) / kJB;
+  const int P = std::max(2, (nblk + 1) & ~1);
+  DSB_CHECK(P / 2 <= js.npairs_ld, DSB_ERR_INVALID, "jacobi_pass: scratch too small");
+  static bool attr_set = false;
+  const size_t apply_smem = sizeof(zc) * (kJ2 * kAT + kJ2 * kJ2);
+  if (!attr_set) {
+    DSB_CUDA(cudaFuncSetAttribute(bj_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem));
+    attr_set = true;
+  }
   DSB_CUDA(cudaMemsetAsync(js.amax, 0, sizeof(unsigned long long) * batch, stream));
   DSB_CUDA(cudaMemsetAsync(js.rot, 0, sizeof(int32_t) * batch, stream));
   DSB_CUDA(cudaMemsetAsync(js.done, 0, sizeof(int32_t) * batch, stream));
-  const dim3 gnorm((nmax + 7) / 8, batch), gpair(P / 2, batch);
+  static const int do_sort = getenv("DSB_SVD_NOSORT") ? 0 : 1;
+  static const int inner_sweeps = getenv("DSB_SVD_INNER") ? atoi(getenv("DSB_SVD_INNER")) : 8;
+  static const bool debug = getenv("DSB_SVD_DEBUG") != nullptr;
+  const dim3 gnorm((nmax + 7) / 8, batch), gpair(P / 2, batch), gapply((ncols + kAT - 1) / kAT, P / 2, batch);
+  row_norm_max_kernel<<<gnorm, 256, 0, stream>>>(R, ldr, ncols, idx, nact, ip0, ip1, js.amax);
+  DSB_LAUNCH_CHECK();
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
-    row_norms_kernel<<<gnorm, 256, 0, stream>>>(R, ldr, ncols, idx, nact, ip0, ip1, js.nrm2, js.amax, sweep == 0,
-                                                js.done);
-    DSB_LAUNCH_CHECK();
     for (int step = 0; step < P - 1; ++step) {
-      jacobi_pair_kernel<<<gpair, kPairThreads, 0, stream>>>(R, ldr, ncols, idx, nact, ip0, ip1, step, tol, js.nrm2,
-                                                             js.amax, js.rot, js.done);
+      bj_gram_eig_kernel<<<gpair, 256, 0, stream>>>(R, ldr, ncols, idx, nact, ip0, ip1, step, tol, js.amax, js.W,
+                                                    js.skip, js.rot, js.done, js.npairs_ld, do_sort, inner_sweeps);
+      bj_apply_kernel<<<gapply, 256, apply_smem, stream>>>(R, ldr, ncols, idx, nact, step, js.W, js.skip,
+                                                           js.npairs_ld);
     }
-    count_launch(P - 2);
+    count_launch(2 * (P - 1) - 1);
     DSB_LAUNCH_CHECK();
     DSB_CUDA(cudaMemsetAsync(js.flag, 0, sizeof(int32_t), stream));
     sweep_end_kernel<<<1, 256, 0, stream>>>(batch, js.rot, js.done, sweeps, js.flag);
     DSB_LAUNCH_CHECK();
     DSB_CUDA(cudaMemcpyAsync(js.h_flag, js.flag, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     DSB_CUDA(cudaStreamSynchronize(stream));
+    if (debug) fprintf(stderr, "[jacobi] ip [%d,%d) nmax %d sweep %d: %d matrices left\n", ip0, ip1, nmax, sweep, js.h_flag[0]);
     if (js.h_flag[0] == 0) break;
   }
   return DSB_OK;
@@ -321,7 +579,7 @@ __global__ void svd_prepare_kernel(const zc *__restrict__ bf, const double *__re
     const int r = (int)(i / ncols), c = (int)(i % ncols);
     zc v;
     if (c < nsky) {
-      const double w = noisew[(size_t)b * ntel + r];
+      const double w = noisew ? noisew[(size_t)b * ntel + r] : 1.0;
       const zc s = B[(size_t)r * nsky + c];
       v = {s.x * w, s.y * w};
     } else {
@@ -391,7 +649,7 @@ __global__ void svd_emit_kernel(const zc *__restrict__ R, const double *__restri
 //   pinv[c][j] = sum_k conj(S[k][c]) / sigma_k^2 * S[k][nsky + j],  sigma_k > rcond * sigma_max
 // written as invbeam[b][c][j] with row pitch svd_len (columns >= nmodes zero).
 __global__ void svd_pinv_kernel(const zc *__restrict__ S, const int32_t *__restrict__ snact, int nsky, int svd_len,
-                                zc *__restrict__ invbeam) {
+                                zc *__restrict__ invbeam, double rcond_in) {
   const int b = blockIdx.y;
   const int nm = snact[b];
   const int scols = nsky + svd_len;
@@ -416,7 +674,7 @@ __global__ void svd_pinv_kernel(const zc *__restrict__ S, const int32_t *__restr
     s_max2 = mx;
   }
   __syncthreads();
-  const double rcond = (double)max(nm, nsky) * 2.220446049250313e-16;
+  const double rcond = rcond_in >= 0.0 ? rcond_in : (double)max(nm, nsky) * 2.220446049250313e-16;
   for (int k = threadIdx.x; k < svd_len; k += blockDim.x) {
     const double a = s_inv[k];
     s_inv[k] = (k < nm && a > rcond * rcond * s_max2 && a > 0.0) ? 1.0 / a : 0.0;
@@ -508,12 +766,7 @@ extern "C" int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int b
   }
 
   JacobiScratch js;
-  DSB_CUDA(cudaMallocAsync((void **)&js.nrm2, sizeof(double) * (size_t)batch * ntel, stream));
-  DSB_CUDA(cudaMallocAsync((void **)&js.amax, sizeof(unsigned long long) * batch, stream));
-  DSB_CUDA(cudaMallocAsync((void **)&js.rot, sizeof(int32_t) * batch, stream));
-  DSB_CUDA(cudaMallocAsync((void **)&js.done, sizeof(int32_t) * batch, stream));
-  DSB_CUDA(cudaMallocAsync((void **)&js.flag, sizeof(int32_t) * 2, stream));
-  DSB_CUDA(cudaMallocHost((void **)&js.h_flag, sizeof(int32_t) * 2));
+  DSB_TRY(js.alloc(batch, ntel, stream));
 
   const int max_sweeps = 60;
   const double tol = 0.0;  // derive from the inner-product length
@@ -547,7 +800,7 @@ extern "C" int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int b
     DSB_TRY(jacobi_pass(S, svd_len, scols, sidx, snact, batch, 0, nsky, -1, max_sweeps, tol, sweeps + 3 * batch, js,
                         stream));
     dim3 gp(32, batch);
-    svd_pinv_kernel<<<gp, 256, sizeof(double) * svd_len, stream>>>(S, snact, nsky, svd_len, (zc *)invbeam_dev);
+    svd_pinv_kernel<<<gp, 256, sizeof(double) * svd_len, stream>>>(S, snact, nsky, svd_len, (zc *)invbeam_dev, -1.0);
     DSB_LAUNCH_CHECK();
   }
   // convergence check
@@ -560,12 +813,7 @@ extern "C" int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int b
   cudaFreeAsync(sig, stream);
   cudaFreeAsync(nact, stream);
   cudaFreeAsync(sweeps, stream);
-  cudaFreeAsync(js.nrm2, stream);
-  cudaFreeAsync(js.amax, stream);
-  cudaFreeAsync(js.rot, stream);
-  cudaFreeAsync(js.done, stream);
-  cudaFreeAsync(js.flag, stream);
-  cudaFreeHost(js.h_flag);
+  js.release(stream);
   if (want_inv) {
     cudaFreeAsync(S, stream);
     cudaFreeAsync(sidx, stream);
@@ -600,5 +848,47 @@ extern "C" int dsb_project_sky_to_svd(const void *beam_svd_dev, const void *vec_
   DSB_LAUNCH_CHECK();
   DSB_CUDA(cudaStreamSynchronize(stream));
   DSB_CUDA(cudaFreeAsync(sv, stream));
+  return DSB_OK;
+}
+
+// scipy.linalg.pinv(A[b], rcond) for a batch of n x m blocks (util/blockla.py:117-138 pinv_dm as
+// used by BeamTransfer.invbeam_m, beamtransfer.py:344): one-sided Jacobi on the rows of [ A | I ].
+extern "C" int dsb_pinv_batched(const void *A_dev, int batch, int n, int m, double rcond, void *pinv_dev,
+                                void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSB_CHECK(A_dev && pinv_dev && batch >= 0 && n > 0 && m > 0, DSB_ERR_INVALID, "dsb_pinv_batched: bad argument");
+  if (batch == 0) return DSB_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("dsb_pinv_batched: no CUDA device available (there is no CPU fallback)");
+    return DSB_ERR_CUDA;
+  }
+  const int ncols = m + n;
+  zc *R = nullptr;
+  int32_t *idx = nullptr, *nact = nullptr, *sweeps = nullptr;
+  DSB_CUDA(cudaMallocAsync((void **)&R, sizeof(zc) * (size_t)batch * n * ncols, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&idx, sizeof(int32_t) * (size_t)batch * n, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&nact, sizeof(int32_t) * batch, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&sweeps, sizeof(int32_t) * batch, stream));
+  JacobiScratch js;
+  DSB_TRY(js.alloc(batch, n, stream));
+  dim3 gprep(64, batch);
+  svd_prepare_kernel<<<gprep, 256, 0, stream>>>((const zc *)A_dev, nullptr, R, n, m, idx, nact);
+  DSB_LAUNCH_CHECK();
+  const int max_sweeps = 60;
+  DSB_TRY(jacobi_pass(R, n, ncols, idx, nact, batch, 0, m, n, max_sweeps, 0.0, sweeps, js, stream));
+  dim3 gp(32, batch);
+  svd_pinv_kernel<<<gp, 256, sizeof(double) * n, stream>>>(R, nact, m, n, (zc *)pinv_dev, rcond);
+  DSB_LAUNCH_CHECK();
+  std::vector<int32_t> hs(batch, 0);
+  DSB_CUDA(cudaMemcpyAsync(hs.data(), sweeps, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, stream));
+  DSB_CUDA(cudaStreamSynchronize(stream));
+  js.release(stream);
+  cudaFreeAsync(R, stream);
+  cudaFreeAsync(idx, stream);
+  cudaFreeAsync(nact, stream);
+  cudaFreeAsync(sweeps, stream);
+  for (int b = 0; b < batch; ++b)
+    DSB_CHECK(hs[b] < max_sweeps, DSB_ERR_NUMERIC, "dsb_pinv_batched: Jacobi did not converge for block %d", b);
   return DSB_OK;
 }

@@ -71,6 +71,15 @@ class Comm:
         self._dist.all_gather(out, mine)
         return np.stack([o.cpu().numpy() for o in out])
 
+    def gather_objects(self, obj):
+        """Gather one picklable object per rank on rank 0 (``mpiutil.world.gather``,
+        kltransform.py:26-29); other ranks receive None."""
+        if self.size == 1:
+            return [obj]
+        out = [None] * self.size if self.rank0 else None
+        self._dist.gather_object(obj, out, dst=0)
+        return out
+
     def exchange_mblocks(self, buf, nfc, moff, nm, f_lo=None):
         """Frequency-major -> m-major regrouping (``mpiutil.transpose_blocks`` at
         beamtransfer.py:632).

@@ -86,6 +86,8 @@ def _decode_dtype(buf, pos=0):
         return np.dtype("<f%d" % size), 8 + 12
     if cls == 0:
         return np.dtype(("<i%d" if b0 & 0x08 else "<u%d") % size), 8 + 4
+    if cls == 3:
+        return np.dtype("S%d" % size), 8
     if cls == 6:
         nmem = b0 | (b1 << 8)
         p = pos + 8
@@ -129,8 +131,16 @@ def _message(mtype, body, flags=0):
 
 def _attr_message(name, value):
     arr = np.asarray(value)
-    if arr.dtype.kind in "US":
-        raise TypeError("string attributes are not supported by h5lite")
+    if arr.dtype.kind == "U":  # stored as a fixed-length, null-padded UTF-8 string
+        enc = [str(v).encode("utf-8") for v in arr.reshape(-1)]
+        arr = np.array(enc, dtype="S%d" % max(1, max(len(e) for e in enc))).reshape(arr.shape)
+    if arr.dtype.kind == "S":
+        nm = name.encode() + b"\0"
+        dt = struct.pack("<BBBBI", 0x13, 0x11, 0, 0, arr.dtype.itemsize)
+        ds = _encode_dataspace(arr.shape)
+        body = (struct.pack("<BxHHH", 1, len(nm), len(dt), len(ds)) + _pad8(nm) + _pad8(dt) + _pad8(ds)
+                + np.ascontiguousarray(arr).tobytes())
+        return _message(0x000C, body)
     if arr.dtype == np.bool_:
         arr = arr.astype(np.uint8)
     arr = np.asarray(arr.astype(arr.dtype.newbyteorder("<")), order="C")  # keeps 0-d scalars 0-d
@@ -190,6 +200,9 @@ def _decode_attr(body):
     p += (ssz + 7) // 8 * 8
     n = int(np.prod(shape)) if shape else 1
     val = np.frombuffer(body, dtype=dt, count=n, offset=p).reshape(shape).copy()
+    if dt.kind == "S":  # strings come back as str, as h5py returns them
+        val = np.char.decode(val, "utf-8")
+        return name, (str(val[()]) if shape == () else val)
     return name, (val[()] if shape == () else val)
 
 

@@ -180,6 +180,47 @@ int dsb_project_sky_to_svd(const void *beam_svd_dev, const void *vec_dev, const 
                            const int32_t *svbounds_host, int nfreq, int svd_len, int npol_sky,
                            int npol_use, int nl, int nrhs, void *out_dev, void *stream);
 
+/* scipy.linalg.pinv(A[b], rcond) of a batch of n x m complex128 blocks -> [batch][m][n]
+ * (drift/util/blockla.py:117-138 pinv_dm, the routine BeamTransfer.invbeam_m uses,
+ * drift/core/beamtransfer.py:344).  rcond < 0 selects max(n, m) * eps. */
+int dsb_pinv_batched(const void *A_dev, int batch, int n, int m, double rcond, void *pinv_dev,
+                     void *stream);
+
+/* ---- KL transform (BASELINE config 5) --------------------------------------
+ * project_matrix_sky_to_svd (drift/core/beamtransfer.py:1135-1188) for one m:
+ *   beam_svd c128 [nfreq][svd_len][npol_sky][nl];  mat f64 [npol_sky][npol_sky][nl][nfreq][nfreq]
+ *   polpair_nonzero_host uint8 [npol_sky][npol_sky] (NULL = all): pairs whose C_l block is zero are skipped
+ *   out c128 [ndof][ndof], ndof = svbounds[nfreq]. */
+int dsb_project_matrix_sky_to_svd(const void *beam_svd_dev, const double *mat_dev,
+                                  const uint8_t *polpair_nonzero_host, const int32_t *svnum_host,
+                                  const int32_t *svbounds_host, int nfreq, int svd_len, int npol_sky,
+                                  int npol_use, int nl, void *out_dev, void *stream);
+
+/* project_matrix_diagonal_telescope_to_svd (drift/core/beamtransfer.py:1190-1231):
+ *   beam_ut c128 [nfreq][svd_len][ntel];  dmat f64 [nfreq][ntel];  out c128 [ndof][ndof]. */
+int dsb_project_matrix_diagonal_telescope_to_svd(const void *beam_ut_dev, const double *dmat_dev,
+                                                 const int32_t *svnum_host, const int32_t *svbounds_host,
+                                                 int nfreq, int svd_len, int ntel, void *out_dev,
+                                                 void *stream);
+
+/* scipy.linalg.eigh(A, B) as called by kltransform.eigh_gen (drift/core/kltransform.py:55-121):
+ * A, B c128 [n][n] Hermitian (device, not modified); evals f64 [n] ascending; evecs c128 [n][n],
+ * eigenvectors in columns with v^H B v = 1.  *info_host = 0, or the order of the leading minor of
+ * B that is not positive definite (LAPACK's info - n); the outputs are then undefined and the
+ * caller regularises B as the reference does (dsb_eigvalsh, dsb_add_diagonal). */
+int dsb_eigh_gen(const void *A_dev, const void *B_dev, int n, double *evals_dev, void *evecs_dev,
+                 int32_t *info_host, void *stream);
+/* scipy.linalg.eigvalsh(A) (kltransform.py:103): ascending eigenvalues of a Hermitian matrix. */
+int dsb_eigvalsh(const void *A_dev, int n, double *evals_dev, void *stream);
+/* A[i][i] += value (kltransform.py:106). */
+int dsb_add_diagonal(void *A_dev, int n, double value, void *stream);
+/* out (r x r) = E C E^H, E c128 [r][n], C c128 [n][n] Hermitian; tmp c128 [r][n]
+ * (drift/core/doublekl.py:72-73, kltransform.py:812). */
+int dsb_herm_congruence(const void *E_dev, const void *C_dev, int r, int n, void *tmp_dev, void *out_dev,
+                        void *stream);
+/* C (M x N) = A (M x K) B (K x N), row-major complex128, B square (K == N). */
+int dsb_zgemm(const void *A_dev, const void *B_dev, int M, int N, int K, void *C_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -270,8 +270,14 @@ def main():
 
     import importlib
 
-    # kltransform imports skymodel (cora cosmology) -> replace before import
-    sys.modules["drift.core.skymodel"] = types.ModuleType("drift.core.skymodel")
+    # kltransform imports skymodel (cora cosmology, not installable) -> the repo's documented
+    # synthetic C_l(nu, nu') models stand in for it on BOTH sides of the comparison
+    from driftscan_b200.core import skymodel as myskymodel
+
+    sys.modules["drift.core.skymodel"] = myskymodel
+    import drift.core
+
+    drift.core.skymodel = myskymodel
     from drift.core import telescope as rtel, visibility as rvis, beamtransfer as rbt
     from drift.telescope import cylinder as rcyl, cylbeam as rcylbeam
     from drift.util import _fast_tools as rft, blockla as rbla
@@ -393,6 +399,38 @@ def main():
     prod["svd_len"] = bt.svd_len
     prod["ndof_7"] = bt.ndof(7)
     np.savez_compressed(os.path.join(OUT, "products_small.npz"), **prod)
+
+    # ---- (5b) KL / DoubleKL transforms of the small product (reference kltransform.py,
+    # doublekl.py unmodified; scipy.linalg.eigh = LAPACK zhegvd) -------------------------
+    from drift.core import kltransform as rkl, doublekl as rdkl
+
+    klg = {}
+    kl = rkl.KLTransform(bt, subdir="kl")
+    kl.read_config(dict(threshold=0.1, subset=False, inverse=False))
+    dk = rdkl.DoubleKL(bt, subdir="dk")
+    dk.read_config(dict(threshold=0.1, subset=False, inverse=False, foreground_threshold=0.05))
+    klg["signal"] = kl.signal()
+    klg["foreground"] = kl.foreground()
+    for mi in (0, 1, 7, tels.mmax):
+        cs, cn = kl.sn_covariance(mi)
+        klg[f"cs_{mi}"], klg[f"cn_{mi}"] = cs, cn
+        evals, evecs, inv, extra = kl._transform_m(mi)
+        klg[f"kl_evals_{mi}"], klg[f"kl_evecs_{mi}"], klg[f"kl_ac_{mi}"] = evals, evecs, extra["ac"]
+        evals, evecs, inv, extra = dk._transform_m(mi)
+        klg[f"dk_evals_{mi}"], klg[f"dk_evecs_{mi}"], klg[f"dk_fevals_{mi}"] = evals, evecs, extra["f_evals"]
+        klg[f"ndof_{mi}"] = bt.ndof(mi)
+    # eigh_gen alone, incl. the not-positive-definite branch and the A == 0 branch
+    n = 24
+    X = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    Y = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    Ah = X @ X.conj().T
+    Bh = Y @ Y.conj().T + 0.5 * np.eye(n)
+    ev, evc, ac = rkl.eigh_gen(Ah.copy(), Bh.copy())
+    klg["eg_A"], klg["eg_B"], klg["eg_evals"], klg["eg_evecs"], klg["eg_ac"] = Ah, Bh, ev, evc, ac
+    Bbad = Bh - 0.6 * np.eye(n) * np.linalg.eigvalsh(Bh)[0] / 0.5 - np.eye(n) * np.linalg.eigvalsh(Bh)[0]
+    ev, evc, ac = rkl.eigh_gen(Ah.copy(), Bbad.copy())
+    klg["eg_Bbad"], klg["eg_bad_evals"], klg["eg_bad_ac"] = Bbad, ev, ac
+    np.savez_compressed(os.path.join(OUT, "kl_small.npz"), **klg)
 
     # default polsvcut (1e-4) exercises the non-trivial null-space branch
     bt2 = run_products(tels, "/fake/small2/bt/")

@@ -74,3 +74,15 @@ def test_empty_and_scalar(tmp_path):
         assert f["empty"].shape == (0, 4) and f["empty"][...].size == 0
         assert f["f32"].dtype == np.float32 and f["c64"].dtype == np.complex64
         assert np.array_equal(f["c64"][:], (np.arange(4) * (1 + 2j)).astype(np.complex64))
+
+
+def test_string_attributes(tmp_path):
+    """KL product files carry a FLAGS string attribute (kltransform.py:423-431)."""
+    path = str(tmp_path / "s.h5")
+    with h5lite.File(path, "w") as f:
+        f.create_dataset("evals", data=np.arange(3.0))
+        f.attrs["FLAGS"] = "NotPositiveDefinite"
+        f.attrs["m"] = 7
+    with h5lite.File(path, "r") as f:
+        assert f.attrs["FLAGS"] == "NotPositiveDefinite" and isinstance(f.attrs["FLAGS"], str)
+        assert int(f.attrs["m"]) == 7

@@ -1,0 +1,160 @@
+"""GPU: KL / DoubleKL transforms, covariance projections, eigh_gen and invbeam_m through the
+drop-in API, against the oracle (oracle/kl.py) and the spectra the REFERENCE's own
+kltransform.py / doublekl.py produced (tests/golden/kl_small.npz)."""
+
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SMALL_CFG = dict(
+    num_freq=3, freq_start=100.0, freq_end=112.0, freq_mode="edge",
+    num_cylinders=2, cylinder_width=5.0, num_feeds=3, feed_spacing=1.5, tsys=1.0,
+)
+
+
+@pytest.fixture(scope="module")
+def products(tmp_path_factory):
+    from driftscan_b200.core import beamtransfer
+    from driftscan_b200.telescope import cylinder
+
+    d = str(tmp_path_factory.mktemp("prodkl") / "bt")
+    tel = cylinder.PolarisedCylinderTelescope.from_config(dict(SMALL_CFG, precision="fp64"))
+    bt = beamtransfer.BeamTransfer(d, telescope=tel)
+    bt.read_config(dict(polsvcut=1.0))
+    bt.generate()
+    return bt
+
+
+def test_eigh_gen_device(golden_dir):
+    from driftscan_b200.core import kltransform
+
+    g = np.load(os.path.join(golden_dir, "kl_small.npz"))
+    A, B = g["eg_A"], g["eg_B"]
+    ev, evc, ac = kltransform.eigh_gen(A, B)
+    assert ac == 0.0
+    assert np.allclose(ev, g["eg_evals"], rtol=1e-10, atol=1e-12 * g["eg_evals"].max())
+    assert np.abs(evc.conj().T @ B @ evc - np.eye(len(ev))).max() < 1e-10  # scipy's normalisation
+    assert np.abs(A @ evc - (B @ evc) * ev).max() <= 1e-10 * np.abs(A).max()
+    # B not positive definite: the reference's diagonal regularisation (kltransform.py:103-108)
+    ev, evc, ac = kltransform.eigh_gen(A, g["eg_Bbad"])
+    assert np.isclose(ac, float(g["eg_bad_ac"]), rtol=1e-9) and ac > 0
+    assert np.allclose(ev, g["eg_bad_evals"], rtol=1e-7)
+    # A == 0 (kltransform.py:82-86)
+    ev, evc, ac = kltransform.eigh_gen(np.zeros((6, 6), dtype=np.complex128), B[:6, :6])
+    assert np.all(ev == 0) and np.array_equal(evc, np.eye(6)) and ac == 0.0
+    # a larger random problem against scipy-free invariants
+    rng = np.random.default_rng(5)
+    n = 150
+    X = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    Y = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    A2, B2 = X @ X.conj().T, Y @ Y.conj().T + n * np.eye(n)
+    ev, evc, ac = kltransform.eigh_gen(A2, B2)
+    assert np.all(np.diff(ev) >= 0)
+    assert np.abs(evc.conj().T @ B2 @ evc - np.eye(n)).max() < 1e-9
+    assert np.abs(A2 @ evc - (B2 @ evc) * ev).max() <= 1e-9 * np.abs(A2).max()
+
+
+@pytest.mark.parametrize("mi", [0, 1, 7, 24])
+def test_kl_against_reference(products, golden_dir, mi):
+    from driftscan_b200.core import kltransform
+    from oracle import kl as okl
+
+    g = np.load(os.path.join(golden_dir, "kl_small.npz"))
+    kl = kltransform.KLTransform(products, subdir="kl")
+    kl.read_config(dict(threshold=0.1, subset=False, inverse=False))
+    assert products.ndof(mi) == int(g[f"ndof_{mi}"])
+    # device projections against the oracle restatement on the same (device-made) product
+    tel = products.telescope
+    bl = np.concatenate([np.arange(tel.npairs)] * 2)
+    npower = tel.noisepower(bl[np.newaxis, :], np.arange(tel.nfreq)[:, np.newaxis]).reshape(tel.nfreq, -1)
+    cs, cn = kl.sn_covariance(mi)
+    ocs, ocn = okl.sn_covariance(products.beam_svd(mi), products.beam_ut(mi), products.beam_singularvalues(mi),
+                                 products.svcut, kl.signal(), kl.foreground(), npower)
+    assert np.abs(cs - ocs).max() <= 1e-12 * np.abs(ocs).max()
+    assert np.abs(cn - ocn).max() <= 1e-12 * np.abs(ocn).max()
+    # moduli are independent of the phases of the SVD basis: compare with the reference's matrices
+    assert np.allclose(np.abs(cs), np.abs(g[f"cs_{mi}"]), rtol=1e-6, atol=1e-8 * np.abs(g[f"cs_{mi}"]).max())
+    assert np.allclose(np.abs(cn), np.abs(g[f"cn_{mi}"]), rtol=1e-6, atol=1e-8 * np.abs(g[f"cn_{mi}"]).max())
+    # the KL spectrum against the reference's (tolerance: see tests/test_oracle_kl.py)
+    evals, evecs, inv, extra = kl._transform_m(mi)
+    ref = g[f"kl_evals_{mi}"]
+    assert extra["ac"] == 0.0 and inv is None
+    assert np.allclose(evals, ref, rtol=2e-5, atol=1e-8 * ref.max())
+    v = evecs.conj().T
+    assert np.abs(v.conj().T @ cn @ v - np.eye(len(evals))).max() < 1e-5
+    assert np.abs(cs @ v - (cn @ v) * evals).max() <= 1e-7 * np.abs(cs).max()
+
+
+@pytest.mark.parametrize("mi", [0, 1, 7, 24])
+def test_double_kl_against_reference(products, golden_dir, mi):
+    from driftscan_b200.core import doublekl
+
+    g = np.load(os.path.join(golden_dir, "kl_small.npz"))
+    dk = doublekl.DoubleKL(products, subdir="dk")
+    dk.read_config(dict(threshold=0.1, subset=False, inverse=False, foreground_threshold=0.05))
+    evals, evecs, inv, extra = dk._transform_m(mi)
+    assert np.allclose(extra["f_evals"], g[f"dk_fevals_{mi}"], rtol=2e-5, atol=1e-8 * g[f"dk_fevals_{mi}"].max())
+    assert evals.shape == g[f"dk_evals_{mi}"].shape
+    if evals.size:
+        assert np.allclose(evals, g[f"dk_evals_{mi}"], rtol=2e-5, atol=1e-8)
+        assert evecs.shape == g[f"dk_evecs_{mi}"].shape
+
+
+def test_kl_products_and_readers(products):
+    from driftscan_b200.core import kltransform
+    from driftscan_b200.util import h5lite
+
+    kl = kltransform.KLTransform(products, subdir="klfiles")
+    kl.read_config(dict(threshold=0.1, subset=True, inverse=True))
+    kl.generate()
+    tel = products.telescope
+    ev_all = kl.evals_all()
+    assert ev_all.shape == (tel.mmax + 1, products.ndofmax)
+    for mi in (0, 7, tel.mmax):
+        with h5lite.File(kl._evfile % mi, "r") as f:
+            assert int(f.attrs["m"]) == mi and f.attrs["FLAGS"] == "Normal"
+            full, ev, evc = f["evals_full"][:], f["evals"][:], f["evecs"][:]
+            assert full.shape == (products.ndof(mi),)
+            assert int(f.attrs["num_modes"]) == ev.size == (full >= 0.1).sum()
+            assert evc.shape == (ev.size, products.ndof(mi))
+            assert np.array_equal(ev_all[mi, products.ndofmax - full.size:], full)
+        modes = kl.modes_m(mi)
+        if ev.size == 0:
+            assert modes == (None, None)
+            continue
+        assert np.array_equal(modes[0], ev)
+        assert kl.evals_m(mi, threshold=1.0) is None or np.all(kl.evals_m(mi, threshold=1.0) >= 1.0)
+        # inverse modes: evecs @ inv^T = 1 on the kept subspace
+        inv = kl.invmodes_m(mi)
+        assert np.abs(modes[1] @ inv - np.eye(ev.size)).max() < 1e-6
+        vec = np.arange(products.ndof(mi)) + 1j
+        klv = kl.project_vector_svd_to_kl(mi, vec)
+        assert np.allclose(klv, modes[1] @ vec)
+        mat = np.eye(products.ndof(mi), dtype=np.complex128)
+        assert np.allclose(kl.project_matrix_svd_to_kl(mi, mat), modes[1] @ modes[1].conj().T, atol=1e-10)
+
+
+def test_invbeam_m(products):
+    """BeamTransfer.invbeam_m (beamtransfer.py:316-358) = blockla.pinv_dm(rcond=1e-6) of the
+    noise-weighted blocks: Moore-Penrose properties against numpy on the same blocks."""
+    from driftscan_b200.util import blockla
+
+    mi = 3
+    ib = products.invbeam_m(mi)
+    tel = products.telescope
+    assert ib.shape == (products.nfreq, tel.num_pol_sky, tel.lmax + 1, products.ntel)
+    rng = np.random.default_rng(2)
+    blocks = rng.standard_normal((4, 9, 14)) + 1j * rng.standard_normal((4, 9, 14))
+    blocks[1, 5:] = blocks[1, :4] * 1e-9  # nearly dependent rows: cut by rcond
+    got = blockla.pinv_dm(blocks, rcond=1e-6)
+    for b in range(4):
+        want = np.linalg.pinv(blocks[b], rcond=1e-6)
+        assert np.abs(got[b] - want).max() <= 1e-9 * np.abs(want).max()
+    noisew = tel.noisepower(np.arange(tel.npairs), 0).flatten() ** (-0.5)
+    beam = (products.beam_m(mi) * noisew[:, np.newaxis, np.newaxis]).reshape(products.nfreq, products.ntel, -1)
+    for fi in range(products.nfreq):
+        want = np.linalg.pinv(beam[fi], rcond=1e-6).reshape(-1, tel.npairs) * noisew
+        assert np.abs(ib[fi].reshape(want.shape) - want).max() <= 1e-8 * np.abs(want).max()

@@ -59,8 +59,16 @@ def run(name, batch, ntel, npol, nl, reps=3):
 
 
 if __name__ == "__main__":
-    run("cfg1  m=0  (8 freqs = 1 m-block)", 8, 104, 4, 97)
-    run("cfg1  8 m-blocks batched", 64, 104, 4, 97)
-    run("cfg2  unpolarised 48 x 126, 32 freqs", 32, 48, 1, 126)
+    only = int(sys.argv[sys.argv.index("--only") + 1]) if "--only" in sys.argv else None
+    cases = [("cfg1  m=0  (8 freqs = 1 m-block)", 8, 104, 4, 97), ("cfg1  8 m-blocks batched", 64, 104, 4, 97),
+             ("cfg2  unpolarised 48 x 126, 32 freqs", 32, 48, 1, 126)]
+    for i, c in enumerate(cases):
+        if only is None or only == i:
+            run(*c, reps=1 if only is not None else 3)
+    if "--big16" in sys.argv:
+        run("cfg3  m=0, 16 freqs", 16, 1520, 4, 234, reps=1)
+    if "--big4" in sys.argv:
+        run("cfg3  m=0, 4 freqs", 4, 1520, 4, 234, reps=1)
     if "--big" in sys.argv:
         run("cfg3  m=0, 2 freqs", 2, 1520, 4, 234, reps=1)
+        run("cfg3  m=0, 16 freqs", 16, 1520, 4, 234, reps=1)
