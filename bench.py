@@ -190,6 +190,113 @@ CPU_SAMPLE_NOTE = ("units = every k-th unit of the lmax-sorted unit list of the 
 # ---------------------------------------------------------------------------------
 
 
+def svd_section(tel, args, rank, world, dev, stream, with_cpu):
+    """Second half of the metric: per-m SVD m-blocks/s on the same workload.
+
+    One m-block = the `--svd-freqs` (default: all 64) frequency blocks `[ntel, 4 (lmax+1)]` of one m:
+    noise whitening, the three-SVD chain and the pseudo-inverse (dsb_svd_chain, everything
+    BeamTransfer._generate_svdfile_m computes per m).  The blocks are REAL beam-transfer blocks:
+    they are produced on the device by the transfer stage (untimed here) for a sample of m values
+    spread over 0..mmax; rank r takes the sample values r, r + world, ... (m-blocks are independent).
+    The timed region holds the blocks resident in HBM and ends with the results in HBM."""
+    import torch
+
+    from driftscan_b200 import _lib
+
+    eng = tel.engine
+    nb, npol, lside, mmax = tel.nbase, 4, tel.lmax, tel.mmax
+    nl, ntel = lside + 1, 2 * tel.nbase
+    svd_len = min(nl, ntel)
+    ms_all = [int(x) for x in args.svd_ms.split(",") if x != ""]
+    ms_mine = ms_all[rank::world]
+    nfs = min(args.svd_freqs, tel.nfreq)
+    f_sel = np.unique(np.linspace(0, tel.nfreq - 1, nfs).astype(int))
+    nfs = len(f_sel)
+    blocks = {m: torch.zeros((nfs, ntel, npol, nl), dtype=torch.complex128, device=dev) for m in ms_mine}
+    # transfer stage, two frequencies at a time, keeping only the sampled m (setup, untimed)
+    total2, moff2 = _lib.mmajor_offsets(2, nb, npol, lside, mmax)
+    buf = torch.zeros(total2, dtype=torch.complex128, device=dev)
+    for c0 in range(0, nfs, 2):
+        fch = f_sel[c0:c0 + 2]
+        nfc = len(fch)
+        fgrid, bgrid = np.meshgrid(np.arange(nfc), np.arange(nb), indexing="ij")
+        f_ind, b_ind = fch[fgrid.ravel()], bgrid.ravel()
+        lmax_u, _ = tel.unit_lmax(b_ind, f_ind)
+        buf.zero_()
+        eng.transfer_mmajor(b_ind, f_ind, lmax_u, fgrid.ravel().astype(np.int32), bgrid.ravel().astype(np.int32),
+                            2, nb, lside, mmax, buf.data_ptr(), False, stream=stream)
+        for m in ms_mine:
+            blk = buf[int(moff2[m]):int(moff2[m + 1])].reshape(2, ntel, npol, nl - m)
+            blocks[m][c0:c0 + nfc, :, :, m:] = blk[:nfc]
+    torch.cuda.synchronize()
+    del buf
+    noise = tel.noisepower(np.arange(tel.npairs)[np.newaxis, :], f_sel[:, np.newaxis]).reshape(nfs, tel.npairs) ** (-0.5)
+    noisew = torch.from_numpy(np.ascontiguousarray(np.concatenate([noise, noise], axis=1))).to(dev)
+    bsvd = torch.empty((nfs, svd_len, npol, nl), dtype=torch.complex128, device=dev)
+    but = torch.empty((nfs, svd_len, ntel), dtype=torch.complex128, device=dev)
+    ibs = torch.empty((nfs, npol, nl, svd_len), dtype=torch.complex128, device=dev)
+    sv = torch.empty((nfs, svd_len), dtype=torch.float64, device=dev)
+    nmodes = torch.empty((nfs,), dtype=torch.int32, device=dev)
+
+    def chain(m):
+        _lib.check(_lib.lib.dsb_svd_chain(blocks[m].data_ptr(), noisew.data_ptr(), nfs, ntel, npol, nl, svd_len, 1e-10,
+                                          1e-4, bsvd.data_ptr(), but.data_ptr(), ibs.data_ptr(), sv.data_ptr(),
+                                          nmodes.data_ptr(), stream))
+
+    if ms_mine:
+        chain(ms_mine[-1])  # warm-up (allocator pools, module load)
+    torch.cuda.synchronize()
+    per_m, modes = {}, {}
+    l0 = _lib.launch_count()
+    for m in ms_mine:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        chain(m)
+        e1.record()
+        torch.cuda.synchronize()
+        per_m[m] = e0.elapsed_time(e1)
+        modes[m] = int(nmodes.max().item())
+    launches = _lib.launch_count() - l0
+    t_mine = sum(per_m.values())
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([t_mine], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_max = float(t.item())
+    else:
+        t_max = t_mine
+    out = {
+        "metric": "per-m SVD m-blocks/s", "unit": "m-blocks/s",
+        "value": len(ms_all) / (t_max * 1e-3) if t_max > 0 else None,
+        "sample": f"m = {ms_all} of 0..{mmax}, {nfs} frequencies per m-block, blocks [{ntel} x {npol}*{nl}] c128 taken "
+                  "from the device transfer stage of this workload; whitening + 3-SVD chain + pinv per (m, freq); "
+                  "value = sampled m-blocks / max-over-ranks device time",
+        "ms_per_mblock_rank0": {str(k): v for k, v in per_m.items()}, "max_modes_rank0": {str(k): v for k, v in modes.items()},
+        "gpu_launches": int(launches), "dtype": "f64 (complex128)",
+    }
+    if with_cpu and ms_mine:
+        # CPU baseline beside it: the oracle's restatement of the reference chain (scipy.linalg.svd /
+        # pinv = LAPACK, multi-threaded BLAS) on a bounded sample of the same blocks
+        from oracle import svd as osvd
+
+        t_cpu, n_cpu = 0.0, 0
+        for m in ms_mine:
+            for fi in np.linspace(0, nfs - 1, min(args.svd_cpu_blocks, nfs)).astype(int):
+                bf = blocks[m][int(fi)].cpu().numpy()
+                nw = noisew[int(fi)].cpu().numpy()
+                t0 = time.time()
+                osvd.svd_chain(bf, nw, npol, nl, svd_len, 1e-4)
+                t_cpu += time.time() - t0
+                n_cpu += 1
+        per_block = t_cpu / max(n_cpu, 1)
+        out["cpu_baseline"] = {"value": 1.0 / (per_block * nfs), "unit": "m-blocks/s", "cores": os.cpu_count(),
+                               "kind": "port",
+                               "sample": f"{n_cpu} (m, freq) blocks of the same sample in {t_cpu:.1f} s, scaled to "
+                                         f"{nfs} frequencies per m-block; oracle/svd.py (scipy LAPACK zgesdd + pinv)"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,6 +308,11 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-svd", action="store_true", help="skip the per-m SVD measurement (second half of the metric)")
+    ap.add_argument("--svd-only", action="store_true", help="diagnostic: run only the per-m SVD measurement")
+    ap.add_argument("--svd-ms", default="0,70,140,210", help="sample of m values the SVD stage is timed on")
+    ap.add_argument("--svd-freqs", type=int, default=64, help="frequencies per m-block in the SVD measurement")
+    ap.add_argument("--svd-cpu-blocks", type=int, default=2, help="(m, freq) blocks per sampled m for the CPU SVD baseline")
     ap.add_argument("--force-scatter", action="store_true", help="use the scatter output path at N = 1 too (diagnostic)")
     ap.add_argument("--no-fence", action="store_true", help="skip the per-step fence collective (diagnostic only)")
     ap.add_argument("--nccl-exchange", action="store_true",
@@ -272,6 +384,14 @@ def main():
     from driftscan_b200 import parallel
 
     comm = parallel.Comm.current()
+
+    if args.svd_only:
+        svd = svd_section(tel, args, rank, world, dev, stream, with_cpu=(world == 1 and not args.no_cpu_baseline))
+        if rank == 0:
+            print(json.dumps({"svd": svd, "n_gpus": world, "config": config}))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
 
     eng = tel.engine
     nb, np_inc, lside, mmax = tel.nbase, 4, tel.lmax, tel.mmax
@@ -499,6 +619,15 @@ def main():
         cpu = {"value": ups, "unit": "units/s", "cores": cores, "kind": "port",
                "sample": f"{n} units in {dt:.1f} s; " + CPU_SAMPLE_NOTE}
 
+    # ---- second half of the metric: per-m SVD m-blocks/s (frees the transfer buffers first)
+    svd = None
+    if not args.no_svd:
+        del out_dev
+        if scatter is not None:
+            scatter.close()
+        torch.cuda.empty_cache()
+        svd = svd_section(tel, args, rank, world, dev, stream, with_cpu=(world == 1 and not args.no_cpu_baseline))
+
     if rank == 0:
         line = {
             "metric": "beam-transfer (baseline*freq)/s", "value": value, "unit": "units/s", "n_gpus": world,
@@ -506,7 +635,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3->f32 (fp64 phase)" if args.precision == "fp32x3" else "f64",
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": dominant, "roofline_all": [roof_ring, roof_leg, roof_pack],
-            "stage_launches_per_run": stage_launch, "cpu_baseline": cpu, "exchange": exchange,
+            "stage_launches_per_run": stage_launch, "cpu_baseline": cpu, "exchange": exchange, "svd": svd,
         }
         print(json.dumps(line))
     if world > 1:

@@ -12,6 +12,11 @@ struct JacobiScratch {
   int32_t *skip = nullptr;                                   // [batch][npairs_ld]
   zc *W = nullptr;                                           // [batch][npairs_ld][32 * 32]
   int npairs_ld = 0;
+  double *nrm2 = nullptr;       // [batch][ldr_max] row norms by position, refreshed every sweep
+  int32_t *nlive = nullptr;     // [batch] live row blocks
+  int32_t *blkstamp = nullptr;  // [batch][nblk_ld] step at which a block was last modified
+  int32_t *pairstamp = nullptr; // [batch][nblk_ld][nblk_ld] step at which a pair was last found orthogonal
+  int nblk_ld = 0, ldr_max = 0;
   int32_t *h_flag = nullptr;  // pinned [2]
   int alloc(int batch, int nrows_max, cudaStream_t stream);
   void release(cudaStream_t stream);

@@ -53,12 +53,14 @@ __device__ __forceinline__ double warp_sum(double v) {
 // cost one Gram evaluation and no update.
 // ---------------------------------------------------------------------------------------------
 
-// amax[b] = max_r |row idx[r]|^2 over columns [ip0, ip1)
+// nrm2[b][r] = |row idx[r]|^2 over columns [ip0, ip1) (by POSITION in the active list);
+// amax[b] = max_r (only when set_max: the floor of a pass is fixed by its first sweep)
 __global__ void __launch_bounds__(256)
-row_norm_max_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
-                    const int32_t *__restrict__ nact_all, int ip0, int ip1,
-                    unsigned long long *__restrict__ amax_all) {
+row_norms_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
+                 const int32_t *__restrict__ nact_all, int ip0, int ip1, double *__restrict__ nrm2_all,
+                 unsigned long long *__restrict__ amax_all, int set_max, const int32_t *__restrict__ done_all) {
   const int b = blockIdx.y;
+  if (done_all[b]) return;
   const int n = nact_all[b];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int r = blockIdx.x * nwarps + warp;
@@ -67,8 +69,15 @@ row_norm_max_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32
   double a = 0.0;
   for (int c = ip0 + lane; c < ip1; c += 32) a += x[c].x * x[c].x + x[c].y * x[c].y;
   a = warp_sum(a);
-  if (lane == 0) atomicMax(&amax_all[b], (unsigned long long)__double_as_longlong(a));
+  if (lane == 0) {
+    nrm2_all[(size_t)b * ldr + r] = a;
+    if (set_max) atomicMax(&amax_all[b], (unsigned long long)__double_as_longlong(a));
+  }
 }
+
+// nlive[b] = number of row blocks holding at least one row above the floor
+__global__ void live_blocks_kernel(const double *__restrict__ nrm2_all, int ldr, const int32_t *__restrict__ nact_all,
+                                   const unsigned long long *__restrict__ amax_all, int32_t *__restrict__ nlive_all);
 
 constexpr int kJB = 16;       // rows per block
 constexpr int kJ2 = 2 * kJB;  // rows per block pair
@@ -76,7 +85,8 @@ constexpr int kGT = 32;       // Gram: columns per shared-memory tile
 constexpr int kAT = 128;      // apply: columns per CTA
 
 // slots of a block pair: the kJ2 row positions (lower block first) and how many are real rows
-__device__ __forceinline__ bool bj_pair_slots(int n, int step, int k, int &pos_a, int &pos_b, int &nvalid) {
+__device__ __forceinline__ bool bj_pair_slots(int n, int step, int k, int &pos_a, int &pos_b, int &nvalid,
+                                              int *blk_a = nullptr, int *blk_b = nullptr) {
   const int nblk = (n + kJB - 1) / kJB;
   const int P = max(2, (nblk + 1) & ~1);
   if (step >= P - 1 || k >= P / 2) return false;
@@ -94,6 +104,8 @@ __device__ __forceinline__ bool bj_pair_slots(int n, int step, int k, int &pos_a
     tb = t;
   }
   if (ta >= nblk) return false;  // both blocks are dummies
+  if (blk_a) *blk_a = ta;
+  if (blk_b) *blk_b = tb;
   pos_a = ta * kJB;
   pos_b = tb * kJB;  // may lie beyond n (dummy block)
   const int na = min(kJB, n - pos_a);
@@ -106,12 +118,34 @@ __device__ __forceinline__ int bj_slot_pos(int s, int pos_a, int pos_b) {
   return s < kJB ? pos_a + s : pos_b + (s - kJB);
 }
 
+__global__ void live_blocks_kernel(const double *__restrict__ nrm2_all, int ldr, const int32_t *__restrict__ nact_all,
+                                   const unsigned long long *__restrict__ amax_all, int32_t *__restrict__ nlive_all) {
+  const int b = blockIdx.x;
+  const int n = nact_all[b];
+  const double floor2 = 1e-28 * __longlong_as_double((long long)amax_all[b]);
+  const double *nrm2 = nrm2_all + (size_t)b * ldr;
+  int live = 0;
+  for (int t = threadIdx.x; t * kJB < n; t += blockDim.x) {
+    bool any = false;
+    for (int r = t * kJB; r < min(n, (t + 1) * kJB); ++r) any |= nrm2[r] >= floor2;
+    live += any;
+  }
+  __shared__ int s_live;
+  if (threadIdx.x == 0) s_live = 0;
+  __syncthreads();
+  if (live) atomicAdd(&s_live, live);
+  __syncthreads();
+  if (threadIdx.x == 0) nlive_all[b] = s_live;
+}
+
 __global__ void __launch_bounds__(256, 2)
 bj_gram_eig_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
                    const int32_t *__restrict__ nact_all, int ip0, int ip1, int step, double tol,
                    const unsigned long long *__restrict__ amax_all, zc *__restrict__ Wall,
                    int32_t *__restrict__ skip_all, int32_t *__restrict__ rot_all,
-                   const int32_t *__restrict__ done_all, int npairs_ld, int do_sort, int inner_sweeps) {
+                   const int32_t *__restrict__ done_all, int npairs_ld, int do_sort, int inner_sweeps,
+                   double *__restrict__ nrm2_all, const int32_t *__restrict__ nlive_all,
+                   int32_t *__restrict__ blkstamp_all, int32_t *__restrict__ pairstamp_all, int nblk_ld, int now) {
   const int b = blockIdx.y, k = blockIdx.x, tid = threadIdx.x;
   int32_t *skip = skip_all + (size_t)b * npairs_ld + k;
   if (done_all[b]) {
@@ -120,9 +154,34 @@ bj_gram_eig_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32_
   }
   const int n = nact_all[b];
   int pos_a, pos_b, nvalid;
-  if (n < 2 || !bj_pair_slots(n, step, k, pos_a, pos_b, nvalid)) {
+  int blk_a = 0, blk_b = 0;
+  if (n < 2 || !bj_pair_slots(n, step, k, pos_a, pos_b, nvalid, &blk_a, &blk_b)) {
     if (tid == 0) *skip = 1;
     return;
+  }
+  const double floor2 = 1e-28 * __longlong_as_double((long long)amax_all[b]);
+  double *nrm2 = nrm2_all + (size_t)b * ldr;
+  int32_t *blkstamp = blkstamp_all + (size_t)b * nblk_ld;
+  int32_t *pairstamp = pairstamp_all + (size_t)b * nblk_ld * nblk_ld + (size_t)blk_a * nblk_ld + blk_b;
+  {
+    // (1) the pair was found orthogonal and neither block has been touched since: nothing to do;
+    // (2) a block without a single row above the floor (the null rows of a rank-deficient matrix,
+    //     which the sorting collects in the last blocks) has nothing to rotate -- as long as at
+    //     least two live blocks exist, every live block is still orthogonalised internally.
+    const bool unchanged = *pairstamp > max(blkstamp[blk_a], blkstamp[blk_b]);
+    bool live_a = false, live_b = false;
+    if (!unchanged && nlive_all[b] >= 2) {
+      for (int i = 0; i < kJB; ++i) {
+        if (i < min(kJB, nvalid)) live_a |= nrm2[pos_a + i] >= floor2;
+        if (kJB + i < nvalid) live_b |= nrm2[pos_b + i] >= floor2;
+      }
+    } else {
+      live_a = live_b = true;
+    }
+    if (unchanged || !live_a || !live_b) {
+      if (tid == 0) *skip = 1;
+      return;
+    }
   }
   static_assert(kGT == kJ2, "the Gram tile is reused for W");
   __shared__ zc s_tile[kGT][kJ2 + 1];  // [column][slot]; dead after the Gram loop
@@ -206,10 +265,9 @@ bj_gram_eig_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32_
   }
   if (tid == 0) s_flag = 0;
   __syncthreads();
-  // Rows whose norm is at the rounding level of the largest row are numerically zero: a
-  // pair involving such a row is not rotated (its angle to anything is noise and would
+  // Rows whose norm is at the rounding level of the largest row (floor2) are numerically zero:
+  // a pair involving such a row is not rotated (its angle to anything is noise and would
   // never settle); singular values below 1e-14 of the largest are noise in any case.
-  const double floor2 = 1e-28 * __longlong_as_double((long long)amax_all[b]);
   if (tol <= 0.0) tol = 2e-15 * sqrt((double)(ip1 - ip0));  // rounding level of the inner product
   const double tol2 = tol * tol;
   // The small problem is solved well below the convergence threshold: G is only updated, not
@@ -231,7 +289,11 @@ bj_gram_eig_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32_
   }
   __syncthreads();
   if (!s_flag) {
-    if (tid == 0) *skip = 1;
+    if (tid < nvalid) nrm2[bj_slot_pos(tid, pos_a, pos_b)] = s_G[tid][tid].x;
+    if (tid == 0) {
+      *skip = 1;
+      *pairstamp = now;
+    }
     return;
   }
   // ---- cyclic two-sided Jacobi on G (parallel ordering: 16 disjoint pairs per step).
@@ -327,8 +389,11 @@ bj_gram_eig_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32_
     const int i = e / kJ2, j = e % kJ2;
     W[s_rank[i] * kJ2 + j] = s_W[i][j];
   }
+  if (tid < nvalid) nrm2[bj_slot_pos(s_rank[tid], pos_a, pos_b)] = fmax(s_G[tid][tid].x, 0.0);
   if (tid == 0) {
     *skip = 0;
+    blkstamp[blk_a] = now;
+    blkstamp[blk_b] = now;
     atomicAdd(&rot_all[b], 1);
   }
 }
@@ -400,16 +465,18 @@ bj_apply_kernel(zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__rest
 // end of a sweep: a matrix that saw no rotation is converged
 __global__ void sweep_end_kernel(int batch, int32_t *__restrict__ rot, int32_t *__restrict__ done,
                                  int32_t *__restrict__ sweeps, int32_t *__restrict__ nleft) {
-  int left = 0;
+  int left = 0, nrot = 0;
   for (int b = threadIdx.x; b < batch; b += blockDim.x) {
     if (!done[b]) {
       sweeps[b] += 1;
       if (rot[b] == 0) done[b] = 1;
       else left += 1;
+      nrot += rot[b];
     }
     rot[b] = 0;
   }
   if (left) atomicAdd(nleft, left);
+  if (nrot) atomicAdd(nleft + 1, nrot);  // block pairs updated in this sweep (diagnostic)
 }
 
 __global__ void max_nact_kernel(int batch, const int32_t *__restrict__ nact, int32_t *__restrict__ out) {
@@ -427,6 +494,12 @@ int JacobiScratch::alloc(int batch, int nrows_max, cudaStream_t stream) {
   DSB_CUDA(cudaMallocAsync((void **)&flag, sizeof(int32_t) * 2, stream));
   DSB_CUDA(cudaMallocAsync((void **)&skip, sizeof(int32_t) * (size_t)batch * npairs_ld, stream));
   DSB_CUDA(cudaMallocAsync((void **)&W, sizeof(zc) * (size_t)batch * npairs_ld * kJ2 * kJ2, stream));
+  nblk_ld = 2 * npairs_ld;
+  ldr_max = nrows_max;
+  DSB_CUDA(cudaMallocAsync((void **)&nrm2, sizeof(double) * (size_t)batch * nrows_max, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&nlive, sizeof(int32_t) * batch, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&blkstamp, sizeof(int32_t) * (size_t)batch * nblk_ld, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&pairstamp, sizeof(int32_t) * (size_t)batch * nblk_ld * nblk_ld, stream));
   DSB_CUDA(cudaMallocHost((void **)&h_flag, sizeof(int32_t) * 2));
   return DSB_OK;
 }
@@ -437,6 +510,10 @@ void JacobiScratch::release(cudaStream_t stream) {
   cudaFreeAsync(flag, stream);
   cudaFreeAsync(skip, stream);
   cudaFreeAsync(W, stream);
+  cudaFreeAsync(nrm2, stream);
+  cudaFreeAsync(nlive, stream);
+  cudaFreeAsync(blkstamp, stream);
+  cudaFreeAsync(pairstamp, stream);
   if (h_flag) cudaFreeHost(h_flag);
 }
 
@@ -471,23 +548,33 @@ int jacobi_pass(zc *R, int ldr, int ncols, const int32_t *idx, const int32_t *na
   static const int inner_sweeps = getenv("DSB_SVD_INNER") ? atoi(getenv("DSB_SVD_INNER")) : 8;
   static const bool debug = getenv("DSB_SVD_DEBUG") != nullptr;
   const dim3 gnorm((nmax + 7) / 8, batch), gpair(P / 2, batch), gapply((ncols + kAT - 1) / kAT, P / 2, batch);
-  row_norm_max_kernel<<<gnorm, 256, 0, stream>>>(R, ldr, ncols, idx, nact, ip0, ip1, js.amax);
-  DSB_LAUNCH_CHECK();
+  DSB_CHECK(ldr <= js.ldr_max, DSB_ERR_INVALID, "jacobi_pass: scratch allocated for fewer rows");
+  DSB_CUDA(cudaMemsetAsync(js.blkstamp, 0, sizeof(int32_t) * (size_t)batch * js.nblk_ld, stream));
+  DSB_CUDA(cudaMemsetAsync(js.pairstamp, 0, sizeof(int32_t) * (size_t)batch * js.nblk_ld * js.nblk_ld, stream));
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    row_norms_kernel<<<gnorm, 256, 0, stream>>>(R, ldr, ncols, idx, nact, ip0, ip1, js.nrm2, js.amax, sweep == 0,
+                                                js.done);
+    DSB_LAUNCH_CHECK();
+    live_blocks_kernel<<<batch, 128, 0, stream>>>(js.nrm2, ldr, nact, js.amax, js.nlive);
+    DSB_LAUNCH_CHECK();
     for (int step = 0; step < P - 1; ++step) {
+      const int now = sweep * (P - 1) + step + 1;
       bj_gram_eig_kernel<<<gpair, 256, 0, stream>>>(R, ldr, ncols, idx, nact, ip0, ip1, step, tol, js.amax, js.W,
-                                                    js.skip, js.rot, js.done, js.npairs_ld, do_sort, inner_sweeps);
+                                                    js.skip, js.rot, js.done, js.npairs_ld, do_sort, inner_sweeps,
+                                                    js.nrm2, js.nlive, js.blkstamp, js.pairstamp, js.nblk_ld, now);
       bj_apply_kernel<<<gapply, 256, apply_smem, stream>>>(R, ldr, ncols, idx, nact, step, js.W, js.skip,
                                                            js.npairs_ld);
     }
     count_launch(2 * (P - 1) - 1);
     DSB_LAUNCH_CHECK();
-    DSB_CUDA(cudaMemsetAsync(js.flag, 0, sizeof(int32_t), stream));
+    DSB_CUDA(cudaMemsetAsync(js.flag, 0, 2 * sizeof(int32_t), stream));
     sweep_end_kernel<<<1, 256, 0, stream>>>(batch, js.rot, js.done, sweeps, js.flag);
     DSB_LAUNCH_CHECK();
-    DSB_CUDA(cudaMemcpyAsync(js.h_flag, js.flag, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    DSB_CUDA(cudaMemcpyAsync(js.h_flag, js.flag, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     DSB_CUDA(cudaStreamSynchronize(stream));
-    if (debug) fprintf(stderr, "[jacobi] ip [%d,%d) nmax %d sweep %d: %d matrices left\n", ip0, ip1, nmax, sweep, js.h_flag[0]);
+    if (debug)
+      fprintf(stderr, "[jacobi] ip [%d,%d) nmax %d sweep %d: %d matrices left, %d of %d block pairs updated\n", ip0,
+              ip1, nmax, sweep, js.h_flag[0], js.h_flag[1], batch * (P / 2) * (P - 1));
     if (js.h_flag[0] == 0) break;
   }
   return DSB_OK;
@@ -498,6 +585,8 @@ int jacobi_pass(zc *R, int ldr, int ncols, const int32_t *idx, const int32_t *na
 //   mode 0 (image):     keep sorted rows [0, #(sigma > rtol * sigma_max))        (beamtransfer.py:97-102)
 //   mode 1 (nullspace): keep sorted rows [#(sigma[:kmax] >= rtol * sigma_max), n) (beamtransfer.py:136-141)
 //   mode 2 (final):     keep sorted rows [0, #(sigma[:kmax] > 0)), also emit sigma
+//   mode 3 (presort):   keep every row, only order them by descending norm (de Rijk: one-sided
+//                       Jacobi converges in fewer sweeps when the large rows come first)
 __global__ void __launch_bounds__(256)
 rank_select_kernel(const zc *__restrict__ Rall, int ldr, int ncols, int32_t *__restrict__ idx_all,
                    int32_t *__restrict__ nact_all, int ip0, int ip1, int mode, double rtol, int kmax,
@@ -551,6 +640,7 @@ rank_select_kernel(const zc *__restrict__ Rall, int ldr, int ncols, int32_t *__r
     if (pos < klim) {
       if (mode == 0) local += (s > s_max * rtol);
       else if (mode == 1) local += (s >= s_max * rtol);
+      else if (mode == 3) local += 1;
       else local += (s > 0.0);
     }
     if (mode == 2 && sv_out && pos < sv_ld) sv_out[(size_t)b * sv_ld + pos] = (pos < klim && s > 0.0) ? s : 0.0;
@@ -774,12 +864,19 @@ extern "C" int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int b
   svd_prepare_kernel<<<gprep, 256, 0, stream>>>((const zc *)bf_dev, noisew_dev, R, ntel, nsky, idx, nact);
   DSB_LAUNCH_CHECK();
   if (npol > 1) {
-    // SVD 1: image of the whole whitened matrix
-    DSB_TRY(jacobi_pass(R, ntel, ncols, idx, nact, batch, 0, nsky, ntel, max_sweeps, tol, sweeps, js, stream));
+    // SVD 1: image of the whole whitened matrix (rows ordered by norm, exactly zero rows -- e.g. the
+    // m = 0 negative-m half -- leave the active set: they cannot be in the image)
+    rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, 0, nsky, 0, 0.0, ntel, sig, tmp,
+                                                  nullptr, 0);
+    DSB_LAUNCH_CHECK();
+    DSB_TRY(jacobi_pass(R, ntel, ncols, idx, nact, batch, 0, nsky, -1, max_sweeps, tol, sweeps, js, stream));
     rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, 0, nsky, 0, rtol1, ntel, sig, tmp,
                                                   nullptr, 0);
     DSB_LAUNCH_CHECK();
     // SVD 2: null space of the polarised columns
+    rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, nl, nsky, 3, 0.0, ntel, sig, tmp,
+                                                  nullptr, 0);
+    DSB_LAUNCH_CHECK();
     DSB_TRY(jacobi_pass(R, ntel, ncols, idx, nact, batch, nl, nsky, -1, max_sweeps, tol, sweeps + batch, js, stream));
     rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, nl, nsky, 1, polsvcut, nsky - nl,
                                                   sig, tmp, nullptr, 0);
@@ -787,6 +884,8 @@ extern "C" int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int b
   }
   // SVD 3: temperature columns of the surviving rows
   DSB_CUDA(cudaMemsetAsync(sv_dev, 0, sizeof(double) * (size_t)batch * svd_len, stream));
+  rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, 0, nl, 3, 0.0, ntel, sig, tmp, nullptr, 0);
+  DSB_LAUNCH_CHECK();
   DSB_TRY(jacobi_pass(R, ntel, ncols, idx, nact, batch, 0, nl, npol > 1 ? -1 : ntel, max_sweeps, tol,
                       sweeps + 2 * batch, js, stream));
   rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, 0, nl, 2, 0.0, nl, sig, tmp, sv_dev,
