@@ -207,7 +207,10 @@ def svd_section(tel, args, rank, world, dev, stream, with_cpu):
     nb, npol, lside, mmax = tel.nbase, 4, tel.lmax, tel.mmax
     nl, ntel = lside + 1, 2 * tel.nbase
     svd_len = min(nl, ntel)
-    ms_all = [int(x) for x in args.svd_ms.split(",") if x != ""]
+    if args.svd_ms == "auto":  # weak scaling: four m-blocks per GPU, every rank sees the whole m range
+        ms_all = [int(x) for x in np.linspace(0, mmax, 4 * world).round()]
+    else:
+        ms_all = [int(x) for x in args.svd_ms.split(",") if x != ""]
     ms_mine = ms_all[rank::world]
     nfs = min(args.svd_freqs, tel.nfreq)
     f_sel = np.unique(np.linspace(0, tel.nfreq - 1, nfs).astype(int))
@@ -310,7 +313,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-svd", action="store_true", help="skip the per-m SVD measurement (second half of the metric)")
     ap.add_argument("--svd-only", action="store_true", help="diagnostic: run only the per-m SVD measurement")
-    ap.add_argument("--svd-ms", default="0,70,140,210", help="sample of m values the SVD stage is timed on")
+    ap.add_argument("--svd-ms", default="auto",
+                    help="sample of m values the SVD stage is timed on (auto: 4 per GPU, evenly spread over 0..mmax)")
     ap.add_argument("--svd-freqs", type=int, default=64, help="frequencies per m-block in the SVD measurement")
     ap.add_argument("--svd-cpu-blocks", type=int, default=2, help="(m, freq) blocks per sampled m for the CPU SVD baseline")
     ap.add_argument("--force-scatter", action="store_true", help="use the scatter output path at N = 1 too (diagnostic)")
@@ -570,21 +574,60 @@ def main():
     # ---- end-to-end through the C ABI with host buffers
     e2e = None
     if not args.no_e2e:
-        out_host = torch.empty(total if scatter is None else 1, dtype=torch.complex128, pin_memory=True)
         h2d = sum(b.nbytes for b in host_beams.values()) + sum(u.nbytes for _, _, u in prepared)
-        d2h = out_host.numel() * 16
 
-        def step_e2e():
-            for nside, plan, units in prepared:
-                for (ns, slot), b in host_beams.items():
-                    if ns == nside:
-                        plan.upload_beam(slot, b, stream)
-                plan.transfer_units(units, 4, True, mmax, eng.precision, _lib.DSB_OUT_MMAJOR_C128, dims,
-                                    out_dev.data_ptr(), False, stream)
-            if world > 1:
+        if scatter is None and world == 1:
+            # One frequency at a time: the product of frequency f goes back to the host (its own
+            # m-major block, which is how the m-files take it: beam_m[f]) on a copy stream while
+            # the next frequency is computed.
+            total1, moff1 = _lib.mmajor_offsets(1, nb, np_inc, lside, mmax)
+            dims1 = [1, nb, np_inc, lside, mmax]
+            out_f_dev = [torch.zeros(total1, dtype=torch.complex128, device=dev) for _ in range(F)]
+            out_f_host = [torch.empty(total1, dtype=torch.complex128, pin_memory=True) for _ in range(F)]
+            prepared_f = []
+            for f in range(F):
+                lst = []
+                for nside, plan, units in prepared:
+                    sel = units[units["out0"] == f].copy()
+                    sel["out0"] = 0
+                    if len(sel):
+                        lst.append((nside, plan, sel))
+                prepared_f.append(lst)
+            copy_stream = torch.cuda.Stream(device=dev)
+            d2h = F * total1 * 16
+
+            def step_e2e():
+                for nside, plan, units in prepared:
+                    for (ns, slot), b in host_beams.items():
+                        if ns == nside:
+                            plan.upload_beam(slot, b, stream)
+                for f in range(F):
+                    for nside, plan, units in prepared_f[f]:
+                        plan.transfer_units(units, 4, True, mmax, eng.precision, _lib.DSB_OUT_MMAJOR_C128, dims1,
+                                            out_f_dev[f].data_ptr(), False, stream)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    copy_stream.wait_event(ev)
+                    with torch.cuda.stream(copy_stream):
+                        out_f_host[f].copy_(out_f_dev[f], non_blocking=True)
+                copy_stream.synchronize()
+                torch.cuda.current_stream().synchronize()
+
+        elif scatter is None:
+            # diagnostic path (--nccl-exchange): one buffer, NCCL all-to-all, then the copy
+            out_host = torch.empty(total, dtype=torch.complex128, pin_memory=True)
+            d2h = out_host.numel() * 16
+
+            def step_e2e():  # noqa: F811
+                for nside, plan, units in prepared:
+                    for (ns, slot), b in host_beams.items():
+                        if ns == nside:
+                            plan.upload_beam(slot, b, stream)
+                    plan.transfer_units(units, 4, True, mmax, eng.precision, _lib.DSB_OUT_MMAJOR_C128, dims,
+                                        out_dev.data_ptr(), False, stream)
                 comm.exchange_mblocks(out_dev, F, moff, mmax + 1, f_lo=rank * F)
-            out_host.copy_(out_dev, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+                out_host.copy_(out_dev, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
 
         if scatter is not None:
             # the product a rank brings back to its host is the m range it owns, all frequencies
@@ -604,9 +647,20 @@ def main():
                                        ctypes.c_size_t(d2h), 2, ctypes.c_void_p(stream))
                 torch.cuda.current_stream().synchronize()
 
-        ms_e2e = timed(step_e2e, max(2, args.steps // 2), 1) / max(2, args.steps // 2)
+        ms_e2e = timed(step_e2e, max(3, args.steps // 2), 2) / max(3, args.steps // 2)
         e2e = {"value": world * units_per_step / (ms_e2e * 1e-3), "unit": "units/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e}
+        if scatter is None and world == 1:
+            # the product copy alone (pinned host memory): the PCIe floor under the e2e step
+            def copy_only():
+                for f in range(F):
+                    out_f_host[f].copy_(out_f_dev[f], non_blocking=True)
+
+            ms_copy = timed(copy_only, 2, 1) / 2
+            e2e["d2h_alone_ms"] = ms_copy
+            e2e["d2h_alone_gbs"] = d2h / (ms_copy * 1e-3) / 1e9
+            e2e["overlap"] = "per-frequency product blocks copied on a second stream while the next frequency is computed"
+            del out_f_dev
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     cpu = None

@@ -545,7 +545,7 @@ int jacobi_pass(zc *R, int ldr, int ncols, const int32_t *idx, const int32_t *na
   DSB_CUDA(cudaMemsetAsync(js.rot, 0, sizeof(int32_t) * batch, stream));
   DSB_CUDA(cudaMemsetAsync(js.done, 0, sizeof(int32_t) * batch, stream));
   static const int do_sort = getenv("DSB_SVD_NOSORT") ? 0 : 1;
-  static const int inner_sweeps = getenv("DSB_SVD_INNER") ? atoi(getenv("DSB_SVD_INNER")) : 8;
+  static const int inner_sweeps = getenv("DSB_SVD_INNER") ? atoi(getenv("DSB_SVD_INNER")) : 2;
   static const bool debug = getenv("DSB_SVD_DEBUG") != nullptr;
   const dim3 gnorm((nmax + 7) / 8, batch), gpair(P / 2, batch), gapply((ncols + kAT - 1) / kAT, P / 2, batch);
   DSB_CHECK(ldr <= js.ldr_max, DSB_ERR_INVALID, "jacobi_pass: scratch allocated for fewer rows");

@@ -158,3 +158,39 @@ def test_invbeam_m(products):
     for fi in range(products.nfreq):
         want = np.linalg.pinv(beam[fi], rcond=1e-6).reshape(-1, tel.npairs) * noisew
         assert np.abs(ib[fi].reshape(want.shape) - want).max() <= 1e-8 * np.abs(want).max()
+
+
+def test_manager_generates_kl_products(tmp_path):
+    """ProductManager with `kltransform` entries (manager.py:232-246, 293-296): the YAML layout of
+    the reference's tests/testparams.yaml, reduced to the small telescope."""
+    import yaml
+
+    from driftscan_b200.core import manager
+    from driftscan_b200.util import h5lite
+
+    conf = {
+        "config": {"beamtransfers": True, "kltransform": True, "psfisher": False,
+                   "output_directory": str(tmp_path / "prod"), "svcut": 1e-6, "polsvcut": 1.0},
+        "telescope": dict(SMALL_CFG, type="PolarisedCylinder", precision="fp64"),
+        "kltransform": [
+            {"type": "KLTransform", "name": "kl", "inverse": False, "threshold": 0.1, "use_thermal": True,
+             "use_foregrounds": True, "use_polarised": True},
+            {"type": "DoubleKL", "name": "dk", "inverse": False, "threshold": 0.1, "use_thermal": True,
+             "use_foregrounds": True, "use_polarised": True, "foreground_threshold": 0.05},
+        ],
+    }
+    cfile = tmp_path / "params.yaml"
+    cfile.write_text(yaml.dump(conf))
+    pm = manager.ProductManager.from_config(str(cfile))
+    assert sorted(pm.kltransforms) == ["dk", "kl"]
+    pm.generate()
+    tel = pm.telescope
+    for name in ("kl", "dk"):
+        kl = pm.kltransforms[name]
+        assert os.path.exists(kl.evdir + "/evals.hdf5")
+        for mi in range(tel.mmax + 1):
+            assert os.path.exists(kl._evfile % mi)
+    with h5lite.File(pm.kltransforms["dk"]._evfile % 7, "r") as f:
+        assert "f_evals" in f and f["f_evals"].shape == (pm.beamtransfer.ndof(7),)
+    with h5lite.File(pm.kltransforms["dk"].evdir + "/evals.hdf5", "r") as f:
+        assert f["evals"].shape == f["f_evals"].shape == (tel.mmax + 1, pm.beamtransfer.ndofmax)

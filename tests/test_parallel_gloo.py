@@ -49,6 +49,14 @@ for src, (s_lo, s_hi, blocks) in enumerate(pieces):
         ok &= bool(torch.equal(b.real, want_re.expand(s_hi - s_lo, -1))) and bool(torch.equal(b.imag, want_im))
 gathered = comm.allgather_ints([rank, nfc])
 ok &= gathered.shape == (size, 2) and list(gathered[:, 0]) == list(range(size))
+# per-m results gathered on rank 0 (kltransform.collect_m_array, reference kltransform.py:21-52)
+from driftscan_b200.core import kltransform
+arr = kltransform.collect_m_array(list(range(7)), lambda mi: np.full(3, 10.0 * mi + rank), (3,), np.float64)
+if rank == 0:
+    owner = np.concatenate([np.full(h - l, r) for r, (l, h) in enumerate(comm.all_ranges(7))])
+    ok &= arr.shape == (7, 3) and bool(np.array_equal(arr[:, 0], 10.0 * np.arange(7) + owner))
+else:
+    ok &= arr is None
 comm.barrier()
 print("RANK", rank, "OK" if ok else "FAIL", flush=True)
 dist.destroy_process_group()
