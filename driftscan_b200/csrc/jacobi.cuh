@@ -29,4 +29,10 @@ struct JacobiScratch {
 int jacobi_pass(zc *R, int ldr, int ncols, const int32_t *idx, const int32_t *nact, int batch, int ip0, int ip1,
                 int nmax, int max_sweeps, double tol, int32_t *sweeps, JacobiScratch &js, cudaStream_t stream);
 
+// Unitary row operations (Householder reflections) that bring columns [ip0, ip1) of the active
+// rows to upper-triangular form before a Jacobi pass: cuts the sweep count of graded matrices
+// from ~25 to ~5.  Every column is carried along, exactly as in jacobi_pass.
+int householder_precondition(zc *R, int ldr, int ncols, const int32_t *idx, const int32_t *nact, int batch, int ip0,
+                             int ip1, int nmax, JacobiScratch &js, cudaStream_t stream);
+
 }  // namespace dsb

@@ -370,6 +370,7 @@ static int herm_eig(const zc *C, int n, zc *R, double *evals, zc *Q, cudaStream_
   eig_prepare_kernel<<<256, 256, 0, stream>>>(C, R, n, idx, nact);
   DSB_LAUNCH_CHECK();
   const int max_sweeps = 60;
+  DSB_TRY(householder_precondition(R, n, 2 * n, idx, nact, 1, 0, n, n, js, stream));
   DSB_TRY(jacobi_pass(R, n, 2 * n, idx, nact, 1, 0, n, n, max_sweeps, 0.0, sweeps, js, stream));
   int32_t hs = 0;
   DSB_CUDA(cudaMemcpyAsync(&hs, sweeps, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));

@@ -517,6 +517,256 @@ void JacobiScratch::release(cudaStream_t stream) {
   if (h_flag) cudaFreeHost(h_flag);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Householder preconditioner.  One-sided Jacobi needs about one sweep per decade of a graded
+// spectrum when it starts from arbitrary rows (27 sweeps on real beam-transfer blocks) but only
+// 4-5 sweeps when the rows are first brought to triangular form (Drmac & Veselic 2008: Jacobi on
+// the rows of the R factor).  Reflections are unitary row operations, so they are applied to the
+// whole augmented rows [ A | U^H accumulator ] exactly like the rotations that follow: the
+// columns [ip0, ip1) of the active rows become upper triangular (in the order of the columns
+// that are not identically zero), every other column is carried along.  A rank-deficient block
+// leaves its null rows at rounding level, where the Jacobi pass skips them from the first sweep.
+// ---------------------------------------------------------------------------------------------
+
+// clist[b][0..ncl[b]) = columns of [ip0, ip1) that are not identically zero over the active rows
+__global__ void __launch_bounds__(256)
+hh_columns_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
+                  const int32_t *__restrict__ nact_all, int ip0, int ip1, int32_t *__restrict__ clist_all,
+                  int32_t *__restrict__ ncl_all) {
+  extern __shared__ int32_t s_nz[];
+  const int b = blockIdx.x, ipw = ip1 - ip0;
+  const int n = nact_all[b];
+  const zc *R = Rall + (size_t)b * ldr * ncols;
+  const int32_t *idx = idx_all + (size_t)b * ldr;
+  for (int c = threadIdx.x; c < ipw; c += blockDim.x) {
+    int nz = 0;
+    for (int r = 0; r < n && !nz; ++r) {
+      const zc v = R[(size_t)idx[r] * ncols + ip0 + c];
+      nz = (v.x != 0.0) || (v.y != 0.0);
+    }
+    s_nz[c] = nz;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t *clist = clist_all + (size_t)b * ipw;
+    int k = 0;
+    for (int c = 0; c < ipw; ++c)
+      if (s_nz[c]) clist[k++] = ip0 + c;
+    ncl_all[b] = k;
+  }
+}
+
+// partial column norms over rows k.. of the active list, for the listed columns
+__global__ void __launch_bounds__(256)
+hh_colnorm_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
+                  const int32_t *__restrict__ nact_all, const int32_t *__restrict__ clist_all,
+                  const int32_t *__restrict__ ncl_all, int ipw, int k, double *__restrict__ cn2_all) {
+  const int b = blockIdx.y;
+  const int n = nact_all[b], ncl = ncl_all[b];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ncl) return;
+  const zc *R = Rall + (size_t)b * ldr * ncols;
+  const int32_t *idx = idx_all + (size_t)b * ldr;
+  const int c = clist_all[(size_t)b * ipw + j];
+  double a = 0.0;
+  for (int r = k; r < n; ++r) {
+    const zc x = R[(size_t)idx[r] * ncols + c];
+    a += x.x * x.x + x.y * x.y;
+  }
+  cn2_all[(size_t)b * ipw + j] = a;
+}
+
+// reflector of step k: the unused column with the largest norm below row k is the pivot (its
+// position is swapped to slot k of the column list: pivoting is virtual, columns never move);
+// v (rows k.. of the active list) and tau, H = I - tau v v^H
+__global__ void __launch_bounds__(256)
+hh_build_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
+                const int32_t *__restrict__ nact_all, int32_t *__restrict__ clist_all,
+                const int32_t *__restrict__ ncl_all, int ipw, int k, int downdate, double *__restrict__ cn2_all,
+                zc *__restrict__ V_all, double *__restrict__ tau_all) {
+  const int b = blockIdx.x;
+  const int n = nact_all[b], ncl = ncl_all[b];
+  if (k >= min(n - 1, ncl)) {
+    if (threadIdx.x == 0) tau_all[b] = 0.0;
+    return;
+  }
+  const zc *R = Rall + (size_t)b * ldr * ncols;
+  const int32_t *idx = idx_all + (size_t)b * ldr;
+  int32_t *clist = clist_all + (size_t)b * ipw;
+  double *cn2 = cn2_all + (size_t)b * ipw;
+  // remove row k - 1 (final after the previous reflection) from the partial norms, pick the pivot
+  __shared__ double s_best[8];
+  __shared__ int s_bestj[8];
+  __shared__ int s_piv;
+  double best = -1.0;
+  int bestj = k;
+  const zc *prev = (downdate && k > 0) ? R + (size_t)idx[k - 1] * ncols : nullptr;
+  for (int j = k + threadIdx.x; j < ncl; j += blockDim.x) {
+    double a = cn2[j];
+    if (prev) {
+      const zc x = prev[clist[j]];
+      a = fmax(a - (x.x * x.x + x.y * x.y), 0.0);
+      cn2[j] = a;
+    }
+    if (a > best) {
+      best = a;
+      bestj = j;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, bestj, o);
+    if (ob > best || (ob == best && oj < bestj)) {
+      best = ob;
+      bestj = oj;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_best[threadIdx.x >> 5] = best;
+    s_bestj[threadIdx.x >> 5] = bestj;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (s_best[w] > s_best[0] || (s_best[w] == s_best[0] && s_bestj[w] < s_bestj[0])) {
+        s_best[0] = s_best[w];
+        s_bestj[0] = s_bestj[w];
+      }
+    const int pj = s_bestj[0];
+    const int32_t ck = clist[k], cp = clist[pj];
+    clist[k] = cp;
+    clist[pj] = ck;
+    const double nk = cn2[k];
+    cn2[k] = cn2[pj];
+    cn2[pj] = nk;
+    s_piv = cp;
+  }
+  __syncthreads();
+  const int c = s_piv;
+  zc *V = V_all + (size_t)b * ldr;
+  double part = 0.0;
+  for (int r = k + threadIdx.x; r < n; r += blockDim.x) {
+    const zc x = R[(size_t)idx[r] * ncols + c];
+    V[r] = x;
+    part += x.x * x.x + x.y * x.y;
+  }
+  part = warp_sum(part);
+  __shared__ double s_part[8];
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double nx2 = 0.0;
+    for (int w = 0; w < 8; ++w) nx2 += s_part[w];
+    const zc x0 = V[k];
+    const double a0 = x0.x * x0.x + x0.y * x0.y;
+    double tau = 0.0;
+    if (nx2 > a0) {  // something below the diagonal to annihilate
+      const double nx = sqrt(nx2), r0 = sqrt(a0);
+      // alpha = -e^{i arg x0} |x|  ->  v0 = x0 - alpha = x0 (1 + |x| / |x0|)
+      zc v0;
+      if (r0 > 0.0) v0 = {x0.x * (1.0 + nx / r0), x0.y * (1.0 + nx / r0)};
+      else v0 = {nx, 0.0};
+      V[k] = v0;
+      const double nv2 = nx2 - a0 + v0.x * v0.x + v0.y * v0.y;
+      tau = 2.0 / nv2;
+    }
+    tau_all[b] = tau;
+  }
+}
+
+// rows k.. of the active list  <-  (I - tau v v^H) rows, 64 columns per CTA
+__global__ void __launch_bounds__(256)
+hh_apply_kernel(zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
+                const int32_t *__restrict__ nact_all, int k, const zc *__restrict__ V_all,
+                const double *__restrict__ tau_all) {
+  const int b = blockIdx.y;
+  const double tau = tau_all[b];
+  if (tau == 0.0) return;
+  const int n = nact_all[b];
+  zc *R = Rall + (size_t)b * ldr * ncols;
+  const int32_t *idx = idx_all + (size_t)b * ldr;
+  const zc *V = V_all + (size_t)b * ldr;
+  const int col = blockIdx.x * 64 + (threadIdx.x & 63), slice = threadIdx.x >> 6;
+  const bool live = col < ncols;
+  double wr = 0.0, wi = 0.0;
+  if (live) {
+    for (int r = k + slice; r < n; r += 4) {
+      const zc v = V[r], x = R[(size_t)idx[r] * ncols + col];
+      // conj(v) x
+      wr += v.x * x.x + v.y * x.y;
+      wi += v.x * x.y - v.y * x.x;
+    }
+  }
+  __shared__ double s_w[4][64][2];
+  s_w[slice][threadIdx.x & 63][0] = wr;
+  s_w[slice][threadIdx.x & 63][1] = wi;
+  __syncthreads();
+  if (!live) return;
+  wr = wi = 0.0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    wr += s_w[q][threadIdx.x & 63][0];
+    wi += s_w[q][threadIdx.x & 63][1];
+  }
+  wr *= tau;
+  wi *= tau;
+  for (int r = k + slice; r < n; r += 4) {
+    const zc v = V[r];
+    zc *x = R + (size_t)idx[r] * ncols + col;
+    zc o = *x;
+    o.x -= v.x * wr - v.y * wi;
+    o.y -= v.x * wi + v.y * wr;
+    *x = o;
+  }
+}
+
+// Triangularise columns [ip0, ip1) of the active rows of every matrix (see above).
+int householder_precondition(zc *R, int ldr, int ncols, const int32_t *idx, const int32_t *nact, int batch, int ip0,
+                             int ip1, int nmax, JacobiScratch &js, cudaStream_t stream) {
+  static const bool off = getenv("DSB_SVD_NOQR") != nullptr;
+  const int ipw = ip1 - ip0;
+  if (off || ipw <= 0) return DSB_OK;
+  if (nmax < 0) {
+    DSB_CUDA(cudaMemsetAsync(js.flag + 1, 0, sizeof(int32_t), stream));
+    max_nact_kernel<<<1, 256, 0, stream>>>(batch, nact, js.flag + 1);
+    DSB_LAUNCH_CHECK();
+    DSB_CUDA(cudaMemcpyAsync(js.h_flag + 1, js.flag + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    DSB_CUDA(cudaStreamSynchronize(stream));
+    nmax = js.h_flag[1];
+  }
+  if (nmax < 2) return DSB_OK;
+  int32_t *clist = nullptr, *ncl = nullptr;
+  zc *V = nullptr;
+  double *tau = nullptr;
+  DSB_CUDA(cudaMallocAsync((void **)&clist, sizeof(int32_t) * (size_t)batch * ipw, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&ncl, sizeof(int32_t) * batch, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&V, sizeof(zc) * (size_t)batch * ldr, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&tau, sizeof(double) * batch, stream));
+  hh_columns_kernel<<<batch, 256, sizeof(int32_t) * ipw, stream>>>(R, ldr, ncols, idx, nact, ip0, ip1, clist, ncl);
+  DSB_LAUNCH_CHECK();
+  const int steps = std::min(nmax - 1, ipw);
+  const dim3 gapply((ncols + 63) / 64, batch), gnorm((ipw + 255) / 256, batch);
+  double *cn2 = nullptr;
+  DSB_CUDA(cudaMallocAsync((void **)&cn2, sizeof(double) * (size_t)batch * ipw, stream));
+  for (int k = 0; k < steps; ++k) {
+    // partial column norms: recomputed every 16 steps, downdated in between
+    const bool fresh = (k % 16) == 0;
+    if (fresh) hh_colnorm_kernel<<<gnorm, 256, 0, stream>>>(R, ldr, ncols, idx, nact, clist, ncl, ipw, k, cn2);
+    hh_build_kernel<<<batch, 256, 0, stream>>>(R, ldr, ncols, idx, nact, clist, ncl, ipw, k, fresh ? 0 : 1, cn2, V,
+                                               tau);
+    hh_apply_kernel<<<gapply, 256, 0, stream>>>(R, ldr, ncols, idx, nact, k, V, tau);
+  }
+  count_launch(2 * steps + steps / 16);
+  cudaFreeAsync(cn2, stream);
+  DSB_LAUNCH_CHECK();
+  cudaFreeAsync(clist, stream);
+  cudaFreeAsync(ncl, stream);
+  cudaFreeAsync(V, stream);
+  cudaFreeAsync(tau, stream);
+  return DSB_OK;
+}
+
 // One Jacobi pass over the active rows of every matrix; sweeps[b] receives the sweep count.
 // `nmax` = upper bound of nact (-1: read it back from the device).
 int jacobi_pass(zc *R, int ldr, int ncols, const int32_t *idx, const int32_t *nact, int batch, int ip0, int ip1,
@@ -869,6 +1119,7 @@ extern "C" int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int b
     rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, 0, nsky, 0, 0.0, ntel, sig, tmp,
                                                   nullptr, 0);
     DSB_LAUNCH_CHECK();
+    DSB_TRY(householder_precondition(R, ntel, ncols, idx, nact, batch, 0, nsky, -1, js, stream));
     DSB_TRY(jacobi_pass(R, ntel, ncols, idx, nact, batch, 0, nsky, -1, max_sweeps, tol, sweeps, js, stream));
     rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, 0, nsky, 0, rtol1, ntel, sig, tmp,
                                                   nullptr, 0);
@@ -877,6 +1128,7 @@ extern "C" int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int b
     rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, nl, nsky, 3, 0.0, ntel, sig, tmp,
                                                   nullptr, 0);
     DSB_LAUNCH_CHECK();
+    DSB_TRY(householder_precondition(R, ntel, ncols, idx, nact, batch, nl, nsky, -1, js, stream));
     DSB_TRY(jacobi_pass(R, ntel, ncols, idx, nact, batch, nl, nsky, -1, max_sweeps, tol, sweeps + batch, js, stream));
     rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, nl, nsky, 1, polsvcut, nsky - nl,
                                                   sig, tmp, nullptr, 0);
@@ -886,6 +1138,7 @@ extern "C" int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int b
   DSB_CUDA(cudaMemsetAsync(sv_dev, 0, sizeof(double) * (size_t)batch * svd_len, stream));
   rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, 0, nl, 3, 0.0, ntel, sig, tmp, nullptr, 0);
   DSB_LAUNCH_CHECK();
+  DSB_TRY(householder_precondition(R, ntel, ncols, idx, nact, batch, 0, nl, npol > 1 ? -1 : ntel, js, stream));
   DSB_TRY(jacobi_pass(R, ntel, ncols, idx, nact, batch, 0, nl, npol > 1 ? -1 : ntel, max_sweeps, tol,
                       sweeps + 2 * batch, js, stream));
   rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, 0, nl, 2, 0.0, nl, sig, tmp, sv_dev,
@@ -896,6 +1149,7 @@ extern "C" int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int b
                                              (zc *)beam_ut_dev, S, sidx, snact, nmodes_dev);
   DSB_LAUNCH_CHECK();
   if (want_inv) {
+    DSB_TRY(householder_precondition(S, svd_len, scols, sidx, snact, batch, 0, nsky, -1, js, stream));
     DSB_TRY(jacobi_pass(S, svd_len, scols, sidx, snact, batch, 0, nsky, -1, max_sweeps, tol, sweeps + 3 * batch, js,
                         stream));
     dim3 gp(32, batch);
@@ -975,6 +1229,7 @@ extern "C" int dsb_pinv_batched(const void *A_dev, int batch, int n, int m, doub
   svd_prepare_kernel<<<gprep, 256, 0, stream>>>((const zc *)A_dev, nullptr, R, n, m, idx, nact);
   DSB_LAUNCH_CHECK();
   const int max_sweeps = 60;
+  DSB_TRY(householder_precondition(R, n, ncols, idx, nact, batch, 0, m, n, js, stream));
   DSB_TRY(jacobi_pass(R, n, ncols, idx, nact, batch, 0, m, n, max_sweeps, 0.0, sweeps, js, stream));
   dim3 gp(32, batch);
   svd_pinv_kernel<<<gp, 256, sizeof(double) * n, stream>>>(R, nact, m, n, (zc *)pinv_dev, rcond);
