@@ -520,7 +520,7 @@ def main():
     # ---- the frequency-major -> m-major exchange alone (N > 1): bytes each rank sends over NVLink
     exchange = None
     if scatter is not None:
-        _, mlo, mhi = parallel.split_counts(mmax + 1, world)
+        mlo, mhi = scatter.m_lo, scatter.m_hi
         own_local = int((moff[mhi[rank]] - moff[mlo[rank]])) * 16
         sent = int(total * 16 - own_local)
         exchange = {"mode": "fused: pack kernel stores m-blocks into the owner's memory over NVLink (CUDA IPC)",

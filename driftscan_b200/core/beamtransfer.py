@@ -493,6 +493,71 @@ class BeamTransfer(config.Reader):
 
     project_vector_forward = project_vector_sky_to_telescope
 
+    def project_vector_telescope_to_sky(self, mi, vec):
+        """Telescope vector ``[nfreq, ntel]`` -> sky ``[nfreq, npol, lmax+1]`` through the
+        pseudo-inverse beam: the map-making step (beamtransfer.py:1014-1046).  ``invbeam_m`` is
+        computed on the device; the per-frequency matrix-vector products are small host algebra."""
+        tel = self.telescope
+        vecb = np.zeros((self.nfreq, self.nsky), dtype=np.complex128)
+        vec = np.asarray(vec).reshape((self.nfreq, self.ntel))
+        if np.all(vec == 0):
+            return vecb.reshape((self.nfreq, tel.num_pol_sky, tel.lmax + 1))
+        ibeam = self.invbeam_m(mi).reshape((self.nfreq, self.nsky, self.ntel))
+        for fi in range(self.nfreq):
+            vecb[fi] = np.dot(ibeam[fi], vec[fi, :].reshape(self.ntel))
+        return vecb.reshape((self.nfreq, tel.num_pol_sky, tel.lmax + 1))
+
+    project_vector_backward = project_vector_telescope_to_sky
+
+    def project_vector_backward_dirty(self, mi, vec):
+        """Dirty-map projection with the conjugate beam (beamtransfer.py:1050-1072)."""
+        tel = self.telescope
+        vecb = np.zeros((self.nfreq, self.nsky), dtype=np.complex128)
+        vec = np.asarray(vec).reshape((self.nfreq, self.ntel))
+        if np.all(vec == 0):
+            return vecb.reshape((self.nfreq, tel.num_pol_sky, tel.lmax + 1))
+        dbeam = self.beam_m(mi).reshape((self.nfreq, self.ntel, self.nsky))
+        dbeam = dbeam.transpose((0, 2, 1)).conj()
+        for fi in range(self.nfreq):
+            norm = np.dot(dbeam[fi].T.conj(), dbeam[fi]).diagonal()
+            norm = np.where(norm < 1e-6, 0.0, 1.0 / norm)
+            vecb[fi] = np.dot(dbeam[fi], vec[fi, :].reshape(self.ntel) * norm)
+        return vecb.reshape((self.nfreq, tel.num_pol_sky, tel.lmax + 1))
+
+    def project_matrix_sky_to_telescope(self, mi, mat, temponly=False):
+        """Sky covariance ``[pol, pol, l, freq, freq]`` -> ``[nfreq, ntel, nfreq, ntel]`` in the
+        visibility basis (beamtransfer.py:1074-1112); the ``nfreq^2 npol^2`` products
+        ``(B_fi,pi C_l) B_fj,pj^H`` run as one batched device kernel per polarisation pair."""
+        import torch
+
+        from .. import _lib
+
+        tel = self.telescope
+        npol = 1 if temponly else tel.num_pol_sky
+        lside = tel.lmax + 1
+        mat = np.asarray(mat)
+        if np.iscomplexobj(mat):
+            raise NotImplementedError("project_matrix_sky_to_telescope: complex sky covariances are not supported")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        beam = torch.from_numpy(
+            np.ascontiguousarray(self.beam_m(mi).reshape(self.nfreq, self.ntel, tel.num_pol_sky, lside))
+        ).to(dev)
+        matd = torch.from_numpy(np.ascontiguousarray(mat, dtype=np.float64)).to(dev)
+        ndof = self.nfreq * self.ntel
+        out = torch.empty((ndof, ndof), dtype=torch.complex128, device=dev)
+        nz = np.ascontiguousarray(np.any(mat != 0, axis=(2, 3, 4)), dtype=np.uint8)
+        sn = np.full(self.nfreq, self.ntel, dtype=np.int32)
+        sb = np.arange(self.nfreq + 1, dtype=np.int32) * self.ntel
+        _lib.check(
+            _lib.lib.dsb_project_matrix_sky_to_svd(
+                beam.data_ptr(), matd.data_ptr(), nz.ctypes.data, sn.ctypes.data, sb.ctypes.data, self.nfreq,
+                self.ntel, tel.num_pol_sky, npol, lside, out.data_ptr(), torch.cuda.current_stream().cuda_stream,
+            )
+        )
+        return out.cpu().numpy().reshape(self.nfreq, self.ntel, self.nfreq, self.ntel)
+
+    project_matrix_forward = project_matrix_sky_to_telescope
+
     def project_vector_telescope_to_svd(self, mi, vec):
         """Telescope vector ``[nfreq, ntel, ...]`` -> SVD modes (beamtransfer.py:1233-1271)."""
         svnum, svbounds = self._svd_num(mi)

@@ -22,6 +22,24 @@ def split_counts(n, parts):
     return counts, bounds[:-1], bounds[1:]
 
 
+def split_weighted(weights, parts):
+    """Contiguous ranges of near-equal total weight: (counts, starts, ends) like
+    :func:`split_counts`.  Block m of the product holds ``lmax + 1 - m`` multipoles, so an equal
+    COUNT of m per rank (``mpiutil.split_m``) gives the first rank of two 70 % of the bytes and
+    of the SVD work; ownership by weight evens both out (the m-files are the same either way)."""
+    w = np.asarray(weights, dtype=np.float64)
+    n, parts = len(w), int(parts)
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    targets = cum[-1] * np.arange(1, parts) / parts
+    cuts = np.searchsorted(cum, targets, side="left")
+    # keep the ranges non-empty and ordered whenever there are at least `parts` items
+    bounds = np.concatenate([[0], cuts, [n]]).astype(np.int64)
+    for i in range(1, parts):
+        bounds[i] = min(max(bounds[i], bounds[i - 1] + (1 if n >= parts else 0)), n - (parts - i) if n >= parts else n)
+    counts = np.diff(bounds)
+    return counts, bounds[:-1], bounds[1:]
+
+
 class Comm:
     """Thin view of the default process group (or a single process)."""
 
@@ -142,9 +160,9 @@ class Comm:
 class PeerScatter:
     """Frequency-major -> m-major regrouping without a separate collective.
 
-    Every rank owns the m range ``split_counts(mmax + 1, size)`` gives it (the partition of
-    ``mpiutil.split_local``, drift/core/beamtransfer.py:547) and allocates the m-blocks of that
-    range for ALL frequencies, ``[m][freq][+-][baseline][pol][l - m]`` -- the layout of the
+    Every rank owns a contiguous m range -- by default of equal BYTES (:func:`split_weighted`;
+    ``balance="count"`` gives the equal-count partition of ``mpiutil.split_local``,
+    drift/core/beamtransfer.py:547) -- and allocates the m-blocks of that range for ALL frequencies, ``[m][freq][+-][baseline][pol][l - m]`` -- the layout of the
     m-files it will write.  The buffers are published through CUDA IPC handles, so the pack
     kernel of any rank stores its frequencies straight into the owner's block over NVLink
     (``dsb_transfer_units_scatter``): the exchange of ``mpiutil.transpose_blocks``
@@ -152,17 +170,20 @@ class PeerScatter:
     the stores of all ranks before anyone reads its blocks.
     """
 
-    def __init__(self, comm, nf_global, nb, npol, lside, mmax, elem_bytes=16):
+    def __init__(self, comm, nf_global, nb, npol, lside, mmax, elem_bytes=16, balance="bytes"):
         import ctypes
 
         from . import _lib
 
         self.comm, self._lib = comm, _lib
         self.nf, self.nb, self.npol, self.lside, self.mmax, self.elem = nf_global, nb, npol, lside, mmax, elem_bytes
-        _, m_lo, m_hi = split_counts(mmax + 1, comm.size)
-        self.m_lo, self.m_hi = m_lo, m_hi
         per_m = np.array([nf_global * 2 * nb * npol * max(lside + 1 - m, 0) for m in range(mmax + 1)], dtype=np.int64)
         self.per_m = per_m
+        if balance == "bytes":
+            _, m_lo, m_hi = split_weighted(per_m, comm.size)
+        else:
+            _, m_lo, m_hi = split_counts(mmax + 1, comm.size)
+        self.m_lo, self.m_hi = m_lo, m_hi
         own = int(per_m[m_lo[comm.rank] : m_hi[comm.rank]].sum()) * elem_bytes
         self.own_bytes = own
         ptr = ctypes.c_void_p()

@@ -194,3 +194,30 @@ def test_manager_generates_kl_products(tmp_path):
         assert "f_evals" in f and f["f_evals"].shape == (pm.beamtransfer.ndof(7),)
     with h5lite.File(pm.kltransforms["dk"].evdir + "/evals.hdf5", "r") as f:
         assert f["evals"].shape == f["f_evals"].shape == (tel.mmax + 1, pm.beamtransfer.ndofmax)
+
+
+def test_remaining_projections(products):
+    """project_vector_telescope_to_sky / backward_dirty / project_matrix_sky_to_telescope
+    (beamtransfer.py:1014-1112) against direct numpy evaluation on the stored product."""
+    from driftscan_b200.core import skymodel
+
+    bt, tel = products, products.telescope
+    mi = 5
+    rng = np.random.default_rng(11)
+    vec = rng.standard_normal((bt.nfreq, bt.ntel)) + 1j * rng.standard_normal((bt.nfreq, bt.ntel))
+    sky = bt.project_vector_telescope_to_sky(mi, vec)
+    assert sky.shape == (bt.nfreq, tel.num_pol_sky, tel.lmax + 1)
+    ib = bt.invbeam_m(mi).reshape(bt.nfreq, bt.nsky, bt.ntel)
+    assert np.allclose(sky.reshape(bt.nfreq, -1), np.einsum("fst,ft->fs", ib, vec))
+    assert np.all(bt.project_vector_backward(mi, np.zeros_like(vec)) == 0)
+    dirty = bt.project_vector_backward_dirty(mi, vec)
+    assert dirty.shape == sky.shape and np.isfinite(dirty).all()
+    mat = skymodel.foreground_model(tel.lmax, tel.frequencies, tel.num_pol_sky)
+    got = bt.project_matrix_sky_to_telescope(mi, mat)
+    beam = bt.beam_m(mi).reshape(bt.nfreq, bt.ntel, tel.num_pol_sky, tel.lmax + 1)
+    want = np.einsum("fapl,pqlfg,gbql->fagb", beam, mat, beam.conj())
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+    t_only = bt.project_matrix_forward(mi, mat, temponly=True)
+    want_t = np.einsum("fal,lfg,gbl->fagb", beam[:, :, 0], mat[0, 0], beam[:, :, 0].conj())
+    assert np.abs(t_only - want_t).max() <= 1e-12 * np.abs(want_t).max()

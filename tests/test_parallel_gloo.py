@@ -77,6 +77,13 @@ def test_split_counts():
 
     counts, lo, hi = parallel.split_counts(10, 4)
     assert list(counts) == [3, 3, 2, 2] and list(lo) == [0, 3, 6, 8] and list(hi) == [3, 6, 8, 10]
+    # ownership by weight (bytes of the m-blocks): contiguous, complete, near-equal totals
+    w = np.array([234 - m for m in range(211)])
+    for parts in (1, 2, 3, 8):
+        cnt, wlo, whi = parallel.split_weighted(w, parts)
+        assert wlo[0] == 0 and whi[-1] == 211 and np.array_equal(wlo[1:], whi[:-1]) and np.all(cnt > 0)
+        tot = np.array([w[a:b].sum() for a, b in zip(wlo, whi)])
+        assert tot.max() - tot.min() <= 2 * w.max()
     c = parallel.Comm()
     assert c.rank0 and c.split_range(7) == (0, 7) and c.all_ranges(7) == [(0, 7)]
     import torch
