@@ -398,67 +398,100 @@ bj_gram_eig_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32_
   }
 }
 
-// X[slot s] <- sum_j W[s][j] X[slot j] over a tile of kAT columns
-__global__ void __launch_bounds__(256, 2)
+// X[slot s] <- sum_j W[s][j] X[slot j].  A CTA owns `tiles_per_cta` consecutive tiles of kAT
+// columns of one block pair: W is loaded once and the next tile streams into the second
+// shared-memory buffer (cp.async) while the current one is multiplied, so the fp64 pipe is not
+// left waiting for HBM (the single-tile version stalled on its loads: 13.5 TFLOP/s).
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1)
 bj_apply_kernel(zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
                 const int32_t *__restrict__ nact_all, int step, const zc *__restrict__ Wall,
-                const int32_t *__restrict__ skip_all, int npairs_ld) {
+                const int32_t *__restrict__ skip_all, int npairs_ld, int tiles_per_cta) {
   const int b = blockIdx.z, k = blockIdx.y, tid = threadIdx.x;
   if (skip_all[(size_t)b * npairs_ld + k]) return;
   const int n = nact_all[b];
   int pos_a, pos_b, nvalid;
   if (!bj_pair_slots(n, step, k, pos_a, pos_b, nvalid)) return;
   extern __shared__ __align__(16) unsigned char s_raw[];
-  zc(*s_X)[kAT] = reinterpret_cast<zc(*)[kAT]>(s_raw);                          // [slot][column]
-  zc(*s_W)[kJ2] = reinterpret_cast<zc(*)[kJ2]>(s_raw + sizeof(zc) * kJ2 * kAT);  // [j][s] (transposed)
+  typedef zc (*tile_t)[kAT];
+  tile_t s_X0 = reinterpret_cast<tile_t>(s_raw);                              // [slot][column]
+  tile_t s_X1 = reinterpret_cast<tile_t>(s_raw + sizeof(zc) * kJ2 * kAT);
+  zc(*s_W)[kJ2] = reinterpret_cast<zc(*)[kJ2]>(s_raw + 2 * sizeof(zc) * kJ2 * kAT);  // [j][s] (transposed)
   __shared__ zc *s_row[kJ2];
   if (tid < kJ2) {
     const int pos = bj_slot_pos(tid, pos_a, pos_b);
     s_row[tid] = (tid < nvalid) ? Rall + ((size_t)b * ldr + idx_all[(size_t)b * ldr + pos]) * ncols : nullptr;
   }
+  __syncthreads();
+  const int ntiles = (ncols + kAT - 1) / kAT;
+  const int t0 = blockIdx.x * tiles_per_cta, t1 = min(t0 + tiles_per_cta, ntiles);
+  if (t0 >= t1) return;
+  auto issue = [&](int t, tile_t buf) {
+    const int c0 = t * kAT;
+    for (int e = tid; e < kJ2 * kAT; e += 256) {
+      const int sl = e / kAT, c = e % kAT;
+      const zc *row = s_row[sl];
+      if (row && c0 + c < ncols) cp_async16(&buf[sl][c], row + c0 + c);
+      else buf[sl][c] = {0.0, 0.0};
+    }
+    cp_async_commit();
+  };
+  issue(t0, s_X0);
   const zc *W = Wall + ((size_t)b * npairs_ld + k) * (kJ2 * kJ2);
   for (int e = tid; e < kJ2 * kJ2; e += 256) s_W[e % kJ2][e / kJ2] = W[e];
-  __syncthreads();
-  const int c0 = blockIdx.x * kAT;
-  for (int e = tid; e < kJ2 * kAT; e += 256) {
-    const int sl = e / kAT, c = e % kAT;
-    zc v = {0.0, 0.0};
-    const zc *row = s_row[sl];
-    if (row && c0 + c < ncols) v = row[c0 + c];
-    s_X[sl][c] = v;
-  }
-  __syncthreads();
   // thread: 4 slots (tid / 32) x 4 columns (lane + 32 q)
   const int sg = (tid >> 5) * 4, cg = tid & 31;
-  double or_[4][4], oi[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) or_[i][j] = oi[i][j] = 0.0;
-#pragma unroll 4
-  for (int j = 0; j < kJ2; ++j) {
-    zc wv[4], xv[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) wv[i] = s_W[j][sg + i];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) xv[q] = s_X[j][cg + 32 * q];
+  for (int t = t0; t < t1; ++t) {
+    tile_t cur = ((t - t0) & 1) ? s_X1 : s_X0;
+    tile_t nxt = ((t - t0) & 1) ? s_X0 : s_X1;
+    if (t + 1 < t1) {
+      issue(t + 1, nxt);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    double or_[4][4], oi[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        or_[i][q] += wv[i].x * xv[q].x - wv[i].y * xv[q].y;
-        oi[i][q] += wv[i].x * xv[q].y + wv[i].y * xv[q].x;
-      }
-  }
+      for (int j = 0; j < 4; ++j) or_[i][j] = oi[i][j] = 0.0;
+#pragma unroll 4
+    for (int j = 0; j < kJ2; ++j) {
+      zc wv[4], xv[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    zc *row = s_row[sg + i];
-    if (!row) continue;
+      for (int i = 0; i < 4; ++i) wv[i] = s_W[j][sg + i];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int c = c0 + cg + 32 * q;
-      if (c < ncols) row[c] = {or_[i][q], oi[i][q]};
+      for (int q = 0; q < 4; ++q) xv[q] = cur[j][cg + 32 * q];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          or_[i][q] += wv[i].x * xv[q].x - wv[i].y * xv[q].y;
+          oi[i][q] += wv[i].x * xv[q].y + wv[i].y * xv[q].x;
+        }
     }
+    const int c0 = t * kAT;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      zc *row = s_row[sg + i];
+      if (!row) continue;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = c0 + cg + 32 * q;
+        if (c < ncols) row[c] = {or_[i][q], oi[i][q]};
+      }
+    }
+    __syncthreads();  // everyone is done with `cur` before the next iteration refills it
   }
 }
 
@@ -485,7 +518,23 @@ __global__ void max_nact_kernel(int batch, const int32_t *__restrict__ nact, int
   atomicMax(out, mx);
 }
 
+// The chain allocates gigabytes of stream-ordered scratch per call.  The default pool hands
+// unused memory back to the driver at every synchronisation, so each call would map it again
+// (measured: 2 s per m-block); keep it cached instead.
+static void keep_pool_memory() {
+  static bool done = false;
+  if (done) return;
+  int dev = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long threshold = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  }
+  done = true;
+}
+
 int JacobiScratch::alloc(int batch, int nrows_max, cudaStream_t stream) {
+  keep_pool_memory();
   const int nblk = (nrows_max + kJB - 1) / kJB;
   npairs_ld = std::max(2, (nblk + 1) & ~1) / 2;
   DSB_CUDA(cudaMallocAsync((void **)&amax, sizeof(unsigned long long) * batch, stream));
@@ -583,11 +632,11 @@ __global__ void __launch_bounds__(256)
 hh_build_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
                 const int32_t *__restrict__ nact_all, int32_t *__restrict__ clist_all,
                 const int32_t *__restrict__ ncl_all, int ipw, int k, int downdate, double *__restrict__ cn2_all,
-                zc *__restrict__ V_all, double *__restrict__ tau_all) {
+                zc *__restrict__ V_all, double *__restrict__ tau_all, double *__restrict__ piv0_all, int steps) {
   const int b = blockIdx.x;
   const int n = nact_all[b], ncl = ncl_all[b];
   if (k >= min(n - 1, ncl)) {
-    if (threadIdx.x == 0) tau_all[b] = 0.0;
+    if (threadIdx.x == 0) tau_all[(size_t)b * steps + k] = 0.0;
     return;
   }
   const zc *R = Rall + (size_t)b * ldr * ncols;
@@ -640,11 +689,19 @@ hh_build_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32_t *
     const double nk = cn2[k];
     cn2[k] = cn2[pj];
     cn2[pj] = nk;
-    s_piv = cp;
+    // Once the largest remaining column is at the rounding level of the first pivot the rest of
+    // the block is numerically zero (the rows left are the null rows the Jacobi pass skips):
+    // no further reflection is built.
+    if (k == 0) piv0_all[b] = s_best[0];
+    s_piv = (s_best[0] <= 1e-30 * piv0_all[b]) ? -1 : cp;
   }
   __syncthreads();
   const int c = s_piv;
-  zc *V = V_all + (size_t)b * ldr;
+  if (c < 0) {
+    if (threadIdx.x == 0) tau_all[(size_t)b * steps + k] = 0.0;
+    return;
+  }
+  zc *V = V_all + ((size_t)b * steps + k) * ldr;
   double part = 0.0;
   for (int r = k + threadIdx.x; r < n; r += blockDim.x) {
     const zc x = R[(size_t)idx[r] * ncols + c];
@@ -671,52 +728,215 @@ hh_build_kernel(const zc *__restrict__ Rall, int ldr, int ncols, const int32_t *
       const double nv2 = nx2 - a0 + v0.x * v0.x + v0.y * v0.y;
       tau = 2.0 / nv2;
     }
-    tau_all[b] = tau;
+    tau_all[(size_t)b * steps + k] = tau;
   }
 }
 
-// rows k.. of the active list  <-  (I - tau v v^H) rows, 64 columns per CTA
-__global__ void __launch_bounds__(256)
+// rows k.. of the active list  <-  (I - tau v v^H) rows, for the columns [c0, c0 + nc) only (the
+// inner-product columns: they alone decide the next reflector).  32 columns x 8 row slices per
+// CTA, four independent row loads in flight per thread: the step is latency bound (a launch per
+// reflector), so the row loop is kept short and wide.
+constexpr int kHC = 32, kHS = 8;
+__global__ void __launch_bounds__(kHC * kHS)
 hh_apply_kernel(zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
-                const int32_t *__restrict__ nact_all, int k, const zc *__restrict__ V_all,
-                const double *__restrict__ tau_all) {
+                const int32_t *__restrict__ nact_all, int k, const zc *__restrict__ Vh_all,
+                const double *__restrict__ tauh_all, int steps, int c0, int nc) {
   const int b = blockIdx.y;
-  const double tau = tau_all[b];
+  const double tau = tauh_all[(size_t)b * steps + k];
   if (tau == 0.0) return;
   const int n = nact_all[b];
   zc *R = Rall + (size_t)b * ldr * ncols;
   const int32_t *idx = idx_all + (size_t)b * ldr;
-  const zc *V = V_all + (size_t)b * ldr;
-  const int col = blockIdx.x * 64 + (threadIdx.x & 63), slice = threadIdx.x >> 6;
-  const bool live = col < ncols;
+  const zc *V = Vh_all + ((size_t)b * steps + k) * ldr;
+  const int lc = threadIdx.x % kHC, slice = threadIdx.x / kHC;
+  const int cl = blockIdx.x * kHC + lc;
+  const bool live = cl < nc;
+  const int col = c0 + cl;
   double wr = 0.0, wi = 0.0;
   if (live) {
-    for (int r = k + slice; r < n; r += 4) {
+    int r = k + slice;
+    for (; r + 3 * kHS < n; r += 4 * kHS) {
+      zc v[4], x[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[q] = V[r + q * kHS];
+        x[q] = R[(size_t)idx[r + q * kHS] * ncols + col];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        wr += v[q].x * x[q].x + v[q].y * x[q].y;  // conj(v) x
+        wi += v[q].x * x[q].y - v[q].y * x[q].x;
+      }
+    }
+    for (; r < n; r += kHS) {
       const zc v = V[r], x = R[(size_t)idx[r] * ncols + col];
-      // conj(v) x
       wr += v.x * x.x + v.y * x.y;
       wi += v.x * x.y - v.y * x.x;
     }
   }
-  __shared__ double s_w[4][64][2];
-  s_w[slice][threadIdx.x & 63][0] = wr;
-  s_w[slice][threadIdx.x & 63][1] = wi;
+  __shared__ double s_w[kHS][kHC][2];
+  s_w[slice][lc][0] = wr;
+  s_w[slice][lc][1] = wi;
   __syncthreads();
   if (!live) return;
   wr = wi = 0.0;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    wr += s_w[q][threadIdx.x & 63][0];
-    wi += s_w[q][threadIdx.x & 63][1];
+  for (int q = 0; q < kHS; ++q) {
+    wr += s_w[q][lc][0];
+    wi += s_w[q][lc][1];
   }
   wr *= tau;
   wi *= tau;
-  for (int r = k + slice; r < n; r += 4) {
+  int r = k + slice;
+  for (; r + 3 * kHS < n; r += 4 * kHS) {
+    zc v[4], o[4];
+    zc *x[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      v[q] = V[r + q * kHS];
+      x[q] = R + (size_t)idx[r + q * kHS] * ncols + col;
+      o[q] = *x[q];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      o[q].x -= v[q].x * wr - v[q].y * wi;
+      o[q].y -= v[q].x * wi + v[q].y * wr;
+      *x[q] = o[q];
+    }
+  }
+  for (; r < n; r += kHS) {
     const zc v = V[r];
     zc *x = R + (size_t)idx[r] * ncols + col;
     zc o = *x;
     o.x -= v.x * wr - v.y * wi;
     o.y -= v.x * wi + v.y * wr;
+    *x = o;
+  }
+}
+
+constexpr int kHB = 8;  // reflectors per block of the deferred application
+
+// compact WY factor of reflectors k0 .. k0 + nb - 1:  H_k0 ... H_(k0+nb-1) = I - V T V^H
+// (LAPACK zlarft, forward / columnwise);  T [batch][kHB * kHB], upper triangular
+__global__ void __launch_bounds__(256)
+hh_T_kernel(const zc *__restrict__ Vh_all, const double *__restrict__ tauh_all, int steps, int ldr,
+            const int32_t *__restrict__ nact_all, int k0, int nb, zc *__restrict__ T_all) {
+  const int b = blockIdx.x;
+  const int n = nact_all[b];
+  __shared__ zc s_S[kHB][kHB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int pq = warp; pq < nb * nb; pq += nwarps) {
+    const int i = pq / nb, j = pq % nb;
+    if (i >= j) continue;
+    const zc *vi = Vh_all + ((size_t)b * steps + k0 + i) * ldr;
+    const zc *vj = Vh_all + ((size_t)b * steps + k0 + j) * ldr;
+    double re = 0.0, im = 0.0;
+    for (int r = k0 + j + lane; r < n; r += 32) {  // v_j vanishes above row k0 + j
+      const zc a = vi[r], c = vj[r];
+      re += a.x * c.x + a.y * c.y;  // conj(a) c
+      im += a.x * c.y - a.y * c.x;
+    }
+    re = warp_sum(re);
+    im = warp_sum(im);
+    if (lane == 0) s_S[i][j] = {re, im};
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    zc T[kHB][kHB];
+    for (int i = 0; i < kHB; ++i)
+      for (int j = 0; j < kHB; ++j) T[i][j] = {0.0, 0.0};
+    for (int j = 0; j < nb; ++j) {
+      const double tj = (k0 + j < n - 1) ? tauh_all[(size_t)b * steps + k0 + j] : 0.0;
+      T[j][j] = {tj, 0.0};
+      for (int i = 0; i < j; ++i) {
+        double re = 0.0, im = 0.0;
+        for (int l = i; l < j; ++l) {
+          re += T[i][l].x * s_S[l][j].x - T[i][l].y * s_S[l][j].y;
+          im += T[i][l].x * s_S[l][j].y + T[i][l].y * s_S[l][j].x;
+        }
+        T[i][j] = {-tj * re, -tj * im};
+      }
+    }
+    zc *out = T_all + (size_t)b * kHB * kHB;
+    for (int i = 0; i < kHB; ++i)
+      for (int j = 0; j < kHB; ++j) out[i * kHB + j] = T[i][j];
+  }
+}
+
+// C <- (I - V T V^H)^H C = C - V T^H (V^H C) for the columns OUTSIDE [ip0, ip1): the reflectors of
+// a block are applied together, two passes over the rows per kHB reflectors instead of two each
+__global__ void __launch_bounds__(256)
+hh_block_apply_kernel(zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
+                      const int32_t *__restrict__ nact_all, const zc *__restrict__ Vh_all, int steps, int k0, int nb,
+                      const zc *__restrict__ T_all, int ip0, int ip1) {
+  const int b = blockIdx.y;
+  const int n = nact_all[b];
+  if (k0 >= n - 1) return;
+  zc *R = Rall + (size_t)b * ldr * ncols;
+  const int32_t *idx = idx_all + (size_t)b * ldr;
+  const zc *V = Vh_all + ((size_t)b * steps + k0) * ldr;  // reflector j at V + j * ldr
+  const int cl = blockIdx.x * 64 + (threadIdx.x & 63), slice = threadIdx.x >> 6, lc = threadIdx.x & 63;
+  const int ncomp = ncols - (ip1 - ip0);
+  const bool live = cl < ncomp;
+  const int col = cl < ip0 ? cl : cl + (ip1 - ip0);
+  __shared__ zc s_T[kHB][kHB];
+  __shared__ zc s_w[4][kHB][64];
+  if (threadIdx.x < kHB * kHB) s_T[threadIdx.x / kHB][threadIdx.x % kHB] = T_all[(size_t)b * kHB * kHB + threadIdx.x];
+  double wr[kHB], wi[kHB];
+#pragma unroll
+  for (int j = 0; j < kHB; ++j) wr[j] = wi[j] = 0.0;
+  if (live) {
+    for (int r = k0 + slice; r < n; r += 4) {
+      const zc x = R[(size_t)idx[r] * ncols + col];
+#pragma unroll
+      for (int j = 0; j < kHB; ++j) {
+        if (j < nb) {
+          const zc v = V[(size_t)j * ldr + r];
+          wr[j] += v.x * x.x + v.y * x.y;  // conj(v) x
+          wi[j] += v.x * x.y - v.y * x.x;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kHB; ++j) s_w[slice][j][lc] = {wr[j], wi[j]};
+  __syncthreads();
+  if (!live) return;
+  // w'_i = sum_{j <= i} conj(T[j][i]) w_j
+  zc w[kHB];
+#pragma unroll
+  for (int j = 0; j < kHB; ++j) {
+    double re = 0.0, im = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      re += s_w[q][j][lc].x;
+      im += s_w[q][j][lc].y;
+    }
+    w[j] = {re, im};
+  }
+  zc wp[kHB];
+#pragma unroll
+  for (int i = 0; i < kHB; ++i) {
+    double re = 0.0, im = 0.0;
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      const zc t = s_T[j][i];
+      re += t.x * w[j].x + t.y * w[j].y;  // conj(t) w
+      im += t.x * w[j].y - t.y * w[j].x;
+    }
+    wp[i] = {re, im};
+  }
+  for (int r = k0 + slice; r < n; r += 4) {
+    zc *x = R + (size_t)idx[r] * ncols + col;
+    zc o = *x;
+#pragma unroll
+    for (int j = 0; j < kHB; ++j) {
+      if (j < nb) {
+        const zc v = V[(size_t)j * ldr + r];
+        o.x -= v.x * wp[j].x - v.y * wp[j].y;
+        o.y -= v.x * wp[j].y + v.y * wp[j].x;
+      }
+    }
     *x = o;
   }
 }
@@ -736,34 +956,69 @@ int householder_precondition(zc *R, int ldr, int ncols, const int32_t *idx, cons
     nmax = js.h_flag[1];
   }
   if (nmax < 2) return DSB_OK;
+  const int steps = std::min(nmax - 1, ipw);
+  if (steps <= 0) return DSB_OK;
   int32_t *clist = nullptr, *ncl = nullptr;
-  zc *V = nullptr;
-  double *tau = nullptr;
+  zc *Vh = nullptr, *T = nullptr;
+  double *tauh = nullptr, *cn2 = nullptr, *piv0 = nullptr;
   DSB_CUDA(cudaMallocAsync((void **)&clist, sizeof(int32_t) * (size_t)batch * ipw, stream));
   DSB_CUDA(cudaMallocAsync((void **)&ncl, sizeof(int32_t) * batch, stream));
-  DSB_CUDA(cudaMallocAsync((void **)&V, sizeof(zc) * (size_t)batch * ldr, stream));
-  DSB_CUDA(cudaMallocAsync((void **)&tau, sizeof(double) * batch, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&Vh, sizeof(zc) * (size_t)batch * steps * ldr, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&tauh, sizeof(double) * (size_t)batch * steps, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&T, sizeof(zc) * (size_t)batch * kHB * kHB, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&cn2, sizeof(double) * (size_t)batch * ipw, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&piv0, sizeof(double) * batch, stream));
+  DSB_CUDA(cudaMemsetAsync(Vh, 0, sizeof(zc) * (size_t)batch * steps * ldr, stream));
+  static const bool debug_t = getenv("DSB_SVD_DEBUG") != nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (debug_t) {
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, stream);
+  }
   hh_columns_kernel<<<batch, 256, sizeof(int32_t) * ipw, stream>>>(R, ldr, ncols, idx, nact, ip0, ip1, clist, ncl);
   DSB_LAUNCH_CHECK();
-  const int steps = std::min(nmax - 1, ipw);
-  const dim3 gapply((ncols + 63) / 64, batch), gnorm((ipw + 255) / 256, batch);
-  double *cn2 = nullptr;
-  DSB_CUDA(cudaMallocAsync((void **)&cn2, sizeof(double) * (size_t)batch * ipw, stream));
+  // phase A: the reflectors, applied at once to the inner-product columns only
+  const dim3 gapply((ipw + kHC - 1) / kHC, batch), gnorm((ipw + 255) / 256, batch);
   for (int k = 0; k < steps; ++k) {
     // partial column norms: recomputed every 16 steps, downdated in between
     const bool fresh = (k % 16) == 0;
     if (fresh) hh_colnorm_kernel<<<gnorm, 256, 0, stream>>>(R, ldr, ncols, idx, nact, clist, ncl, ipw, k, cn2);
-    hh_build_kernel<<<batch, 256, 0, stream>>>(R, ldr, ncols, idx, nact, clist, ncl, ipw, k, fresh ? 0 : 1, cn2, V,
-                                               tau);
-    hh_apply_kernel<<<gapply, 256, 0, stream>>>(R, ldr, ncols, idx, nact, k, V, tau);
+    hh_build_kernel<<<batch, 256, 0, stream>>>(R, ldr, ncols, idx, nact, clist, ncl, ipw, k, fresh ? 0 : 1, cn2, Vh,
+                                               tauh, piv0, steps);
+    hh_apply_kernel<<<gapply, kHC * kHS, 0, stream>>>(R, ldr, ncols, idx, nact, k, Vh, tauh, steps, ip0, ipw);
   }
   count_launch(2 * steps + steps / 16);
-  cudaFreeAsync(cn2, stream);
   DSB_LAUNCH_CHECK();
+  // phase B: every other column (the U^H accumulator, sky columns outside the inner product)
+  // receives the same reflectors in blocks of kHB (compact WY form)
+  const int ncomp = ncols - ipw;
+  if (ncomp > 0) {
+    const dim3 gblock((ncomp + 63) / 64, batch);
+    for (int k0 = 0; k0 < steps; k0 += kHB) {
+      const int nb = std::min(kHB, steps - k0);
+      hh_T_kernel<<<batch, 256, 0, stream>>>(Vh, tauh, steps, ldr, nact, k0, nb, T);
+      hh_block_apply_kernel<<<gblock, 256, 0, stream>>>(R, ldr, ncols, idx, nact, Vh, steps, k0, nb, T, ip0, ip1);
+    }
+    count_launch(2 * ((steps + kHB - 1) / kHB) - 1);
+    DSB_LAUNCH_CHECK();
+  }
+  if (debug_t) {
+    cudaEventRecord(ev1, stream);
+    cudaEventSynchronize(ev1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    fprintf(stderr, "[householder] ip [%d,%d) nmax %d: %d steps, %.1f ms\n", ip0, ip1, nmax, steps, ms);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+  }
   cudaFreeAsync(clist, stream);
   cudaFreeAsync(ncl, stream);
-  cudaFreeAsync(V, stream);
-  cudaFreeAsync(tau, stream);
+  cudaFreeAsync(Vh, stream);
+  cudaFreeAsync(tauh, stream);
+  cudaFreeAsync(T, stream);
+  cudaFreeAsync(cn2, stream);
+  cudaFreeAsync(piv0, stream);
   return DSB_OK;
 }
 
@@ -786,7 +1041,7 @@ int jacobi_pass(zc *R, int ldr, int ncols, const int32_t *idx, const int32_t *na
   const int P = std::max(2, (nblk + 1) & ~1);
   DSB_CHECK(P / 2 <= js.npairs_ld, DSB_ERR_INVALID, "jacobi_pass: scratch too small");
   static bool attr_set = false;
-  const size_t apply_smem = sizeof(zc) * (kJ2 * kAT + kJ2 * kJ2);
+  const size_t apply_smem = sizeof(zc) * (2 * kJ2 * kAT + kJ2 * kJ2);
   if (!attr_set) {
     DSB_CUDA(cudaFuncSetAttribute(bj_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem));
     attr_set = true;
@@ -797,8 +1052,21 @@ int jacobi_pass(zc *R, int ldr, int ncols, const int32_t *idx, const int32_t *na
   static const int do_sort = getenv("DSB_SVD_NOSORT") ? 0 : 1;
   static const int inner_sweeps = getenv("DSB_SVD_INNER") ? atoi(getenv("DSB_SVD_INNER")) : 2;
   static const bool debug = getenv("DSB_SVD_DEBUG") != nullptr;
-  const dim3 gnorm((nmax + 7) / 8, batch), gpair(P / 2, batch), gapply((ncols + kAT - 1) / kAT, P / 2, batch);
+  // column tiles per CTA of the update kernel: as many as leave about three waves of CTAs
+  const int ntiles = (ncols + kAT - 1) / kAT;
+  static const int tpc_env = getenv("DSB_SVD_TPC") ? atoi(getenv("DSB_SVD_TPC")) : 0;
+  const long long pair_ctas = (long long)(P / 2) * batch;
+  const int nsplit = (int)std::min<long long>(ntiles, std::max<long long>(1, (444 + pair_ctas - 1) / pair_ctas));
+  const int tiles_per_cta = tpc_env > 0 ? tpc_env : (ntiles + nsplit - 1) / nsplit;
+  const dim3 gnorm((nmax + 7) / 8, batch), gpair(P / 2, batch),
+      gapply((ntiles + tiles_per_cta - 1) / tiles_per_cta, P / 2, batch);
   DSB_CHECK(ldr <= js.ldr_max, DSB_ERR_INVALID, "jacobi_pass: scratch allocated for fewer rows");
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (debug) {
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, stream);
+  }
   DSB_CUDA(cudaMemsetAsync(js.blkstamp, 0, sizeof(int32_t) * (size_t)batch * js.nblk_ld, stream));
   DSB_CUDA(cudaMemsetAsync(js.pairstamp, 0, sizeof(int32_t) * (size_t)batch * js.nblk_ld * js.nblk_ld, stream));
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
@@ -813,7 +1081,7 @@ int jacobi_pass(zc *R, int ldr, int ncols, const int32_t *idx, const int32_t *na
                                                     js.skip, js.rot, js.done, js.npairs_ld, do_sort, inner_sweeps,
                                                     js.nrm2, js.nlive, js.blkstamp, js.pairstamp, js.nblk_ld, now);
       bj_apply_kernel<<<gapply, 256, apply_smem, stream>>>(R, ldr, ncols, idx, nact, step, js.W, js.skip,
-                                                           js.npairs_ld);
+                                                           js.npairs_ld, tiles_per_cta);
     }
     count_launch(2 * (P - 1) - 1);
     DSB_LAUNCH_CHECK();
@@ -826,6 +1094,15 @@ int jacobi_pass(zc *R, int ldr, int ncols, const int32_t *idx, const int32_t *na
       fprintf(stderr, "[jacobi] ip [%d,%d) nmax %d sweep %d: %d matrices left, %d of %d block pairs updated\n", ip0,
               ip1, nmax, sweep, js.h_flag[0], js.h_flag[1], batch * (P / 2) * (P - 1));
     if (js.h_flag[0] == 0) break;
+  }
+  if (debug) {
+    cudaEventRecord(ev1, stream);
+    cudaEventSynchronize(ev1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    fprintf(stderr, "[jacobi] ip [%d,%d) nmax %d: pass took %.1f ms\n", ip0, ip1, nmax, ms);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
   }
   return DSB_OK;
 }
