@@ -4,7 +4,7 @@
 set -u
 OUT=gpurun_out
 mkdir -p $OUT
-B="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline"
+B="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-svd"
 # (1) launch list with durations and DRAM traffic of every kernel of warm-up + 1 step
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 800 --csv \
     --log-file $OUT/r01_launches.csv $B > $OUT/ncu_launches.log 2>&1

@@ -6,6 +6,8 @@ B="python tools/bench_svd.py --only 9 ${SVD_CASE:---big4}"
 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 300 -c 400 --csv --log-file $OUT/r01_svd_launches.csv $B > $OUT/ncu_svd_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:bj_ --launch-skip 300 -c 4 -f -o /tmp/svd $B > $OUT/ncu_svd.log 2>&1
 python profiles/ncu_summary.py /tmp/svd.ncu-rep > $OUT/r01_ncu_svd.txt 2>&1
+ncu --set full --clock-control none --import-source on -k regex:hh_.*apply --launch-skip 400 -c 2 -f -o /tmp/svdhh $B > $OUT/ncu_svdhh.log 2>&1
+python profiles/ncu_summary.py /tmp/svdhh.ncu-rep >> $OUT/r01_ncu_svd.txt 2>&1
 python - <<'PY'
 import csv
 rows=list(csv.reader(open('gpurun_out/r01_svd_launches.csv')))
