@@ -460,12 +460,14 @@ bj_apply_kernel(zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__rest
       cp_async_wait<0>();
     }
     __syncthreads();
-    double or_[4][4], oi[4][4];
+    // four independent accumulators per output (re = a - b, im = c + d): one DFMA per
+    // accumulator and step, no dependent pairs in the inner loop
+    double oa[4][4], ob[4][4], oc[4][4], od[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) or_[i][j] = oi[i][j] = 0.0;
-#pragma unroll 4
+      for (int j = 0; j < 4; ++j) oa[i][j] = ob[i][j] = oc[i][j] = od[i][j] = 0.0;
+#pragma unroll 2
     for (int j = 0; j < kJ2; ++j) {
       zc wv[4], xv[4];
 #pragma unroll
@@ -476,10 +478,20 @@ bj_apply_kernel(zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__rest
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          or_[i][q] += wv[i].x * xv[q].x - wv[i].y * xv[q].y;
-          oi[i][q] += wv[i].x * xv[q].y + wv[i].y * xv[q].x;
+          oa[i][q] = fma(wv[i].x, xv[q].x, oa[i][q]);
+          ob[i][q] = fma(wv[i].y, xv[q].y, ob[i][q]);
+          oc[i][q] = fma(wv[i].x, xv[q].y, oc[i][q]);
+          od[i][q] = fma(wv[i].y, xv[q].x, od[i][q]);
         }
     }
+    double or_[4][4], oi[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        or_[i][q] = oa[i][q] - ob[i][q];
+        oi[i][q] = oc[i][q] + od[i][q];
+      }
     const int c0 = t * kAT;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
