@@ -82,6 +82,8 @@ def _load():
         "dsb_get_profile": (i32, [P(dbl), P(u64)]),
         "dsb_debug_gemm_tc": (i32, [i32, i32, i32, i32, i32, vp, vp, vp, vp]),
         "dsb_svd_chain": (i32, [vp, vp, i32, i32, i32, i32, i32, dbl, dbl, vp, vp, vp, vp, vp, vp]),
+        "dsb_svd_temponly": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+        "dsb_host_widen_c64": (i32, [vp, vp, ctypes.c_size_t, i32]),
         "dsb_project_sky_to_svd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
         "dsb_project_matrix_sky_to_svd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
         "dsb_project_matrix_diagonal_telescope_to_svd": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp]),

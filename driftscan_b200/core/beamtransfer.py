@@ -603,3 +603,134 @@ class BeamTransfer(config.Reader):
                     fbeam = beam[fi, pi, :, : svnum[fi]]
                 vecf[fi, pi] += np.dot(fbeam, vec[svbounds[fi] : svbounds[fi + 1]])
         return vecf
+
+
+class _SingleSVDBase(BeamTransfer):
+    """Shared file writer of the two single-SVD variants: ``_svd_device`` returns
+    ``(beam_svd, beam_ut, invbeam_svd, singularvalues)`` for all frequencies of one m."""
+
+    def _svd_device(self, bf, noisew, skip_svd_inv):
+        raise NotImplementedError
+
+    def _svd_chain_device(self, bf_host, noisew_host, skip_svd_inv):
+        out = self._svd_device(bf_host, noisew_host, skip_svd_inv)
+        return out[0], out[1], out[2], out[3], None
+
+
+def _run_svd_entry(entry, bf_host, noisew_host, npol, nl, svd_len, want_inv, extra=()):
+    """Device buffers + one call of a dsb_svd_* entry point; returns host arrays."""
+    import torch
+
+    from .. import _lib
+
+    batch, ntel = bf_host.shape[:2]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    bf = torch.from_numpy(np.ascontiguousarray(bf_host)).to(dev)
+    nw = torch.from_numpy(np.ascontiguousarray(noisew_host, dtype=np.float64)).to(dev)
+    bsvd = torch.empty((batch, svd_len, npol, nl), dtype=torch.complex128, device=dev)
+    but = torch.empty((batch, svd_len, ntel), dtype=torch.complex128, device=dev)
+    ibs = torch.empty((batch, npol, nl, svd_len), dtype=torch.complex128, device=dev) if want_inv else None
+    sv = torch.empty((batch, svd_len), dtype=torch.float64, device=dev)
+    nmodes = torch.empty((batch,), dtype=torch.int32, device=dev)
+    _lib.check(
+        entry(
+            bf.data_ptr(), nw.data_ptr(), batch, ntel, npol, nl, svd_len, *extra, bsvd.data_ptr(), but.data_ptr(),
+            0 if ibs is None else ibs.data_ptr(), sv.data_ptr(), nmodes.data_ptr(),
+            torch.cuda.current_stream().cuda_stream,
+        )
+    )
+    return bsvd.cpu().numpy(), but.cpu().numpy(), None if ibs is None else ibs.cpu().numpy(), sv.cpu().numpy()
+
+
+class BeamTransferTempSVD(_SingleSVDBase):
+    """The old temperature-only SVD (beamtransfer.py:1458-1592): one SVD of the whitened
+    temperature columns per (m, frequency); its left singular vectors compress all
+    polarisations.  ``dsb_svd_temponly`` on the device.  Modes whose singular value is exactly
+    zero are left zero (the reference stores arbitrary null vectors there)."""
+
+    def _svd_device(self, bf, noisew, skip_svd_inv):
+        from .. import _lib
+
+        _, _, npol, nl = bf.shape
+        return _run_svd_entry(_lib.lib.dsb_svd_temponly, bf, noisew, npol, nl, self.svd_len, not skip_svd_inv)
+
+
+class BeamTransferFullSVD(_SingleSVDBase):
+    """One SVD of the whole whitened block, all polarisations as one matrix
+    (beamtransfer.py:1595-1733); ``svd_len = min(npol_sky*(lmax+1), ntel)``.  On the device this
+    is ``dsb_svd_chain`` on the block seen as a single-polarisation matrix with
+    ``npol_sky*(lmax+1)`` columns (an unpolarised block takes the final SVD only,
+    beamtransfer.py:821-823)."""
+
+    @property
+    def svd_len(self):
+        return min((self.telescope.lmax + 1) * self.telescope.num_pol_sky, self.ntel)
+
+    def _svd_device(self, bf, noisew, skip_svd_inv):
+        from .. import _lib
+
+        batch, ntel, npol, nl = bf.shape
+        svd_len = self.svd_len
+        bsvd, but, ibs, sv = _run_svd_entry(
+            _lib.lib.dsb_svd_chain, bf.reshape(batch, ntel, 1, npol * nl), noisew, 1, npol * nl, svd_len,
+            not skip_svd_inv, extra=(1e-10, float(self.polsvcut)),
+        )
+        bsvd = bsvd.reshape(batch, svd_len, npol, nl)
+        if ibs is not None:
+            ibs = ibs.reshape(batch, npol, nl, svd_len)
+        return bsvd, but, ibs, sv
+
+
+class BeamTransferNoSVD(BeamTransfer):
+    """BeamTransfer without the SVD compression (beamtransfer.py:1736-1968): the "SVD basis" is
+    the telescope basis itself, every projection maps onto the m-mode visibilities."""
+
+    svcut = 0.0
+    noise_weight = False
+
+    def _svd_num(self, mi):
+        svnum = (np.ones(self.nfreq) * self.ntel).astype(int)
+        return svnum, np.cumsum(np.insert(svnum, 0, 0))
+
+    def _generate_svdfiles(self, regen=False, skip_svd_inv=False):
+        print("======== Skipping telescope SVD step ========")
+
+    def project_matrix_sky_to_svd(self, mi, mat, temponly=False):
+        return self.project_matrix_sky_to_telescope(mi, mat, temponly=temponly).reshape(self.ndof(mi), self.ndof(mi))
+
+    def project_vector_sky_to_svd(self, mi, vec, *args, **kwargs):
+        return self.project_vector_sky_to_telescope(mi, vec).flatten()
+
+    def project_matrix_telescope_to_svd(self, mi, mat):
+        return np.asarray(mat).reshape(self.ndof(mi), self.ndof(mi))
+
+    def project_matrix_diagonal_telescope_to_svd(self, mi, dmat, *args, **kwargs):
+        return np.diag(np.asarray(dmat).flatten())
+
+    def project_vector_telescope_to_svd(self, mi, vec, *args, **kwargs):
+        return np.asarray(vec).flatten()
+
+    def project_vector_svd_to_sky(self, mi, vec, temponly=False, conj=False):
+        if temponly:
+            raise NotImplementedError("temponly not implemented for no-SVD project_vector_svd_to_sky!")
+        tel = self.telescope
+        vec = np.asarray(vec)
+        svec = np.zeros((self.nfreq, tel.num_pol_sky, tel.lmax + 1) + vec.shape[1:], dtype=np.complex128)
+        if conj:
+            mats = self.beam_m(mi).reshape((self.nfreq, self.ntel, self.nsky)).transpose(0, 2, 1).conj()
+        else:
+            mats = self.invbeam_m(mi).reshape((self.nfreq, self.nsky, self.ntel))
+        v = vec.reshape(self.nfreq, self.ntel, -1)
+        for fi in range(self.nfreq):
+            svec[fi] = np.dot(mats[fi], v[fi]).reshape((tel.num_pol_sky, tel.lmax + 1) + vec.shape[1:])
+        return svec
+
+    def beam_svd(self, mi, *args, **kwargs):
+        return self.beam_m(mi)
+
+    def ndof(self, mi, *args, **kwargs):
+        return self.ntel * self.nfreq
+
+    @property
+    def ndofmax(self):
+        return self.ntel * self.nfreq

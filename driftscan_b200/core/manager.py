@@ -104,9 +104,13 @@ class ProductManager(object):
         self.telescope = telclass.from_config(yconf["telescope"])
 
         conf = yconf["config"]
-        if conf.get("nosvd") or conf.get("fullsvd"):
-            raise NotImplementedError("the nosvd / fullsvd BeamTransfer variants are not part of this build")
-        self.beamtransfer = beamtransfer.BeamTransfer(self.directory + "/bt/", telescope=self.telescope)
+        # BeamTransfer variant (manager.py:217-221): plain, no SVD, or the single full SVD
+        btclass = beamtransfer.BeamTransfer
+        if conf.get("nosvd"):
+            btclass = beamtransfer.BeamTransferNoSVD
+        if conf.get("fullsvd"):
+            btclass = beamtransfer.BeamTransferFullSVD
+        self.beamtransfer = btclass(self.directory + "/bt/", telescope=self.telescope)
         self.beamtransfer.read_config(conf)
 
         self.gen_beams = bool(conf.get("beamtransfers"))

@@ -1358,11 +1358,14 @@ __global__ void project_sky_to_svd_kernel(const zc *__restrict__ beam_svd, const
 
 using namespace dsb;
 
-extern "C" int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int batch, int ntel, int npol,
-                             int nl, int svd_len, double rtol1, double polsvcut, void *beam_svd_dev,
-                             void *beam_ut_dev, void *invbeam_dev, double *sv_dev, int32_t *nmodes_dev,
-                             void *stream_) {
+// temp_only: the single-SVD variant of BeamTransferTempSVD (beamtransfer.py:1549-1581): no image /
+// null-space passes, left singular vectors of the temperature columns of the whole whitened block.
+static int svd_chain_impl(const void *bf_dev, const double *noisew_dev, int batch, int ntel, int npol, int nl,
+                          int svd_len, double rtol1, double polsvcut, void *beam_svd_dev, void *beam_ut_dev,
+                          void *invbeam_dev, double *sv_dev, int32_t *nmodes_dev, bool temp_only,
+                          void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  const bool chain = npol > 1 && !temp_only;
   DSB_CHECK(bf_dev && noisew_dev && beam_svd_dev && beam_ut_dev && sv_dev, DSB_ERR_INVALID,
             "dsb_svd_chain: NULL argument");
   DSB_CHECK(batch >= 0 && ntel > 0 && npol > 0 && nl > 0 && svd_len > 0 && svd_len <= ntel, DSB_ERR_INVALID,
@@ -1402,7 +1405,7 @@ extern "C" int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int b
   dim3 gprep(64, batch);
   svd_prepare_kernel<<<gprep, 256, 0, stream>>>((const zc *)bf_dev, noisew_dev, R, ntel, nsky, idx, nact);
   DSB_LAUNCH_CHECK();
-  if (npol > 1) {
+  if (chain) {
     // SVD 1: image of the whole whitened matrix (rows ordered by norm, exactly zero rows -- e.g. the
     // m = 0 negative-m half -- leave the active set: they cannot be in the image)
     rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, 0, nsky, 0, 0.0, ntel, sig, tmp,
@@ -1427,8 +1430,8 @@ extern "C" int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int b
   DSB_CUDA(cudaMemsetAsync(sv_dev, 0, sizeof(double) * (size_t)batch * svd_len, stream));
   rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, 0, nl, 3, 0.0, ntel, sig, tmp, nullptr, 0);
   DSB_LAUNCH_CHECK();
-  DSB_TRY(householder_precondition(R, ntel, ncols, idx, nact, batch, 0, nl, npol > 1 ? -1 : ntel, js, stream));
-  DSB_TRY(jacobi_pass(R, ntel, ncols, idx, nact, batch, 0, nl, npol > 1 ? -1 : ntel, max_sweeps, tol,
+  DSB_TRY(householder_precondition(R, ntel, ncols, idx, nact, batch, 0, nl, chain ? -1 : ntel, js, stream));
+  DSB_TRY(jacobi_pass(R, ntel, ncols, idx, nact, batch, 0, nl, chain ? -1 : ntel, max_sweeps, tol,
                       sweeps + 2 * batch, js, stream));
   rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, 0, nl, 2, 0.0, nl, sig, tmp, sv_dev,
                                                 svd_len);
@@ -1463,11 +1466,26 @@ extern "C" int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int b
   }
   const int npass = want_inv ? 4 : 3;
   for (int i = 0; i < npass * batch; ++i) {
-    if (npol == 1 && i < 2 * batch) continue;
+    if (!chain && i < 2 * batch) continue;
     DSB_CHECK(hs[i] < max_sweeps, DSB_ERR_NUMERIC, "dsb_svd_chain: Jacobi pass %d of matrix %d did not converge",
               i / batch, i % batch);
   }
   return DSB_OK;
+}
+
+extern "C" int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int batch, int ntel, int npol,
+                             int nl, int svd_len, double rtol1, double polsvcut, void *beam_svd_dev,
+                             void *beam_ut_dev, void *invbeam_dev, double *sv_dev, int32_t *nmodes_dev,
+                             void *stream) {
+  return svd_chain_impl(bf_dev, noisew_dev, batch, ntel, npol, nl, svd_len, rtol1, polsvcut, beam_svd_dev,
+                        beam_ut_dev, invbeam_dev, sv_dev, nmodes_dev, false, stream);
+}
+
+extern "C" int dsb_svd_temponly(const void *bf_dev, const double *noisew_dev, int batch, int ntel, int npol,
+                                int nl, int svd_len, void *beam_svd_dev, void *beam_ut_dev, void *invbeam_dev,
+                                double *sv_dev, int32_t *nmodes_dev, void *stream) {
+  return svd_chain_impl(bf_dev, noisew_dev, batch, ntel, npol, nl, svd_len, 0.0, 0.0, beam_svd_dev, beam_ut_dev,
+                        invbeam_dev, sv_dev, nmodes_dev, true, stream);
 }
 
 extern "C" int dsb_project_sky_to_svd(const void *beam_svd_dev, const void *vec_dev, const int32_t *svnum_host,

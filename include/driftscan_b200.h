@@ -139,6 +139,12 @@ int dsb_peer_free(void *dev_ptr);
  * offsets (mmax+2 entries, last = total). */
 int64_t dsb_mmajor_size(int n_out0, int n_out1, int npol, int lside, int mmax, int64_t *offsets);
 
+/* Host helper: widen n complex64 numbers to complex128 with `nthreads` host threads (<= 0: all
+ * cores).  Exact.  The fp32x3 product is fp32 on the device, so it can cross PCIe as
+ * DSB_OUT_MMAJOR_C64 and be widened into the complex128 array the reference's callers expect
+ * (drift/core/telescope.py:809-814, beamtransfer.py:567-572) while the next block is in flight. */
+int dsb_host_widen_c64(const void *src_c64_host, void *dst_c128_host, size_t n, int nthreads);
+
 /* Workspace cap (bytes) for the library-owned scratch (ring spectra, GEMM
  * output).  Default 24 GiB. */
 int dsb_set_workspace_limit(size_t bytes);
@@ -172,6 +178,14 @@ int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int batch, int n
                   int nl, int svd_len, double rtol1, double polsvcut, void *beam_svd_dev,
                   void *beam_ut_dev, void *invbeam_dev, double *sv_dev, int32_t *nmodes_dev,
                   void *stream);
+
+/* Single-SVD variant of BeamTransferTempSVD (drift/core/beamtransfer.py:1549-1581): left singular
+ * vectors of the temperature columns of the whitened block, applied to all polarisations.
+ * Same buffers as dsb_svd_chain; modes with a singular value of exactly zero are dropped.
+ * (BeamTransferFullSVD, :1684-1716, is dsb_svd_chain with npol = 1 and nl = npol_sky*(lmax+1).) */
+int dsb_svd_temponly(const void *bf_dev, const double *noisew_dev, int batch, int ntel, int npol,
+                     int nl, int svd_len, void *beam_svd_dev, void *beam_ut_dev, void *invbeam_dev,
+                     double *sv_dev, int32_t *nmodes_dev, void *stream);
 
 /* project_vector_sky_to_svd (drift/core/beamtransfer.py:1324-1364) for one m:
  *   beam_svd c128 [nfreq][svd_len][npol_sky][nl], vec c128 [nfreq][npol_sky][nl][nrhs]

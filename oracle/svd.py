@@ -90,3 +90,23 @@ def project_vector_sky_to_svd(beam_svd, sv, vec, svcut=1e-6, temponly=False):
             if svnum[fi] > 0:
                 out[svb[fi] : svb[fi + 1]] += beam_svd[fi, : svnum[fi], pi, :] @ vec[fi, pi]
     return out
+
+
+def svd_single(bf, noisew, svd_len, temponly, want_inv=True):
+    """The single-SVD variants for one (m, frequency): ``BeamTransferTempSVD``
+    (beamtransfer.py:1549-1581, ``temponly=True``: SVD of the temperature columns) and
+    ``BeamTransferFullSVD`` (:1684-1716, SVD of the whole block).  ``svd_gen(...,
+    full_matrices=False)`` keeps every one of the min(ntel, ncols) modes, null ones included.
+
+    ``bf`` [ntel, npol, nl], ``noisew`` [ntel].  Returns (beam_svd [svd_len, npol, nl],
+    beam_ut [svd_len, ntel], invbeam [npol, nl, svd_len] or None, sv [svd_len]).
+    PINNED by tests/golden/products_variants.npz (the reference's own classes under stubs).
+    """
+    ntel, npol, nl = bf.shape
+    bfw = bf * noisew[:, None, None]
+    target = bfw[:, 0, :] if temponly else bfw.reshape(ntel, -1)
+    u, sig, _ = la.svd(target, full_matrices=False)
+    ut = u.T.conj()
+    bsvd = ut @ bfw.reshape(ntel, -1)
+    inv = la.pinv(bsvd).reshape(npol, nl, svd_len) if want_inv else None
+    return bsvd.reshape(svd_len, npol, nl), ut * noisew[None, :], inv, sig

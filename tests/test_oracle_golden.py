@@ -122,3 +122,29 @@ def test_projection_against_reference(golden_dir):
     prod = np.load(os.path.join(golden_dir, "products_small.npz"))
     got = osvd.project_vector_sky_to_svd(prod["beam_svd_7"], prod["sv_7"], prod["proj_vec"])
     assert np.allclose(got, prod["proj_sky_to_svd_7"], rtol=1e-12, atol=1e-9)
+
+
+def test_single_svd_variants_against_reference_products(golden_dir):
+    """oracle.svd.svd_single vs the files the reference's BeamTransferTempSVD / FullSVD wrote
+    (tests/golden/make_golden_variants.py)."""
+    var = np.load(os.path.join(golden_dir, "products_variants.npz"))
+    full = np.load(os.path.join(golden_dir, "products_small.npz"))
+    t = np.load(os.path.join(golden_dir, "telescope.npz"))
+    bm = full["beam_m_7"]
+    for tag, temponly in (("temp", True), ("full", False)):
+        svd_len = int(var[f"{tag}_svd_len"])
+        assert svd_len == (26 if temponly else 56)
+        for fi in range(bm.shape[0]):
+            bf = bm[fi].reshape(-1, 4, bm.shape[-1])
+            nw = np.concatenate([t["small_noisepower"][:, fi]] * 2) ** -0.5
+            bsvd, but, inv, sv = osvd.svd_single(bf, nw, svd_len, temponly)
+            ref_sv = var[f"{tag}_sv_7"][fi]
+            assert np.allclose(sv, ref_sv, rtol=1e-9, atol=1e-12 * ref_sv.max())
+            k = int((ref_sv > 1e-8 * ref_sv.max()).sum())
+            a, b = but[:k], var[f"{tag}_beam_ut_7"][fi, :k]
+            pa = a.conj().T @ np.linalg.pinv(a.conj().T)
+            pb = b.conj().T @ np.linalg.pinv(b.conj().T)
+            assert np.abs(pa - pb).max() < 1e-7
+            ra, rb = bsvd[:k].reshape(k, -1), var[f"{tag}_beam_svd_7"][fi, :k].reshape(k, -1)
+            assert np.abs(ra.conj().T @ ra - rb.conj().T @ rb).max() <= 1e-9 * ref_sv.max() ** 2
+            assert inv.shape == tuple(var[f"{tag}_invbeam_shape_7"][1:])
