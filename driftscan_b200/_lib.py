@@ -84,6 +84,8 @@ def _load():
         "dsb_svd_chain": (i32, [vp, vp, i32, i32, i32, i32, i32, dbl, dbl, vp, vp, vp, vp, vp, vp]),
         "dsb_svd_temponly": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
         "dsb_host_widen_c64": (i32, [vp, vp, ctypes.c_size_t, i32]),
+        "dsb_lzf_compress": (ctypes.c_size_t, [vp, ctypes.c_size_t, vp, ctypes.c_size_t]),
+        "dsb_lzf_decompress": (ctypes.c_size_t, [vp, ctypes.c_size_t, vp, ctypes.c_size_t]),
         "dsb_project_sky_to_svd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
         "dsb_project_matrix_sky_to_svd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
         "dsb_project_matrix_diagonal_telescope_to_svd": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp]),

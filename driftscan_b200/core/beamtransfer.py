@@ -55,6 +55,9 @@ class BeamTransfer(config.Reader):
     truncate_rel = config.Property(proptype=float, default=1e-7)
     truncate_maxl = config.Property(proptype=float, default=1e-8)
     chunk_cache_size = config.Property(proptype=int, default=128)
+    # not in the reference: write the products contiguously instead of with the reference's
+    # chunk shapes and LZF filter (beamtransfer.py:549-555, 741-789); readers take both
+    compress_products = config.Property(proptype=bool, default=True)
 
     noise_weight = True
 
@@ -174,6 +177,12 @@ class BeamTransfer(config.Reader):
 
     generate_cache = generate
 
+    def _storage(self, chunks):
+        """h5py storage keywords of the reference's product datasets."""
+        if not self.compress_products or any(c < 1 for c in chunks):
+            return {}
+        return dict(chunks=tuple(int(c) for c in chunks), compression="lzf")
+
     def _generate_dirs(self):
         if self.comm.rank0:
             os.makedirs(self.directory, exist_ok=True)
@@ -211,7 +220,9 @@ class BeamTransfer(config.Reader):
                 logger.info(f"m index {mi}. File: {self._mfile(mi)} exists. Skipping...")
                 continue
             with h5lite.File(self._mfile(mi), "w") as f:
-                f.create_dataset("beam_m", (nf_inc, 2, nb_inc, np_inc, nl - mi), dtype=np.complex128)
+                # chunk shape and filter of beamtransfer.py:549-572 (truncate = False)
+                f.create_dataset("beam_m", (nf_inc, 2, nb_inc, np_inc, nl - mi), dtype=np.complex128,
+                                 **self._storage((1, 2, min(10, nb_inc), np_inc, nl - mi)))
                 f.attrs["m"] = mi
                 f.attrs["frequencies"] = tel.frequencies
         comm.barrier()
@@ -322,10 +333,12 @@ class BeamTransfer(config.Reader):
         final = self._svdfile(mi)
         tmp = os.path.join(os.path.dirname(final), "." + os.path.basename(final))
         with h5lite.File(tmp, "w") as fs:
-            fs.create_dataset("beam_svd", data=bsvd)
+            # chunk shapes of beamtransfer.py:747-789
+            k = min(10, bsvd.shape[1])
+            fs.create_dataset("beam_svd", data=bsvd, **self._storage((1, k) + bsvd.shape[2:]))
             if not skip_svd_inv:
-                fs.create_dataset("invbeam_svd", data=ibs)
-            fs.create_dataset("beam_ut", data=but)
+                fs.create_dataset("invbeam_svd", data=ibs, **self._storage((1,) + ibs.shape[1:3] + (k,)))
+            fs.create_dataset("beam_ut", data=but, **self._storage((1, k, but.shape[2])))
             fs.create_dataset("singularvalues", data=sv)
             try:
                 fs.attrs["baselines"] = tel.baselines

@@ -145,6 +145,12 @@ int64_t dsb_mmajor_size(int n_out0, int n_out1, int npol, int lside, int mmax, i
  * (drift/core/telescope.py:809-814, beamtransfer.py:567-572) while the next block is in flight. */
 int dsb_host_widen_c64(const void *src_c64_host, void *dst_c128_host, size_t n, int nthreads);
 
+/* Host helpers: LZF codec of the HDF5 "lzf" filter (id 32000) the reference's products are
+ * written with (drift/core/beamtransfer.py:553-555, 567-572).  Both return the number of bytes
+ * produced, 0 when the result does not fit `out_cap` (or the stream is malformed). */
+size_t dsb_lzf_compress(const void *in, size_t in_len, void *out, size_t out_cap);
+size_t dsb_lzf_decompress(const void *in, size_t in_len, void *out, size_t out_cap);
+
 /* Workspace cap (bytes) for the library-owned scratch (ring spectra, GEMM
  * output).  Default 24 GiB. */
 int dsb_set_workspace_limit(size_t bytes);
