@@ -314,6 +314,8 @@ def main():
     ap.add_argument("--no-e2e-c64", action="store_true",
                     help="skip the complex64-over-PCIe + host-widening variant of the end-to-end step")
     ap.add_argument("--e2e-pieces", type=int, default=4, help="copy/widen pieces per frequency in that variant")
+    ap.add_argument("--bucket-streams", action="store_true",
+                    help="run the nside buckets of a step on separate streams")
     ap.add_argument("--no-svd", action="store_true", help="skip the per-m SVD measurement (second half of the metric)")
     ap.add_argument("--svd-only", action="store_true", help="diagnostic: run only the per-m SVD measurement")
     ap.add_argument("--svd-ms", default="auto",
@@ -454,17 +456,39 @@ def main():
             for _, _, units in prepared:
                 units["out0"] += rank * F
 
+    # One stream per nside bucket (largest first): the buckets are independent (own plan, own
+    # workspace, disjoint output rows), and the issue-bound ring kernel of one bucket overlaps the
+    # TMA / tensor-pipe bound Legendre kernel of another.
+    order = sorted(range(len(prepared)), key=lambda i: -len(prepared[i][2]))
+    if os.environ.get("DSB_BENCH_ORDER") == "asc":
+        order = list(range(len(prepared)))
+    bstreams = [torch.cuda.Stream(device=dev) for _ in prepared] if args.bucket_streams else None
+
+    def fork_join(launch):
+        if bstreams is None:
+            for i in order:
+                launch(prepared[i], stream)
+            return
+        cur = torch.cuda.current_stream()
+        ev0 = torch.cuda.Event()
+        ev0.record(cur)
+        for i in order:
+            bstreams[i].wait_event(ev0)
+            launch(prepared[i], bstreams[i].cuda_stream)
+            ev = torch.cuda.Event()
+            ev.record(bstreams[i])
+            cur.wait_event(ev)
+
     def step_device():
         if scatter is not None:
-            for nside, plan, units in prepared:
-                plan.transfer_units_scatter(units, 4, True, mmax, eng.precision, _lib.DSB_OUT_MMAJOR_C128, gdims,
-                                            scatter.block_ptrs, stream)
+            fork_join(lambda b, st: b[1].transfer_units_scatter(b[2], 4, True, mmax, eng.precision,
+                                                                _lib.DSB_OUT_MMAJOR_C128, gdims,
+                                                                scatter.block_ptrs, st))
             if not args.no_fence:
                 scatter.fence()
             return None
-        for nside, plan, units in prepared:
-            plan.transfer_units(units, 4, True, mmax, eng.precision, _lib.DSB_OUT_MMAJOR_C128, dims,
-                                out_dev.data_ptr(), False, stream)
+        fork_join(lambda b, st: b[1].transfer_units(b[2], 4, True, mmax, eng.precision, _lib.DSB_OUT_MMAJOR_C128,
+                                                    dims, out_dev.data_ptr(), False, st))
         if world > 1:
             return comm.exchange_mblocks(out_dev, F, moff, mmax + 1, f_lo=rank * F)
         return None
@@ -498,11 +522,14 @@ def main():
     barrier()
     _lib.lib.dsb_set_profiling(1)
     launches0 = _lib.launch_count()
-    sampler.start()
+    if not os.environ.get("DSB_BENCH_NOCLOCKS"):
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         step_device()
+    host_ms_step = (time.perf_counter() - t_host0) * 1e3 / args.steps  # time the host spends enqueueing a step
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -745,7 +772,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3->f32 (fp64 phase)" if args.precision == "fp32x3" else "f64",
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": dominant, "roofline_all": [roof_ring, roof_leg, roof_pack],
-            "stage_launches_per_run": stage_launch, "cpu_baseline": cpu, "exchange": exchange, "svd": svd,
+            "stage_launches_per_run": stage_launch, "host_enqueue_ms_per_step": host_ms_step, "cpu_baseline": cpu, "exchange": exchange, "svd": svd,
         }
         print(json.dumps(line))
     if world > 1:

@@ -10,7 +10,7 @@ LIB = os.path.join(HERE, "libdriftb200.so")
 SOURCES = ["plan.cu", "tables.cu", "ringfft.cu", "legendre_f64.cu", "legendre_tc.cu", "pack.cu", "api.cu", "svd.cu", "kl.cu", "hostutil.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--use_fast_math=false".replace("=false", "") if False else "-Xcompiler", "-O2",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
 ]
 
 

@@ -6,6 +6,9 @@
 #include <numeric>
 #include <map>
 #include <cstring>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 #include "dsb_common.cuh"
 
@@ -186,6 +189,27 @@ int pair_weights_for_units(dsb_plan *plan, const dsb_unit *units, int nunits, in
 
 }  // namespace
 
+namespace {
+// DSB_HOST_TIMING=1: host-side milliseconds of each phase of dsb_transfer_units, printed per call
+struct HostClock {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  HostClock() : on(getenv("DSB_HOST_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void lap(int i) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    acc[i] += std::chrono::duration<double, std::milli>(t1 - t0).count();
+    t0 = t1;
+  }
+  void report(int nunits) {
+    if (!on) return;
+    fprintf(stderr, "[dsb host] units %d: validate+weights %.2f sort+tables %.2f items %.2f workspace %.2f copies %.2f "
+            "ring %.2f legendre %.2f pack %.2f ms\n", nunits, acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6], acc[7]);
+  }
+};
+}  // namespace
+
 // block_ptrs_host != NULL: scatter mode -- m-major block m is written at device address
 // block_ptrs_host[m] (local or peer memory) instead of out + offset(m).
 static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int nunits, int npol_sky, int polarised,
@@ -217,6 +241,7 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
   DSB_CHECK(tarray || npol_out == npol_sky, DSB_ERR_INVALID,
             "dsb_transfer_units: m-major output stores exactly the computed polarisations");
 
+  HostClock hc;
   // ---- validate units (mirrors the ValueError of telescope.py:784-788) and sort by lmax
   int lmax_b = 0;
   for (int i = 0; i < nunits; ++i) {
@@ -240,6 +265,7 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
   const void **wptr_dev = nullptr;
   DSB_TRY(pair_weights_for_units(plan, units_host, nunits, polarised, precision, unit_pair, &wptr_dev, stream));
 
+  hc.lap(0);
   std::vector<int> order(nunits);
   std::iota(order.begin(), order.end(), 0);
   // Descending lmax in steps of 8, units of one beam pair together inside a step: a CTA of the
@@ -307,6 +333,7 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
     }
   }
 
+  hc.lap(1);
   int rc = DSB_OK;
   for (long c0 = 0; c0 < nunits && rc == DSB_OK; c0 += chunk) {
     const int nu = (int)std::min<long>(chunk, nunits - c0);
@@ -343,6 +370,7 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
           }
     }
 
+    hc.lap(2);
     // carve the workspace
     size_t need;
     {
@@ -374,6 +402,7 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
     int64_t *moff_dev = cv.take<int64_t>(moff.size());
     char *stage = (tarray && out_is_host) ? cv.take<char>((size_t)nu * plane_out) : nullptr;
 
+    hc.lap(3);
     // Padding rows of the operand (fold-ring count rounded up to the k-tile) are written by
     // no ring and must be finite: clear the operand whenever the layout has such rows.
     // Columns of the last partial 128-column tile may hold stale (finite or not) data: each
@@ -382,18 +411,45 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
       DSB_CUDA(cudaMemsetAsync(F0, 0, f0_bytes, stream));
       if (f2_bytes) DSB_CUDA(cudaMemsetAsync(F2, 0, f2_bytes, stream));
     }
-    DSB_CUDA(cudaMemcpyAsync(ud_dev, ud.data(), nu * sizeof(UnitDev), cudaMemcpyHostToDevice, stream));
-    DSB_CUDA(cudaMemcpyAsync(o0_dev, o0.data(), nu * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
-    DSB_CUDA(cudaMemcpyAsync(o1_dev, o1.data(), nu * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
-    DSB_CUDA(cudaMemcpyAsync(items_dev, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice,
-                             stream));
-    DSB_CUDA(cudaMemcpyAsync(moff_dev, moff.data(), moff.size() * sizeof(int64_t), cudaMemcpyHostToDevice,
-                             stream));
+    {
+      // descriptors go through a pinned staging slot (see dsb_plan::stage_host): stream-ordered
+      // copies, the host does not wait for the device
+      const size_t b_ud = nu * sizeof(UnitDev), b_o = nu * sizeof(int32_t), b_it = items.size() * sizeof(WorkItem),
+                   b_mo = moff.size() * sizeof(int64_t);
+      auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+      const size_t o_ud = 0, o_o0 = al(b_ud), o_o1 = o_o0 + al(b_o), o_it = o_o1 + al(b_o), o_mo = o_it + al(b_it),
+                   total = o_mo + al(b_mo);
+      const int slot = plan->stage_next;
+      plan->stage_next = (slot + 1) % dsb_plan::kStageSlots;
+      if (!plan->stage_ev[slot]) DSB_CUDA(cudaEventCreateWithFlags(&plan->stage_ev[slot], cudaEventDisableTiming));
+      else DSB_CUDA(cudaEventSynchronize(plan->stage_ev[slot]));  // copies that last used this slot are done
+      if (plan->stage_bytes[slot] < total) {
+        if (plan->stage_host[slot]) DSB_CUDA(cudaFreeHost(plan->stage_host[slot]));
+        plan->stage_host[slot] = nullptr;
+        plan->stage_bytes[slot] = 0;
+        DSB_CUDA(cudaHostAlloc((void **)&plan->stage_host[slot], total + total / 4, cudaHostAllocDefault));
+        plan->stage_bytes[slot] = total + total / 4;
+      }
+      char *h = plan->stage_host[slot];
+      memcpy(h + o_ud, ud.data(), b_ud);
+      memcpy(h + o_o0, o0.data(), b_o);
+      memcpy(h + o_o1, o1.data(), b_o);
+      memcpy(h + o_it, items.data(), b_it);
+      memcpy(h + o_mo, moff.data(), b_mo);
+      DSB_CUDA(cudaMemcpyAsync(ud_dev, h + o_ud, b_ud, cudaMemcpyHostToDevice, stream));
+      DSB_CUDA(cudaMemcpyAsync(o0_dev, h + o_o0, b_o, cudaMemcpyHostToDevice, stream));
+      DSB_CUDA(cudaMemcpyAsync(o1_dev, h + o_o1, b_o, cudaMemcpyHostToDevice, stream));
+      DSB_CUDA(cudaMemcpyAsync(items_dev, h + o_it, b_it, cudaMemcpyHostToDevice, stream));
+      DSB_CUDA(cudaMemcpyAsync(moff_dev, h + o_mo, b_mo, cudaMemcpyHostToDevice, stream));
+      DSB_CUDA(cudaEventRecord(plan->stage_ev[slot], stream));
+    }
 
+    hc.lap(4);
     StageTimer timer(stream);
     timer.mark(0);
     if ((rc = launch_ringfft(plan, lay, ud_dev, precision, wptr_dev, F0, F2, stream)) != DSB_OK) break;
     timer.mark(1);
+    hc.lap(5);
     if (f64)
       rc = launch_legendre_f64(plan, t, lay, items, items_dev, (const double *)F0, (const double *)F2,
                                (double *)C0, (double *)C2, stream);
@@ -402,6 +458,7 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
                               (float *)C2, stream);
     if (rc != DSB_OK) break;
     timer.mark(2);
+    hc.lap(6);
 
     PackParams pp;
     pp.out_kind = out_kind;
@@ -427,6 +484,7 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
       break;
     timer.mark(3);
     timer.finish();
+    hc.lap(7);
     if (tarray && out_is_host) {
       for (int i = 0; i < nu; ++i) {
         const dsb_unit &u = units_host[order[c0 + i]];
@@ -439,6 +497,7 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
     // (or the next call) are protected by stream order, so nothing blocks here.
   }
 
+  hc.report(nunits);
   if (!tarray && out_is_host) {
     if (rc == DSB_OK)
       DSB_CUDA(cudaMemcpyAsync(out, out_dev, (size_t)mm_total * out_elem, cudaMemcpyDeviceToHost, stream));

@@ -173,9 +173,23 @@ struct dsb_plan {
   void *ws = nullptr;
   size_t ws_bytes = 0;
   dsb::RingDesc *dummy = nullptr;
+  // Pinned staging slots for the per-chunk descriptors (units, output slots, work items, block
+  // offsets): copies from pageable memory wait for the stream to drain, which would stall the
+  // host at every call; from pinned memory they are stream-ordered and the host runs ahead.
+  static constexpr int kStageSlots = 4;
+  char *stage_host[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+  size_t stage_bytes[kStageSlots] = {0, 0, 0, 0};
+  cudaEvent_t stage_ev[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+  int stage_next = 0;
 };
 
 namespace dsb {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the function, not of a launch:
+// lowering it while an earlier launch that needs more is still queued (another stream, or the
+// host running ahead of the device) lets that kernel start with too small a carve-out.  Only
+// ever raise it.
+cudaError_t raise_dynamic_smem(const void *kernel, size_t bytes);  // plan.cu
 
 // plan.cu
 int ensure_workspace(dsb_plan *plan, size_t bytes);

@@ -527,7 +527,7 @@ int launch_legendre_tc_raw(int nprobA, int nprobT, int Kp, int NP, int ncols0, i
   DSB_CHECK(nstages >= 2, DSB_ERR_UNSUPPORTED, "pipeline does not fit shared memory");
   P.nstages = nstages;
   const size_t smem = nstages * stage_bytes + (3 * nstages + 8) * 8 + 16 + 1024;
-  DSB_CUDA(cudaFuncSetAttribute(legendre_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DSB_CUDA(raise_dynamic_smem((const void *)legendre_tc_kernel, smem));
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);

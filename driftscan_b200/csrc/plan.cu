@@ -7,6 +7,9 @@
 #include <algorithm>
 #include <tuple>
 
+#include <map>
+#include <mutex>
+
 #include "dsb_common.cuh"
 #include "fft16.cuh"
 
@@ -285,9 +288,26 @@ static void free_tables(Tables &t) {
   t = Tables();
 }
 
+namespace dsb {
+cudaError_t raise_dynamic_smem(const void *kernel, size_t bytes) {
+  static std::map<const void *, size_t> current;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t &cur = current[kernel];
+  if (bytes <= cur) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
+}  // namespace dsb
+
 extern "C" int dsb_plan_destroy(dsb_plan *plan) {
   if (!plan) return DSB_OK;
   cudaDeviceSynchronize();
+  for (int i = 0; i < dsb_plan::kStageSlots; ++i) {
+    if (plan->stage_host[i]) cudaFreeHost(plan->stage_host[i]);
+    if (plan->stage_ev[i]) cudaEventDestroy(plan->stage_ev[i]);
+  }
   cudaFree(plan->rings);
   cudaFree(plan->horizon);
   cudaFree(plan->trig);

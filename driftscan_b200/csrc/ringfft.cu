@@ -673,7 +673,7 @@ static int launch_class(const dsb_plan::RingClass &cls, RingFFTParams<T> &P, con
   while (upc > G && (long)cls.count * ((lay.nunits + upc - 1) / upc) < 4 * 148) upc >>= 1;
   P.units_per_cta = upc;
   auto kern = ringfft_kernel<T, LOG2L, KIND>;
-  DSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DSB_CUDA(raise_dynamic_smem((const void *)kern, smem));
   dim3 grid(cls.count, (lay.nunits + upc - 1) / upc);
   kern<<<grid, 256, smem, stream>>>(P);
   DSB_LAUNCH_CHECK();

@@ -1055,7 +1055,7 @@ int jacobi_pass(zc *R, int ldr, int ncols, const int32_t *idx, const int32_t *na
   static bool attr_set = false;
   const size_t apply_smem = sizeof(zc) * (2 * kJ2 * kAT + kJ2 * kJ2);
   if (!attr_set) {
-    DSB_CUDA(cudaFuncSetAttribute(bj_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem));
+    DSB_CUDA(raise_dynamic_smem((const void *)bj_apply_kernel, apply_smem));
     attr_set = true;
   }
   DSB_CUDA(cudaMemsetAsync(js.amax, 0, sizeof(unsigned long long) * batch, stream));
