@@ -86,7 +86,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark_start(self):
+        """Samples from here on belong to the timed region."""
+        self.t_start = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -98,7 +102,10 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t_start = getattr(self, "t_start", 0.0)
+        for t_line, ln in self.lines:
+            if t_line < t_start:
+                continue
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 6:
                 continue
@@ -314,6 +321,8 @@ def main():
     ap.add_argument("--no-e2e-c64", action="store_true",
                     help="skip the complex64-over-PCIe + host-widening variant of the end-to-end step")
     ap.add_argument("--e2e-pieces", type=int, default=4, help="copy/widen pieces per frequency in that variant")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="enqueue every kernel of every timed step from the host instead of replaying a CUDA graph")
     ap.add_argument("--bucket-streams", action="store_true",
                     help="run the nside buckets of a step on separate streams")
     ap.add_argument("--no-svd", action="store_true", help="skip the per-m SVD measurement (second half of the metric)")
@@ -384,9 +393,17 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dist = None
+    stdout_fd = None
     if world > 1:
         import torch.distributed as dist
 
+        # stdout carries the one JSON line: whatever libraries print there meanwhile (the NCCL
+        # version banner) goes to stderr
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
+
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.current_stream().cuda_stream
@@ -396,6 +413,9 @@ def main():
 
     if args.svd_only:
         svd = svd_section(tel, args, rank, world, dev, stream, with_cpu=(world == 1 and not args.no_cpu_baseline))
+        if stdout_fd is not None:
+            sys.stdout.flush()
+            os.dup2(stdout_fd, 1)
         if rank == 0:
             print(json.dumps({"svd": svd, "n_gpus": world, "config": config}))
         if world > 1:
@@ -460,14 +480,12 @@ def main():
     # workspace, disjoint output rows), and the issue-bound ring kernel of one bucket overlaps the
     # TMA / tensor-pipe bound Legendre kernel of another.
     order = sorted(range(len(prepared)), key=lambda i: -len(prepared[i][2]))
-    if os.environ.get("DSB_BENCH_ORDER") == "asc":
-        order = list(range(len(prepared)))
     bstreams = [torch.cuda.Stream(device=dev) for _ in prepared] if args.bucket_streams else None
 
-    def fork_join(launch):
+    def fork_join(launch, st):
         if bstreams is None:
             for i in order:
-                launch(prepared[i], stream)
+                launch(prepared[i], st)
             return
         cur = torch.cuda.current_stream()
         ev0 = torch.cuda.Event()
@@ -479,16 +497,27 @@ def main():
             ev.record(bstreams[i])
             cur.wait_event(ev)
 
-    def step_device():
+    def step_compute(st):
+        """The kernels of one step (every nside bucket), enqueued on stream ``st``."""
         if scatter is not None:
-            fork_join(lambda b, st: b[1].transfer_units_scatter(b[2], 4, True, mmax, eng.precision,
+            fork_join(lambda b, s_: b[1].transfer_units_scatter(b[2], 4, True, mmax, eng.precision,
                                                                 _lib.DSB_OUT_MMAJOR_C128, gdims,
-                                                                scatter.block_ptrs, st))
+                                                                scatter.block_ptrs, s_), st)
+        else:
+            fork_join(lambda b, s_: b[1].transfer_units(b[2], 4, True, mmax, eng.precision, _lib.DSB_OUT_MMAJOR_C128,
+                                                        dims, out_dev.data_ptr(), False, s_), st)
+
+    graph = {"g": None, "launches": 0}
+
+    def step_device():
+        if graph["g"] is not None:
+            graph["g"].replay()
+        else:
+            step_compute(stream)
+        if scatter is not None:
             if not args.no_fence:
                 scatter.fence()
             return None
-        fork_join(lambda b, st: b[1].transfer_units(b[2], 4, True, mmax, eng.precision, _lib.DSB_OUT_MMAJOR_C128,
-                                                    dims, out_dev.data_ptr(), False, st))
         if world > 1:
             return comm.exchange_mblocks(out_dev, F, moff, mmax + 1, f_lo=rank * F)
         return None
@@ -517,13 +546,46 @@ def main():
 
     # ---- device-resident measurement with per-stage event timing and clock sampling
     sampler = ClockSampler(local_rank)
+    if not os.environ.get("DSB_BENCH_NOCLOCKS"):
+        sampler.start()  # before the warm-up: nvidia-smi's start-up must not fall into the timed region
     for _ in range(args.warmup):
         step_device()
     barrier()
+    # per-stage times for the rooflines: a profiled pass of direct launches (CUDA events between
+    # the stages on the launching stream); it is not the pass that is timed for `value`
     _lib.lib.dsb_set_profiling(1)
     launches0 = _lib.launch_count()
-    if not os.environ.get("DSB_BENCH_NOCLOCKS"):
-        sampler.start()
+    for _ in range(args.steps):
+        step_device()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    prof_ms = (ctypes.c_double * 3)()
+    prof_n = (ctypes.c_uint64 * 3)()
+    _lib.lib.dsb_get_profile(prof_ms, prof_n)
+    _lib.lib.dsb_set_profiling(0)
+    # The kernels of a step are recorded once into a CUDA graph and replayed: one launch per step
+    # from the host, so the measurement does not depend on how fast this process can enqueue ~50
+    # kernels and copies per step (it does on a busy host).  The exchange fence stays outside.
+    if not args.no_graph and bstreams is None:
+        try:
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(g, capture_error_mode="relaxed"):
+                step_compute(torch.cuda.current_stream().cuda_stream)
+            graph["launches"] = _lib.launch_count() - n0
+            graph["g"] = g
+        except Exception as exc:  # noqa: BLE001
+            sys.stderr.write(f"[bench] rank {rank}: CUDA graph capture failed ({exc}); direct launches\n")
+            graph["g"] = None
+            torch.cuda.synchronize()
+        if world > 1:  # every rank takes the same path
+            if not comm.allgather_ints([1 if graph["g"] is not None else 0]).all():
+                graph["g"] = None
+        if graph["g"] is not None:
+            for _ in range(2):
+                step_device()
+    barrier()
+    sampler.mark_start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     t_host0 = time.perf_counter()
@@ -538,11 +600,6 @@ def main():
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    launches = _lib.launch_count() - launches0
-    prof_ms = (ctypes.c_double * 3)()
-    prof_n = (ctypes.c_uint64 * 3)()
-    _lib.lib.dsb_get_profile(prof_ms, prof_n)
-    _lib.lib.dsb_set_profiling(0)
     ms_step = ms_total / args.steps
     value = world * units_per_step / (ms_step * 1e-3)
 
@@ -681,6 +738,65 @@ def main():
         e2e = {"value": world * units_per_step / (ms_e2e * 1e-3), "unit": "units/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
                "mode": "c128_dma"}
+        if scatter is not None and args.precision == "fp32x3" and not args.no_e2e_c64:
+            # The same second way for the fused-exchange path: the owners' m-blocks are complex64 (half
+            # the NVLink and PCIe bytes), each rank widens its own m range on its share of the host cores.
+            own_np = own_host.numpy()
+            chk = (float(own_np.real.sum()), float(own_np.imag.sum()), own_np[::97].copy())
+            del own_np
+            n_own = own_host.numel()
+            del own_host  # keep the host footprint per rank bounded
+            ok, scatter64 = 1, None
+            try:
+                scatter64 = parallel.PeerScatter(comm, world * F, nb, np_inc, lside, mmax, elem_bytes=8)
+                stage64 = torch.empty(n_own, dtype=torch.complex64, pin_memory=True)
+                final_own = np.zeros(n_own, dtype=np.complex128)
+            except Exception as exc:  # noqa: BLE001 -- agreed on by all ranks below
+                sys.stderr.write(f"[bench] rank {rank}: c64 end-to-end mode unavailable ({exc})\n")
+                ok = 0
+            if comm.allgather_ints([ok]).all():
+                npiece = max(2, args.e2e_pieces * F)
+                edges = [(n_own * i // npiece) & ~1 for i in range(npiece)] + [n_own]
+                host_threads = max(1, (os.cpu_count() or 1) // world)
+
+                def step_e2e_c64_scatter():
+                    for nside, plan, units in prepared:
+                        for (ns, slot), b in host_beams.items():
+                            if ns == nside:
+                                plan.upload_beam(slot, b, stream)
+                        plan.transfer_units_scatter(units, 4, True, mmax, eng.precision, _lib.DSB_OUT_MMAJOR_C64,
+                                                    gdims, scatter64.block_ptrs, stream)
+                    scatter64.fence()
+                    pending = []
+                    for a, b in zip(edges[:-1], edges[1:]):
+                        cudart.cudaMemcpyAsync(ctypes.c_void_p(stage64.data_ptr() + 8 * a),
+                                               ctypes.c_void_p(scatter64.own_ptr + 8 * a),
+                                               ctypes.c_size_t(8 * (b - a)), 2, ctypes.c_void_p(stream))
+                        done = torch.cuda.Event()
+                        done.record()
+                        pending.append((a, b, done))
+                    for a, b, done in pending:
+                        done.synchronize()
+                        _lib.check(_lib.lib.dsb_host_widen_c64(stage64.data_ptr() + 8 * a,
+                                                               final_own.ctypes.data + 16 * a, b - a, host_threads))
+                    torch.cuda.current_stream().synchronize()
+
+                ms_c64 = timed(step_e2e_c64_scatter, max(3, args.steps // 2), 2) / max(3, args.steps // 2)
+                same = (float(final_own.real.sum()) == chk[0] and float(final_own.imag.sum()) == chk[1]
+                        and np.array_equal(final_own[::97], chk[2]))
+                same = bool(comm.allgather_ints([1 if same else 0]).all())
+                modes = {"c128_dma": {"ms_per_step": ms_e2e, "d2h_bytes_per_step": int(d2h)},
+                         "c64_widen": {"ms_per_step": ms_c64, "d2h_bytes_per_step": int(d2h // 2),
+                                       "host_threads": host_threads, "pieces": npiece,
+                                       "identical_to_c128": same,
+                                       "check": "sums of the real and imaginary parts and every 97th element"}}
+                if same and ms_c64 < ms_e2e:
+                    e2e.update({"value": world * units_per_step / (ms_c64 * 1e-3), "ms_per_step": ms_c64,
+                                "d2h_bytes_per_step": int(d2h // 2), "mode": "c64_widen"})
+                e2e["modes"] = modes
+                del stage64, final_own
+            if scatter64 is not None:
+                scatter64.close()
         if scatter is None and world == 1 and args.precision == "fp32x3" and not args.no_e2e_c64:
             # Second way through the same call: the fp32x3 product is fp32 on the device and the pack
             # kernel only widens it, so it may cross PCIe as complex64 (half the bytes) and be widened
@@ -765,6 +881,9 @@ def main():
         torch.cuda.empty_cache()
         svd = svd_section(tel, args, rank, world, dev, stream, with_cpu=(world == 1 and not args.no_cpu_baseline))
 
+    if stdout_fd is not None:
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
     if rank == 0:
         line = {
             "metric": "beam-transfer (baseline*freq)/s", "value": value, "unit": "units/s", "n_gpus": world,
@@ -772,7 +891,10 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3->f32 (fp64 phase)" if args.precision == "fp32x3" else "f64",
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": dominant, "roofline_all": [roof_ring, roof_leg, roof_pack],
-            "stage_launches_per_run": stage_launch, "host_enqueue_ms_per_step": host_ms_step, "cpu_baseline": cpu, "exchange": exchange, "svd": svd,
+            "stage_launches_per_run": stage_launch, "host_enqueue_ms_per_step": host_ms_step,
+            "launch_mode": ("CUDA graph of one step (%d kernels), replayed; stage times from a separate profiled "
+                            "pass of direct launches" % graph["launches"]) if graph["g"] is not None
+            else "direct launches", "cpu_baseline": cpu, "exchange": exchange, "svd": svd,
         }
         print(json.dumps(line))
     if world > 1:

@@ -45,6 +45,9 @@ struct StageTimer {
   bool on;
   cudaStream_t st;
   explicit StageTimer(cudaStream_t s) : on(g_prof), st(s) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (on && cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
+      on = false;  // timing events cannot be read back from a captured launch
     if (on)
       for (auto &x : ev.e) cudaEventCreate(&x);
   }
@@ -419,18 +422,30 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
       auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
       const size_t o_ud = 0, o_o0 = al(b_ud), o_o1 = o_o0 + al(b_o), o_it = o_o1 + al(b_o), o_mo = o_it + al(b_it),
                    total = o_mo + al(b_mo);
-      const int slot = plan->stage_next;
-      plan->stage_next = (slot + 1) % dsb_plan::kStageSlots;
-      if (!plan->stage_ev[slot]) DSB_CUDA(cudaEventCreateWithFlags(&plan->stage_ev[slot], cudaEventDisableTiming));
-      else DSB_CUDA(cudaEventSynchronize(plan->stage_ev[slot]));  // copies that last used this slot are done
-      if (plan->stage_bytes[slot] < total) {
-        if (plan->stage_host[slot]) DSB_CUDA(cudaFreeHost(plan->stage_host[slot]));
-        plan->stage_host[slot] = nullptr;
-        plan->stage_bytes[slot] = 0;
-        DSB_CUDA(cudaHostAlloc((void **)&plan->stage_host[slot], total + total / 4, cudaHostAllocDefault));
-        plan->stage_bytes[slot] = total + total / 4;
+      // A call recorded into a CUDA graph (the stream is capturing) is replayed with the copies
+      // it recorded: its descriptors get a buffer of their own that lives as long as the plan.
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      DSB_CUDA(cudaStreamIsCapturing(stream, &cap));
+      const bool capturing = cap != cudaStreamCaptureStatusNone;
+      char *h = nullptr;
+      int slot = -1;
+      if (capturing) {
+        DSB_CUDA(cudaHostAlloc((void **)&h, total, cudaHostAllocDefault));
+        plan->graph_stage.push_back(h);
+      } else {
+        slot = plan->stage_next;
+        plan->stage_next = (slot + 1) % dsb_plan::kStageSlots;
+        if (!plan->stage_ev[slot]) DSB_CUDA(cudaEventCreateWithFlags(&plan->stage_ev[slot], cudaEventDisableTiming));
+        else DSB_CUDA(cudaEventSynchronize(plan->stage_ev[slot]));  // copies that last used this slot are done
+        if (plan->stage_bytes[slot] < total) {
+          if (plan->stage_host[slot]) DSB_CUDA(cudaFreeHost(plan->stage_host[slot]));
+          plan->stage_host[slot] = nullptr;
+          plan->stage_bytes[slot] = 0;
+          DSB_CUDA(cudaHostAlloc((void **)&plan->stage_host[slot], total + total / 4, cudaHostAllocDefault));
+          plan->stage_bytes[slot] = total + total / 4;
+        }
+        h = plan->stage_host[slot];
       }
-      char *h = plan->stage_host[slot];
       memcpy(h + o_ud, ud.data(), b_ud);
       memcpy(h + o_o0, o0.data(), b_o);
       memcpy(h + o_o1, o1.data(), b_o);
@@ -441,7 +456,7 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
       DSB_CUDA(cudaMemcpyAsync(o1_dev, h + o_o1, b_o, cudaMemcpyHostToDevice, stream));
       DSB_CUDA(cudaMemcpyAsync(items_dev, h + o_it, b_it, cudaMemcpyHostToDevice, stream));
       DSB_CUDA(cudaMemcpyAsync(moff_dev, h + o_mo, b_mo, cudaMemcpyHostToDevice, stream));
-      DSB_CUDA(cudaEventRecord(plan->stage_ev[slot], stream));
+      if (!capturing) DSB_CUDA(cudaEventRecord(plan->stage_ev[slot], stream));
     }
 
     hc.lap(4);

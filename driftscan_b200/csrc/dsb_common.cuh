@@ -181,6 +181,7 @@ struct dsb_plan {
   size_t stage_bytes[kStageSlots] = {0, 0, 0, 0};
   cudaEvent_t stage_ev[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
   int stage_next = 0;
+  std::vector<char *> graph_stage;  // descriptor buffers of calls captured into CUDA graphs
 };
 
 namespace dsb {

@@ -308,6 +308,7 @@ extern "C" int dsb_plan_destroy(dsb_plan *plan) {
     if (plan->stage_host[i]) cudaFreeHost(plan->stage_host[i]);
     if (plan->stage_ev[i]) cudaEventDestroy(plan->stage_ev[i]);
   }
+  for (char *p : plan->graph_stage) cudaFreeHost(p);
   cudaFree(plan->rings);
   cudaFree(plan->horizon);
   cudaFree(plan->trig);

@@ -113,7 +113,9 @@ typedef enum {
  *   polarised: 0 -> beams have 1 component (UnpolarisedTelescope), 1 -> 2 components
  *   out      : device pointer (out_is_host = 0) or host pointer (out_is_host = 1)
  * Output entries of the given units are overwritten (zero where l > unit lmax);
- * other entries are left untouched. */
+ * other entries are left untouched.  * With device buffers the call is stream-ordered and never waits for the device (descriptors
+ * travel through pinned staging memory); it may be recorded into a CUDA graph (relaxed capture
+ * mode: the first recording allocates the graph's own descriptor buffer) and replayed. */
 int dsb_transfer_units(dsb_plan *plan, const dsb_unit *units_host, int nunits, int npol_sky,
                        int polarised, int mmax, int precision, int out_kind, const int64_t *dims,
                        void *out, int out_is_host, void *stream);
