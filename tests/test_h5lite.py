@@ -240,3 +240,43 @@ def test_reads_a_file_written_by_libhdf5():
         d = f["testdouble"]
         assert d.shape == (9, 1) and d.dtype == np.float64
         assert np.allclose(d[...].ravel(), np.linspace(0, 2 * np.pi, 9))
+
+
+def test_chunked_indexing_matches_numpy(tmp_path):
+    """Random reads and writes through a chunked, filtered dataset behave like the same
+    operations on a numpy array (edge chunks, strides, negative indices, index arrays)."""
+    from hypothesis import given, settings, strategies as st
+
+    shape, chunks = (7, 5, 9), (2, 5, 4)
+    p = str(tmp_path / "h.hdf5")
+    rng = np.random.default_rng(4)
+    ref = np.round(rng.standard_normal(shape), 1)
+    with h5lite.File(p, "w") as f:
+        f.create_dataset("x", data=ref, chunks=chunks, compression="lzf")
+
+    def axis_index(n):
+        return st.one_of(
+            st.integers(-n, n - 1),
+            st.builds(slice, st.one_of(st.none(), st.integers(-n, n)), st.one_of(st.none(), st.integers(-n, n)),
+                      st.one_of(st.none(), st.integers(1, 3))),
+        )
+
+    index = st.one_of(
+        st.tuples(*[axis_index(n) for n in shape]),
+        st.tuples(axis_index(shape[0])),
+        st.tuples(axis_index(shape[0]), st.just(Ellipsis), axis_index(shape[2])),
+        st.tuples(st.lists(st.integers(0, shape[0] - 1), min_size=1, max_size=4, unique=True)),
+    )
+
+    @settings(max_examples=60, deadline=None)
+    @given(index, st.floats(-5, 5, allow_nan=False))
+    def run(ind, val):
+        ind = ind if len(ind) > 1 else ind[0]
+        with h5lite.File(p, "r+") as f:
+            assert np.array_equal(f["x"][ind], ref[ind])
+            f["x"][ind] = val
+            ref[ind] = val
+        with h5lite.File(p, "r") as f:
+            assert np.array_equal(f["x"][...], ref)
+
+    run()
