@@ -127,3 +127,17 @@ def test_complex_packing_conventions():
     assert (full[lmax + 1 :] == 0).all()
     with pytest.raises(NotImplementedError):
         sht.ring_weights(8, "ring")
+
+
+def test_jacobi_refinement_in_ring_spectra_space():
+    """The design of the device-side ``iter > 0``: synthesis + aliasing fold +
+    analysis on ring spectra equals healpy-style refinement through pixel maps."""
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(__file__), "..", "tools", "proto_sht_iter_fold.py")
+    spec = importlib.util.spec_from_file_location("proto_sht_iter_fold", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.check(nside=4, lmax=11, niter=1) < 1e-13
+    assert mod.check(nside=8, lmax=20, niter=2) < 1e-13

@@ -1,0 +1,82 @@
+"""Prototype (numpy, CPU) of Jacobi-refined HEALPix analysis WITHOUT pixel maps.
+
+healpy's ``map2alm(iter=k)`` -- what ``cora.util.hputil`` is recalled to request for the
+reference's SHTs (drift/core/telescope.py:1189-1191, 1300-1314) -- refines
+
+    a(0) = A M,        a(k+1) = a(k) + A (M - S a(k)) = a(0) + a(k) - (A S) a(k)
+
+with A = analysis, S = synthesis.  On the device the maps never exist (the ring kernel forms
+fringe x beam on the fly), and they are not needed: A S acts on ring spectra.  Synthesis gives
+per ring r the coefficients g_m' (|m'| <= mmax) of  map_j = sum_m' g_m' exp(i m' phi_j),
+phi_j = phi0 + 2 pi j / n, and the ring DFT of that map is the aliasing fold
+
+    F_m(r) = n * sum_{m' = m (mod n), |m'| <= mmax} g_m' exp(i (m' - m) phi0)
+
+(identity for the equatorial rings, n = 4 nside > 2 mmax; genuine aliasing only on the short
+polar rings).  One refinement is therefore: Legendre synthesis (the same tables contracted over l
+instead of over rings), this fold (a gather), Legendre analysis -- two more contractions per
+iteration, no FFT, no pixel data.  This script checks the algebra against the oracle's map-based
+iteration (oracle/sht.py map2alm(niter=k)); tests/test_oracle_sht.py runs it.
+"""
+
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+
+from oracle import healpix, sht  # noqa: E402
+
+
+def analysis_from_spectra(F, info, nside, lmax, mmax):
+    """alm[l, m] from ring spectra F[r, m] (plain quadrature)."""
+    return sht._analysis_pass(F, info, nside, lmax, mmax, np.ones(info["start"].size))
+
+
+def synthesis_spectra(alm, info, nside):
+    """g[r, m] for m >= 0 of the REAL map with coefficients alm (g[-m] = conj(g[m]))."""
+    lmax, mmax = alm.shape[0] - 1, alm.shape[1] - 1
+    G = np.empty((info["start"].size, mmax + 1), dtype=np.complex128)
+    for m in range(mmax + 1):
+        lam = sht._cached_tables(nside, lmax, m, 0, info["theta"])
+        G[:, m] = lam.T @ alm[:, m]
+    return G
+
+
+def alias_fold(G, info):
+    """Ring DFT (m = 0..mmax) of the map synthesised from G, without forming the map."""
+    nring, nm = G.shape
+    mmax = nm - 1
+    F = np.zeros_like(G)
+    mp = np.arange(-mmax, mmax + 1)
+    for r in range(nring):
+        n, p0 = int(info["nphi"][r]), info["phi0"][r]
+        g = np.concatenate([np.conj(G[r, :0:-1]), G[r]])  # coefficients of m' = -mmax..mmax
+        for m in range(mmax + 1):
+            sel = (mp - m) % n == 0
+            F[r, m] = n * np.sum(g[sel] * np.exp(1.0j * (mp[sel] - m) * p0))
+    return F
+
+
+def map2alm_fold(hpmap, lmax, niter):
+    nside = int(round(np.sqrt(hpmap.size / 12)))
+    info = healpix.ring_info(nside)
+    a0 = analysis_from_spectra(sht.ring_analysis(hpmap, info, lmax), info, nside, lmax, lmax)
+    a = a0
+    for _ in range(niter):
+        a = a0 + a - analysis_from_spectra(alias_fold(synthesis_spectra(a, info, nside), info), info, nside, lmax, lmax)
+    return a
+
+
+def check(nside=8, lmax=20, niter=2, seed=0):
+    rng = np.random.default_rng(seed)
+    hpmap = rng.standard_normal(healpix.nside2npix(nside))
+    ref = sht.map2alm(hpmap, lmax, niter=niter)
+    got = map2alm_fold(hpmap, lmax, niter)
+    return np.abs(got - ref).max() / np.abs(ref).max()
+
+
+if __name__ == "__main__":
+    for nside, lmax, niter in ((4, 11, 1), (8, 20, 2), (8, 23, 3), (16, 40, 2)):
+        print(f"nside {nside} lmax {lmax} iter {niter}: max rel diff {check(nside, lmax, niter):.2e}")
