@@ -100,9 +100,14 @@ class TransitTelescope(config.Reader, metaclass=abc.ABCMeta):
     # B200 engine options (not present in the reference)
     precision = config.enum(["fp32x3", "fp64"], default="fp32x3")
 
+    # The reference inherits the observer position from caput.time.Observer
+    # (drift/core/telescope.py:125, 245-255), whose longitude / latitude / altitude are
+    # config properties: they can be given to the constructor or in the YAML section.
+    latitude = config.Property(proptype=float, default=45.0)
+    longitude = config.Property(proptype=float, default=0.0)
+    altitude = config.Property(proptype=float, default=0.0)
+
     def __init__(self, latitude=45, longitude=0, **kwargs):
-        # The reference inherits the observer position from caput.time.Observer
-        # (drift/core/telescope.py:245-255); only latitude/longitude are used here.
         self.latitude = latitude
         self.longitude = longitude
         self.altitude = kwargs.get("altitude", 0.0)
