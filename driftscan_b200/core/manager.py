@@ -19,16 +19,22 @@ import warnings
 import yaml
 
 from .. import parallel
-from ..telescope import cylinder
+from ..telescope import cylinder, exotic_cylinder, restrictedcylinder
 from . import beamtransfer, doublekl, kltransform
 
 logger = logging.getLogger(__name__)
 
 kltype_dict = {"KLTransform": kltransform.KLTransform, "DoubleKL": doublekl.DoubleKL}
 
+# manager.py:28-38 of the reference; GMRT and FocalPlane are not built
 teltype_dict = {
     "UnpolarisedCylinder": cylinder.UnpolarisedCylinderTelescope,
     "PolarisedCylinder": cylinder.PolarisedCylinderTelescope,
+    "RestrictedCylinder": restrictedcylinder.RestrictedCylinder,
+    "RestrictedPolarisedCylinder": restrictedcylinder.RestrictedPolarisedCylinder,
+    "RestrictedExtra": restrictedcylinder.RestrictedExtra,
+    "GradientCylinder": exotic_cylinder.GradientCylinder,
+    "PertCylinder": exotic_cylinder.CylinderPerturbed,
 }
 
 
