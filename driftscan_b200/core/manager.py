@@ -26,7 +26,8 @@ logger = logging.getLogger(__name__)
 
 kltype_dict = {"KLTransform": kltransform.KLTransform, "DoubleKL": doublekl.DoubleKL}
 
-# manager.py:28-38 of the reference; GMRT and FocalPlane are not built
+# manager.py:28-38 of the reference.  Not built: GMRT (needs the antenna-position data file) and
+# FocalPlane (the reference class itself cannot be instantiated: it lacks the abstract `beamclass`)
 teltype_dict = {
     "UnpolarisedCylinder": cylinder.UnpolarisedCylinderTelescope,
     "PolarisedCylinder": cylinder.PolarisedCylinderTelescope,
