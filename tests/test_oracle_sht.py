@@ -141,3 +141,4 @@ def test_jacobi_refinement_in_ring_spectra_space():
     spec.loader.exec_module(mod)
     assert mod.check(nside=4, lmax=11, niter=1) < 1e-13
     assert mod.check(nside=8, lmax=20, niter=2) < 1e-13
+    assert mod.check_pol(nside=4, lmax=11, niter=2) < 1e-13
