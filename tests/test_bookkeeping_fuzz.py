@@ -1,0 +1,80 @@
+"""Baseline bookkeeping on random feed layouts against the reference's own
+`TransitTelescope` code (drift/core/telescope.py:507-675), executed under the dependency stubs
+of tests/golden/make_golden.py.  Needs /root/reference (build container only): skipped elsewhere.
+Integer grids, rounded Gaussian positions, near-duplicate positions around the 1e-6 rounding of
+`_bl_tol`, cylinder-like layouts; random beam classes, auto-correlations and length cuts."""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "drift")), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref_telescope_module():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden as mg
+
+    mg.install_stubs()
+    mg.build_reference()
+    from drift.core import telescope as rtel
+
+    return rtel
+
+
+def _make(base, pos, cls, polarised, **cfg):
+    parent = base.PolarisedTelescope if polarised else base.UnpolarisedTelescope
+
+    class T(parent):
+        feedpositions = property(lambda self: pos)
+        beamclass = property(lambda self: cls)
+        u_width = property(lambda self: 1.0)
+        v_width = property(lambda self: 0.5)
+        polarisation = property(lambda self: np.array(["X"] * len(cls)))
+
+        def beam(self, feed, freq):
+            return None
+
+        beamx = beamy = beam
+
+    t = T(latitude=40.0)
+    t.read_config(dict(num_freq=2, freq_start=300.0, freq_end=400.0, freq_mode="edge", **cfg))
+    return t
+
+
+def test_random_layouts_bit_exact(ref_telescope_module):
+    from driftscan_b200.core import telescope as mtel
+
+    rng = np.random.default_rng(0)
+    compared = 0
+    for trial in range(80):
+        n = int(rng.integers(2, 9))
+        kind = trial % 4
+        if kind == 0:
+            pos = rng.integers(-3, 4, size=(n, 2)).astype(float) * rng.choice([0.5, 1.0, 0.3048])
+        elif kind == 1:
+            pos = np.round(rng.standard_normal((n, 2)) * 3, int(rng.integers(0, 3)))
+        elif kind == 2:
+            pos = rng.integers(0, 3, size=(n, 2)).astype(float) + rng.choice([0, 1e-7, 2e-6], size=(n, 2))
+        else:
+            pos = np.stack([rng.integers(0, 2, n) * 5.0, rng.integers(0, 4, n) * 0.7], 1)
+        cls = rng.integers(0, int(rng.integers(1, 4)), n)
+        cfg = dict(auto_correlations=bool(rng.integers(0, 2)))
+        if rng.random() < 0.3:
+            cfg.update(minlength=float(rng.uniform(0, 1.5)), maxlength=float(rng.uniform(2, 6)))
+        try:
+            ref = _make(ref_telescope_module, pos, cls, bool(trial % 2), **cfg)
+            want = {k: np.array(getattr(ref, k)) for k in
+                    ("uniquepairs", "redundancy", "feedmap", "feedmask", "feedconj", "baselines")}
+        except Exception:  # noqa: BLE001 -- degenerate layout (no pair survives): nothing to compare
+            continue
+        mine = _make(mtel, pos, cls, bool(trial % 2), **cfg)
+        for k, v in want.items():
+            got = np.array(getattr(mine, k))
+            assert got.shape == v.shape and np.array_equal(got, v), (trial, k)
+        compared += 1
+    assert compared >= 60
