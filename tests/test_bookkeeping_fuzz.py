@@ -78,3 +78,71 @@ def test_random_layouts_bit_exact(ref_telescope_module):
             assert got.shape == v.shape and np.array_equal(got, v), (trial, k)
         compared += 1
     assert compared >= 60
+
+
+def test_random_configurations_bit_exact(ref_telescope_module):
+    """Frequencies (all three modes, binning, channel ranges), wavelengths, lmax / mmax (with
+    l_boost), noise power, included_* index lists and per-unit lmax of random configurations."""
+    from driftscan_b200.core import telescope as mtel
+
+    rng = np.random.default_rng(1)
+    pos = np.stack([np.repeat(np.arange(3), 3) * 4.0, np.tile(np.arange(3), 3) * 0.9], 1)
+    cls = np.zeros(9, dtype=np.int64)
+    compared = 0
+    for trial in range(60):
+        nf = int(rng.choice([4, 6, 8, 12]))
+        f0 = float(rng.uniform(100, 700))
+        cfg = dict(num_freq=nf, freq_start=f0, freq_end=f0 + float(rng.uniform(5, 200)),
+                   freq_mode=str(rng.choice(["centre", "centre_nyquist", "edge"])),
+                   tsys_flat=float(rng.uniform(10, 100)), ndays=int(rng.integers(1, 1000)),
+                   l_boost=float(rng.choice([1.0, 1.1, 1.5])), auto_correlations=bool(rng.integers(0, 2)))
+        if rng.random() < 0.3:
+            cfg["channel_bin"] = 2
+        if rng.random() < 0.3:
+            cfg["channel_range"] = [1, 3]
+        if rng.random() < 0.4:
+            cfg["skip_freq"] = [0]
+            cfg["skip_baselines"] = [1, 2]
+        polarised = bool(trial % 2)
+        if polarised and rng.random() < 0.5:
+            cfg["skip_V" if rng.random() < 0.5 else "skip_pol"] = True
+
+        def build(base):
+            parent = base.PolarisedTelescope if polarised else base.UnpolarisedTelescope
+
+            class T(parent):
+                feedpositions = property(lambda self: pos)
+                beamclass = property(lambda self: cls)
+                u_width = property(lambda self: 2.0)
+                v_width = property(lambda self: 0.3)
+                polarisation = property(lambda self: np.array(["X"] * len(cls)))
+
+                def beam(self, feed, freq):
+                    return None
+
+                beamx = beamy = beam
+
+            t = T(latitude=float(cfg.get("latitude", 45.0)))
+            t.read_config({k: v for k, v in cfg.items()})
+            return t
+
+        ref, mine = build(ref_telescope_module), build(mtel)
+        for key in ("frequencies", "wavelengths", "included_freq", "included_baseline", "included_pol"):
+            want, got = np.asarray(getattr(ref, key)), np.asarray(getattr(mine, key))
+            assert got.shape == want.shape and np.array_equal(got, want), (trial, key, cfg)
+        assert (mine.lmax, mine.mmax, mine.nfreq, mine.npairs) == (ref.lmax, ref.mmax, ref.nfreq, ref.npairs), (trial, cfg)
+        bl, fi = np.arange(ref.npairs)[:, None], np.arange(ref.nfreq)[None, :]
+        assert np.array_equal(mine.noisepower(bl, fi), ref.noisepower(bl, fi)), (trial, cfg)
+        # per-unit lmax / mmax as transfer_matrices computes them (telescope.py:792-802)
+        from drift.core.telescope import max_lm as ref_max_lm
+
+        blf = np.broadcast_to(bl, (ref.npairs, ref.nfreq)).ravel()
+        fif = np.broadcast_to(fi, (ref.npairs, ref.nfreq)).ravel()
+        lm_ref = ref_max_lm(ref.baselines[blf], ref.wavelengths[fif], ref.u_width, ref.v_width)
+        lmax_u, mmax_u = mine.unit_lmax(blf, fif)
+        want_l = np.ceil(ref.l_boost * np.asarray(lm_ref[0])).astype(np.int64).ravel()
+        want_m = np.ceil(ref.l_boost * np.asarray(lm_ref[1])).astype(np.int64).ravel()
+        assert np.array_equal(np.asarray(lmax_u).ravel(), want_l), (trial, cfg)
+        assert np.array_equal(np.asarray(mmax_u).ravel(), want_m), (trial, cfg)
+        compared += 1
+    assert compared == 60
