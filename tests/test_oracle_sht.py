@@ -142,3 +142,5 @@ def test_jacobi_refinement_in_ring_spectra_space():
     assert mod.check(nside=4, lmax=11, niter=1) < 1e-13
     assert mod.check(nside=8, lmax=20, niter=2) < 1e-13
     assert mod.check_pol(nside=4, lmax=11, niter=2) < 1e-13
+    # complex map, the product's +m / -m slots and phases (the formulas the device fold kernel needs)
+    assert mod.check_transfer(nside=4, lmax=11, niter=2) < 1e-13
