@@ -30,6 +30,7 @@ The API follows the small part of h5py the reference uses::
 import itertools
 import os
 import struct
+import warnings
 import zlib
 from concurrent.futures import ThreadPoolExecutor
 
@@ -457,12 +458,16 @@ class ChunkedDataset:
         return a if dtype is None else a.astype(dtype)
 
     # -- chunk i/o ------------------------------------------------------------------
-    def _read_chunk(self, coord):
+    def _read_chunk(self, coord, fh=None):
         ent = self._st["index"].get(coord)
         if ent is None:
             return None
         addr, size, mask = ent
-        with open(self._file.filename, "rb") as fh:
+        if fh is None:
+            with open(self._file.filename, "rb") as own:
+                own.seek(addr + self._file._base)
+                blob = own.read(size)
+        else:
             fh.seek(addr + self._file._base)
             blob = fh.read(size)
         blob = _filter_decode(self._st["filters"], mask, blob, self._nbytes, self.dtype.itemsize)
@@ -496,10 +501,11 @@ class ChunkedDataset:
     def _read_box(self, lo, hi):
         out = np.zeros([b - a for a, b in zip(lo, hi)], dtype=self.dtype)
         if out.size:
-            for coord, cs, bs in self._overlaps(lo, hi):
-                data = self._read_chunk(coord)
-                if data is not None:
-                    out[bs] = data[cs]
+            with open(self._file.filename, "rb") as fh:  # one handle for all chunks of the box
+                for coord, cs, bs in self._overlaps(lo, hi):
+                    data = self._read_chunk(coord, fh)
+                    if data is not None:
+                        out[bs] = data[cs]
         return out
 
     def __getitem__(self, ind):
@@ -869,7 +875,13 @@ class File:
                 if mtype == 0x0011:
                     btree_addr, heap_addr = struct.unpack("<QQ", body[:16])
                 elif mtype == 0x000C:
-                    k, v = _decode_attr(body)
+                    try:
+                        k, v = _decode_attr(body)
+                    except (TypeError, IOError, ValueError, struct.error) as exc:
+                        # e.g. the variable-length strings h5py writes for str attributes: the data
+                        # live in a global heap this reader does not follow; the file stays usable
+                        warnings.warn(f"{self.filename}: skipping an attribute h5lite cannot decode ({exc})")
+                        continue
                     self.attrs[k] = v
             self._attrs_loaded = dict(self.attrs)
             if btree_addr is None:
@@ -927,7 +939,11 @@ class File:
                     if mtype == 0x0001:
                         shape = _decode_dataspace(body)
                     elif mtype == 0x0003:
-                        dtype, _ = _decode_dtype(body)
+                        try:
+                            dtype, _ = _decode_dtype(body)
+                        except TypeError as exc:
+                            warnings.warn(f"{self.filename}: dataset {name!r} skipped ({exc})")
+                            dtype = None
                     elif mtype == 0x0008:
                         layout = _decode_layout(body)
                         layout_pos = pos + (3 if body[0] == 3 else 8)

@@ -280,3 +280,24 @@ def test_chunked_indexing_matches_numpy(tmp_path):
             assert np.array_equal(f["x"][...], ref)
 
     run()
+
+
+def test_undecodable_attribute_is_skipped(tmp_path):
+    """h5py stores `str` attributes (the KL files' FLAGS, kltransform.py:423-431) as variable-length
+    strings whose data sit in a global heap; the reader must skip what it cannot decode and keep
+    the rest of the file usable."""
+    p = str(tmp_path / "v.hdf5")
+    with h5lite.File(p, "w") as f:
+        f.create_dataset("evals", data=np.arange(4.0))
+        f.attrs["m"] = 5
+        f.attrs["FLAGS"] = "xyz"
+    blob = bytearray(open(p, "rb").read())
+    i = blob.index(b"FLAGS\0")
+    j = blob.index(bytes([0x13, 0x11]), i)  # the fixed-length string datatype of that attribute
+    blob[j] = 0x19                           # ... turned into class 9 (variable length)
+    open(p, "wb").write(bytes(blob))
+    with pytest.warns(UserWarning, match="cannot decode"):
+        f = h5lite.File(p, "r")
+    assert int(f.attrs["m"]) == 5 and "FLAGS" not in f.attrs
+    assert np.array_equal(f["evals"][...], np.arange(4.0))
+    f.close()
