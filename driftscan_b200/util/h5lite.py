@@ -43,6 +43,7 @@ _INT_K = 16
 _CHUNK_K = 32  # chunk B-tree nodes hold 2 * _CHUNK_K entries (the superblock-v0 default)
 _FILTER_DEFLATE, _FILTER_SHUFFLE, _FILTER_LZF = 1, 2, 32000
 _META_RESERVE = 16384
+_LZF_PROBE = 32768
 
 
 def _pad8(b):
@@ -281,6 +282,17 @@ def _encode_filters(filters):
     return body
 
 
+_POOL = None
+
+
+def _pool():
+    """Process-wide worker threads for chunk compression (the codec releases the GIL)."""
+    global _POOL
+    if _POOL is None:
+        _POOL = ThreadPoolExecutor(max_workers=os.cpu_count() or 1)
+    return _POOL
+
+
 def _lzf():
     from .. import _lib  # the codec lives in the C library (host code, no device needed)
 
@@ -323,6 +335,13 @@ def _lzf_compress(blob):
     cap = len(blob) - 1
     if cap < 1:
         return None
+    if len(blob) > _LZF_PROBE * 2:
+        # Noise-like chunks (most of a beam-transfer matrix) do not shrink; find out on the first
+        # 32 KiB instead of running the matcher over the whole chunk only to throw the result away.
+        probe = ctypes.create_string_buffer(_LZF_PROBE)
+        n = _lzf().dsb_lzf_compress(bytes(blob[:_LZF_PROBE]), _LZF_PROBE, probe, _LZF_PROBE)
+        if n == 0 or n > 0.9 * _LZF_PROBE:
+            return None
     out = ctypes.create_string_buffer(cap)
     n = _lzf().dsb_lzf_compress(bytes(blob), len(blob), out, cap)
     return out.raw[:n] if n else None
@@ -532,9 +551,8 @@ class ChunkedDataset:
                 data = np.zeros(self.chunks, dtype=self.dtype) if data is None else data.copy()
                 data[cs] = box[bs]
                 jobs.append((coord, data))
-        if len(jobs) > 1 and self._nbytes >= (1 << 16):
-            with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
-                enc = list(pool.map(lambda j: self._encode_chunk(j[1]), jobs))
+        if len(jobs) > 1 and self._nbytes >= (1 << 16) and self._st["filters"]:
+            enc = list(_pool().map(lambda j: self._encode_chunk(j[1]), jobs))
         else:
             enc = [self._encode_chunk(j[1]) for j in jobs]
         with open(self._file.filename, "r+b") as fh:
