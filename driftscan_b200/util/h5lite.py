@@ -519,12 +519,31 @@ class ChunkedDataset:
 
     def _read_box(self, lo, hi):
         out = np.zeros([b - a for a, b in zip(lo, hi)], dtype=self.dtype)
-        if out.size:
-            with open(self._file.filename, "rb") as fh:  # one handle for all chunks of the box
-                for coord, cs, bs in self._overlaps(lo, hi):
-                    data = self._read_chunk(coord, fh)
-                    if data is not None:
-                        out[bs] = data[cs]
+        if not out.size:
+            return out
+        todo = [(coord, cs, bs) for coord, cs, bs in self._overlaps(lo, hi) if coord in self._st["index"]]
+        if len(todo) > 3 and self._st["filters"] and self._nbytes >= (1 << 16):
+            # read the stored chunks with one handle, undo the filters on the worker threads
+            raw = []
+            with open(self._file.filename, "rb") as fh:
+                for coord, _, _ in todo:
+                    addr, size, mask = self._st["index"][coord]
+                    fh.seek(addr + self._file._base)
+                    raw.append((fh.read(size), mask))
+            count = int(np.prod(self.chunks))
+
+            def decode(item):
+                blob = _filter_decode(self._st["filters"], item[1], item[0], self._nbytes, self.dtype.itemsize)
+                return np.frombuffer(blob, dtype=self.dtype, count=count).reshape(self.chunks)
+
+            for (_, cs, bs), data in zip(todo, _pool().map(decode, raw)):
+                out[bs] = data[cs]
+            return out
+        with open(self._file.filename, "rb") as fh:  # one handle for all chunks of the box
+            for coord, cs, bs in todo:
+                data = self._read_chunk(coord, fh)
+                if data is not None:
+                    out[bs] = data[cs]
         return out
 
     def __getitem__(self, ind):
