@@ -146,3 +146,24 @@ def test_random_configurations_bit_exact(ref_telescope_module):
         assert np.array_equal(np.asarray(mmax_u).ravel(), want_m), (trial, cfg)
         compared += 1
     assert compared == 60
+
+
+def test_cylinder_beams_random_parameters(ref_telescope_module):
+    """cylbeam.beam_x / beam_y / beam_amp (drift/telescope/cylbeam.py:101-212) for random cylinder
+    widths, antenna widths and latitudes.  The reference's spline is cora's natural cubic spline
+    (stubbed with scipy's under make_golden.py), ours is util/cubicspline.py."""
+    from drift.telescope import cylbeam as rcb
+
+    from driftscan_b200.telescope import cylbeam as mcb
+    from driftscan_b200.util import hputil
+
+    ang = hputil.ang_positions(8)
+    rng = np.random.default_rng(2)
+    for _ in range(12):
+        zen = np.array([np.pi / 2 - np.radians(rng.uniform(-60, 70)), 0.0])
+        width, fe, fh = rng.uniform(3, 40), rng.uniform(0.8, 3.0), rng.uniform(0.8, 3.0)
+        for name in ("beam_x", "beam_y", "beam_amp"):
+            want = getattr(rcb, name)(ang, zen, width, fe, fh)
+            got = getattr(mcb, name)(ang, zen, width, fe, fh)
+            assert got.shape == want.shape
+            assert np.allclose(got, want, rtol=1e-10, atol=1e-12 * np.abs(want).max()), (name, width, fe, fh)
