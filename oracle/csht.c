@@ -10,8 +10,8 @@
  *   _beam_map_single (unpol)    drift/core/telescope.py:1156-1176
  *   _transfer_single            drift/core/telescope.py:1178-1193, 1287-1316
  *     -> cora.util.hputil.sphtrans_complex[_pol] -> healpy.map2alm (EXTERNAL, libsharp):
- *        restated as in oracle/sht.py (plain HEALPix quadrature, use_weights=False,
- *        iter=0): ring FFT, then scaled three-term Wigner-d recurrences in l for
+ *        restated as in oracle/sht.py (plain HEALPix quadrature, use_weights=False;
+ *        iter = 0 by default, iter > 0 through oracle_transfer_unit_iter): ring FFT, then scaled three-term Wigner-d recurrences in l for
  *        d^l_{m,0} (T, V) and d^l_{m,-+2} (Q,U -> E,B, HEALPix W/X convention).
  * The two implementations share no code: oracle/sht.py builds dense tables and uses
  * matrix products over all rings, this file runs the recurrences ring pair by ring pair
@@ -253,16 +253,157 @@ static void wigner_run(const wrec_t *w, double theta, double *out) {
   }
 }
 
+/* ---- Legendre stage, both directions -----------------------------------------------------
+ * Ring pairs (north ring r, southern mirror nring-1-r) share the recurrence:
+ *   lambda_lm(pi - t) = (-1)^{l+m} lambda_lm(t);  W likewise;  X_lm(pi - t) = -(-1)^{l+m} X_lm(t)
+ * G[map][ring][m + lmax] (m = -lmax..lmax) are ring spectra, a[pol][l][column] coefficients in the
+ * output layout (column m for m >= 0, ncol - |m| for m < 0).
+ *   synth = 0: analysis,  a += quad * sum_rings lambda * G          (a zeroed by the caller)
+ *   synth = 1: synthesis, G  = sum_l a * lambda  (no quadrature weight): the ring spectra of the map
+ *              sum_lm a_lm Y_lm, spin 2 in the convention of oracle/sht.py alm2map_pol. */
+static void legendre_stage(const ctx_t *c, int npol, int lmax, int lside, cplx *G, cplx *out, int synth) {
+  const int npix = c->npix, nring = c->nring, nside = c->nside;
+  const int ncol = 2 * lside + 1;
+  const size_t plane = (size_t)(lside + 1) * ncol;
+  const int nm = 2 * lmax + 1;
+  const double quad = synth ? 1.0 : 4.0 * M_PI / npix;
+  double *d0 = (double *)malloc(sizeof(double) * (lmax + 1));
+  double *dp = (double *)malloc(sizeof(double) * (lmax + 1));
+  double *dm = (double *)malloc(sizeof(double) * (lmax + 1));
+  double *nrm = (double *)malloc(sizeof(double) * (lmax + 1));
+  double *coef = (double *)malloc(sizeof(double) * 9 * (lmax + 1));
+  wrec_t w0, wp, wm;
+  w0.A = coef, w0.B = coef + (lmax + 1), w0.C = coef + 2 * (lmax + 1);
+  wp.A = coef + 3 * (lmax + 1), wp.B = coef + 4 * (lmax + 1), wp.C = coef + 5 * (lmax + 1);
+  wm.A = coef + 6 * (lmax + 1), wm.B = coef + 7 * (lmax + 1), wm.C = coef + 8 * (lmax + 1);
+  for (int l = 0; l <= lmax; ++l) nrm[l] = sqrt((2.0 * l + 1.0) / (4.0 * M_PI)) * quad;
+  const int nfold = 2 * nside; /* pairs incl. the equator */
+  const int has2 = npol >= 3;
+  for (int m = 0; m <= lmax; ++m) {
+    const double sgm = (m & 1) ? -1.0 : 1.0;
+    wigner_prepare(&w0, m, 0, lmax);
+    if (has2) {
+      wigner_prepare(&wp, m, -2, lmax); /* spin +2: sY = (-1)^s sqrt() d^l_{m,-s} */
+      wigner_prepare(&wm, m, 2, lmax);  /* spin -2 */
+    }
+    for (int k = 0; k < nfold; ++k) {
+      const int rn = k, rs = nring - 1 - k;
+      const int eq = (rn == rs);
+      const double theta = c->theta[rn];
+      wigner_run(&w0, theta, d0);
+      if (has2) {
+        wigner_run(&wp, theta, dp);
+        wigner_run(&wm, theta, dm);
+      }
+      for (int pm = 0; pm < 2; ++pm) {
+        if (m == 0 && pm == 1) break;
+        const int mm = pm ? -m : m;
+        const int col = mm >= 0 ? mm : ncol + mm;
+        const double fac = pm ? sgm : 1.0; /* a_{l,-m} carries (-1)^m */
+        /* m >= 0: aE = -(W Q + i X U), aB = -(W U - i X Q); m < 0: the signs of the X terms flip */
+        const double sx = pm ? -1.0 : 1.0;
+        if (synth) {
+          cplx sN[4] = {0, 0, 0, 0}, sS[4] = {0, 0, 0, 0};
+          for (int l = m; l <= lmax; ++l) {
+            const double par = ((l + m) & 1) ? -1.0 : 1.0;
+            const double norm = nrm[l] * fac;
+            const double lam = norm * d0[l];
+            const cplx aT = out[0 * plane + (size_t)l * ncol + col];
+            sN[0] += lam * aT;
+            sS[0] += par * lam * aT;
+            if (npol == 4) {
+              const cplx aV = out[3 * plane + (size_t)l * ncol + col];
+              sN[3] += lam * aV;
+              sS[3] += par * lam * aV;
+            }
+            if (has2 && l >= 2) {
+              const double lp = norm * dp[l], lm_ = norm * dm[l];
+              const double W = 0.5 * (lp + lm_), X = 0.5 * (lp - lm_);
+              const cplx aE = out[1 * plane + (size_t)l * ncol + col], aB = out[2 * plane + (size_t)l * ncol + col];
+              /* Q = -(W aE + i X aB), U = -(W aB - i X aE)  (oracle/sht.py alm2map_pol) */
+              sN[1] += -(W * aE + sx * I * X * aB);
+              sN[2] += -(W * aB - sx * I * X * aE);
+              sS[1] += -(par * W * aE - par * sx * I * X * aB);
+              sS[2] += -(par * W * aB + par * sx * I * X * aE);
+            }
+          }
+          for (int q = 0; q < npol; ++q) {
+            G[((size_t)q * nring + rn) * nm + mm + lmax] = sN[q];
+            if (!eq) G[((size_t)q * nring + rs) * nm + mm + lmax] = sS[q];
+          }
+          continue;
+        }
+        cplx gN[4], gS[4];
+        for (int q = 0; q < npol; ++q) {
+          gN[q] = G[((size_t)q * nring + rn) * nm + mm + lmax];
+          gS[q] = eq ? 0.0 : G[((size_t)q * nring + rs) * nm + mm + lmax];
+        }
+        for (int l = m; l <= lmax; ++l) {
+          const double par = ((l + m) & 1) ? -1.0 : 1.0;
+          const double norm = nrm[l] * fac;
+          const double lam = norm * d0[l];
+          /* T (and V): spin 0 */
+          out[0 * plane + (size_t)l * ncol + col] += lam * (gN[0] + par * gS[0]);
+          if (npol == 4) out[3 * plane + (size_t)l * ncol + col] += lam * (gN[3] + par * gS[3]);
+          if (has2 && l >= 2) {
+            const double lp = norm * dp[l], lm_ = norm * dm[l];
+            const double W = 0.5 * (lp + lm_), X = 0.5 * (lp - lm_);
+            const cplx Qw = gN[1] + par * gS[1], Uw = gN[2] + par * gS[2];
+            const cplx Qx = gN[1] - par * gS[1], Ux = gN[2] - par * gS[2];
+            out[1 * plane + (size_t)l * ncol + col] += -(W * Qw + sx * I * X * Ux);
+            out[2 * plane + (size_t)l * ncol + col] += -(W * Uw - sx * I * X * Qx);
+          }
+        }
+      }
+    }
+  }
+  free(nrm);
+  free(coef);
+  free(d0);
+  free(dp);
+  free(dm);
+}
+
+/* Ring spectra of the pixelised map whose continuous ring spectra are G (in place): on a ring of
+ * n pixels the coefficients m' = m (mod n) alias,
+ *   G'_m = n * sum_{m' = m (mod n)} G_m' e^{i (m' - m) phi0}
+ * (G_m = sum_j X_j e^{-i m phi_j} of X_j = sum_m' g_m' e^{i m' phi_j}; healpy's map2alm(iter > 0)
+ * analyses alm2map's output, and this is all the pixel map does to the spectra). */
+static void alias_fold(const ctx_t *c, int npol, int lmax, cplx *G) {
+  const int nring = c->nring, nm = 2 * lmax + 1;
+  cplx *bins = (cplx *)malloc(sizeof(cplx) * (size_t)(4 * c->nside));
+  for (int q = 0; q < npol; ++q)
+    for (int r = 0; r < nring; ++r) {
+      const int n = c->nphi[r];
+      cplx *g = G + ((size_t)q * nring + r) * nm;
+      for (int k = 0; k < n; ++k) bins[k] = 0.0;
+      for (int m = -lmax; m <= lmax; ++m) {
+        int k = m % n;
+        if (k < 0) k += n;
+        const double a = m * c->phi0[r];
+        bins[k] += g[m + lmax] * (cos(a) + I * sin(a));
+      }
+      for (int m = -lmax; m <= lmax; ++m) {
+        int k = m % n;
+        if (k < 0) k += n;
+        const double a = -m * c->phi0[r];
+        g[m + lmax] = (double)n * bins[k] * (cos(a) + I * sin(a));
+      }
+    }
+  free(bins);
+}
+
 /* ---- one unit --------------------------------------------------------------------------
  * beam_i, beam_j: [npix][ncomp] float64 (ncomp = 2 polarised (theta, phi), 1 unpolarised)
  * horizon: [npix] bytes; zenith = (theta, phi); uv = (u, v) in wavelengths
  * npol: sky polarisations computed (1, 3 or 4; unpolarised: 1)
  * out: complex128 [npol][lside+1][2*lside+1], column m for m >= 0, 2*lside+1-|m| for m < 0,
  *      zero for l > lmax  (telescope.py:809-828)
+ * niter: Jacobi refinement passes of the analysis (healpy map2alm's `iter`; 0 = plain quadrature)
  * returns 0 on success */
-int oracle_transfer_unit(void *ctxp, int polarised, int npol, const double *beam_i, const double *beam_j,
-                         const uint8_t *horizon, const double *zenith, const double *uv, int lmax, int lside,
-                         double *out_) {
+int oracle_transfer_unit_iter(void *ctxp, int polarised, int npol, const double *beam_i, const double *beam_j,
+                              const uint8_t *horizon, const double *zenith, const double *uv, int lmax, int lside,
+                              int niter, double *out_) {
   const ctx_t *c = (const ctx_t *)ctxp;
   cplx *out = (cplx *)out_;
   const int npix = c->npix, nring = c->nring, nside = c->nside;
@@ -342,79 +483,35 @@ int oracle_transfer_unit(void *ctxp, int polarised, int npol, const double *beam
     }
   }
 
-  /* Legendre stage, ring pairs (north ring r, southern mirror nring-1-r) share the recurrence:
-   *   lambda_lm(pi - t) = (-1)^{l+m} lambda_lm(t);  W likewise;  X_lm(pi - t) = -(-1)^{l+m} X_lm(t) */
-  const double quad = 4.0 * M_PI / npix;
-  double *d0 = (double *)malloc(sizeof(double) * (lmax + 1));
-  double *dp = (double *)malloc(sizeof(double) * (lmax + 1));
-  double *dm = (double *)malloc(sizeof(double) * (lmax + 1));
-  double *nrm = (double *)malloc(sizeof(double) * (lmax + 1));
-  double *coef = (double *)malloc(sizeof(double) * 9 * (lmax + 1));
-  wrec_t w0, wp, wm;
-  w0.A = coef, w0.B = coef + (lmax + 1), w0.C = coef + 2 * (lmax + 1);
-  wp.A = coef + 3 * (lmax + 1), wp.B = coef + 4 * (lmax + 1), wp.C = coef + 5 * (lmax + 1);
-  wm.A = coef + 6 * (lmax + 1), wm.B = coef + 7 * (lmax + 1), wm.C = coef + 8 * (lmax + 1);
-  for (int l = 0; l <= lmax; ++l) nrm[l] = sqrt((2.0 * l + 1.0) / (4.0 * M_PI)) * quad;
-  const int nfold = 2 * nside; /* pairs incl. the equator */
-  const int has2 = npol >= 3;
-  for (int m = 0; m <= lmax; ++m) {
-    const double sgm = (m & 1) ? -1.0 : 1.0;
-    wigner_prepare(&w0, m, 0, lmax);
-    if (has2) {
-      wigner_prepare(&wp, m, -2, lmax); /* spin +2: sY = (-1)^s sqrt() d^l_{m,-s} */
-      wigner_prepare(&wm, m, 2, lmax);  /* spin -2 */
+  /* Legendre stage; niter > 0: Jacobi refinement a <- a0 + a - A S a as healpy's map2alm(iter)
+   * does it through pixel maps, carried out on the ring spectra (alias_fold) */
+  legendre_stage(c, npol, lmax, lside, G, out, 0);
+  if (niter > 0) {
+    cplx *a0 = (cplx *)malloc(sizeof(cplx) * plane * npol);
+    cplx *a1 = (cplx *)malloc(sizeof(cplx) * plane * npol);
+    memcpy(a0, out, sizeof(cplx) * plane * npol);
+    for (int it = 0; it < niter; ++it) {
+      legendre_stage(c, npol, lmax, lside, G, out, 1);
+      alias_fold(c, npol, lmax, G);
+      memset(a1, 0, sizeof(cplx) * plane * npol);
+      legendre_stage(c, npol, lmax, lside, G, a1, 0);
+      for (size_t i = 0; i < plane * npol; ++i) out[i] = a0[i] + out[i] - a1[i];
     }
-    for (int k = 0; k < nfold; ++k) {
-      const int rn = k, rs = nring - 1 - k;
-      const int eq = (rn == rs);
-      const double theta = c->theta[rn];
-      wigner_run(&w0, theta, d0);
-      if (has2) {
-        wigner_run(&wp, theta, dp);
-        wigner_run(&wm, theta, dm);
-      }
-      for (int pm = 0; pm < 2; ++pm) {
-        if (m == 0 && pm == 1) break;
-        const int mm = pm ? -m : m;
-        const int col = mm >= 0 ? mm : ncol + mm;
-        const double fac = pm ? sgm : 1.0; /* a_{l,-m} carries (-1)^m */
-        cplx gN[4], gS[4];
-        for (int q = 0; q < npol; ++q) {
-          gN[q] = G[((size_t)q * nring + rn) * nm + mm + lmax];
-          gS[q] = eq ? 0.0 : G[((size_t)q * nring + rs) * nm + mm + lmax];
-        }
-        /* m >= 0: aE = -(W Q + i X U), aB = -(W U - i X Q); m < 0: the signs of the X terms flip */
-        const double sx = pm ? -1.0 : 1.0;
-        for (int l = m; l <= lmax; ++l) {
-          const double par = ((l + m) & 1) ? -1.0 : 1.0;
-          const double norm = nrm[l] * fac;
-          const double lam = norm * d0[l];
-          /* T (and V): spin 0 */
-          out[0 * plane + (size_t)l * ncol + col] += lam * (gN[0] + par * gS[0]);
-          if (npol == 4) out[3 * plane + (size_t)l * ncol + col] += lam * (gN[3] + par * gS[3]);
-          if (has2 && l >= 2) {
-            const double lp = norm * dp[l], lm_ = norm * dm[l];
-            const double W = 0.5 * (lp + lm_), X = 0.5 * (lp - lm_);
-            const cplx Qw = gN[1] + par * gS[1], Uw = gN[2] + par * gS[2];
-            const cplx Qx = gN[1] - par * gS[1], Ux = gN[2] - par * gS[2];
-            out[1 * plane + (size_t)l * ncol + col] += -(W * Qw + sx * I * X * Ux);
-            out[2 * plane + (size_t)l * ncol + col] += -(W * Uw - sx * I * X * Qx);
-          }
-        }
-      }
-    }
+    free(a0);
+    free(a1);
   }
-  free(nrm);
-  free(coef);
   /* B = conj(a)  (telescope.py:1193,1302,1316) */
   for (size_t i = 0; i < plane * npol; ++i) out[i] = conj(out[i]);
 
-  free(d0);
-  free(dp);
-  free(dm);
   free(G);
   free(xbuf);
   free(Xbuf);
   free(work);
   return 0;
+}
+
+int oracle_transfer_unit(void *ctxp, int polarised, int npol, const double *beam_i, const double *beam_j,
+                         const uint8_t *horizon, const double *zenith, const double *uv, int lmax, int lside,
+                         double *out_) {
+  return oracle_transfer_unit_iter(ctxp, polarised, npol, beam_i, beam_j, horizon, zenith, uv, lmax, lside, 0, out_);
 }

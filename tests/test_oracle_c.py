@@ -14,7 +14,7 @@ from oracle import transfer as otr
 
 def test_builds_and_exports():
     lib = cbuild.lib()
-    for name in ("oracle_ctx_create", "oracle_ctx_destroy", "oracle_transfer_unit"):
+    for name in ("oracle_ctx_create", "oracle_ctx_destroy", "oracle_transfer_unit", "oracle_transfer_unit_iter"):
         assert hasattr(lib, name)
 
 
@@ -36,6 +36,30 @@ def test_c_matches_numpy_oracle(nside, lmax, uv, lat):
     ref = otr.transfer_single_unpol(ang, hor, bi[:, 0], bj[:, 0], zen, np.array(uv), lmax, lside)
     got = cbuild.transfer_unit(nside, bi[:, 0], bj[:, 0], hor, zen, uv, lmax, lside, npol=1)
     assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("nside,lmax,uv,lat", [(4, 6, (0.4, 0.9), 45.0), (8, 13, (1.3, -0.7), 30.0)])
+def test_c_jacobi_refinement_matches_numpy_oracle(nside, lmax, uv, lat):
+    """healpy's map2alm(iter = k): the numpy oracle iterates through pixel maps (oracle/sht.py), the C
+    code on the ring spectra (synthesis, aliasing fold, analysis -- the design of the device-side
+    `sht_iter`); spin 0 and spin 2, +m and -m, polarised and unpolarised."""
+    zen = np.array([np.radians(90.0 - lat), 0.0])
+    ang = ohp.ang_positions(nside)
+    hor = obeam.horizon(ang, zen)
+    rng = np.random.default_rng(nside + lmax)
+    bi = rng.standard_normal((12 * nside * nside, 2))
+    bj = rng.standard_normal((12 * nside * nside, 2))
+    lside = lmax + 1
+    plain = cbuild.transfer_unit(nside, bi, bj, hor, zen, uv, lmax, lside)
+    for niter in (1, 3):
+        for npol in (4, 3, 1):
+            ref = otr.transfer_single_pol(ang, hor, bi, bj, zen, np.array(uv), lmax, lside, npol=npol, niter=niter)[:npol]
+            got = cbuild.transfer_unit(nside, bi, bj, hor, zen, uv, lmax, lside, npol=npol, niter=niter)
+            assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+            assert np.abs(got - plain[:npol]).max() > 1e-6 * np.abs(ref).max()  # the refinement does something
+        ref = otr.transfer_single_unpol(ang, hor, bi[:, 0], bj[:, 0], zen, np.array(uv), lmax, lside, niter=niter)
+        got = cbuild.transfer_unit(nside, bi[:, 0], bj[:, 0], hor, zen, uv, lmax, lside, npol=1, niter=niter)
+        assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
 
 
 def test_c_matches_reference_golden(golden_dir):
