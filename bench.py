@@ -10,14 +10,21 @@ configuration -- PolarisedCylinder pathfinder scale, 2 cylinders x 64 feeds x
 units spread over nside 64/128/256.  One "step" = the transfer matrices of all
 760 baselines at `--freqs-per-gpu` frequencies per GPU (weak scaling: each GPU
 owns its own frequencies), i.e. fringe x beam on rings -> ring FFT -> Legendre
-contraction (tcgen05) -> m-major pack, followed for N > 1 by the NCCL all-to-all
-that regroups frequency-major blocks into the m ranges each GPU owns.
+contraction (tcgen05) -> m-major pack; for N > 1 the pack kernel stores every
+m-block straight into the memory of the GPU that owns that m range (NVLink, CUDA
+IPC) and a one-element all-reduce fences the step (--nccl-exchange: a separate
+NCCL all-to-all instead).
 
 metric  = beam-transfer (baseline*freq) units per second, whole job.
-value   = device-resident (beams, tables and unit descriptors already in HBM).
+value   = device-resident (beams, tables and unit descriptors already in HBM); the
+          kernels of a step are recorded once into a CUDA graph and replayed, the
+          per-stage times of the rooflines come from a separate profiled pass of
+          direct launches.
 e2e     = same call through the C ABI with HOST buffers: host beam maps are
-          uploaded and the m-major complex128 product is copied back to pinned
-          host memory inside the timed region.
+          uploaded and the m-major complex128 product ends up in host memory
+          inside the timed region -- as complex128 over PCIe, or (fp32x3) as
+          complex64 widened exactly by host threads; both are timed, the faster
+          is reported and they are checked to be identical.
 """
 
 import argparse
@@ -324,7 +331,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true",
                     help="enqueue every kernel of every timed step from the host instead of replaying a CUDA graph")
     ap.add_argument("--bucket-streams", action="store_true",
-                    help="run the nside buckets of a step on separate streams")
+                    help="diagnostic: run the nside buckets of a step on separate streams (faults at present: two "
+                         "Legendre launches in flight raise an illegal instruction, DESIGN.md section 7)")
     ap.add_argument("--no-svd", action="store_true", help="skip the per-m SVD measurement (second half of the metric)")
     ap.add_argument("--svd-only", action="store_true", help="diagnostic: run only the per-m SVD measurement")
     ap.add_argument("--svd-ms", default="auto",
