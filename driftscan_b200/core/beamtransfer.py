@@ -209,6 +209,14 @@ class BeamTransfer(config.Reader):
             return
         st = time.time()
         tel, comm = self.telescope, self.comm
+        from . import telescope as _telescope
+
+        if type(tel)._transfer_single is not _telescope.TransitTelescope._transfer_single:
+            # fail loudly rather than ignore the user's unit: the m-files are produced by the device
+            # engine, which evaluates the units itself (beams may be customised freely)
+            raise NotImplementedError(
+                "BeamTransfer.generate: this telescope overrides _transfer_single; the m-file stage runs on "
+                "the device engine and does not call it (transfer_matrices does)")
         freq_inc, bl_inc = tel.included_freq, tel.included_baseline
         nf_inc, nb_inc, np_inc = len(freq_inc), len(bl_inc), len(tel.included_pol)
         nl, nm = tel.lmax + 1, tel.mmax + 1

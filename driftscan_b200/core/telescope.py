@@ -394,6 +394,15 @@ class TransitTelescope(config.Reader, metaclass=abc.ABCMeta):
             "Size: %i elements. Memory %f GB." % (np.prod(tshape), 2 * np.prod(tshape) * 8.0 / 2**30)
         )
         tarray = np.zeros(tshape, dtype=np.complex128)
+        if type(self)._transfer_single is not TransitTelescope._transfer_single:
+            # a subclass supplies its own unit (the hook of telescope.py:1095-1119): keep the
+            # reference's unit loop, in ascending-lmax order (telescope.py:818-828)
+            for iflat in np.argsort(lmax.flat):
+                ind = np.unravel_index(iflat, lmax.shape)
+                trans = self._transfer_single(bl_indices[ind], f_indices[ind], lmax[ind], lside)
+                for pi in range(self.num_pol_sky):
+                    tarray[ind + (pi, slice(None), slice(None))] = trans[pi]
+            return tarray
         if bl_indices.size:
             self.engine.transfer_dense(bl_indices.ravel(), f_indices.ravel(), lmax.ravel(), lside, tarray)
         return tarray

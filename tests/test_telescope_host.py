@@ -98,3 +98,32 @@ def test_pickle_roundtrip():
     tel2 = pickle.loads(pickle.dumps(tel))
     assert tel2._feedmap is None and tel2.num_feeds == 5 and tel2.tsys_flat == 1.0
     assert np.array_equal(tel2.baselines, tel.baselines)
+
+
+def test_transfer_single_override_is_honoured():
+    """`_transfer_single` is an overridable hook in the reference (telescope.py:1095-1119):
+    `transfer_matrices` must route through a subclass's version, unit by unit in ascending-lmax
+    order (telescope.py:818-828), instead of the device engine."""
+    calls = []
+
+    class Custom(cylinder.UnpolarisedCylinderTelescope):
+        def _transfer_single(self, bl_index, f_index, lmax, lside):
+            calls.append((int(bl_index), int(f_index), int(lmax)))
+            out = np.zeros((1, lside + 1, 2 * lside + 1), dtype=np.complex128)
+            out[0, : lmax + 1, 0] = bl_index + 1j * f_index
+            return out
+
+    tel = Custom.from_config(dict(SMALL_CFG, num_feeds=4))
+    # 1-D index arrays: like the reference's max_lm (telescope.py:116), the per-unit lmax takes them only
+    bl = np.repeat(np.arange(tel.npairs), tel.nfreq)
+    fi = np.tile(np.arange(tel.nfreq), tel.npairs)
+    tm = tel.transfer_matrices(bl, fi)
+    assert tm.shape == (bl.size, 1, tel.lmax + 1, 2 * tel.lmax + 1)
+    assert len(calls) == bl.size
+    assert [c[2] for c in calls] == sorted(c[2] for c in calls)
+    lmax_u, _ = tel.unit_lmax(bl, fi)
+    for i in (0, 1, bl.size - 1):
+        col = tm[i, 0, :, 0]
+        assert (col[: lmax_u[i] + 1] == bl[i] + 1j * fi[i]).all() and not col[lmax_u[i] + 1:].any()
+    small = tel.transfer_matrices(np.array([0]), np.array([0]), global_lmax=False)
+    assert small.shape[-2] == int(lmax_u[0]) + 1
