@@ -1,4 +1,9 @@
-"""Cylinder telescopes (mirrors drift/telescope/cylinder.py)."""
+"""Cylinder telescopes: N-S parabolic cylinders side by side, a line of feeds along each.
+
+Host-side description only (geometry, primary beams as numpy maps); the transfer matrices are
+computed by the device engine.  Names, configuration keys and defaults are those of the reference
+classes (drift/telescope/cylinder.py) so that its YAML files and pickles of user code carry over.
+"""
 
 import numpy as np
 
@@ -6,95 +11,87 @@ from .. import config
 from ..core import telescope
 from . import cylbeam
 
+_THIRD_TURN = 2.0 * np.pi / 3.0  # nominal full width at half maximum of the antenna pattern
+
 
 class CylinderTelescope(telescope.TransitTelescope):
-    """Geometry shared by all cylinder telescopes: ``num_cylinders`` N-S cylinders of
-    ``cylinder_width`` metres side by side, ``num_feeds`` feeds ``feed_spacing`` apart on
-    each (drift/telescope/cylinder.py:9-163)."""
+    """Geometry common to the cylinder telescopes (cylinder.py:9-163)."""
 
+    # -- layout ------------------------------------------------------------------------------
     num_cylinders = config.Property(proptype=int, default=2)
     num_feeds = config.Property(proptype=int, default=6)
-    cylinder_width = config.Property(proptype=float, default=20.0)
-    feed_spacing = config.Property(proptype=float, default=0.5)
-    in_cylinder = config.Property(proptype=bool, default=True)
-    touching = config.Property(proptype=bool, default=True)
-    cylspacing = config.Property(proptype=float, default=0.0)
-    non_commensurate = config.Property(proptype=bool, default=False)
+    cylinder_width = config.Property(proptype=float, default=20.0)     # metres, East-West
+    feed_spacing = config.Property(proptype=float, default=0.5)        # metres along the cylinder
+    touching = config.Property(proptype=bool, default=True)            # cylinders edge to edge ...
+    cylspacing = config.Property(proptype=float, default=0.0)          # ... or this far apart (centres)
+    non_commensurate = config.Property(proptype=bool, default=False)   # one feed fewer per further cylinder
+    in_cylinder = config.Property(proptype=bool, default=True)         # keep baselines within a cylinder
+    # -- antenna pattern widths, in units of the nominal one --------------------------------------
     e_width = config.Property(proptype=float, default=0.7)
     h_width = config.Property(proptype=float, default=1.0)
 
-    _fwhm_e = 2.0 * np.pi / 3.0
-    _fwhm_h = 2.0 * np.pi / 3.0
+    _fwhm_e = _THIRD_TURN
+    _fwhm_h = _THIRD_TURN
 
-    @property
-    def fwhm_e(self):
-        """Full width at half maximum of the E-plane antenna beam."""
-        return self._fwhm_e * self.e_width
+    fwhm_e = property(lambda self: self._fwhm_e * self.e_width, doc="E-plane FWHM of the antenna beam (radians)")
+    fwhm_h = property(lambda self: self._fwhm_h * self.h_width, doc="H-plane FWHM of the antenna beam (radians)")
 
-    @property
-    def fwhm_h(self):
-        """Full width at half maximum of the H-plane antenna beam."""
-        return self._fwhm_h * self.h_width
-
-    @property
-    def u_width(self):
-        return self.cylinder_width
-
-    @property
-    def v_width(self):
-        return 0.0
-
-    def _baseline_mask(self, sep):
-        mask = super()._baseline_mask(sep)
-        if not self.in_cylinder:
-            # drop correlations between feeds of the same cylinder (cylinder.py:93-107)
-            mask &= sep[..., 0] != 0.0
-        return mask
+    # an element is as wide as the cylinder East-West and has no North-South extent
+    u_width = property(lambda self: self.cylinder_width)
+    v_width = property(lambda self: 0.0)
 
     @property
     def cylinder_spacing(self):
+        """Distance between the axes of neighbouring cylinders."""
         if self.touching:
             return self.cylinder_width
         if self.cylspacing is None:
             raise Exception("Need to set cylinder spacing if not touching.")
         return self.cylspacing
 
+    def _baseline_mask(self, sep):
+        keep = super()._baseline_mask(sep)
+        if self.in_cylinder:
+            return keep
+        # without intra-cylinder correlations a pair needs an East-West separation (cylinder.py:93-107)
+        return keep & (sep[..., 0] != 0.0)
+
     def feed_positions_cylinder(self, cylinder_index):
-        """[nfeed, 2] (East, North) positions of the feeds of one cylinder."""
-        if cylinder_index >= self.num_cylinders or cylinder_index < 0:
+        """(East, North) positions, one row per feed, of cylinder ``cylinder_index``."""
+        if not 0 <= cylinder_index < self.num_cylinders:
             raise Exception("Cylinder index is invalid.")
-        nf, sp = self.num_feeds, self.feed_spacing
+        count, step = self.num_feeds, self.feed_spacing
         if self.non_commensurate:
-            nf = self.num_feeds - cylinder_index
-            sp = self.feed_spacing / (nf - 1.0) * nf
-        pos = np.empty([nf, 2], dtype=np.float64)
+            # the same length shared by fewer feeds on every further cylinder
+            count = self.num_feeds - cylinder_index
+            step = self.feed_spacing / (count - 1.0) * count
+        pos = np.empty([count, 2], dtype=np.float64)
         pos[:, 0] = cylinder_index * self.cylinder_spacing
-        pos[:, 1] = np.arange(nf) * sp
+        pos[:, 1] = np.arange(count) * step
         return pos
 
     @property
     def _single_feedpositions(self):
-        return np.vstack([self.feed_positions_cylinder(i) for i in range(self.num_cylinders)])
+        return np.vstack([self.feed_positions_cylinder(c) for c in range(self.num_cylinders)])
+
+    def _scaled_width(self, freq):
+        """Cylinder width in wavelengths at channel ``freq``."""
+        return self.cylinder_width / self.wavelengths[freq]
 
 
 class UnpolarisedCylinderTelescope(CylinderTelescope, telescope.SimpleUnpolarisedTelescope):
-    """Unpolarised cylinder (cylinder.py:166-194)."""
+    """One sky polarisation; the beam is the cylinder's amplitude pattern (cylinder.py:166-194)."""
 
     def beam(self, feed, freq):
-        return cylbeam.beam_amp(
-            self._angpos, self.zenith, self.cylinder_width / self.wavelengths[freq], self.fwhm_h, self.fwhm_h
-        )
+        # NB the reference passes the H-plane width for both planes (cylinder.py:188-194)
+        return cylbeam.beam_amp(self._angpos, self.zenith, self._scaled_width(freq), self.fwhm_h, self.fwhm_h)
 
 
 class PolarisedCylinderTelescope(CylinderTelescope, telescope.SimplePolarisedTelescope):
-    """Dual-polarisation cylinder (cylinder.py:197-218)."""
+    """Dual-polarisation feeds: X dipoles across, Y dipoles along the cylinder (cylinder.py:197-218)."""
 
     def beamx(self, feed, freq):
-        return cylbeam.beam_x(
-            self._angpos, self.zenith, self.cylinder_width / self.wavelengths[freq], self.fwhm_e, self.fwhm_h
-        )
+        return cylbeam.beam_x(self._angpos, self.zenith, self._scaled_width(freq), self.fwhm_e, self.fwhm_h)
 
     def beamy(self, feed, freq):
-        return cylbeam.beam_y(
-            self._angpos, self.zenith, self.cylinder_width / self.wavelengths[freq], self.fwhm_e, self.fwhm_h
-        )
+        return cylbeam.beam_y(self._angpos, self.zenith, self._scaled_width(freq), self.fwhm_e, self.fwhm_h)

@@ -1,5 +1,8 @@
-"""Cylinders whose beam is restricted in elevation (mirrors drift/telescope/restrictedcylinder.py):
-the cylinder beam times a window in polar angle around the zenith, ``beam_height`` degrees high."""
+"""Cylinder telescopes with an elevation-limited beam: the cylinder pattern is multiplied by a
+window in polar angle, ``beam_height`` degrees high and centred on the zenith -- a top hat
+(``beam_type: box``) or a Gaussian of that full width at half maximum.  Configuration keys and YAML
+type names (``RestrictedCylinder``, ``RestrictedPolarisedCylinder``, ``RestrictedExtra``) follow
+drift/telescope/restrictedcylinder.py."""
 
 import numpy as np
 
@@ -7,60 +10,64 @@ from .. import config
 from . import cylinder
 
 
+
 def gaussian_fwhm(x, fwhm):
-    """Unit-peak Gaussian of the given full width at half maximum (restrictedcylinder.py:8-13)."""
+    """``exp(-x^2 / 2 sigma^2)`` with ``sigma = fwhm / sqrt(8 ln 2)`` (restrictedcylinder.py:8-13)."""
     sigma = fwhm / (8.0 * np.log(2.0)) ** 0.5
     return np.exp(-(x**2) / (2 * sigma**2))
 
 
 class RestrictedBeam(cylinder.CylinderTelescope):
-    """Adds the elevation window (restrictedcylinder.py:16-52)."""
+    """The window itself (restrictedcylinder.py:16-52)."""
 
-    beam_height = config.Property(proptype=float, default=30.0)
     beam_type = config.Property(proptype=str, default="box")
+    beam_height = config.Property(proptype=float, default=30.0)
 
-    def _zenith_offset(self):
-        """|theta - theta_zenith| per pixel (the reference also wraps the azimuth difference,
-        which the windows do not use)."""
+    def _polar_offset(self):
+        # |theta - theta_zenith| of every pixel; the reference also wraps the azimuth offset into
+        # (-pi, pi] before taking absolute values, but neither window looks at it
         return np.abs(self._angpos[:, 0] - self.zenith[0])
 
-    def bmask_gaussian(self, feed, freq):
-        return gaussian_fwhm(self._zenith_offset(), np.radians(self.beam_height))
-
     def bmask_box(self, feed, freq):
-        return np.abs(self._zenith_offset() / np.radians(self.beam_height)) < 0.5
+        """True inside the band ``|theta - theta_z| < beam_height / 2``."""
+        return np.abs(self._polar_offset() / np.radians(self.beam_height)) < 0.5
+
+    def bmask_gaussian(self, feed, freq):
+        return gaussian_fwhm(self._polar_offset(), np.radians(self.beam_height))
 
     def _window(self, feed, freq):
-        return {"gaussian": self.bmask_gaussian, "box": self.bmask_box}[self.beam_type](feed, freq)
+        shapes = {"box": self.bmask_box, "gaussian": self.bmask_gaussian}
+        return shapes[self.beam_type](feed, freq)
 
 
 class RestrictedCylinder(RestrictedBeam, cylinder.UnpolarisedCylinderTelescope):
-    """Unpolarised (restrictedcylinder.py:55-60)."""
+    """Single sky polarisation (restrictedcylinder.py:55-60)."""
 
     def beam(self, feed, freq):
         return self._window(feed, freq) * cylinder.UnpolarisedCylinderTelescope.beam(self, feed, freq)
 
 
 class RestrictedPolarisedCylinder(RestrictedBeam, cylinder.PolarisedCylinderTelescope):
-    """Dual polarisation (restrictedcylinder.py:63-75)."""
+    """Both feed polarisations get the same window (restrictedcylinder.py:63-75)."""
+
+    def _windowed(self, pattern, feed, freq):
+        return self._window(feed, freq)[:, np.newaxis] * pattern(self, feed, freq)
 
     def beamx(self, feed, freq):
-        return self._window(feed, freq)[:, np.newaxis] * cylinder.PolarisedCylinderTelescope.beamx(self, feed, freq)
+        return self._windowed(cylinder.PolarisedCylinderTelescope.beamx, feed, freq)
 
     def beamy(self, feed, freq):
-        return self._window(feed, freq)[:, np.newaxis] * cylinder.PolarisedCylinderTelescope.beamy(self, feed, freq)
+        return self._windowed(cylinder.PolarisedCylinderTelescope.beamy, feed, freq)
 
 
 class RestrictedExtra(RestrictedCylinder):
-    """Extra feeds at given North positions on every cylinder (restrictedcylinder.py:78-89)."""
+    """``extra_feeds``: North positions (metres) of additional feeds placed on every cylinder,
+    listed before the regular ones (restrictedcylinder.py:78-89)."""
 
     extra_feeds = config.Property(proptype=np.array, default=[])
 
     def feed_positions_cylinder(self, cylinder_index):
         regular = super().feed_positions_cylinder(cylinder_index)
-        extra = np.asarray(self.extra_feeds, dtype=np.float64).reshape(-1)
-        pos = np.zeros((extra.size + regular.shape[0], 2), dtype=np.float64)
-        pos[: extra.size, 0] = cylinder_index * self.cylinder_spacing
-        pos[: extra.size, 1] = extra
-        pos[extra.size :] = regular
-        return pos
+        north = np.asarray(self.extra_feeds, dtype=np.float64).reshape(-1)
+        east = np.full(north.size, cylinder_index * self.cylinder_spacing, dtype=np.float64)
+        return np.vstack([np.stack([east, north], axis=1), regular])
