@@ -1,13 +1,12 @@
-"""Configuration-driven access to the analysis products (mirrors drift/core/manager.py).
+"""Configuration-driven access to the analysis products (drop-in for drift/core/manager.py).
 
-``ProductManager.from_config(path)`` reads the same YAML layout as the reference
-(``config:`` / ``telescope:`` sections, ``type:`` either a registered name or a
-``{class, module, file}`` mapping for user telescopes), creates
-``<output_directory>/config.yaml`` and builds the telescope and ``BeamTransfer``
-objects; ``generate()`` runs the beam-transfer stage on the GPU.  The KL and
-power-spectrum stages of the reference are outside the scope of this package
-(SURVEY section 8): their configuration entries are accepted and skipped with a
-warning.
+``ProductManager.from_config(path)`` takes the reference's YAML layout: a ``config:`` section
+(output directory, which stages to run, BeamTransfer options), a ``telescope:`` section whose
+``type:`` is a registered name or a ``{class, module, file}`` mapping for user-defined telescopes,
+and an optional ``kltransform:`` list.  It installs ``<output_directory>/config.yaml``, builds the
+telescope, the ``BeamTransfer`` variant asked for and the KL transforms; ``generate()`` runs the
+beam-transfer, SVD and KL stages on the GPU.  ``psfisher`` entries are accepted and skipped with a
+warning (power-spectrum estimation is outside this package).
 """
 
 import importlib
@@ -66,37 +65,40 @@ class ProductManager(object):
     skip_svd = False
     skip_svd_inv = False
 
-    @classmethod
-    def from_config(cls, configfile):
+    @staticmethod
+    def _installed_config(configfile):
+        """Path of ``<output_directory>/config.yaml``, written from ``configfile`` (with the output
+        directory made absolute) unless it is that very file (manager.py:119-166)."""
         comm = parallel.Comm.current()
         configfile = os.path.normpath(os.path.expandvars(os.path.expanduser(configfile)))
         if not os.path.exists(configfile):
             raise Exception(f"Configuration file does not exist {configfile}.")
-        if os.path.isdir(configfile):
+        if os.path.isdir(configfile):  # a product directory stands for the copy inside it
             configfile = configfile + "/config.yaml"
         with open(configfile, "r") as f:
-            yconf = yaml.safe_load(f)
-        outdir = yconf["config"]["output_directory"]
-        outdir_orig = outdir
-        if not os.path.isabs(outdir):
+            given = yaml.safe_load(f)["config"]["output_directory"]
+        outdir = given
+        if not os.path.isabs(outdir):  # relative to the configuration file, not to the cwd
             outdir = os.path.abspath(os.path.normpath(os.path.join(os.path.dirname(configfile), outdir)))
-        dfile = os.path.join(outdir, "config.yaml")
-
+        installed = os.path.join(outdir, "config.yaml")
         if comm.rank0:
             os.makedirs(outdir, exist_ok=True)
-            if not os.path.exists(dfile) or not os.path.samefile(configfile, dfile):
+            if not os.path.exists(installed) or not os.path.samefile(configfile, installed):
                 with open(configfile, "r") as f:
-                    contents = f.read()
-                if outdir_orig != outdir:
-                    contents = contents.replace(outdir_orig, outdir)
-                with open(dfile, "w+") as f:
-                    f.write(contents)
+                    text = f.read()
+                if given != outdir:
+                    text = text.replace(given, outdir)
+                with open(installed, "w+") as f:
+                    f.write(text)
         comm.barrier()
+        return installed
 
-        c = cls()
-        with open(dfile) as f:
-            c.apply_config(yaml.safe_load(f))
-        return c
+    @classmethod
+    def from_config(cls, configfile):
+        manager = cls()
+        with open(cls._installed_config(configfile)) as f:
+            manager.apply_config(yaml.safe_load(f))
+        return manager
 
     def apply_config(self, yconf):
         if "config" not in yconf:
