@@ -90,3 +90,26 @@ def test_oracle_transfer_matrices(gold):
                                       tel.baselines[bl[i]] / tel.wavelengths[fi[i]], int(lmax[i]), tel.lmax)
         want = gold["pol_transfer"][i]
         assert np.abs(np.array(got) - want).max() <= 1e-12 * np.abs(want).max()
+
+
+def test_example_yaml_loads_the_user_class(tmp_path):
+    """examples/disharray/prod_params.yaml through ProductManager.from_config: the telescope class
+    comes from the file named in `type:`, latitude from the YAML (manager.py:59-73, 205-215)."""
+    import shutil
+
+    from driftscan_b200.core import manager
+
+    for name in ("simplearray.py", "prod_params.yaml"):
+        shutil.copy(os.path.join(ROOT, "examples", "disharray", name), tmp_path / name)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)  # the example names its class file relative to the working directory
+    try:
+        pm = manager.ProductManager.from_config(str(tmp_path / "prod_params.yaml"))
+    finally:
+        os.chdir(cwd)
+    tel = pm.telescope
+    assert type(tel).__name__ == "DishArray" and tel._polarised_
+    assert tel.zenith[0] == pytest.approx(np.pi / 3) and (tel.nfeed, tel.npairs, tel.nfreq) == (32, 96, 5)
+    assert pm.gen_beams and not pm.gen_kl
+    assert os.path.isfile(tmp_path / "products" / "disharray" / "config.yaml")
+    assert pm.beamtransfer.directory.startswith(str(tmp_path))
