@@ -183,7 +183,8 @@ class CpuArm:
     def unit(self, task):
         nside, f, uv, lmax, ci, cj = task
         b = self.beams[(nside, f)]
-        self.cbuild.transfer_unit(nside, b[ci], b[cj], self.geom[nside][1], self.tel.zenith, uv, lmax, self.tel.lmax)
+        self.cbuild.transfer_unit(nside, b[ci], b[cj], self.geom[nside][1], self.tel.zenith, uv, lmax, self.tel.lmax,
+                                  niter=int(self.tel.sht_iter))
         return 1
 
     def run(self, tasks, cores):
@@ -322,6 +323,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--freqs-per-gpu", type=int, default=2)
     ap.add_argument("--precision", default="fp32x3", choices=["fp32x3", "fp64"])
+    ap.add_argument("--sht-iter", type=int, default=None,
+                    help="Jacobi refinement passes of the analysis (healpy map2alm iter); default: the telescope "
+                         "default, i.e. the value cora.util.hputil is recalled to use (2)")
     ap.add_argument("--cpu-sample", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -352,11 +356,14 @@ def main():
     from driftscan_b200.telescope import cylinder
 
     tel = cylinder.PolarisedCylinderTelescope.from_config(dict(WORKLOAD, precision=args.precision))
+    if args.sht_iter is not None:
+        tel.sht_iter = args.sht_iter
     F = args.freqs_per_gpu
     config = {
         "workload": WORKLOAD_NAME, "nbase": int(tel.nbase), "nfreq_total": int(tel.nfreq),
         "freqs_per_gpu_per_step": F, "units_per_step_per_gpu": int(tel.nbase * F), "lmax": int(tel.lmax),
         "mmax": int(tel.mmax), "npol_sky": 4, "precision": args.precision,
+        "sht": f"healpy map2alm(iter={int(tel.sht_iter)}, use_weights=False) on both arms",
         "l2": "per-step working set (ring spectra + product, several GB) is far larger than the 126 MB L2",
         "sharding": "frequency per GPU; NCCL all-to-all of m-major blocks when N>1",
     }

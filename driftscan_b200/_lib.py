@@ -67,6 +67,8 @@ def _load():
         "dsb_launch_count": (u64, []),
         "dsb_plan_create": (i32, [i32, vp, P(vp)]),
         "dsb_plan_destroy": (i32, [vp]),
+        "dsb_plan_set_sht": (i32, [vp, i32, vp]),
+        "dsb_get_profile_refine": (i32, [P(dbl), P(u64)]),
         "dsb_beam_upload": (i32, [vp, i32, vp, i32, i32, P(dbl), vp]),
         "dsb_beam_slots": (i32, [vp, i32]),
         "dsb_plan_build_tables": (i32, [vp, i32, i32, i32, i32, vp]),
@@ -136,6 +138,15 @@ class Plan:
         self._h = ctypes.c_void_p()
         check(lib.dsb_plan_create(nside, horizon.ctypes.data_as(ctypes.c_void_p), ctypes.byref(self._h)))
         self.omega = {}
+
+    def set_sht(self, sht_iter=0, ring_weights=None):
+        """healpy ``map2alm(iter=..., use_weights=...)`` settings of this plan's analysis."""
+        w = None
+        if ring_weights is not None:
+            w = np.ascontiguousarray(ring_weights, dtype=np.float64)
+            if w.shape != (2 * self.nside,):
+                raise ValueError(f"ring_weights needs {2 * self.nside} entries (north pole to equator)")
+        check(lib.dsb_plan_set_sht(self._h, int(sht_iter), w.ctypes.data_as(ctypes.c_void_p) if w is not None else None))
 
     def close(self):
         if self._h:

@@ -13,6 +13,7 @@ import importlib
 import importlib.util
 import logging
 import os
+import sys
 import warnings
 
 import yaml
@@ -45,6 +46,9 @@ def _resolve_class(clstype, clsdict, objtype=""):
         if "file" in clstype:
             spec = importlib.util.spec_from_file_location(modname, clstype["file"])
             module = importlib.util.module_from_spec(spec)
+            # registered like imp.load_source does (manager.py:69 of the reference): pickling the
+            # telescope (BeamTransfer.generate) looks the class up through sys.modules
+            sys.modules[modname] = module
             spec.loader.exec_module(module)
         else:
             module = importlib.import_module(modname)

@@ -99,6 +99,15 @@ class TransitTelescope(config.Reader, metaclass=abc.ABCMeta):
 
     # B200 engine options (not present in the reference)
     precision = config.enum(["fp32x3", "fp64"], default="fp32x3")
+    # Settings of the spherical-harmonic analysis.  The reference does not expose them: it calls
+    # cora.util.hputil.sphtrans_complex[_pol] (drift/core/telescope.py:1189-1191, 1300-1314), which
+    # hands its module-level ``_weight`` / ``_iter`` to healpy.map2alm(use_weights=, iter=).  cora is
+    # external and not available offline; its values are recalled as ``_weight = True`` and
+    # ``_iter = 2`` (unverified).  ``sht_iter`` defaults to that recalled value; healpy's ring-weight
+    # data files do not exist here, so ``sht_ring_weights`` defaults to none (use_weights=False) and
+    # takes ``{nside: array of 2*nside multiplicative weights, north pole to equator}`` when given.
+    sht_iter = config.Property(proptype=int, default=2)
+    sht_ring_weights = config.Property(default=None)
 
     # The reference inherits the observer position from caput.time.Observer
     # (drift/core/telescope.py:125, 245-255), whose longitude / latitude / altitude are

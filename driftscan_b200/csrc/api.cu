@@ -30,11 +30,12 @@ namespace {
 // Optional per-stage device timing (CUDA events on the launching stream), used by bench.py
 // for the roofline figures.  Stages: 0 ring FFT, 1 Legendre contraction, 2 pack.
 bool g_prof = false;
-double g_prof_ms[3] = {0, 0, 0};
-uint64_t g_prof_n[3] = {0, 0, 0};
+constexpr int kStages = 4;  // ring FFT, Legendre analysis, Jacobi refinement (sht_iter > 0), pack
+double g_prof_ms[kStages] = {0, 0, 0, 0};
+uint64_t g_prof_n[kStages] = {0, 0, 0, 0};
 
 struct StageEvents {
-  cudaEvent_t e[4];
+  cudaEvent_t e[kStages + 1];
 };
 std::vector<StageEvents> g_prof_pending;  // recorded, not yet read back
 
@@ -61,8 +62,8 @@ struct StageTimer {
 
 void collect_profile() {
   for (auto &ev : g_prof_pending) {
-    cudaEventSynchronize(ev.e[3]);
-    for (int i = 0; i < 3; ++i) {
+    cudaEventSynchronize(ev.e[kStages]);
+    for (int i = 0; i < kStages; ++i) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, ev.e[i], ev.e[i + 1]);
       g_prof_ms[i] += ms;
@@ -91,7 +92,7 @@ struct Carve {
 extern "C" int dsb_set_profiling(int enable) {
   collect_profile();
   g_prof = enable != 0;
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < kStages; ++i) {
     g_prof_ms[i] = 0;
     g_prof_n[i] = 0;
   }
@@ -100,10 +101,18 @@ extern "C" int dsb_set_profiling(int enable) {
 
 extern "C" int dsb_get_profile(double *ms3, uint64_t *launches3) {
   collect_profile();
+  const int src[3] = {0, 1, 3};
   for (int i = 0; i < 3; ++i) {
-    if (ms3) ms3[i] = g_prof_ms[i];
-    if (launches3) launches3[i] = g_prof_n[i];
+    if (ms3) ms3[i] = g_prof_ms[src[i]];
+    if (launches3) launches3[i] = g_prof_n[src[i]];
   }
+  return DSB_OK;
+}
+
+extern "C" int dsb_get_profile_refine(double *ms, uint64_t *calls) {
+  collect_profile();
+  if (ms) *ms = g_prof_ms[2];
+  if (calls) *calls = g_prof_n[2];
   return DSB_OK;
 }
 
@@ -288,14 +297,18 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
   lay.has2 = npol_sky >= 3 ? 1 : 0;
   lay.cpu0 = 4 * lay.nsp0;
   lay.cpu2 = 8;
-  lay.mcap = std::min(std::min(mmax, mmax_out), lmax_b);
+  // healpy's map2alm(lmax = unit lmax) carries every m <= lmax through its Jacobi refinement
+  // (the aliasing on the polar rings couples m' = m mod nphi), so with sht_iter > 0 all m are
+  // computed even where the product only stores m <= mmax
+  const int niter = plan->sht_iter;
+  lay.mcap = niter > 0 ? lmax_b : std::min(std::min(mmax, mmax_out), lmax_b);
   lay.lmax_b = lmax_b;
   lay.Kp = plan->Kp;
 
-  const Tables *tab = find_tables(plan, lmax_b, lay.mcap, lay.has2, precision);
+  const Tables *tab = find_tables(plan, lmax_b, lay.mcap, lay.has2, precision, niter > 0);
   if (!tab) {
     DSB_TRY(dsb_plan_build_tables(plan, lmax_b, lay.mcap, lay.has2, precision, stream_));
-    tab = find_tables(plan, lmax_b, lay.mcap, lay.has2, precision);
+    tab = find_tables(plan, lmax_b, lay.mcap, lay.has2, precision, niter > 0);
     DSB_CHECK(tab != nullptr, DSB_ERR_CUDA, "dsb_transfer_units: table construction failed");
   }
   const Tables &t = *tab;
@@ -305,8 +318,12 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
   // ring spectra: fp64 with the spin-2 block in both operand roles, or fp32 stored once
   const size_t es = f64 ? 8 : 4, cs = f64 ? 8 : 4;
   const size_t k2mul = f64 ? 2 : 1;
-  const size_t per_unit = nprob * lay.Kp * lay.cpu0 * es + (lay.has2 ? nprob * k2mul * lay.Kp * 8 * es : 0) +
-                          nprob * t.NP * (lay.cpu0 + (lay.has2 ? 8 : 0)) * cs;
+  size_t per_unit = nprob * lay.Kp * lay.cpu0 * es + (lay.has2 ? nprob * k2mul * lay.Kp * 8 * es : 0) +
+                    nprob * t.NP * (lay.cpu0 + (lay.has2 ? 8 : 0)) * cs;
+  if (niter > 0)  // a(0), transposed coefficients (fp64 spin 2: both roles), synthesised ring functions
+    per_unit += nprob * t.NP * (lay.cpu0 + (lay.has2 ? 8 : 0)) * cs +
+                nprob * t.NPk * (lay.cpu0 + (lay.has2 ? 8 * k2mul : 0)) * cs +
+                nprob * lay.Kp * (lay.cpu0 + (lay.has2 ? 8 : 0)) * es;
   const size_t plane_out = (size_t)npol_out * (lside + 1) * (2 * lside + 1) * 16;
   const size_t per_unit_tot = per_unit + ((tarray && out_is_host) ? plane_out : 0);
   size_t budget = workspace_limit();
@@ -373,37 +390,68 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
           }
     }
 
+    // Synthesis items of the Jacobi refinement: rows = fold rings, contraction over the l-index n of
+    // the tile's rows (the X role of spin 2 runs over the rows of the opposite l - m parity)
+    std::vector<WorkItem> sitems;
+    if (niter > 0) {
+      for (int s = 0; s <= (lay.has2 ? 2 : 0); s += 2) {
+        const int cpu = s == 0 ? lay.cpu0 : 8;
+        const int upt = 128 / cpu;
+        const int ntile = (nu + upt - 1) / upt;
+        std::vector<int> Lt(ntile, 0);
+        for (int i = 0; i < nu; ++i) Lt[i / upt] = std::max(Lt[i / upt], ud[i].lmax);
+        for (int m = 0; m <= lay.mcap; ++m)
+          for (int p = 0; p < 2; ++p)
+            for (int ct = 0; ct < ntile; ++ct) {
+              if (m > Lt[ct]) continue;
+              int nr = nrows_mp(Lt[ct], m, p);
+              if (s == 2) nr = std::max(nr, nrows_mp(Lt[ct], m, 1 - p));
+              const int klen = std::max(32, (int)round_up(nr, 32));
+              for (int r0 = 0; r0 < plan->nfold; r0 += 128)
+                sitems.push_back({2 * m + p, ct, std::min(128, plan->nfold - r0), s, r0, klen});
+            }
+      }
+    }
+
     hc.lap(2);
     // carve the workspace
-    size_t need;
-    {
-      Carve cv(nullptr);
-      cv.take<char>(nprob * lay.Kp * lay.ncols0 * es);
-      cv.take<char>(lay.has2 ? nprob * k2mul * lay.Kp * lay.ncols2 * es : 0);
-      cv.take<char>(nprob * lay.ncols0 * t.NP * cs);
-      cv.take<char>(lay.has2 ? nprob * lay.ncols2 * t.NP * cs : 0);
-      cv.take<UnitDev>(nu);
-      cv.take<int32_t>(nu);
-      cv.take<int32_t>(nu);
-      cv.take<WorkItem>(items.size());
-      cv.take<int64_t>(moff.size());
-      if (tarray && out_is_host) cv.take<char>((size_t)nu * plane_out);
-      need = cv.off + 256;
-    }
-    if ((rc = ensure_workspace(plan, need)) != DSB_OK) break;
-    Carve cv(plan->ws);
     const size_t f0_bytes = nprob * lay.Kp * lay.ncols0 * es;
     const size_t f2_bytes = lay.has2 ? nprob * k2mul * lay.Kp * lay.ncols2 * es : 0;
-    char *F0 = cv.take<char>(f0_bytes);
-    char *F2 = cv.take<char>(f2_bytes);
-    char *C0 = cv.take<char>(nprob * lay.ncols0 * t.NP * cs);
-    char *C2 = cv.take<char>(lay.has2 ? nprob * lay.ncols2 * t.NP * cs : 0);
-    UnitDev *ud_dev = cv.take<UnitDev>(nu);
-    int32_t *o0_dev = cv.take<int32_t>(nu);
-    int32_t *o1_dev = cv.take<int32_t>(nu);
-    WorkItem *items_dev = cv.take<WorkItem>(items.size());
-    int64_t *moff_dev = cv.take<int64_t>(moff.size());
-    char *stage = (tarray && out_is_host) ? cv.take<char>((size_t)nu * plane_out) : nullptr;
+    const size_t c0_bytes = nprob * lay.ncols0 * t.NP * cs;
+    const size_t c2_bytes = lay.has2 ? nprob * lay.ncols2 * t.NP * cs : 0;
+    const size_t ct0_bytes = niter > 0 ? nprob * t.NPk * lay.ncols0 * cs : 0;
+    const size_t ct2_bytes = (niter > 0 && lay.has2) ? nprob * k2mul * t.NPk * lay.ncols2 * cs : 0;
+    const size_t g0_bytes = niter > 0 ? nprob * lay.ncols0 * lay.Kp * es : 0;
+    const size_t g2_bytes = (niter > 0 && lay.has2) ? nprob * lay.ncols2 * lay.Kp * es : 0;
+    char *F0, *F2, *C0, *C2, *A0, *A2, *Ct0, *Ct2, *G0, *G2, *stage;
+    UnitDev *ud_dev;
+    int32_t *o0_dev, *o1_dev;
+    WorkItem *items_dev, *sitems_dev;
+    int64_t *moff_dev;
+    auto carve = [&](void *base) {
+      Carve cv(base);
+      F0 = cv.take<char>(f0_bytes);
+      F2 = cv.take<char>(f2_bytes);
+      C0 = cv.take<char>(c0_bytes);
+      C2 = cv.take<char>(c2_bytes);
+      A0 = cv.take<char>(niter > 0 ? c0_bytes : 0);  // a(0) of the refinement
+      A2 = cv.take<char>(niter > 0 ? c2_bytes : 0);
+      Ct0 = cv.take<char>(ct0_bytes);
+      Ct2 = cv.take<char>(ct2_bytes);
+      G0 = cv.take<char>(g0_bytes);
+      G2 = cv.take<char>(g2_bytes);
+      ud_dev = cv.take<UnitDev>(nu);
+      o0_dev = cv.take<int32_t>(nu);
+      o1_dev = cv.take<int32_t>(nu);
+      items_dev = cv.take<WorkItem>(items.size());
+      sitems_dev = cv.take<WorkItem>(sitems.size());
+      moff_dev = cv.take<int64_t>(moff.size());
+      stage = (tarray && out_is_host) ? cv.take<char>((size_t)nu * plane_out) : nullptr;
+      return cv.off + 256;
+    };
+    const size_t need = carve(nullptr);
+    if ((rc = ensure_workspace(plan, need)) != DSB_OK) break;
+    carve(plan->ws);
 
     hc.lap(3);
     // Padding rows of the operand (fold-ring count rounded up to the k-tile) are written by
@@ -418,10 +466,10 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
       // descriptors go through a pinned staging slot (see dsb_plan::stage_host): stream-ordered
       // copies, the host does not wait for the device
       const size_t b_ud = nu * sizeof(UnitDev), b_o = nu * sizeof(int32_t), b_it = items.size() * sizeof(WorkItem),
-                   b_mo = moff.size() * sizeof(int64_t);
+                   b_mo = moff.size() * sizeof(int64_t), b_si = sitems.size() * sizeof(WorkItem);
       auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
       const size_t o_ud = 0, o_o0 = al(b_ud), o_o1 = o_o0 + al(b_o), o_it = o_o1 + al(b_o), o_mo = o_it + al(b_it),
-                   total = o_mo + al(b_mo);
+                   o_si = o_mo + al(b_mo), total = o_si + al(b_si);
       // A call recorded into a CUDA graph (the stream is capturing) is replayed with the copies
       // it recorded: its descriptors get a buffer of their own that lives as long as the plan.
       cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -451,11 +499,13 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
       memcpy(h + o_o1, o1.data(), b_o);
       memcpy(h + o_it, items.data(), b_it);
       memcpy(h + o_mo, moff.data(), b_mo);
+      if (b_si) memcpy(h + o_si, sitems.data(), b_si);
       DSB_CUDA(cudaMemcpyAsync(ud_dev, h + o_ud, b_ud, cudaMemcpyHostToDevice, stream));
       DSB_CUDA(cudaMemcpyAsync(o0_dev, h + o_o0, b_o, cudaMemcpyHostToDevice, stream));
       DSB_CUDA(cudaMemcpyAsync(o1_dev, h + o_o1, b_o, cudaMemcpyHostToDevice, stream));
       DSB_CUDA(cudaMemcpyAsync(items_dev, h + o_it, b_it, cudaMemcpyHostToDevice, stream));
       DSB_CUDA(cudaMemcpyAsync(moff_dev, h + o_mo, b_mo, cudaMemcpyHostToDevice, stream));
+      if (b_si) DSB_CUDA(cudaMemcpyAsync(sitems_dev, h + o_si, b_si, cudaMemcpyHostToDevice, stream));
       if (!capturing) DSB_CUDA(cudaEventRecord(plan->stage_ev[slot], stream));
     }
 
@@ -465,15 +515,49 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
     if ((rc = launch_ringfft(plan, lay, ud_dev, precision, wptr_dev, F0, F2, stream)) != DSB_OK) break;
     timer.mark(1);
     hc.lap(5);
-    if (f64)
-      rc = launch_legendre_f64(plan, t, lay, items, items_dev, (const double *)F0, (const double *)F2,
-                               (double *)C0, (double *)C2, stream);
-    else
-      rc = launch_legendre_tc(plan, t, lay, items, items_dev, (const float *)F0, (const float *)F2, (float *)C0,
-                              (float *)C2, stream);
-    if (rc != DSB_OK) break;
+    // analysis: A = ring spectra, B = T tables (the tables may cover more m than this bucket)
+    ContractDesc da;
+    da.nprobA = (int)nprob;
+    da.nprobB = 2 * (t.mmax + 1);
+    da.K = da.kx = t.Kp;
+    da.pitch = t.NP;
+    da.ncols0 = lay.ncols0;
+    da.ncols2 = lay.ncols2;
+    da.has2 = lay.has2;
+    int max_rows = 16;
+    for (const auto &w : items) max_rows = std::max(max_rows, w.nrows);
+    auto contract = [&](const ContractDesc &d, const std::vector<WorkItem> &its, const WorkItem *its_dev, int mrows,
+                        const char *a0, const char *a2, bool synth, char *c0, char *c2) {
+      if (f64)
+        return launch_contract_f64(d, (int)its.size(), its_dev, (const double *)a0, (const double *)a2,
+                                   synth ? t.s0_f64 : t.t0_f64, synth ? t.s2_f64 : t.t2_f64, (double *)c0,
+                                   (double *)c2, (const double *)A0, (const double *)A2, stream);
+      return launch_contract_tc(d, (int)its.size(), its_dev, mrows, (const float *)a0, (const float *)a2,
+                                synth ? t.s0_bf : t.t0_bf, synth ? t.s2_bf : t.t2_bf, (float *)c0, (float *)c2,
+                                (const float *)A0, (const float *)A2, stream);
+    };
+    if ((rc = contract(da, items, items_dev, max_rows, F0, F2, false, C0, C2)) != DSB_OK) break;
     timer.mark(2);
     hc.lap(6);
+    if (niter > 0) {
+      // Jacobi refinement (healpy map2alm iter): a <- a(0) + a - A S a, S a on ring spectra
+      DSB_CUDA(cudaMemcpyAsync(A0, C0, c0_bytes, cudaMemcpyDeviceToDevice, stream));
+      if (c2_bytes) DSB_CUDA(cudaMemcpyAsync(A2, C2, c2_bytes, cudaMemcpyDeviceToDevice, stream));
+      ContractDesc ds = da;  // synthesis: A = transposed coefficients, B = S tables, rows = fold rings
+      ds.K = ds.kx = t.NPk;
+      ds.pitch = t.Kp;
+      ContractDesc du = da;
+      du.update = 1;
+      for (int it = 0; it < niter && rc == DSB_OK; ++it) {
+        if ((rc = launch_transpose_coeffs(lay, ud_dev, t.NP, t.NPk, precision, C0, C2, Ct0, Ct2, stream)) != DSB_OK)
+          break;
+        if ((rc = contract(ds, sitems, sitems_dev, std::min(128, plan->nfold), Ct0, Ct2, true, G0, G2)) != DSB_OK) break;
+        if ((rc = launch_alias_fold(plan, lay, ud_dev, precision, G0, G2, F0, F2, stream)) != DSB_OK) break;
+        rc = contract(du, items, items_dev, max_rows, F0, F2, false, C0, C2);
+      }
+      if (rc != DSB_OK) break;
+    }
+    timer.mark(3);
 
     PackParams pp;
     pp.out_kind = out_kind;
@@ -497,7 +581,7 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
     if ((rc = launch_pack(pp, ud_dev, o0_dev, o1_dev, moff_dev, C0, C2, f64 ? 1 : 0, pack_out, stream)) !=
         DSB_OK)
       break;
-    timer.mark(3);
+    timer.mark(4);
     timer.finish();
     hc.lap(7);
     if (tarray && out_is_host) {

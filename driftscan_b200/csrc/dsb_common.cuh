@@ -102,6 +102,7 @@ struct RingDesc {
   double ch2, sh2;    // cos / sin of half the northern colatitude
   double quad;        // quadrature weight 4 pi / npix (x ring weight)
 };
+static_assert(sizeof(RingDesc) == 88, "RingDesc layout");
 
 struct BeamSlot {
   double *d64 = nullptr;  // [npix][ncomp] fp64
@@ -124,6 +125,16 @@ struct Tables {
   // bf16 x3 planes
   __nv_bfloat16 *t0_bf = nullptr, *t2_bf = nullptr;  // [3][nprob][NP][K]
   size_t plane0 = 0, plane2 = 0;                     // elements per plane
+  // Synthesis direction (Jacobi refinement, sht_iter > 0): the same functions without the
+  // quadrature weight, stored ring-major so that the contraction over l is again a K-major
+  // table:  S0[prob][k][n] = lambda_lm(theta_k);  S2[prob][k][n | NPk + n'] = [-W_lm | -X_l'm],
+  // l = m + p + 2n, l' = m + (1 - p) + 2n' (the X role pairs a problem with the rows of the
+  // opposite l - m parity).  Row pitch Kp, NPk = NP rounded up to the k-tile.
+  int synth = 0;
+  int NPk = 0;
+  double *s0_f64 = nullptr, *s2_f64 = nullptr;
+  __nv_bfloat16 *s0_bf = nullptr, *s2_bf = nullptr;  // [3][nprob][Kp][NPk or 2 NPk]
+  size_t splane0 = 0, splane2 = 0;
 };
 
 }  // namespace dsb
@@ -169,6 +180,10 @@ struct dsb_plan {
   const void **wptr_dev = nullptr;
   int w_precision = -1, w_polarised = -1;
   std::vector<dsb::Tables> tables;
+  // SHT settings of healpy.map2alm as cora.util.hputil calls it (telescope.py:1189,1300,1310):
+  // Jacobi refinement passes and optional ring weights (multiplicative, one per fold ring)
+  int sht_iter = 0;
+  std::vector<double> ring_weights;
   // workspace (grown on demand, capped by dsb_set_workspace_limit)
   void *ws = nullptr;
   size_t ws_bytes = 0;
@@ -198,7 +213,8 @@ size_t workspace_limit();
 
 // tables.cu
 int build_tables(dsb_plan *plan, Tables &t, cudaStream_t stream);
-const Tables *find_tables(const dsb_plan *plan, int lmax, int mmax, int spin2, int precision);
+const Tables *find_tables(const dsb_plan *plan, int lmax, int mmax, int spin2, int precision, int synth = 0);
+void free_tables(Tables &t);
 __host__ __device__ inline int nrows_mp(int lmax, int m, int p) {
   // rows l = m + p + 2n <= lmax
   int span = lmax - m - p;
@@ -249,17 +265,38 @@ struct WorkItem {
   int32_t nrows;    // valid rows in this item (<= 128)
   int32_t spin;     // 0 or 2
   int32_t row0;     // first row (multiple of 16)
+  int32_t klen;     // contraction length per operand role (multiple of 32); 0 = the launch's K
 };
-int launch_legendre_f64(dsb_plan *plan, const Tables &t, const BucketLayout &lay,
-                        const std::vector<WorkItem> &items, const WorkItem *items_dev, const double *F0,
-                        const double *F2, double *C0, double *C2, cudaStream_t stream);
-int launch_legendre_tc_raw(int nprobA, int nprobT, int Kp, int NP, int ncols0, int ncols2, int has2, int nitems,
-                           const WorkItem *items_dev, int max_rows, const float *F0, const float *F2,
-                           const __nv_bfloat16 *T0, const __nv_bfloat16 *T2, float *C0, float *C2,
-                           cudaStream_t stream);
-int launch_legendre_tc(dsb_plan *plan, const Tables &t, const BucketLayout &lay,
-                       const std::vector<WorkItem> &items, const WorkItem *items_dev, const float *F0,
-                       const float *F2, float *C0, float *C2, cudaStream_t stream);
+// One contraction launch:  C[prob][col][row] (+)= sum_k A[prob][k][col] * B[prob][row][k]
+//   analysis : A = ring spectra F (k = fold ring),  B = T tables, rows = l-index n, pitch NP
+//   synthesis: A = transposed coefficients Ct (k = l-index n), B = S tables, rows = fold ring, pitch Kp
+// Spin 2 runs two roles per item: role W reads A[prob] rows [0, klen) against B columns
+// [0, klen); role X reads A[prob ^ 1] (fp32 path: permuted on the fly; fp64 path: stored at row
+// offset kx) against B columns [kx, kx + klen).
+struct ContractDesc {
+  int nprobA = 0, nprobB = 0;  // problems in the A buffer / in the table
+  int K = 0;         // rows of one role of A per problem; default contraction length
+  int kx = 0;        // offset of the X role in the table (and in the fp64 A buffer)
+  int pitch = 0;     // row pitch of C and number of table rows per problem
+  int ncols0 = 0, ncols2 = 0, has2 = 0;
+  int update = 0;    // 0: C = r;  1: C = base + C - r  (Jacobi refinement step)
+};
+int launch_contract_f64(const ContractDesc &d, int nitems, const WorkItem *items_dev, const double *A0,
+                        const double *A2, const double *B0, const double *B2, double *C0, double *C2,
+                        const double *base0, const double *base2, cudaStream_t stream);
+int launch_contract_tc(const ContractDesc &d, int nitems, const WorkItem *items_dev, int max_rows,
+                       const float *A0, const float *A2, const __nv_bfloat16 *B0, const __nv_bfloat16 *B2,
+                       float *C0, float *C2, const float *base0, const float *base2, cudaStream_t stream);
+
+// shtiter.cu -- the pieces of healpy's map2alm(iter > 0) that are not contractions
+// C[prob][col][NP] -> Ct[prob][n][col] (fp64 spin 2: both operand roles, X role at row NPk),
+// rows above a unit's own lmax zeroed
+int launch_transpose_coeffs(const BucketLayout &lay, const UnitDev *units_dev, int NP, int NPk, int precision,
+                            const void *C0, const void *C2, void *Ct0, void *Ct2, cudaStream_t stream);
+// G[prob][col][Kp] (synthesised ring functions) -> ring spectra of the pixelised map in the
+// operand layout of the analysis (F0 / F2 of ringfft.cu)
+int launch_alias_fold(dsb_plan *plan, const BucketLayout &lay, const UnitDev *units_dev, int precision,
+                      const void *G0, const void *G2, void *F0, void *F2, cudaStream_t stream);
 
 // pack.cu
 struct PackParams {

@@ -37,6 +37,7 @@
 // over work items of <= 128 rows; TMEM: 2 x 128 columns of leading-product chunks (ping-pong
 // per stage) + 2 x 128 columns of correction accumulators (ping-pong per item).
 #include <cuda.h>
+#include <cstdlib>
 
 #include "dsb_common.cuh"
 
@@ -55,10 +56,13 @@ constexpr int TC_A_RAW = TC_KC * TC_M * 4;    // bytes of the fp32 staging tile 
 struct TcParams {
   const WorkItem *items;
   int nitems;
-  int K0, K2;        // contraction length of the spin-0 / spin-2 blocks
+  int K0;            // default contraction length per operand role (items may carry their own)
+  int kx;            // table column where the X role of the spin-2 block starts
   int ncols0, ncols2;
-  int NP;            // row pitch of C and of the tables
+  int NP;            // row pitch of C
   float *C0, *C2;
+  const float *base0, *base2;  // update mode: C = base + C - result
+  int update;
   int NB;            // table box rows (TMA box), multiple of 16, <= 256
   int nstages;
 };
@@ -218,8 +222,8 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         const bool s2 = wi.spin == 2;
         const CUtensorMap *mA = s2 ? &mapA2 : &mapA0;
         const CUtensorMap *mB = s2 ? &mapB2 : &mapB0;
-        const int nkA = P.K0 / TC_KC;            // stages per role
-        const int nk = s2 ? 2 * nkA : nkA;       // spin 2: W role then X role
+        const int nkA = (wi.klen ? wi.klen : P.K0) / TC_KC;  // stages per role
+        const int nk = s2 ? 2 * nkA : nkA;                   // spin 2: W role then X role
         const uint32_t tx = TC_A_RAW + 3 * b_plane;
         for (int kc = 0; kc < nk; ++kc) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -233,7 +237,8 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
                       xrole ? (wi.prob ^ 1) : wi.prob);
 #pragma unroll
           for (int pl = 0; pl < 3; ++pl)
-            tma_load_4d(mB, &full[stage], sB + pl * b_plane, kc * TC_KC, wi.row0, wi.prob, pl);
+            tma_load_4d(mB, &full[stage], sB + pl * b_plane, xrole ? P.kx + (kc - nkA) * TC_KC : kc * TC_KC, wi.row0,
+                        wi.prob, pl);
           if (++stage == P.nstages) {
             stage = 0;
             phase ^= 1;
@@ -252,7 +257,7 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       for (int it = blockIdx.x; it < P.nitems; it += gridDim.x, ++local) {
         const WorkItem wi = P.items[it];
         const bool s2 = wi.spin == 2;
-        const int nk = (s2 ? 2 : 1) * (P.K0 / TC_KC);
+        const int nk = (s2 ? 2 : 1) * ((wi.klen ? wi.klen : P.K0) / TC_KC);
         const int cb = local & 1;
         const uint32_t cb_phase = (local >> 1) & 1;
         const uint32_t N = (uint32_t)((wi.nrows + 15) & ~15);
@@ -312,7 +317,7 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
     for (int it = blockIdx.x; it < P.nitems; it += gridDim.x, ++local) {
       const WorkItem wi = P.items[it];
       const bool s2 = wi.spin == 2;
-      const int nk = (s2 ? 2 : 1) * (P.K0 / TC_KC);
+      const int nk = (s2 ? 2 : 1) * ((wi.klen ? wi.klen : P.K0) / TC_KC);
       const int cb = local & 1;
       const uint32_t cb_phase = (local >> 1) & 1;
       const int N = (wi.nrows + 15) & ~15;
@@ -350,9 +355,10 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       // corrections, then store this thread's operand column contiguously in l
       mbar_wait(&cfull[cb], cb_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float *C = (s2 ? P.C2 : P.C0) +
-                 ((size_t)wi.prob * ncols + (size_t)wi.coltile * TC_M + quarter * 32 + lane) * P.NP + wi.row0 +
-                 half * 64;
+      const size_t cidx =
+          ((size_t)wi.prob * ncols + (size_t)wi.coltile * TC_M + quarter * 32 + lane) * P.NP + wi.row0 + half * 64;
+      float *C = (s2 ? P.C2 : P.C0) + cidx;
+      const float *base = P.update ? (s2 ? P.base2 : P.base0) + cidx : nullptr;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         if (half * 64 + g * 16 < N) {
@@ -361,11 +367,17 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           float4 *dst = reinterpret_cast<float4 *>(C + g * 16);
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            dst[q] = make_float4(sums[g * 16 + 4 * q] + __uint_as_float(v[4 * q]),
-                                 sums[g * 16 + 4 * q + 1] + __uint_as_float(v[4 * q + 1]),
-                                 sums[g * 16 + 4 * q + 2] + __uint_as_float(v[4 * q + 2]),
-                                 sums[g * 16 + 4 * q + 3] + __uint_as_float(v[4 * q + 3]));
+          for (int q = 0; q < 4; ++q) {
+            float4 r = make_float4(sums[g * 16 + 4 * q] + __uint_as_float(v[4 * q]),
+                                   sums[g * 16 + 4 * q + 1] + __uint_as_float(v[4 * q + 1]),
+                                   sums[g * 16 + 4 * q + 2] + __uint_as_float(v[4 * q + 2]),
+                                   sums[g * 16 + 4 * q + 3] + __uint_as_float(v[4 * q + 3]));
+            if (P.update) {  // Jacobi refinement: a <- a0 + a - (A S a)
+              const float4 b = reinterpret_cast<const float4 *>(base + g * 16)[q], c = dst[q];
+              r = make_float4((b.x - r.x) + c.x, (b.y - r.y) + c.y, (b.z - r.z) + c.z, (b.w - r.w) + c.w);
+            }
+            dst[q] = r;
+          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -380,7 +392,7 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
     for (int it = blockIdx.x; it < P.nitems; it += gridDim.x) {
       const WorkItem wi = P.items[it];
       const bool s2 = wi.spin == 2;
-      const int nkA = P.K0 / TC_KC;
+      const int nkA = (wi.klen ? wi.klen : P.K0) / TC_KC;
       const int nk = s2 ? 2 * nkA : nkA;
       for (int kc = 0; kc < nk; ++kc) {
         const bool xrole = kc >= nkA;
@@ -485,26 +497,29 @@ static int encode4(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1,
   return DSB_OK;
 }
 
-int launch_legendre_tc_raw(int nprobA, int nprobT, int Kp, int NP, int ncols0, int ncols2, int has2, int nitems,
-                           const WorkItem *items_dev, int max_rows, const float *F0, const float *F2,
-                           const __nv_bfloat16 *T0, const __nv_bfloat16 *T2, float *C0, float *C2,
-                           cudaStream_t stream) {
+int launch_contract_tc(const ContractDesc &d, int nitems, const WorkItem *items_dev, int max_rows,
+                       const float *A0, const float *A2, const __nv_bfloat16 *B0, const __nv_bfloat16 *B2,
+                       float *C0, float *C2, const float *base0, const float *base2, cudaStream_t stream) {
   if (nitems == 0) return DSB_OK;
-  DSB_CHECK(Kp % TC_KC == 0, DSB_ERR_INVALID, "contraction length must be a multiple of %d", TC_KC);
-  DSB_CHECK(ncols0 % TC_M == 0 && ncols2 % TC_M == 0, DSB_ERR_INVALID, "column counts must be multiples of 128");
-  DSB_CHECK(NP % 16 == 0, DSB_ERR_INVALID, "row pitch must be a multiple of 16");
+  DSB_CHECK(d.K % TC_KC == 0 && d.kx % TC_KC == 0, DSB_ERR_INVALID, "contraction length must be a multiple of %d",
+            TC_KC);
+  DSB_CHECK(d.ncols0 % TC_M == 0 && d.ncols2 % TC_M == 0, DSB_ERR_INVALID,
+            "column counts must be multiples of 128");
+  DSB_CHECK(d.pitch % 16 == 0, DSB_ERR_INVALID, "row pitch must be a multiple of 16");
   DSB_CHECK(max_rows <= TC_MAXROWS, DSB_ERR_INVALID, "work items hold at most %d rows", TC_MAXROWS);
+  DSB_CHECK(!d.update || (base0 && (!d.has2 || base2)), DSB_ERR_INVALID, "update mode needs the base coefficients");
   int NB = (int)round_up(std::min(std::max(max_rows, 16), TC_MAXROWS), 16);
 
   CUtensorMap mA0, mA2, mB0, mB2;
-  const uint64_t K0 = Kp, K2 = 2 * (uint64_t)Kp;
-  DSB_TRY(encode3_f32(&mA0, F0, ncols0, K0, nprobA, TC_M, TC_KC));
-  DSB_TRY(encode4(&mB0, T0, K0, NP, nprobT, 3, K0, (uint64_t)NP * K0, (uint64_t)nprobT * NP * K0, TC_KC, NB,
+  const uint64_t K0 = d.K, W0 = d.K, W2 = (uint64_t)d.kx + d.K;  // table widths (spin 0 / spin 2)
+  const uint64_t rows = d.pitch;
+  DSB_TRY(encode3_f32(&mA0, A0, d.ncols0, K0, d.nprobA, TC_M, TC_KC));
+  DSB_TRY(encode4(&mB0, B0, W0, rows, d.nprobB, 3, W0, rows * W0, (uint64_t)d.nprobB * rows * W0, TC_KC, NB,
                   CU_TENSOR_MAP_SWIZZLE_64B));
-  if (has2) {
-    DSB_CHECK(nprobA % 2 == 0, DSB_ERR_INVALID, "spin-2 problems come in fold-parity pairs");
-    DSB_TRY(encode3_f32(&mA2, F2, ncols2, K0, nprobA, TC_M, TC_KC));
-    DSB_TRY(encode4(&mB2, T2, K2, NP, nprobT, 3, K2, (uint64_t)NP * K2, (uint64_t)nprobT * NP * K2, TC_KC, NB,
+  if (d.has2) {
+    DSB_CHECK(d.nprobA % 2 == 0, DSB_ERR_INVALID, "spin-2 problems come in fold-parity pairs");
+    DSB_TRY(encode3_f32(&mA2, A2, d.ncols2, K0, d.nprobA, TC_M, TC_KC));
+    DSB_TRY(encode4(&mB2, B2, W2, rows, d.nprobB, 3, W2, rows * W2, (uint64_t)d.nprobB * rows * W2, TC_KC, NB,
                     CU_TENSOR_MAP_SWIZZLE_64B));
   } else {
     mA2 = mA0;
@@ -514,19 +529,25 @@ int launch_legendre_tc_raw(int nprobA, int nprobT, int Kp, int NP, int ncols0, i
   TcParams P;
   P.items = items_dev;
   P.nitems = nitems;
-  P.K0 = (int)K0;
-  P.K2 = (int)K2;
-  P.ncols0 = ncols0;
-  P.ncols2 = ncols2;
-  P.NP = NP;
+  P.K0 = d.K;
+  P.kx = d.kx;
+  P.ncols0 = d.ncols0;
+  P.ncols2 = d.ncols2;
+  P.NP = d.pitch;
   P.C0 = C0;
   P.C2 = C2;
+  P.base0 = base0;
+  P.base2 = base2;
+  P.update = d.update;
   P.NB = NB;
   const size_t stage_bytes = 3 * TC_A_PLANE + TC_A_RAW + (((size_t)3 * NB * 64 + 1023) & ~(size_t)1023);
   int nstages = (int)std::min<size_t>(8, (220 * 1024) / stage_bytes);
   DSB_CHECK(nstages >= 2, DSB_ERR_UNSUPPORTED, "pipeline does not fit shared memory");
   P.nstages = nstages;
-  const size_t smem = nstages * stage_bytes + (3 * nstages + 8) * 8 + 16 + 1024;
+  size_t smem = nstages * stage_bytes + (3 * nstages + 8) * 8 + 16 + 1024;
+  // diagnostic (two launches in flight): give every launch the same carve-out
+  static const bool fixed_smem = getenv("DSB_TC_FIXED_SMEM") != nullptr;
+  if (fixed_smem) smem = 226 * 1024;
   DSB_CUDA(raise_dynamic_smem((const void *)legendre_tc_kernel, smem));
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);
@@ -535,18 +556,6 @@ int launch_legendre_tc_raw(int nprobA, int nprobT, int Kp, int NP, int ncols0, i
   legendre_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mA0, mA2, mB0, mB2, P);
   DSB_LAUNCH_CHECK();
   return DSB_OK;
-}
-
-int launch_legendre_tc(dsb_plan *plan, const Tables &t, const BucketLayout &lay,
-                       const std::vector<WorkItem> &items, const WorkItem *items_dev, const float *F0,
-                       const float *F2, float *C0, float *C2, cudaStream_t stream) {
-  int max_rows = 16;
-  for (const auto &w : items) max_rows = std::max(max_rows, w.nrows);
-  // the tables may cover more m than this bucket needs: separate problem counts
-  const int nprobA = 2 * (lay.mcap + 1);
-  const int nprobT = 2 * (t.mmax + 1);
-  return launch_legendre_tc_raw(nprobA, nprobT, t.Kp, t.NP, lay.ncols0, lay.ncols2, lay.has2, (int)items.size(),
-                                items_dev, max_rows, F0, F2, t.t0_bf, t.t2_bf, C0, C2, stream);
 }
 
 }  // namespace dsb
@@ -563,6 +572,10 @@ extern "C" int dsb_debug_gemm_tc(int nprob, int K, int NP, int ncols, int nitems
   __nv_bfloat16 *T = nullptr;
   float *F = nullptr, *C = nullptr;
   WorkItem *items = nullptr;
+  std::vector<WorkItem> items_h(nitems);
+  for (int i = 0; i < nitems; ++i)
+    items_h[i] = {items_host[5 * i], items_host[5 * i + 1], items_host[5 * i + 2], items_host[5 * i + 3],
+                  items_host[5 * i + 4], 0};
   DSB_CUDA(cudaMalloc(&F, nF * 4));
   DSB_CUDA(cudaMalloc(&T, nT * 2));
   DSB_CUDA(cudaMalloc(&C, nC * 4));
@@ -570,11 +583,15 @@ extern "C" int dsb_debug_gemm_tc(int nprob, int K, int NP, int ncols, int nitems
   DSB_CUDA(cudaMemcpy(F, F_host, nF * 4, cudaMemcpyHostToDevice));
   DSB_CUDA(cudaMemcpy(T, T_host, nT * 2, cudaMemcpyHostToDevice));
   DSB_CUDA(cudaMemset(C, 0, nC * 4));
-  DSB_CUDA(cudaMemcpy(items, items_host, nitems * sizeof(WorkItem), cudaMemcpyHostToDevice));
+  DSB_CUDA(cudaMemcpy(items, items_h.data(), nitems * sizeof(WorkItem), cudaMemcpyHostToDevice));
   int max_rows = 16;
   for (int i = 0; i < nitems; ++i) max_rows = std::max(max_rows, items_host[5 * i + 2]);
-  int rc = launch_legendre_tc_raw(nprob, nprob, K, NP, ncols, ncols, 0, nitems, items, max_rows, F, nullptr, T,
-                                  nullptr, C, nullptr, 0);
+  ContractDesc d;
+  d.nprobA = d.nprobB = nprob;
+  d.K = d.kx = K;
+  d.pitch = NP;
+  d.ncols0 = d.ncols2 = ncols;
+  int rc = launch_contract_tc(d, nitems, items, max_rows, F, nullptr, T, nullptr, C, nullptr, nullptr, nullptr, 0);
   if (rc == DSB_OK) {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {

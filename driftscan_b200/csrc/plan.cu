@@ -280,14 +280,6 @@ extern "C" int dsb_plan_create(int nside, const uint8_t *horizon_host, dsb_plan 
   return DSB_OK;
 }
 
-static void free_tables(Tables &t) {
-  cudaFree(t.t0_f64);
-  cudaFree(t.t2_f64);
-  cudaFree(t.t0_bf);
-  cudaFree(t.t2_bf);
-  t = Tables();
-}
-
 namespace dsb {
 cudaError_t raise_dynamic_smem(const void *kernel, size_t bytes) {
   static std::map<const void *, size_t> current;
@@ -300,6 +292,36 @@ cudaError_t raise_dynamic_smem(const void *kernel, size_t bytes) {
   return e;
 }
 }  // namespace dsb
+
+// SHT settings: what cora.util.hputil passes to healpy.map2alm (iter, use_weights) on behalf of
+// TransitTelescope._transfer_single (drift/core/telescope.py:1189-1191, 1300-1302, 1310-1314).
+extern "C" int dsb_plan_set_sht(dsb_plan *plan, int sht_iter, const double *ring_weights_host) {
+  DSB_CHECK(plan != nullptr, DSB_ERR_INVALID, "dsb_plan_set_sht: plan is NULL");
+  DSB_CHECK(sht_iter >= 0 && sht_iter <= 16, DSB_ERR_INVALID, "dsb_plan_set_sht: sht_iter %d outside [0, 16]",
+            sht_iter);
+  std::vector<double> w;
+  if (ring_weights_host) {
+    w.assign(ring_weights_host, ring_weights_host + plan->nfold);
+    for (double x : w)
+      DSB_CHECK(std::isfinite(x) && x > 0.0, DSB_ERR_INVALID, "dsb_plan_set_sht: ring weights must be positive");
+  }
+  const bool weights_changed = w != plan->ring_weights;
+  if (weights_changed || (sht_iter > 0) != (plan->sht_iter > 0)) {
+    // the tables carry the quadrature weights (analysis) and exist in the synthesis direction
+    // only when refinement is on: rebuild on next use
+    DSB_CUDA(cudaDeviceSynchronize());
+    for (auto &t : plan->tables) free_tables(t);
+    plan->tables.clear();
+  }
+  if (weights_changed) {
+    const double quad = 4.0 * M_PI / plan->npix;
+    for (int k = 0; k < plan->nfold; ++k) plan->rings_h[k].quad = quad * (w.empty() ? 1.0 : w[k]);
+    DSB_CUDA(cudaMemcpy(plan->rings, plan->rings_h.data(), sizeof(RingDesc) * plan->nfold, cudaMemcpyHostToDevice));
+    plan->ring_weights = w;
+  }
+  plan->sht_iter = sht_iter;
+  return DSB_OK;
+}
 
 extern "C" int dsb_plan_destroy(dsb_plan *plan) {
   if (!plan) return DSB_OK;

@@ -1,0 +1,255 @@
+// Jacobi refinement of the HEALPix analysis -- healpy.map2alm(iter > 0), which the reference
+// reaches through cora.util.hputil.sphtrans_complex[_pol] (drift/core/telescope.py:1189-1191,
+// 1300-1302, 1310-1314):
+//
+//     a(0) = A M,      a(j+1) = a(j) + A (M - S a(j)) = a(0) + a(j) - (A S) a(j)
+//
+// with A = analysis, S = synthesis.  The pixel maps never exist on the device and are not
+// needed: A S acts on ring spectra.  Synthesis is the Legendre contraction read the other way
+// (legendre_*.cu with the ring-major tables of tables.cu); on a ring of n pixels the map
+// sampled from the synthesised ring function aliases the coefficients m' = m (mod n), and the
+// ring DFT of that map -- the operand of the next analysis -- is
+//
+//     F+_m = n sum_q s^q h_{m - q n},        F-_m = n sum_q s^q conj(h_{q n - m})        (per ring)
+//     h_m' = G+_m' (m' >= 0),  conj(G-_|m'|) (m' < 0);   s = -1 on rings with phi0 = pi/n, else +1
+//
+// (tools/proto_sht_iter_fold.py::transfer_fold, checked against the map-based iteration; the
+// phases e^{i (m - m') phi0} of the general formula are these signs because m - m' = q n and
+// phi0 is 0 or pi/n).  G+- are the syntheses of the two product slots.  The fold acts within a
+// fold parity: lambda_lm(pi - theta) = (-1)^(l+m) lambda_lm(theta) gives the even (odd) l - m
+// rows the parity of the even (odd) north/south combination for every m.
+//
+// This file holds the two data-movement kernels of an iteration; the contractions are
+// launch_contract_{tc,f64}, the update a(0) + a - (A S) a is fused into their epilogue.
+#include <algorithm>
+
+#include "dsb_common.cuh"
+
+namespace dsb {
+
+// ---- C[prob][col][NP] -> Ct[prob][n][col], rows above the unit's lmax zeroed ------------------
+// ROLE2: fp64 spin-2 block, which stores the operand in both roles ([prob][2 NPk][ncols]):
+//   rows [0, NPk)      W role:  (E | B) columns of the same problem
+//   rows [NPk, 2 NPk)  X role:  (-i B | +i E) of the problem with the opposite l - m parity
+// (the fp32 path stores the block once, the tensor-core kernel permutes while splitting).
+template <typename T, bool ROLE2>
+__global__ void __launch_bounds__(256)
+transpose_coeffs_kernel(const T *__restrict__ C, T *__restrict__ Ct, const UnitDev *__restrict__ units, int nunits,
+                        int cpu, int ncols, int NP, int NPk) {
+  __shared__ T tile[32][33];
+  const int prob = blockIdx.z;
+  const int m = prob >> 1, p = prob & 1;
+  const int col0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int nrole = ROLE2 ? 2 : 1;
+  for (int role = 0; role < nrole; ++role) {
+    const int sprob = role ? (prob ^ 1) : prob;  // source problem
+    const int sp = role ? 1 - p : p;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = col0 + ty + 8 * i, n = n0 + tx;
+      const int u = c / cpu;
+      T v = T(0);
+      if (u < nunits && n < NP && m + sp + 2 * n <= units[u].lmax) v = C[((size_t)sprob * ncols + c) * NP + n];
+      tile[ty + 8 * i][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + ty + 8 * i;
+      int cs = tx;
+      T sg = T(1);
+      if (role) {  // columns (E: a0..a3 | B: b0..b3) -> (b1, -b0, b3, -b2 | -a1, a0, -a3, a2)
+        const int j = tx & 7;
+        cs = (tx & ~7) | (j ^ 5);  // 0<->5, 1<->4, 2<->7, 3<->6
+        sg = (j == 1 || j == 3 || j == 4 || j == 6) ? T(-1) : T(1);
+      }
+      Ct[((size_t)prob * (nrole * NPk) + role * NPk + n) * ncols + col0 + tx] = sg * tile[cs][ty + 8 * i];
+    }
+  }
+}
+
+int launch_transpose_coeffs(const BucketLayout &lay, const UnitDev *units_dev, int NP, int NPk, int precision,
+                            const void *C0, const void *C2, void *Ct0, void *Ct2, cudaStream_t stream) {
+  const int nprob = 2 * (lay.mcap + 1);
+  const bool f64 = precision == DSB_PREC_FP64;
+  dim3 g0(lay.ncols0 / 32, NPk / 32, nprob);
+  if (f64)
+    transpose_coeffs_kernel<double, false><<<g0, 256, 0, stream>>>((const double *)C0, (double *)Ct0, units_dev,
+                                                                   lay.nunits, lay.cpu0, lay.ncols0, NP, NPk);
+  else
+    transpose_coeffs_kernel<float, false><<<g0, 256, 0, stream>>>((const float *)C0, (float *)Ct0, units_dev,
+                                                                  lay.nunits, lay.cpu0, lay.ncols0, NP, NPk);
+  DSB_LAUNCH_CHECK();
+  if (lay.has2) {
+    dim3 g2(lay.ncols2 / 32, NPk / 32, nprob);
+    if (f64)
+      transpose_coeffs_kernel<double, true><<<g2, 256, 0, stream>>>((const double *)C2, (double *)Ct2, units_dev,
+                                                                    lay.nunits, 8, lay.ncols2, NP, NPk);
+    else
+      transpose_coeffs_kernel<float, false><<<g2, 256, 0, stream>>>((const float *)C2, (float *)Ct2, units_dev,
+                                                                    lay.nunits, 8, lay.ncols2, NP, NPk);
+    DSB_LAUNCH_CHECK();
+  }
+  return DSB_OK;
+}
+
+// ---- aliasing fold: G[prob][col][Kp] -> F[prob][k][col] ------------------------------------------
+struct FoldParams {
+  const RingDesc *rings;
+  const UnitDev *units;
+  int nunits, nfold, Kp, mcap;
+  int nsp0, has2, cpu0, ncols0, ncols2;
+  const void *G0, *G2;
+  void *F0, *F2;
+};
+
+// One slot pair (+re, +im, -re, -im) of one Stokes map: columns col .. col+3 of G
+template <typename T>
+__device__ __forceinline__ void fold_map(const T *__restrict__ G, size_t ncols, int Kp, int k, size_t col, int m,
+                                         int mmax, int n, int shifted, int p, T fn, T (&out)[4]) {
+  // q range: |m - q n| <= mmax
+  const int qlo = -((mmax - m) / n), qhi = (m + mmax) / n;
+  T fpr = T(0), fpi = T(0), fmr = T(0), fmi = T(0);
+  for (int q = qlo; q <= qhi; ++q) {
+    const T sg = (shifted && (q & 1)) ? T(-1) : T(1);
+    const int m1 = m - q * n;  // F+ : h_{m1}
+    {
+      const int am = m1 < 0 ? -m1 : m1;
+      const T *g = G + ((size_t)(2 * am + p) * ncols + col + (m1 < 0 ? 2 : 0)) * Kp + k;
+      const T re = g[0], im = g[Kp];
+      fpr += sg * re;
+      fpi += m1 < 0 ? -sg * im : sg * im;
+    }
+    const int m2 = q * n - m;  // F- : conj(h_{m2})
+    {
+      const int am = m2 < 0 ? -m2 : m2;
+      const T *g = G + ((size_t)(2 * am + p) * ncols + col + (m2 < 0 ? 2 : 0)) * Kp + k;
+      const T re = g[0], im = g[Kp];
+      fmr += sg * re;
+      fmi += m2 < 0 ? sg * im : -sg * im;
+    }
+  }
+  out[0] = fn * fpr, out[1] = fn * fpi, out[2] = fn * fmr, out[3] = fn * fmi;
+}
+
+template <typename T>
+__device__ __forceinline__ void alias_fold_unit(const FoldParams &P, const RingDesc &rd, int k, int m, int u);
+
+template <typename T>
+__global__ void __launch_bounds__(256) alias_fold_kernel(const FoldParams P) {
+  const int k = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int m = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (k >= P.nfold || m > P.mcap) return;
+  const RingDesc rd = P.rings[k];
+  for (int u = blockIdx.z; u < P.nunits; u += gridDim.z) alias_fold_unit<T>(P, rd, k, m, u);
+}
+
+template <typename T>
+__device__ __forceinline__ void alias_fold_unit(const FoldParams &P, const RingDesc &rd, int k, int m, int u) {
+  const UnitDev ud = P.units[u];
+  if (m > ud.mmax) return;
+  const int n = rd.nphi, shifted = rd.shifted;
+  const bool equator = rd.startS < 0;
+  const int Kp = P.Kp;
+  // even = north + south = 2 G(even l - m), odd = north - south = 2 G(odd l - m); the equator is
+  // its own mirror and only feeds the even fold
+  const T fn = (T)(equator ? n : 2 * n);
+
+  // spin 0: I (and V)
+  {
+    const T *G = reinterpret_cast<const T *>(P.G0);
+    T *F = reinterpret_cast<T *>(P.F0);
+    for (int q = 0; q < P.nsp0; ++q) {
+      const size_t col = (size_t)u * P.cpu0 + 4 * q;
+      T ev[4], od[4];
+      fold_map<T>(G, P.ncols0, Kp, k, col, m, ud.mmax, n, shifted, 0, fn, ev);
+      fold_map<T>(G, P.ncols0, Kp, k, col, m, ud.mmax, n, shifted, 1, fn, od);
+      if (equator) od[0] = od[1] = od[2] = od[3] = T(0);
+      T *d0 = F + ((size_t)(2 * m + 0) * Kp + k) * P.ncols0 + col;
+      T *d1 = F + ((size_t)(2 * m + 1) * Kp + k) * P.ncols0 + col;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        d0[i] = ev[i];
+        d1[i] = od[i];
+      }
+    }
+  }
+  if (!P.has2) return;
+  // spin 2: Q, U
+  {
+    const T *G = reinterpret_cast<const T *>(P.G2);
+    T *F = reinterpret_cast<T *>(P.F2);
+    T ev[2][4], od[2][4];
+    for (int q = 0; q < 2; ++q) {
+      const size_t col = (size_t)u * 8 + 4 * q;
+      fold_map<T>(G, P.ncols2, Kp, k, col, m, ud.mmax, n, shifted, 0, fn, ev[q]);
+      fold_map<T>(G, P.ncols2, Kp, k, col, m, ud.mmax, n, shifted, 1, fn, od[q]);
+      if (equator) od[q][0] = od[q][1] = od[q][2] = od[q][3] = T(0);
+    }
+    const size_t cu = (size_t)u * 8;
+    if (sizeof(T) == 4) {
+      // fp32: stored once, [prob][Kp][ncols2]
+      T *d0 = F + ((size_t)(2 * m + 0) * Kp + k) * P.ncols2 + cu;
+      T *d1 = F + ((size_t)(2 * m + 1) * Kp + k) * P.ncols2 + cu;
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          d0[4 * q + i] = ev[q][i];
+          d1[4 * q + i] = od[q][i];
+        }
+    } else {
+      // fp64: both operand roles, [prob][2 Kp][ncols2] (same emission as ringfft.cu gather_emit)
+      const size_t K2 = 2 * (size_t)Kp;
+      T *w0 = F + ((size_t)(2 * m + 0) * K2 + k) * P.ncols2 + cu;
+      T *w1 = F + ((size_t)(2 * m + 1) * K2 + k) * P.ncols2 + cu;
+      T *x0 = F + ((size_t)(2 * m + 0) * K2 + Kp + k) * P.ncols2 + cu;
+      T *x1 = F + ((size_t)(2 * m + 1) * K2 + Kp + k) * P.ncols2 + cu;
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          w0[4 * q + i] = ev[q][i];
+          w1[4 * q + i] = od[q][i];
+        }
+      const T xa[8] = {od[1][1], -od[1][0], od[1][3], -od[1][2], -od[0][1], od[0][0], -od[0][3], od[0][2]};
+      const T xb[8] = {ev[1][1], -ev[1][0], ev[1][3], -ev[1][2], -ev[0][1], ev[0][0], -ev[0][3], ev[0][2]};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        x0[i] = xa[i];
+        x1[i] = xb[i];
+      }
+    }
+  }
+}
+
+int launch_alias_fold(dsb_plan *plan, const BucketLayout &lay, const UnitDev *units_dev, int precision,
+                      const void *G0, const void *G2, void *F0, void *F2, cudaStream_t stream) {
+  FoldParams P;
+  P.rings = plan->rings;
+  P.units = units_dev;
+  P.nunits = lay.nunits;
+  P.nfold = plan->nfold;
+  P.Kp = lay.Kp;
+  P.mcap = lay.mcap;
+  P.nsp0 = lay.nsp0;
+  P.has2 = lay.has2;
+  P.cpu0 = lay.cpu0;
+  P.ncols0 = lay.ncols0;
+  P.ncols2 = lay.ncols2;
+  P.G0 = G0;
+  P.G2 = G2;
+  P.F0 = F0;
+  P.F2 = F2;
+  dim3 grid((plan->nfold + 31) / 32, (lay.mcap + 8) / 8, std::min(lay.nunits, 65535));
+  if (precision == DSB_PREC_FP64)
+    alias_fold_kernel<double><<<grid, 256, 0, stream>>>(P);
+  else
+    alias_fold_kernel<float><<<grid, 256, 0, stream>>>(P);
+  DSB_LAUNCH_CHECK();
+  return DSB_OK;
+}
+
+}  // namespace dsb

@@ -103,13 +103,18 @@ __device__ __forceinline__ void split3(double v, __nv_bfloat16 &h, __nv_bfloat16
   l = __float2bfloat16_rn((float)r);
 }
 
-template <bool SPIN2, bool BF16>
+// SYN = false: analysis tables (quadrature weight folded in), [prob][n][k | Kp + k]
+// SYN = true : synthesis tables (no weight), [prob][k][n | NPk + n'], pitch Kp rows per problem;
+//              NP is then NPk and the X value of degree l goes to the problem of the opposite
+//              l - m parity (see Tables in dsb_common.cuh)
+template <bool SPIN2, bool BF16, bool SYN>
 __global__ void tables_kernel(const RingDesc *__restrict__ rings, int nfold, int Kp, int lmax, int NP,
                               double *__restrict__ tf64, __nv_bfloat16 *__restrict__ tbf, size_t plane) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = blockIdx.y;
   if (k >= nfold) return;
-  const RingDesc rd = rings[k];
+  RingDesc rd = rings[k];
+  if (SYN) rd.quad = 1.0;
   const int K = SPIN2 ? 2 * Kp : Kp;
   const double x = rd.cth;
   const double norm0 = 0.28209479177387814;  // 1/sqrt(4 pi)
@@ -117,7 +122,12 @@ __global__ void tables_kernel(const RingDesc *__restrict__ rings, int nfold, int
   auto store = [&](int l, double v, int kk) {
     const int p = (l - m) & 1;
     const int n = (l - m) >> 1;
-    const size_t idx = ((size_t)(2 * m + p) * NP + n) * K + kk;
+    size_t idx = ((size_t)(2 * m + p) * NP + n) * K + kk;
+    if (SYN) {
+      const bool xrole = kk >= Kp;
+      const int W = SPIN2 ? 2 * NP : NP;
+      idx = ((size_t)(2 * m + (xrole ? 1 - p : p)) * Kp + (xrole ? kk - Kp : kk)) * W + (xrole ? NP : 0) + n;
+    }
     if (BF16) {
       __nv_bfloat16 h, mm, lo;
       split3(v, h, mm, lo);
@@ -161,45 +171,59 @@ __global__ void tables_kernel(const RingDesc *__restrict__ rings, int nfold, int
   }
 }
 
-const Tables *find_tables(const dsb_plan *plan, int lmax, int mmax, int spin2, int precision) {
+const Tables *find_tables(const dsb_plan *plan, int lmax, int mmax, int spin2, int precision, int synth) {
   for (const auto &t : plan->tables)
-    if (t.lmax >= lmax && t.mmax >= mmax && t.spin2 >= spin2 && t.precision == precision) return &t;
+    if (t.lmax >= lmax && t.mmax >= mmax && t.spin2 >= spin2 && t.precision == precision && t.synth >= synth)
+      return &t;
   return nullptr;
+}
+
+void free_tables(Tables &t) {
+  cudaFree(t.t0_f64);
+  cudaFree(t.t2_f64);
+  cudaFree(t.t0_bf);
+  cudaFree(t.t2_bf);
+  cudaFree(t.s0_f64);
+  cudaFree(t.s2_f64);
+  cudaFree(t.s0_bf);
+  cudaFree(t.s2_bf);
+  t = Tables();
+}
+
+template <bool SPIN2, bool SYN>
+static int build_one(dsb_plan *plan, const Tables &t, int precision, size_t plane, double **f64,
+                     __nv_bfloat16 **bf, cudaStream_t stream) {
+  dim3 block(128), grid((plan->nfold + 127) / 128, t.mmax + 1);
+  const int np = SYN ? t.NPk : t.NP;
+  if (precision == DSB_PREC_FP64) {
+    DSB_CUDA(cudaMalloc(f64, plane * sizeof(double)));
+    DSB_CUDA(cudaMemsetAsync(*f64, 0, plane * sizeof(double), stream));
+    tables_kernel<SPIN2, false, SYN><<<grid, block, 0, stream>>>(plan->rings, plan->nfold, t.Kp, t.lmax, np, *f64,
+                                                                 nullptr, 0);
+  } else {
+    DSB_CUDA(cudaMalloc(bf, 3 * plane * sizeof(__nv_bfloat16)));
+    DSB_CUDA(cudaMemsetAsync(*bf, 0, 3 * plane * sizeof(__nv_bfloat16), stream));
+    tables_kernel<SPIN2, true, SYN><<<grid, block, 0, stream>>>(plan->rings, plan->nfold, t.Kp, t.lmax, np,
+                                                                nullptr, *bf, plane);
+  }
+  DSB_LAUNCH_CHECK();
+  return DSB_OK;
 }
 
 int build_tables(dsb_plan *plan, Tables &t, cudaStream_t stream) {
   const int nprob = 2 * (t.mmax + 1);
   t.Kp = plan->Kp;
   t.NP = (int)round_up(nrows_mp(t.lmax, 0, 0), 16);
+  t.NPk = (int)round_up(t.NP, 32);
   t.plane0 = (size_t)nprob * t.NP * t.Kp;
   t.plane2 = (size_t)nprob * t.NP * 2 * t.Kp;
-  dim3 block(128), grid((plan->nfold + 127) / 128, t.mmax + 1);
-  if (t.precision == DSB_PREC_FP64) {
-    DSB_CUDA(cudaMalloc(&t.t0_f64, t.plane0 * sizeof(double)));
-    DSB_CUDA(cudaMemsetAsync(t.t0_f64, 0, t.plane0 * sizeof(double), stream));
-    tables_kernel<false, false><<<grid, block, 0, stream>>>(plan->rings, plan->nfold, t.Kp, t.lmax, t.NP,
-                                                            t.t0_f64, nullptr, 0);
-    DSB_LAUNCH_CHECK();
-    if (t.spin2) {
-      DSB_CUDA(cudaMalloc(&t.t2_f64, t.plane2 * sizeof(double)));
-      DSB_CUDA(cudaMemsetAsync(t.t2_f64, 0, t.plane2 * sizeof(double), stream));
-      tables_kernel<true, false><<<grid, block, 0, stream>>>(plan->rings, plan->nfold, t.Kp, t.lmax, t.NP,
-                                                             t.t2_f64, nullptr, 0);
-      DSB_LAUNCH_CHECK();
-    }
-  } else {
-    DSB_CUDA(cudaMalloc(&t.t0_bf, 3 * t.plane0 * sizeof(__nv_bfloat16)));
-    DSB_CUDA(cudaMemsetAsync(t.t0_bf, 0, 3 * t.plane0 * sizeof(__nv_bfloat16), stream));
-    tables_kernel<false, true><<<grid, block, 0, stream>>>(plan->rings, plan->nfold, t.Kp, t.lmax, t.NP,
-                                                           nullptr, t.t0_bf, t.plane0);
-    DSB_LAUNCH_CHECK();
-    if (t.spin2) {
-      DSB_CUDA(cudaMalloc(&t.t2_bf, 3 * t.plane2 * sizeof(__nv_bfloat16)));
-      DSB_CUDA(cudaMemsetAsync(t.t2_bf, 0, 3 * t.plane2 * sizeof(__nv_bfloat16), stream));
-      tables_kernel<true, true><<<grid, block, 0, stream>>>(plan->rings, plan->nfold, t.Kp, t.lmax, t.NP,
-                                                            nullptr, t.t2_bf, t.plane2);
-      DSB_LAUNCH_CHECK();
-    }
+  t.splane0 = (size_t)nprob * t.Kp * t.NPk;
+  t.splane2 = (size_t)nprob * t.Kp * 2 * t.NPk;
+  DSB_TRY((build_one<false, false>(plan, t, t.precision, t.plane0, &t.t0_f64, &t.t0_bf, stream)));
+  if (t.spin2) DSB_TRY((build_one<true, false>(plan, t, t.precision, t.plane2, &t.t2_f64, &t.t2_bf, stream)));
+  if (t.synth) {
+    DSB_TRY((build_one<false, true>(plan, t, t.precision, t.splane0, &t.s0_f64, &t.s0_bf, stream)));
+    if (t.spin2) DSB_TRY((build_one<true, true>(plan, t, t.precision, t.splane2, &t.s2_f64, &t.s2_bf, stream)));
   }
   return DSB_OK;
 }
@@ -215,15 +239,13 @@ extern "C" int dsb_plan_build_tables(dsb_plan *plan, int lmax, int mmax, int wan
             "dsb_plan_build_tables: need 0 <= mmax <= lmax (got lmax=%d mmax=%d)", lmax, mmax);
   DSB_CHECK(precision == DSB_PREC_FP64 || precision == DSB_PREC_FP32X3, DSB_ERR_INVALID,
             "dsb_plan_build_tables: unknown precision %d", precision);
-  if (find_tables(plan, lmax, mmax, want_spin2 ? 1 : 0, precision)) return DSB_OK;
+  const int synth = plan->sht_iter > 0 ? 1 : 0;
+  if (find_tables(plan, lmax, mmax, want_spin2 ? 1 : 0, precision, synth)) return DSB_OK;
   // drop tables of the same precision (only one resolution is live at a time)
   for (size_t i = 0; i < plan->tables.size();) {
     if (plan->tables[i].precision == precision) {
       cudaStreamSynchronize((cudaStream_t)stream_);
-      cudaFree(plan->tables[i].t0_f64);
-      cudaFree(plan->tables[i].t2_f64);
-      cudaFree(plan->tables[i].t0_bf);
-      cudaFree(plan->tables[i].t2_bf);
+      free_tables(plan->tables[i]);
       plan->tables.erase(plan->tables.begin() + i);
     } else {
       ++i;
@@ -234,6 +256,7 @@ extern "C" int dsb_plan_build_tables(dsb_plan *plan, int lmax, int mmax, int wan
   t.mmax = mmax;
   t.spin2 = want_spin2 ? 1 : 0;
   t.precision = precision;
+  t.synth = synth;
   DSB_TRY(build_tables(plan, t, (cudaStream_t)stream_));
   plan->tables.push_back(t);
   return DSB_OK;

@@ -27,6 +27,8 @@ class TransferEngine:
         self.tel = telescope
         self.precision = _lib.PRECISIONS[precision or getattr(telescope, "precision", "fp32x3")]
         self.beam_budget = int(getattr(telescope, "beam_cache_size", 200)) << 25  # bytes on device
+        # healpy map2alm settings (see TransitTelescope.sht_iter)
+        self.sht_iter = int(getattr(telescope, "sht_iter", 0) or 0)
         self._plans = {}  # nside -> Plan
         self._slots = {}  # nside -> {(freq, beamclass): slot}
 
@@ -41,8 +43,20 @@ class TransferEngine:
         if nside not in self._plans:
             self.tel._init_trans(nside)
             self._plans[nside] = _lib.Plan(nside, self.tel._horizon)
+            self._plans[nside].set_sht(self.sht_iter, self._ring_weights(nside))
             self._slots[nside] = {}
         return self._plans[nside]
+
+    def _ring_weights(self, nside):
+        w = getattr(self.tel, "sht_ring_weights", None)
+        if w is None:
+            return None
+        if callable(w):
+            return w(nside)
+        w = {int(k): v for k, v in dict(w).items()}
+        if nside not in w:
+            raise ValueError(f"sht_ring_weights has no entry for nside {nside}")
+        return w[nside]
 
     def drop_beams(self, nside):
         """Forget the uploaded beams of one resolution (slots are reused)."""

@@ -60,6 +60,20 @@ uint64_t dsb_launch_count(void);
 int dsb_plan_create(int nside, const uint8_t *horizon_host, dsb_plan **out);
 int dsb_plan_destroy(dsb_plan *plan);
 
+/* SHT settings of the plan: the arguments cora.util.hputil.sphtrans_complex[_pol] hands to
+ * healpy.map2alm(..., use_weights=_weight, iter=_iter) on behalf of _transfer_single
+ * (drift/core/telescope.py:1189-1191, 1300-1302, 1310-1314; cora is external, its module
+ * values are recalled as _weight = True, _iter = 2 and could not be verified offline).
+ *   sht_iter     : Jacobi refinement passes a <- a + A(M - S a) of the analysis, 0 = plain
+ *                  quadrature.  Each pass costs one synthesis and one analysis contraction.
+ *   ring_weights : NULL (use_weights=False: every ring weighs 4 pi / npix) or 2*nside
+ *                  multiplicative weights, one per ring from the north pole to the equator
+ *                  (the southern rings mirror them) -- the values 1 + w of healpy's
+ *                  weight_ring_n*.fits data files, which are not available offline.
+ * New plans have sht_iter = 0 and no ring weights.  Changing the settings drops the plan's
+ * Legendre tables (they are rebuilt on the next use). */
+int dsb_plan_set_sht(dsb_plan *plan, int sht_iter, const double *ring_weights_host);
+
 /* Upload one primary-beam map -- what TransitTelescope._beam caches per
  * (nside, freq, beamclass) (drift/core/telescope.py:956-974).  `beam_host` is
  * float64 [npix][ncomp] (ncomp = 1 unpolarised, 2 = (theta, phi) components).
@@ -162,6 +176,9 @@ int dsb_set_workspace_limit(size_t bytes);
  * since profiling was last enabled.  Used by bench.py for the roofline figures. */
 int dsb_set_profiling(int enable);
 int dsb_get_profile(double *ms3, uint64_t *launches3);
+/* Same clock for the Jacobi refinement passes (sht_iter > 0), which dsb_get_profile's Legendre
+ * figure does not include: accumulated milliseconds and number of timed calls. */
+int dsb_get_profile_refine(double *ms, uint64_t *calls);
 
 /* Unit-test entry for the tensor-core contraction kernel alone (host buffers):
  *   C[prob][col][n] = sum_k F[prob][k][col] * T[prob][n][k]

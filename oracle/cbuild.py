@@ -45,6 +45,9 @@ def lib():
         _lib.oracle_transfer_unit_iter.restype = ctypes.c_int
         _lib.oracle_transfer_unit_iter.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 5 + [
             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        _lib.oracle_transfer_unit_sht.restype = ctypes.c_int
+        _lib.oracle_transfer_unit_sht.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 5 + [
+            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     return _lib
 
 
@@ -55,12 +58,13 @@ def _context(nside):
         return _ctx[nside]
 
 
-def transfer_unit(nside, beami, beamj, horizon, zenith, uv, lmax, lside, npol=4, niter=0):
+def transfer_unit(nside, beami, beamj, horizon, zenith, uv, lmax, lside, npol=4, niter=0, ring_weights=None):
     """One (baseline, frequency) unit: ``[npol, lside+1, 2*lside+1]`` complex128, the layout
     ``TransitTelescope._transfer_single`` returns (drift/core/telescope.py:1178-1193, 1287-1316).
     ``beami/beamj``: ``[npix, 2]`` (polarised) or ``[npix]`` float64.  Thread-safe (the GIL is
     released while the C code runs).  ``niter``: Jacobi refinement passes of the analysis (healpy
-    ``map2alm(iter=...)``), carried out on the ring spectra; 0 = plain quadrature."""
+    ``map2alm(iter=...)``), carried out on the ring spectra; 0 = plain quadrature.  ``ring_weights``:
+    ``2*nside`` multiplicative weights (healpy ``use_weights=True``), None = unity."""
     beami = np.ascontiguousarray(beami, dtype=np.float64)
     beamj = np.ascontiguousarray(beamj, dtype=np.float64)
     polarised = int(beami.ndim == 2)
@@ -68,9 +72,12 @@ def transfer_unit(nside, beami, beamj, horizon, zenith, uv, lmax, lside, npol=4,
     zen = np.ascontiguousarray(zenith, dtype=np.float64)
     uvv = np.ascontiguousarray(uv, dtype=np.float64)
     out = np.empty((npol, lside + 1, 2 * lside + 1), dtype=np.complex128)
-    rc = lib().oracle_transfer_unit_iter(_context(nside), polarised, int(npol), beami.ctypes.data, beamj.ctypes.data,
-                                         hor.ctypes.data, zen.ctypes.data, uvv.ctypes.data, int(lmax), int(lside),
-                                         int(niter), out.ctypes.data)
+    rw = None if ring_weights is None else np.ascontiguousarray(ring_weights, dtype=np.float64)
+    if rw is not None and rw.shape != (2 * nside,):
+        raise ValueError("ring_weights: need 2*nside values (north pole to equator)")
+    rc = lib().oracle_transfer_unit_sht(_context(nside), polarised, int(npol), beami.ctypes.data, beamj.ctypes.data,
+                                        hor.ctypes.data, zen.ctypes.data, uvv.ctypes.data, int(lmax), int(lside),
+                                        int(niter), None if rw is None else rw.ctypes.data, out.ctypes.data)
     if rc != 0:
         raise ValueError("oracle_transfer_unit: lmax > lside")
     return out

@@ -261,7 +261,8 @@ static void wigner_run(const wrec_t *w, double theta, double *out) {
  *   synth = 0: analysis,  a += quad * sum_rings lambda * G          (a zeroed by the caller)
  *   synth = 1: synthesis, G  = sum_l a * lambda  (no quadrature weight): the ring spectra of the map
  *              sum_lm a_lm Y_lm, spin 2 in the convention of oracle/sht.py alm2map_pol. */
-static void legendre_stage(const ctx_t *c, int npol, int lmax, int lside, cplx *G, cplx *out, int synth) {
+static void legendre_stage(const ctx_t *c, int npol, int lmax, int lside, cplx *G, cplx *out, int synth,
+                           const double *ringw) {
   const int npix = c->npix, nring = c->nring, nside = c->nside;
   const int ncol = 2 * lside + 1;
   const size_t plane = (size_t)(lside + 1) * ncol;
@@ -334,9 +335,10 @@ static void legendre_stage(const ctx_t *c, int npol, int lmax, int lside, cplx *
           continue;
         }
         cplx gN[4], gS[4];
+        const double rw = ringw ? ringw[k] : 1.0; /* healpy use_weights: ring weight, mirrored north/south */
         for (int q = 0; q < npol; ++q) {
-          gN[q] = G[((size_t)q * nring + rn) * nm + mm + lmax];
-          gS[q] = eq ? 0.0 : G[((size_t)q * nring + rs) * nm + mm + lmax];
+          gN[q] = rw * G[((size_t)q * nring + rn) * nm + mm + lmax];
+          gS[q] = eq ? 0.0 : rw * G[((size_t)q * nring + rs) * nm + mm + lmax];
         }
         for (int l = m; l <= lmax; ++l) {
           const double par = ((l + m) & 1) ? -1.0 : 1.0;
@@ -400,10 +402,11 @@ static void alias_fold(const ctx_t *c, int npol, int lmax, cplx *G) {
  * out: complex128 [npol][lside+1][2*lside+1], column m for m >= 0, 2*lside+1-|m| for m < 0,
  *      zero for l > lmax  (telescope.py:809-828)
  * niter: Jacobi refinement passes of the analysis (healpy map2alm's `iter`; 0 = plain quadrature)
+ * ringw: NULL (healpy use_weights=False) or 2*nside multiplicative ring weights, north pole to equator
  * returns 0 on success */
-int oracle_transfer_unit_iter(void *ctxp, int polarised, int npol, const double *beam_i, const double *beam_j,
-                              const uint8_t *horizon, const double *zenith, const double *uv, int lmax, int lside,
-                              int niter, double *out_) {
+int oracle_transfer_unit_sht(void *ctxp, int polarised, int npol, const double *beam_i, const double *beam_j,
+                             const uint8_t *horizon, const double *zenith, const double *uv, int lmax, int lside,
+                             int niter, const double *ringw, double *out_) {
   const ctx_t *c = (const ctx_t *)ctxp;
   cplx *out = (cplx *)out_;
   const int npix = c->npix, nring = c->nring, nside = c->nside;
@@ -485,16 +488,16 @@ int oracle_transfer_unit_iter(void *ctxp, int polarised, int npol, const double 
 
   /* Legendre stage; niter > 0: Jacobi refinement a <- a0 + a - A S a as healpy's map2alm(iter)
    * does it through pixel maps, carried out on the ring spectra (alias_fold) */
-  legendre_stage(c, npol, lmax, lside, G, out, 0);
+  legendre_stage(c, npol, lmax, lside, G, out, 0, ringw);
   if (niter > 0) {
     cplx *a0 = (cplx *)malloc(sizeof(cplx) * plane * npol);
     cplx *a1 = (cplx *)malloc(sizeof(cplx) * plane * npol);
     memcpy(a0, out, sizeof(cplx) * plane * npol);
     for (int it = 0; it < niter; ++it) {
-      legendre_stage(c, npol, lmax, lside, G, out, 1);
+      legendre_stage(c, npol, lmax, lside, G, out, 1, NULL);
       alias_fold(c, npol, lmax, G);
       memset(a1, 0, sizeof(cplx) * plane * npol);
-      legendre_stage(c, npol, lmax, lside, G, a1, 0);
+      legendre_stage(c, npol, lmax, lside, G, a1, 0, ringw);
       for (size_t i = 0; i < plane * npol; ++i) out[i] = a0[i] + out[i] - a1[i];
     }
     free(a0);
@@ -508,6 +511,13 @@ int oracle_transfer_unit_iter(void *ctxp, int polarised, int npol, const double 
   free(Xbuf);
   free(work);
   return 0;
+}
+
+int oracle_transfer_unit_iter(void *ctxp, int polarised, int npol, const double *beam_i, const double *beam_j,
+                              const uint8_t *horizon, const double *zenith, const double *uv, int lmax, int lside,
+                              int niter, double *out_) {
+  return oracle_transfer_unit_sht(ctxp, polarised, npol, beam_i, beam_j, horizon, zenith, uv, lmax, lside, niter, NULL,
+                                  out_);
 }
 
 int oracle_transfer_unit(void *ctxp, int polarised, int npol, const double *beam_i, const double *beam_j,

@@ -195,8 +195,15 @@ def ring_weights(nside, kind="none"):
     available offline, so that mode cannot be restated here.
     """
     nring = 4 * nside - 1
-    if kind in (None, "none", False):
+    if kind is None or kind is False or (isinstance(kind, str) and kind == "none"):
         return np.ones(nring)
+    if not isinstance(kind, str):
+        # explicit weights, north pole to equator (2*nside values, what a HEALPix weight_ring file
+        # holds as 1 + w); the southern rings mirror them
+        w = np.asarray(kind, dtype=np.float64)
+        if w.shape != (2 * nside,):
+            raise ValueError("ring weights: need 2*nside values (north pole to equator)")
+        return np.concatenate([w, w[-2::-1]])
     raise NotImplementedError(
         "HEALPix ring-weight files are not available offline; only 'none' is supported"
     )

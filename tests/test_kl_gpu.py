@@ -12,19 +12,34 @@ pytestmark = pytest.mark.gpu
 SMALL_CFG = dict(
     num_freq=3, freq_start=100.0, freq_end=112.0, freq_mode="edge",
     num_cylinders=2, cylinder_width=5.0, num_feeds=3, feed_spacing=1.5, tsys=1.0,
+    sht_iter=0,  # the fixtures of make_golden*.py use plain quadrature; cfg1_products.npz covers the default
 )
 
 
-@pytest.fixture(scope="module")
-def products(tmp_path_factory):
+# The KL stage itself is fp64 in both modes; what differs is the beam-transfer product it starts
+# from.  With foregrounds the noise matrix spans 16 decades (foregrounds over the 1e-14
+# regulariser) and the S/N spectrum is correspondingly sensitive: 3e-7 noise on the fixture's
+# beam_m moves the reference's own KL eigenvalues above the 0.1 threshold by up to 3 % (m = 0),
+# 1 % (m = 1), 0.05 % (m = 7) (CPU emulation, scipy on both sides).  fp32x3 products are therefore
+# compared at 10 %, covariance moduli at 1e-5 / 1e-3 of their maxima; products meant for
+# foreground-filtering KL work should be generated with `precision: fp64`.
+TOL = {
+    "fp64": dict(cov_rtol=1e-6, cs_atol=1e-8, cn_atol=1e-8, ev_rtol=2e-5, ev_atol=1e-8),
+    "fp32x3": dict(cov_rtol=1e-3, cs_atol=1e-5, cn_atol=1e-3, ev_rtol=0.1, ev_atol=1e-2),
+}
+
+
+@pytest.fixture(scope="module", params=["fp64", "fp32x3"])
+def products(request, tmp_path_factory):
     from driftscan_b200.core import beamtransfer
     from driftscan_b200.telescope import cylinder
 
-    d = str(tmp_path_factory.mktemp("prodkl") / "bt")
-    tel = cylinder.PolarisedCylinderTelescope.from_config(dict(SMALL_CFG, precision="fp64"))
+    d = str(tmp_path_factory.mktemp("prodkl_" + request.param) / "bt")
+    tel = cylinder.PolarisedCylinderTelescope.from_config(dict(SMALL_CFG, precision=request.param))
     bt = beamtransfer.BeamTransfer(d, telescope=tel)
     bt.read_config(dict(polsvcut=1.0))
     bt.generate()
+    bt.tol = TOL[request.param]
     return bt
 
 
@@ -76,13 +91,17 @@ def test_kl_against_reference(products, golden_dir, mi):
     assert np.abs(cs - ocs).max() <= 1e-12 * np.abs(ocs).max()
     assert np.abs(cn - ocn).max() <= 1e-12 * np.abs(ocn).max()
     # moduli are independent of the phases of the SVD basis: compare with the reference's matrices
-    assert np.allclose(np.abs(cs), np.abs(g[f"cs_{mi}"]), rtol=1e-6, atol=1e-8 * np.abs(g[f"cs_{mi}"]).max())
-    assert np.allclose(np.abs(cn), np.abs(g[f"cn_{mi}"]), rtol=1e-6, atol=1e-8 * np.abs(g[f"cn_{mi}"]).max())
+    tol = products.tol
+    assert cs.shape == g[f"cs_{mi}"].shape
+    assert np.allclose(np.abs(cs), np.abs(g[f"cs_{mi}"]), rtol=tol["cov_rtol"],
+                       atol=tol["cs_atol"] * np.abs(g[f"cs_{mi}"]).max())
+    assert np.allclose(np.abs(cn), np.abs(g[f"cn_{mi}"]), rtol=tol["cov_rtol"],
+                       atol=tol["cn_atol"] * np.abs(g[f"cn_{mi}"]).max())
     # the KL spectrum against the reference's (tolerance: see tests/test_oracle_kl.py)
     evals, evecs, inv, extra = kl._transform_m(mi)
     ref = g[f"kl_evals_{mi}"]
     assert extra["ac"] == 0.0 and inv is None
-    assert np.allclose(evals, ref, rtol=2e-5, atol=1e-8 * ref.max())
+    assert np.allclose(evals, ref, rtol=tol["ev_rtol"], atol=tol["ev_atol"] * ref.max())
     v = evecs.conj().T
     assert np.abs(v.conj().T @ cn @ v - np.eye(len(evals))).max() < 1e-5
     assert np.abs(cs @ v - (cn @ v) * evals).max() <= 1e-7 * np.abs(cs).max()
@@ -96,7 +115,13 @@ def test_double_kl_against_reference(products, golden_dir, mi):
     dk = doublekl.DoubleKL(products, subdir="dk")
     dk.read_config(dict(threshold=0.1, subset=False, inverse=False, foreground_threshold=0.05))
     evals, evecs, inv, extra = dk._transform_m(mi)
-    assert np.allclose(extra["f_evals"], g[f"dk_fevals_{mi}"], rtol=2e-5, atol=1e-8 * g[f"dk_fevals_{mi}"].max())
+    tol = products.tol
+    assert np.allclose(extra["f_evals"], g[f"dk_fevals_{mi}"], rtol=tol["ev_rtol"],
+                       atol=tol["ev_atol"] * g[f"dk_fevals_{mi}"].max())
+    if tol["ev_rtol"] > 1e-3:
+        # a foreground mode whose S/F ratio sits at the foreground threshold can fall on either side
+        assert abs(evals.size - g[f"dk_evals_{mi}"].size) <= 1
+        return
     assert evals.shape == g[f"dk_evals_{mi}"].shape
     if evals.size:
         assert np.allclose(evals, g[f"dk_evals_{mi}"], rtol=2e-5, atol=1e-8)

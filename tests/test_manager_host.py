@@ -87,6 +87,18 @@ def test_errors_and_custom_class(tmp_path):
     tel = cls.from_config({"num_freq": 2, "freq_start": 100.0, "freq_end": 120.0})
     assert tel.nbase == 3 and tel.num_pol_sky == 1
     assert np.array_equal(tel.redundancy, [1, 1, 1])
+    # BeamTransfer.generate pickles the telescope: a file-loaded class must be reachable through
+    # sys.modules from any working directory (the reference's imp.load_source registers it)
+    import os
+    import pickle
+
+    cwd = os.getcwd()
+    os.chdir("/")
+    try:
+        back = pickle.loads(pickle.dumps(tel))
+    finally:
+        os.chdir(cwd)
+    assert type(back).__name__ == "Pair" and back.nbase == 3
 
 
 def test_patterns():

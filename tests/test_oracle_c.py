@@ -38,6 +38,25 @@ def test_c_matches_numpy_oracle(nside, lmax, uv, lat):
     assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("niter", [0, 2])
+def test_c_ring_weights_match_numpy_oracle(niter):
+    """healpy's use_weights=True as explicit multiplicative ring weights (analysis only)."""
+    nside, lmax, uv = 8, 14, (2.1, 0.7)
+    zen = np.array([np.radians(45.0), 0.0])
+    ang = ohp.ang_positions(nside)
+    hor = obeam.horizon(ang, zen)
+    rng = np.random.default_rng(1)
+    bi, bj = rng.standard_normal((12 * nside * nside, 2)), rng.standard_normal((12 * nside * nside, 2))
+    w = 1.0 + 0.01 * rng.standard_normal(2 * nside)
+    got = cbuild.transfer_unit(nside, bi, bj, hor, zen, uv, lmax, lmax + 1, niter=niter, ring_weights=w)
+    ref = otr.transfer_single_pol(ang, hor, bi, bj, zen, np.array(uv), lmax, lmax + 1, weights=w, niter=niter)
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+    unw = cbuild.transfer_unit(nside, bi, bj, hor, zen, uv, lmax, lmax + 1, niter=niter)
+    assert np.abs(got - unw).max() > 1e-4 * np.abs(ref).max()
+    with pytest.raises(ValueError):
+        cbuild.transfer_unit(nside, bi, bj, hor, zen, uv, lmax, lmax + 1, ring_weights=w[:-1])
+
+
 @pytest.mark.parametrize("nside,lmax,uv,lat", [(4, 6, (0.4, 0.9), 45.0), (8, 13, (1.3, -0.7), 30.0)])
 def test_c_jacobi_refinement_matches_numpy_oracle(nside, lmax, uv, lat):
     """healpy's map2alm(iter = k): the numpy oracle iterates through pixel maps (oracle/sht.py), the C

@@ -126,7 +126,10 @@ def test_complex_packing_conventions():
         assert np.allclose(full[: lmax + 1, -m], neg)
     assert (full[lmax + 1 :] == 0).all()
     with pytest.raises(NotImplementedError):
-        sht.ring_weights(8, "ring")
+        sht.ring_weights(8, "ring")  # healpy's data files are not available: only explicit weights
+    w = 1.0 + 0.01 * np.arange(16)
+    full_w = sht.ring_weights(8, w)
+    assert full_w.shape == (31,) and np.array_equal(full_w[:16], w) and np.array_equal(full_w[16:], w[-2::-1])
 
 
 def test_jacobi_refinement_in_ring_spectra_space():
@@ -144,3 +147,20 @@ def test_jacobi_refinement_in_ring_spectra_space():
     assert mod.check_pol(nside=4, lmax=11, niter=2) < 1e-13
     # complex map, the product's +m / -m slots and phases (the formulas the device fold kernel needs)
     assert mod.check_transfer(nside=4, lmax=11, niter=2) < 1e-13
+
+
+def test_device_data_flow_of_the_refinement():
+    """tools/emulate_device_iter.py restates the CUDA path's refinement step by step in numpy with
+    the device's array layouts (operand roles and problem pairing of the spin-2 synthesis, the
+    (+-i, Q<->U) permutation, the sign-only aliasing fold, the factor 2 of the north/south fold):
+    equal to the oracle's map-based healpy-style iteration."""
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(__file__), "..", "tools", "emulate_device_iter.py")
+    spec = importlib.util.spec_from_file_location("emulate_device_iter", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.check(nside=4, lmax=9, niter=0) < 1e-13
+    assert mod.check(nside=4, lmax=11, niter=2) < 1e-13
+    assert mod.check(nside=8, lmax=14, niter=1) < 1e-13

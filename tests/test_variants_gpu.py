@@ -12,6 +12,7 @@ pytestmark = pytest.mark.gpu
 SMALL_CFG = dict(
     num_freq=3, freq_start=100.0, freq_end=112.0, freq_mode="edge",
     num_cylinders=2, cylinder_width=5.0, num_feeds=3, feed_spacing=1.5, tsys=1.0,
+    sht_iter=0,  # the fixtures of make_golden*.py use plain quadrature; cfg1_products.npz covers the default
 )
 
 

@@ -2,11 +2,7 @@
 user-class example) against the reference's own `transfer_matrices` run under stubs
 (tests/golden/make_golden_disharray.py).
 
-Written after round 1's GPU budget was spent: the host side of these telescopes is verified on the
-CPU (tests/test_disharray_host.py) and the device path is the one the cylinder tests exercise, but
-this file itself has not run on a GPU yet -- hence the non-strict xfail (an XPASS is the
-expected outcome; a failure is reported without turning the suite red) and its place at the end
-of the collection order."""
+The fixture uses plain quadrature (sht_iter = 0)."""
 
 import importlib.util
 import os
@@ -14,8 +10,7 @@ import os
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first run on a GPU happens at round end (see module docstring)")]
+pytestmark = pytest.mark.gpu
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
@@ -29,7 +24,7 @@ def gold(golden_dir):
 def test_unpolarised_dish_array(gold, precision, tol):
     from driftscan_b200.telescope import disharray
 
-    tel = disharray.UnpolarisedDishArray.from_config(dict(freq_mode="edge", latitude=30.0, precision=precision))
+    tel = disharray.UnpolarisedDishArray.from_config(dict(freq_mode="edge", latitude=30.0, precision=precision, sht_iter=0))
     got = tel.transfer_matrices(gold["unpol_bl"], gold["unpol_fi"])
     want = gold["unpol_transfer"]
     assert got.shape == want.shape
@@ -43,7 +38,7 @@ def test_user_class_example(gold, precision, tol):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     tel = mod.DishArray(latitude=30.0)
-    tel.read_config(dict(precision=precision))
+    tel.read_config(dict(precision=precision, sht_iter=0))
     got = tel.transfer_matrices(gold["pol_bl"], gold["pol_fi"])
     want = gold["pol_transfer"]
     assert got.shape == want.shape
