@@ -79,6 +79,9 @@ def _load():
         "dsb_peer_close": (i32, [vp]),
         "dsb_peer_free": (i32, [vp]),
         "dsb_mmajor_size": (i64, [i32, i32, i32, i32, i32, P(i64)]),
+        "dsb_memcpy": (i32, [vp, vp, ctypes.c_size_t, i32, vp, i32]),
+        "dsb_host_alloc": (i32, [ctypes.c_size_t, P(vp)]),
+        "dsb_host_free": (i32, [vp]),
         "dsb_set_workspace_limit": (i32, [ctypes.c_size_t]),
         "dsb_set_profiling": (i32, [i32]),
         "dsb_get_profile": (i32, [P(dbl), P(u64)]),
@@ -115,6 +118,43 @@ def check(rc):
     if rc != 0:
         msg = lib.dsb_last_error().decode(errors="replace")
         raise _ERRORS.get(rc, RuntimeError)(f"libdriftb200: {msg} (status {rc})")
+
+
+class PinnedBuffer:
+    """Page-locked host staging memory (cudaHostAlloc), viewed as numpy arrays."""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        p = ctypes.c_void_p()
+        check(lib.dsb_host_alloc(self.nbytes, ctypes.byref(p)))
+        self.ptr = p.value
+        self._raw = (ctypes.c_ubyte * max(self.nbytes, 1)).from_address(self.ptr)
+
+    def view(self, dtype, count, offset=0):
+        return np.frombuffer(self._raw, dtype=dtype, count=int(count), offset=int(offset))
+
+    def close(self):
+        if self.ptr:
+            self._raw = None
+            lib.dsb_host_free(ctypes.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def memcpy(dst_ptr, src_ptr, nbytes, kind, stream=None, sync=True):
+    """kind: 'h2d', 'd2h' or 'd2d' (raw pointers)."""
+    check(lib.dsb_memcpy(ctypes.c_void_p(int(dst_ptr)), ctypes.c_void_p(int(src_ptr)), int(nbytes),
+                         {"h2d": 0, "d2h": 1, "d2d": 2}[kind], ctypes.c_void_p(stream or 0), int(sync)))
+
+
+def widen_c64(src_ptr, dst_ptr, n, nthreads=0):
+    """n complex64 at src -> n complex128 at dst (host pointers), exact."""
+    check(lib.dsb_host_widen_c64(ctypes.c_void_p(int(src_ptr)), ctypes.c_void_p(int(dst_ptr)), int(n), int(nthreads)))
 
 
 def launch_count():

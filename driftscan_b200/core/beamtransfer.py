@@ -169,8 +169,11 @@ class BeamTransfer(config.Reader):
                 logger.info("Saving Telescope object.")
                 pickle.dump(self.telescope, f)
         self._generate_mfiles(regen)
-        if not skip_svd:
-            self._generate_svdfiles(regen, skip_svd_inv)
+        try:
+            if not skip_svd:
+                self._generate_svdfiles(regen, skip_svd_inv)
+        finally:
+            self._release_resident()
         self.comm.barrier()
         if self.comm.rank0:
             logger.info(f"Beam generation time: {time.time() - st:f}")
@@ -199,9 +202,11 @@ class BeamTransfer(config.Reader):
         it owns (the ``split_local`` partition of the reference) for all frequencies, and
         every rank writes only its own m-files.
         """
+        import ctypes
+
         import torch
 
-        from .. import _lib
+        from .. import _lib, parallel
 
         if os.path.exists(self.directory + "/beam_m/COMPLETED") and not regen:
             if self.comm.rank0:
@@ -210,6 +215,14 @@ class BeamTransfer(config.Reader):
         st = time.time()
         tel, comm = self.telescope, self.comm
         from . import telescope as _telescope
+
+        if self.truncate:
+            # beamtransfer.py:549-555, 641-646 of the reference: caput's bit_truncate_max_complex and the
+            # bitshuffle + LZ4 filter, neither of which exists here
+            import warnings
+
+            warnings.warn("BeamTransfer: `truncate: true` is not implemented by driftscan_b200; the beam "
+                          "transfers are written at full precision with the LZF filter")
 
         if type(tel)._transfer_single is not _telescope.TransitTelescope._transfer_single:
             # fail loudly rather than ignore the user's unit: the m-files are produced by the device
@@ -232,50 +245,144 @@ class BeamTransfer(config.Reader):
                 f.create_dataset("beam_m", (nf_inc, 2, nb_inc, np_inc, nl - mi), dtype=np.complex128,
                                  **self._storage((1, 2, min(10, nb_inc), np_inc, nl - mi)))
                 f.attrs["m"] = mi
-                f.attrs["frequencies"] = tel.frequencies
+                try:
+                    f.attrs["frequencies"] = tel.frequencies
+                except ValueError:  # more than 8190 channels: see the baselines attribute of svd.hdf5
+                    logger.warning("frequencies attribute too large for an HDF5 object header; omitted")
         comm.barrier()
+
+        # The device product is exact in complex64 when the transfer stage runs in fp32x3 (the pack
+        # kernel only widens fp32): it then crosses NVLink and PCIe as complex64 and is widened by host
+        # threads straight into the file mapping -- half the bytes on every link.
+        c64 = tel.engine.precision == _lib.DSB_PREC_FP32X3
+        elem = 8 if c64 else 16
+        out_kind = _lib.DSB_OUT_MMAJOR_C64 if c64 else _lib.DSB_OUT_MMAJOR_C128
+        tdtype = torch.complex64 if c64 else torch.complex128
+        ndtype = np.complex64 if c64 else np.complex128
 
         # chunk the frequency axis so that one chunk of m-major output is ~mem_chunk GB per rank
         per_freq = 16 * _lib.mmajor_offsets(1, nb_inc, np_inc, tel.lmax, tel.mmax)[0]
         nf_chunk = max(1, int(self.mem_chunk * 2**30 / max(per_freq, 1)))
-        f_lo, f_hi = comm.split_range(nf_inc)
-        nf_loc_max = max(hi - lo for lo, hi in comm.all_ranges(nf_inc))
+        franges = comm.all_ranges(nf_inc)
+        f_lo, f_hi = franges[comm.rank]
+        nf_loc_max = max(hi - lo for lo, hi in franges)
+        nf_chunk = min(nf_chunk, max(nf_loc_max, 1))
         nchunks = max(1, -(-nf_loc_max // nf_chunk))
         if comm.rank0:
             logger.info(f"Splitting into {nchunks} chunks....")
 
         dev = torch.device("cuda", torch.cuda.current_device())
+        stream = torch.cuda.current_stream().cuda_stream
+        # N > 1: every rank's pack kernel stores its frequencies straight into the m-blocks of the rank
+        # that owns (and writes) that m -- the transpose_blocks of beamtransfer.py:632 fused into the
+        # kernel that produces the data (parallel.PeerScatter).  Without CUDA IPC: NCCL all-to-all.
+        scatter = None
+        if comm.size > 1 and comm.is_nccl and not os.environ.get("DSB_NO_PEER_SCATTER"):
+            try:
+                scatter = parallel.PeerScatter(comm, comm.size * nf_chunk, nb_inc, np_inc, tel.lmax, tel.mmax,
+                                               elem_bytes=elem, balance="count")
+            except Exception as exc:  # noqa: BLE001 -- raised on every rank alike
+                logger.warning(f"peer scatter unavailable ({exc}); regrouping with the NCCL all-to-all")
+        self.exchange_path = "single" if comm.size == 1 else ("peer-scatter" if scatter else "nccl-all-to-all")
+        self._resident = {}
+        per_m = [2 * nb_inc * np_inc * (nl - mi) for mi in range(nm)]  # elements per frequency of block m
+        nslots = (comm.size if scatter else 1) * nf_chunk
+        stage = _lib.PinnedBuffer(max(nslots * max(per_m[m_lo:m_hi], default=0) * elem, 64))
+        t_compute = t_write = 0.0
+
+        def write_rows(f, mi, rows, src_ptr, nfr):
+            """``nfr`` frequencies of block ``mi`` at host address ``src_ptr`` -> f['beam_m'][rows]."""
+            ds = f["beam_m"]
+            n = nfr * per_m[mi]
+            if isinstance(ds, h5lite.Dataset) and not isinstance(ds, h5lite._CompactDataset) and c64:
+                mm = ds._map()  # contiguous dataset: widen directly into the file mapping
+                _lib.widen_c64(src_ptr, mm.ctypes.data + rows.start * per_m[mi] * 16, n)
+                mm.flush()
+                return
+            data = np.frombuffer((ctypes.c_ubyte * (n * elem)).from_address(src_ptr), dtype=ndtype)
+            ds[rows] = data.astype(np.complex128).reshape((nfr, 2, nb_inc, np_inc, nl - mi))
+
         for ci in range(nchunks):
             c_lo = min(f_lo + ci * nf_chunk, f_hi)
             c_hi = min(c_lo + nf_chunk, f_hi)
             nfc = c_hi - c_lo
+            t0 = time.time()
             total, moff = _lib.mmajor_offsets(max(nfc, 1), nb_inc, np_inc, tel.lmax, tel.mmax)
-            buf = torch.zeros(total if nfc else 0, dtype=torch.complex128, device=dev)
+            buf = None
+            if scatter is None:
+                buf = torch.zeros(total if nfc else 0, dtype=tdtype, device=dev)
             if nfc:
                 fgrid, bgrid = np.meshgrid(np.arange(c_lo, c_hi), np.arange(nb_inc), indexing="ij")
                 f_ind, b_ind = freq_inc[fgrid.ravel()], bl_inc[bgrid.ravel()]
                 lmax_u, _ = tel.unit_lmax(b_ind, f_ind)
+                slot0 = comm.rank * nf_chunk if scatter else 0
                 tel.engine.transfer_mmajor(
-                    b_ind, f_ind, lmax_u, (fgrid.ravel() - c_lo).astype(np.int32),
-                    bgrid.ravel().astype(np.int32), nfc, nb_inc, tel.lmax, tel.mmax, buf.data_ptr(), False,
-                    stream=torch.cuda.current_stream().cuda_stream,
+                    b_ind, f_ind, lmax_u, (fgrid.ravel() - c_lo + slot0).astype(np.int32),
+                    bgrid.ravel().astype(np.int32), nslots if scatter else nfc, nb_inc, tel.lmax, tel.mmax,
+                    0 if scatter else buf.data_ptr(), False, out_kind=out_kind, stream=stream,
+                    block_ptrs=scatter.block_ptrs if scatter else None,
                 )
-            # regroup: every rank receives, for the m range it owns, the blocks of all
-            # ranks' frequency chunks (frequency-major -> m-major transpose, beamtransfer.py:632)
-            pieces = comm.exchange_mblocks(buf, nfc, moff, nm, f_lo=c_lo)
-            for src, (s_lo, s_hi, blocks) in enumerate(pieces):
-                if s_hi <= s_lo:
-                    continue
-                for mi, block in zip(range(m_lo, m_hi), blocks):
-                    data = block.reshape(s_hi - s_lo, 2, nb_inc, np_inc, nl - mi).cpu().numpy()
-                    with h5lite.File(self._mfile(mi), "r+") as f:
-                        f["beam_m"][s_lo:s_hi] = data
-            del buf, pieces
+            # (source rank, first file row, rows, device address of block mi for that source)
+            if scatter is not None:
+                scatter.fence()  # every rank's stores into my blocks have landed
+                torch.cuda.synchronize()
+                sources = []
+                for s, (s_lo, s_hi) in enumerate(franges):
+                    a = min(s_lo + ci * nf_chunk, s_hi)
+                    b = min(a + nf_chunk, s_hi)
+                    if b > a:
+                        sources.append((a, b, s * nf_chunk))
+
+                def block_addr(mi, slot):
+                    return scatter.own_ptr + scatter.own_block_offset(mi) + slot * per_m[mi] * elem
+            elif comm.size > 1:
+                pieces = comm.exchange_mblocks(buf, nfc, moff, nm, f_lo=c_lo)
+                torch.cuda.synchronize()
+                sources = [(s_lo, s_hi, i) for i, (s_lo, s_hi, _) in enumerate(pieces) if s_hi > s_lo]
+
+                def block_addr(mi, i):
+                    return pieces[i][2][mi - m_lo].data_ptr()
+            else:
+                torch.cuda.synchronize()
+                sources = [(c_lo, c_hi, 0)] if nfc else []
+
+                def block_addr(mi, _):
+                    return buf.data_ptr() + int(moff[mi]) * elem
+            t_compute += time.time() - t0
+            t0 = time.time()
+            for mi in range(m_lo, m_hi):
+                if not sources:
+                    break
+                with h5lite.File(self._mfile(mi), "r+") as f:  # one open file per m and chunk
+                    for a, b, key in sources:
+                        nbytes = (b - a) * per_m[mi] * elem
+                        _lib.memcpy(stage.ptr, block_addr(mi, key), nbytes, "d2h", stream, sync=True)
+                        write_rows(f, mi, slice(a, b), stage.ptr, b - a)
+            t_write += time.time() - t0
+            if nchunks == 1:
+                # single chunk: the blocks stay on the device for the SVD stage (no re-read of beam_m)
+                for mi in range(m_lo, m_hi):
+                    self._resident[mi] = [(a, b, block_addr(mi, key)) for a, b, key in sources]
+                self._resident_keep = (buf, scatter, locals().get("pieces"), elem)
+            elif scatter is not None:
+                scatter.fence()  # owners are done reading before the next chunk overwrites the blocks
+            if nchunks > 1:
+                del buf
+        stage.close()
+        if scatter is not None and nchunks > 1:
+            scatter.close()
+        self.timing = dict(getattr(self, "timing", {}), mfiles_compute_s=t_compute, mfiles_write_s=t_write)
 
         comm.barrier()
         if comm.rank0:
             open(self.directory + "/beam_m/COMPLETED", "a").close()
             logger.info(f"=== MPI transpose took {time.time() - st:f} s ===")
+
+    def _release_resident(self):
+        keep = self.__dict__.pop("_resident_keep", None)
+        self._resident = {}
+        if keep is not None and keep[1] is not None:
+            keep[1].close()
 
     def _generate_svdfiles(self, regen=False, skip_svd_inv=False):
         """Per-m SVD files (beamtransfer.py:678-728)."""
@@ -301,16 +408,28 @@ class BeamTransfer(config.Reader):
         comm.barrier()
         self._collect_svd_spectrum()
 
-    def _svd_chain_device(self, bf_host, noisew_host, skip_svd_inv):
-        """Run dsb_svd_chain on ``bf_host [batch, ntel, npol, nl]``; returns host arrays."""
+    def _pinned_out(self, name, shape, dtype):
+        """Page-locked host array for a device result (cached per name: cudaHostAlloc is slow)."""
+        import torch
+
+        cache = self.__dict__.setdefault("_pinned_cache", {})
+        t = cache.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = cache[name] = torch.empty(shape, dtype=dtype, pin_memory=True)
+        return t
+
+    def _svd_chain_device(self, bf, noisew_host, skip_svd_inv):
+        """Run dsb_svd_chain on ``bf [batch, ntel, npol, nl]`` (host array or device tensor); returns
+        host arrays (views of page-locked staging buffers, valid until the next call)."""
         import torch
 
         from .. import _lib
 
-        batch, ntel, npol, nl = bf_host.shape
+        batch, ntel, npol, nl = bf.shape
         svd_len = self.svd_len
         dev = torch.device("cuda", torch.cuda.current_device())
-        bf = torch.from_numpy(np.ascontiguousarray(bf_host)).to(dev)
+        if not isinstance(bf, torch.Tensor):
+            bf = torch.from_numpy(np.ascontiguousarray(bf)).to(dev)
         nw = torch.from_numpy(np.ascontiguousarray(noisew_host, dtype=np.float64)).to(dev)
         bsvd = torch.empty((batch, svd_len, npol, nl), dtype=torch.complex128, device=dev)
         but = torch.empty((batch, svd_len, ntel), dtype=torch.complex128, device=dev)
@@ -324,19 +443,57 @@ class BeamTransfer(config.Reader):
                 nmodes.data_ptr(), torch.cuda.current_stream().cuda_stream,
             )
         )
-        return (bsvd.cpu().numpy(), but.cpu().numpy(), None if ibs is None else ibs.cpu().numpy(),
-                sv.cpu().numpy(), nmodes.cpu().numpy())
+        outs = []
+        for name, t in (("bsvd", bsvd), ("but", but), ("ibs", ibs), ("sv", sv), ("nmodes", nmodes)):
+            if t is None:
+                outs.append(None)
+                continue
+            h = self._pinned_out(name, t.shape, t.dtype)
+            h.copy_(t, non_blocking=True)
+            outs.append(h)
+        torch.cuda.synchronize()
+        return tuple(None if h is None else h.numpy() for h in outs)
+
+    def _resident_block(self, mi):
+        """``beam_m(mi)`` as a device tensor ``[nfreq, 2, npairs, npol_sky, lmax+1]`` built from the
+        blocks the m-file stage left on the device (single-chunk runs), or None."""
+        import torch
+
+        from .. import _lib
+
+        pieces = getattr(self, "_resident", {}).get(mi)
+        if not pieces:
+            return None
+        tel = self.telescope
+        elem = self._resident_keep[3]
+        tdtype = torch.complex64 if elem == 8 else torch.complex128
+        dev = torch.device("cuda", torch.cuda.current_device())
+        nb_inc, np_inc, nlm = len(tel.included_baseline), len(tel.included_pol), tel.lmax + 1 - mi
+        full = torch.zeros((tel.nfreq, 2, tel.nbase, tel.num_pol_sky, tel.lmax + 1), dtype=torch.complex128, device=dev)
+        ix = lambda a, pos: torch.as_tensor(np.asarray(a), device=dev).reshape([-1 if i == pos else 1 for i in range(5)])
+        for a, b, addr in pieces:
+            blk = torch.empty((b - a, 2, nb_inc, np_inc, nlm), dtype=tdtype, device=dev)
+            _lib.memcpy(blk.data_ptr(), addr, blk.numel() * elem, "d2d", torch.cuda.current_stream().cuda_stream,
+                        sync=False)
+            full[ix(tel.included_freq[a:b], 0), ix(np.arange(2), 1), ix(tel.included_baseline, 2),
+                 ix(tel.included_pol, 3), ix(np.arange(mi, tel.lmax + 1), 4)] = blk.to(torch.complex128)
+        return full
 
     def _generate_svdfile_m(self, mi, skip_svd_inv=False):
         """SVD products of one m (beamtransfer.py:730-929); written to a dot-prefixed
         temporary and renamed on success, as ``caput.misc.lock_file`` does."""
         tel = self.telescope
         nfreq, npol, nl = tel.nfreq, tel.num_pol_sky, tel.lmax + 1
-        bf = self.beam_m(mi).reshape(nfreq, self.ntel, npol, nl)
+        t0 = time.time()
+        bf = self._resident_block(mi)
+        if bf is None:
+            bf = self.beam_m(mi)
+        bf = bf.reshape(nfreq, self.ntel, npol, nl)
         noisew = tel.noisepower(np.arange(tel.npairs)[np.newaxis, :], np.arange(nfreq)[:, np.newaxis])
         noisew = noisew.reshape(nfreq, tel.npairs) ** (-0.5)
         noisew = np.concatenate([noisew, noisew], axis=1)
         bsvd, but, ibs, sv, nmodes = self._svd_chain_device(bf, noisew, skip_svd_inv)
+        t1 = time.time()
 
         final = self._svdfile(mi)
         tmp = os.path.join(os.path.dirname(final), "." + os.path.basename(final))
@@ -351,10 +508,18 @@ class BeamTransfer(config.Reader):
             try:
                 fs.attrs["baselines"] = tel.baselines
             except ValueError:
+                # > 64 KiB (nbase > ~4000): h5py with its default format version refuses such an attribute
+                # too; the baselines are in telescopeobject.pickle
                 logger.warning("baselines attribute too large for an HDF5 object header; omitted")
             fs.attrs["m"] = mi
-            fs.attrs["frequencies"] = tel.frequencies
+            try:
+                fs.attrs["frequencies"] = tel.frequencies
+            except ValueError:
+                logger.warning("frequencies attribute too large for an HDF5 object header; omitted")
         os.replace(tmp, final)
+        tm = self.__dict__.setdefault("timing", {})
+        tm["svd_compute_s"] = tm.get("svd_compute_s", 0.0) + (t1 - t0)
+        tm["svd_write_s"] = tm.get("svd_write_s", 0.0) + (time.time() - t1)
 
     def _collect_svd_spectrum(self):
         """Gather all singular values into ``svdspectrum.hdf5`` (beamtransfer.py:931-947)."""
@@ -646,7 +811,10 @@ def _run_svd_entry(entry, bf_host, noisew_host, npol, nl, svd_len, want_inv, ext
 
     batch, ntel = bf_host.shape[:2]
     dev = torch.device("cuda", torch.cuda.current_device())
-    bf = torch.from_numpy(np.ascontiguousarray(bf_host)).to(dev)
+    if isinstance(bf_host, torch.Tensor):  # block left on the device by the m-file stage
+        bf = bf_host.contiguous()
+    else:
+        bf = torch.from_numpy(np.ascontiguousarray(bf_host)).to(dev)
     nw = torch.from_numpy(np.ascontiguousarray(noisew_host, dtype=np.float64)).to(dev)
     bsvd = torch.empty((batch, svd_len, npol, nl), dtype=torch.complex128, device=dev)
     but = torch.empty((batch, svd_len, ntel), dtype=torch.complex128, device=dev)

@@ -236,6 +236,8 @@ class KLTransform(config.Reader):
         return evals, evecs
 
     def _ev_save_hook(self, f, evextra):
+        if type(self).signal is KLTransform.signal or type(self).foreground is KLTransform.foreground:
+            f.attrs["skymodel"] = skymodel.MODEL_TAG  # not a reference attribute: marks the stand-in models
         ac = evextra["ac"]
         if ac != 0.0:
             f.attrs["add_const"] = ac

@@ -117,6 +117,10 @@ class ProductManager(object):
         self.telescope = telclass.from_config(yconf["telescope"])
 
         conf = yconf["config"]
+        if conf.get("reionisation"):  # manager.py:210-211 of the reference
+            from . import skymodel
+
+            skymodel._reionisation = True
         # BeamTransfer variant (manager.py:217-221): plain, no SVD, or the single full SVD
         btclass = beamtransfer.BeamTransfer
         if conf.get("nosvd"):

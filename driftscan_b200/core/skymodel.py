@@ -17,9 +17,28 @@ They are SYNTHETIC stand-ins; users with ``cora`` can pass
 their own arrays through ``KLTransform.signal`` / ``foreground`` overrides.
 """
 
+import warnings
+
 import numpy as np
 
 _reionisation = False
+
+# Written into the KL product files (attribute `skymodel`) so that products made with these
+# stand-ins cannot be mistaken for ones made with cora's models.
+MODEL_TAG = "driftscan_b200 synthetic power laws (Santos et al. 2005 forms; NOT cora)"
+_warned = False
+
+
+def _warn_once():
+    global _warned
+    if not _warned:
+        _warned = True
+        warnings.warn(
+            "driftscan_b200.core.skymodel: cora is not available; the KL stage uses synthetic power-law "
+            "C_l(nu, nu') stand-ins.  Eigenvalues, mode counts at the default thresholds and everything "
+            "derived from them are NOT comparable with products of the reference (which uses cora's "
+            "FullSkySynchrotron / PointSources / Corr21cm).  Pass your own covariances through "
+            "KLTransform.signal / foreground overrides for physical results.", stacklevel=3)
 
 # (A [K^2], alpha, beta, zeta), nu_0 = 130 MHz, l_0 = 100 (Santos et al. 2005 table 1, in K^2)
 _SYNC = (7.00e-4, 2.80, 2.8, 4.0)
@@ -40,6 +59,7 @@ def _power_law(lmax, frequencies, A, alpha, beta, zeta):
 
 def foreground_model(lmax, frequencies, npol, pol_frac=1.0, pol_length=None):
     """Foreground covariance ``[npol, npol, lmax+1, nfreq, nfreq]`` (skymodel.py:23-50)."""
+    _warn_once()
     nfreq = np.asarray(frequencies).size
     cv_fg = np.zeros((npol, npol, lmax + 1, nfreq, nfreq))
     cv_fg[0, 0] = _power_law(lmax, frequencies, *_SYNC)
@@ -60,6 +80,8 @@ def im21cm_model(lmax, frequencies, npol, cr=None, temponly=False):
     f = np.asarray(frequencies, dtype=np.float64)
     nfreq = f.size
     ell = np.arange(lmax + 1, dtype=np.float64)
+    if cr is None:
+        _warn_once()
     if cr is not None:
         cv_t = np.asarray(cr(ell[:, np.newaxis, np.newaxis], f[np.newaxis, :, np.newaxis], f[np.newaxis, np.newaxis, :]))
     else:

@@ -650,3 +650,24 @@ extern "C" int dsb_peer_free(void *dev_ptr) {
   if (dev_ptr) DSB_CUDA(cudaFree(dev_ptr));
   return DSB_OK;
 }
+
+// ---- raw copies and pinned host memory for the host side of the product path ------------------
+extern "C" int dsb_memcpy(void *dst, const void *src, size_t bytes, int kind, void *stream_, int sync) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSB_CHECK((dst && src) || bytes == 0, DSB_ERR_INVALID, "dsb_memcpy: NULL argument");
+  DSB_CHECK(kind >= 0 && kind <= 2, DSB_ERR_INVALID, "dsb_memcpy: kind must be 0 (H2D), 1 (D2H) or 2 (D2D)");
+  const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost
+                                                                           : cudaMemcpyDeviceToDevice;
+  if (bytes) DSB_CUDA(cudaMemcpyAsync(dst, src, bytes, k, stream));
+  if (sync) DSB_CUDA(cudaStreamSynchronize(stream));
+  return DSB_OK;
+}
+extern "C" int dsb_host_alloc(size_t bytes, void **host_ptr) {
+  DSB_CHECK(host_ptr != nullptr, DSB_ERR_INVALID, "dsb_host_alloc: NULL argument");
+  DSB_CUDA(cudaHostAlloc(host_ptr, bytes ? bytes : 64, cudaHostAllocDefault));
+  return DSB_OK;
+}
+extern "C" int dsb_host_free(void *host_ptr) {
+  if (host_ptr) DSB_CUDA(cudaFreeHost(host_ptr));
+  return DSB_OK;
+}

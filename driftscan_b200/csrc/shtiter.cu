@@ -22,6 +22,7 @@
 // This file holds the two data-movement kernels of an iteration; the contractions are
 // launch_contract_{tc,f64}, the update a(0) + a - (A S) a is fused into their epilogue.
 #include <algorithm>
+#include <cstdlib>
 
 #include "dsb_common.cuh"
 
@@ -100,10 +101,20 @@ struct FoldParams {
   const RingDesc *rings;
   const UnitDev *units;
   int nunits, nfold, Kp, mcap;
+  int ktile0;  // first 32-ring tile without aliasing for any unit of the bucket (4 (k + 1) > 2 mcap)
   int nsp0, has2, cpu0, ncols0, ncols2;
   const void *G0, *G2;
   void *F0, *F2;
 };
+
+// four consecutive values, 16-byte aligned destination (columns of a map group start at a multiple of 4)
+__device__ __forceinline__ void store4(float *d, const float *v) {
+  *reinterpret_cast<float4 *>(d) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(double *d, const double *v) {
+  reinterpret_cast<double2 *>(d)[0] = make_double2(v[0], v[1]);
+  reinterpret_cast<double2 *>(d)[1] = make_double2(v[2], v[3]);
+}
 
 // One slot pair (+re, +im, -re, -im) of one Stokes map: columns col .. col+3 of G
 template <typename T>
@@ -141,7 +152,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) alias_fold_kernel(const FoldParams P) {
   const int k = blockIdx.x * 32 + (threadIdx.x & 31);
   const int m = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (k >= P.nfold || m > P.mcap) return;
+  if (k >= P.nfold || k >= P.ktile0 * 32 || m > P.mcap) return;
   const RingDesc rd = P.rings[k];
   for (int u = blockIdx.z; u < P.nunits; u += gridDim.z) alias_fold_unit<T>(P, rd, k, m, u);
 }
@@ -167,13 +178,8 @@ __device__ __forceinline__ void alias_fold_unit(const FoldParams &P, const RingD
       fold_map<T>(G, P.ncols0, Kp, k, col, m, ud.mmax, n, shifted, 0, fn, ev);
       fold_map<T>(G, P.ncols0, Kp, k, col, m, ud.mmax, n, shifted, 1, fn, od);
       if (equator) od[0] = od[1] = od[2] = od[3] = T(0);
-      T *d0 = F + ((size_t)(2 * m + 0) * Kp + k) * P.ncols0 + col;
-      T *d1 = F + ((size_t)(2 * m + 1) * Kp + k) * P.ncols0 + col;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        d0[i] = ev[i];
-        d1[i] = od[i];
-      }
+      store4(F + ((size_t)(2 * m + 0) * Kp + k) * P.ncols0 + col, ev);
+      store4(F + ((size_t)(2 * m + 1) * Kp + k) * P.ncols0 + col, od);
     }
   }
   if (!P.has2) return;
@@ -194,12 +200,10 @@ __device__ __forceinline__ void alias_fold_unit(const FoldParams &P, const RingD
       T *d0 = F + ((size_t)(2 * m + 0) * Kp + k) * P.ncols2 + cu;
       T *d1 = F + ((size_t)(2 * m + 1) * Kp + k) * P.ncols2 + cu;
 #pragma unroll
-      for (int q = 0; q < 2; ++q)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          d0[4 * q + i] = ev[q][i];
-          d1[4 * q + i] = od[q][i];
-        }
+      for (int q = 0; q < 2; ++q) {
+        store4(d0 + 4 * q, ev[q]);
+        store4(d1 + 4 * q, od[q]);
+      }
     } else {
       // fp64: both operand roles, [prob][2 Kp][ncols2] (same emission as ringfft.cu gather_emit)
       const size_t K2 = 2 * (size_t)Kp;
@@ -208,18 +212,67 @@ __device__ __forceinline__ void alias_fold_unit(const FoldParams &P, const RingD
       T *x0 = F + ((size_t)(2 * m + 0) * K2 + Kp + k) * P.ncols2 + cu;
       T *x1 = F + ((size_t)(2 * m + 1) * K2 + Kp + k) * P.ncols2 + cu;
 #pragma unroll
-      for (int q = 0; q < 2; ++q)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          w0[4 * q + i] = ev[q][i];
-          w1[4 * q + i] = od[q][i];
-        }
+      for (int q = 0; q < 2; ++q) {
+        store4(w0 + 4 * q, ev[q]);
+        store4(w1 + 4 * q, od[q]);
+      }
       const T xa[8] = {od[1][1], -od[1][0], od[1][3], -od[1][2], -od[0][1], od[0][0], -od[0][3], od[0][2]};
       const T xb[8] = {ev[1][1], -ev[1][0], ev[1][3], -ev[1][2], -ev[0][1], ev[0][0], -ev[0][3], ev[0][2]};
+      store4(x0, xa);
+      store4(x0 + 4, xa + 4);
+      store4(x1, xb);
+      store4(x1 + 4, xb + 4);
+    }
+  }
+}
+
+// Rings with more than 2 mcap pixels do not alias (q = 0 only): the fold is a scaled transpose
+//   F+-_m = fn G+-_m   (m = 0: F-_0 = conj(F+_0)),
+// done through shared memory so that both the reads (contiguous in k) and the writes (contiguous
+// in the operand columns) are full 128-byte lines.  One CTA = one (32-ring tile, m, 32 columns).
+// XROLE (fp64 spin-2 block only): also emit the X operand role, the (-i U | +i Q) permutation of
+// the opposite fold parity, at row offset Kp of the problem with the other parity.
+template <typename T, bool XROLE>
+__global__ void __launch_bounds__(256)
+fold_identity_kernel(const RingDesc *__restrict__ rings, const UnitDev *__restrict__ units, int nunits, int nfold,
+                     int Kp, int ktile0, int cpu, int ncols, const T *__restrict__ G, T *__restrict__ F) {
+  __shared__ T tile[32][33];
+  const int k0 = (ktile0 + blockIdx.x) * 32, m = blockIdx.y, col0 = blockIdx.z * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int Arows = XROLE ? 2 * Kp : Kp;
+  // output lane = column tx: its unit, and whether the column is the (-re, -im) half of m = 0
+  const int u = (col0 + tx) / cpu;
+  const bool live = u < nunits && m <= units[min(u, nunits - 1)].mmax;
+  const int j4 = tx & 3;
+  for (int p = 0; p < 2; ++p) {
+    const size_t prob = 2 * (size_t)m + p;
+    __syncthreads();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        x0[i] = xa[i];
-        x1[i] = xb[i];
+    for (int i = 0; i < 4; ++i) {
+      const int c = ty + 8 * i;
+      tile[c][tx] = (k0 + tx < nfold) ? G[(prob * ncols + col0 + c) * Kp + k0 + tx] : T(0);
+    }
+    __syncthreads();
+    if (!live) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty + 8 * i, k = k0 + r;
+      if (k >= nfold) continue;
+      const RingDesc &rd = rings[k];
+      const bool equator = rd.startS < 0;
+      T fn = (T)(equator ? rd.nphi : 2 * rd.nphi);
+      if (equator && p == 1) fn = T(0);
+      T v = tile[tx][r];
+      if (m == 0 && j4 >= 2) v = (j4 == 2) ? tile[tx - 2][r] : -tile[tx - 2][r];  // F-_0 = conj(F+_0)
+      F[(prob * Arows + k) * ncols + col0 + tx] = fn * v;
+      if (XROLE) {
+        const int j = tx & 7;
+        const int cs = (tx & ~7) | (j ^ 5);
+        T x = tile[cs][r];
+        const int js = cs & 3;
+        if (m == 0 && js >= 2) x = (js == 2) ? tile[cs - 2][r] : -tile[cs - 2][r];
+        const T sg = (j == 1 || j == 3 || j == 4 || j == 6) ? T(-1) : T(1);
+        F[((prob ^ 1) * Arows + Kp + k) * ncols + col0 + tx] = sg * fn * x;
       }
     }
   }
@@ -243,12 +296,41 @@ int launch_alias_fold(dsb_plan *plan, const BucketLayout &lay, const UnitDev *un
   P.G2 = G2;
   P.F0 = F0;
   P.F2 = F2;
-  dim3 grid((plan->nfold + 31) / 32, (lay.mcap + 8) / 8, std::min(lay.nunits, 65535));
-  if (precision == DSB_PREC_FP64)
-    alias_fold_kernel<double><<<grid, 256, 0, stream>>>(P);
-  else
-    alias_fold_kernel<float><<<grid, 256, 0, stream>>>(P);
-  DSB_LAUNCH_CHECK();
+  // rings k < mcap / 2 can alias for some unit of the bucket: general gather; the rest: transpose
+  const int ktiles = (plan->nfold + 31) / 32;
+  static const bool no_fast = getenv("DSB_FOLD_GENERAL") != nullptr;  // diagnostic: gather kernel everywhere
+  P.ktile0 = no_fast ? ktiles : std::min(ktiles, (lay.mcap / 2 + 31) / 32);
+  const bool f64 = precision == DSB_PREC_FP64;
+  if (P.ktile0 > 0) {
+    dim3 grid(P.ktile0, (lay.mcap + 8) / 8, std::min(lay.nunits, 65535));
+    if (f64)
+      alias_fold_kernel<double><<<grid, 256, 0, stream>>>(P);
+    else
+      alias_fold_kernel<float><<<grid, 256, 0, stream>>>(P);
+    DSB_LAUNCH_CHECK();
+  }
+  if (P.ktile0 < ktiles) {
+    const int nk = ktiles - P.ktile0;
+    dim3 g0(nk, lay.mcap + 1, lay.ncols0 / 32), g2(nk, lay.mcap + 1, lay.ncols2 / 32);
+    if (f64) {
+      fold_identity_kernel<double, false><<<g0, 256, 0, stream>>>(plan->rings, units_dev, lay.nunits, plan->nfold, lay.Kp,
+                                                                  P.ktile0, lay.cpu0, lay.ncols0, (const double *)G0,
+                                                                  (double *)F0);
+      if (lay.has2)
+        fold_identity_kernel<double, true><<<g2, 256, 0, stream>>>(plan->rings, units_dev, lay.nunits, plan->nfold,
+                                                                   lay.Kp, P.ktile0, 8, lay.ncols2, (const double *)G2,
+                                                                   (double *)F2);
+    } else {
+      fold_identity_kernel<float, false><<<g0, 256, 0, stream>>>(plan->rings, units_dev, lay.nunits, plan->nfold, lay.Kp,
+                                                                 P.ktile0, lay.cpu0, lay.ncols0, (const float *)G0,
+                                                                 (float *)F0);
+      if (lay.has2)
+        fold_identity_kernel<float, false><<<g2, 256, 0, stream>>>(plan->rings, units_dev, lay.nunits, plan->nfold,
+                                                                   lay.Kp, P.ktile0, 8, lay.ncols2, (const float *)G2,
+                                                                   (float *)F2);
+    }
+    DSB_LAUNCH_CHECK();
+  }
   return DSB_OK;
 }
 

@@ -131,14 +131,19 @@ class TransferEngine:
 
     # ---- m-major output (BeamTransfer._generate_mfiles) ---------------------------
     def transfer_mmajor(self, bl, fi, lmax, fslot, bslot, nf, nb, lside, mmax, out_ptr, out_is_host,
-                        out_kind=_lib.DSB_OUT_MMAJOR_C128, stream=None):
+                        out_kind=_lib.DSB_OUT_MMAJOR_C128, stream=None, block_ptrs=None):
         """Write the compact m-major beam_m blocks of the given units into ``out_ptr``
-        (layout documented at DSB_OUT_MMAJOR_* in include/driftscan_b200.h)."""
+        (layout documented at DSB_OUT_MMAJOR_* in include/driftscan_b200.h), or -- ``block_ptrs``
+        given -- block m at the device address ``block_ptrs[m]`` (possibly a peer GPU's memory:
+        the fused frequency -> m exchange of :class:`driftscan_b200.parallel.PeerScatter`)."""
         tel = self.tel
         npol = self._npol_compute()
         for nside, idx in self._buckets(lmax):
             plan, units = self._units_for(nside, bl[idx], fi[idx], lmax[idx], fslot[idx], bslot[idx])
-            plan.transfer_units(
-                units, npol, tel._polarised_, mmax, self.precision, out_kind, [nf, nb, npol, lside, mmax],
-                out_ptr, out_is_host, stream,
-            )
+            dims = [nf, nb, npol, lside, mmax]
+            if block_ptrs is not None:
+                plan.transfer_units_scatter(units, npol, tel._polarised_, mmax, self.precision, out_kind, dims,
+                                            block_ptrs, stream)
+            else:
+                plan.transfer_units(units, npol, tel._polarised_, mmax, self.precision, out_kind, dims, out_ptr,
+                                    out_is_host, stream)

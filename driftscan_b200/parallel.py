@@ -61,6 +61,10 @@ class Comm:
     def rank0(self):
         return self.rank == 0
 
+    @property
+    def is_nccl(self):
+        return self.size > 1 and self._dist.get_backend() == "nccl"
+
     def barrier(self):
         if self.size > 1:
             self._dist.barrier()

@@ -593,6 +593,20 @@ def _guess_chunks(shape, itemsize, target=1 << 20):
     return tuple(chunks)
 
 
+class _Attrs(dict):
+    """Root attributes.  An HDF5 attribute lives in an object-header message, 64 KiB at most (the
+    limit h5py / libhdf5 enforce with their default format version, too): checked when the value is
+    assigned, so that the caller can react, not when the file is closed."""
+
+    def __setitem__(self, name, value):
+        _attr_message(name, value)  # raises ValueError for a value that cannot be stored
+        super().__setitem__(name, value)
+
+    def update(self, *args, **kwargs):
+        for k, v in dict(*args, **kwargs).items():
+            self[k] = v
+
+
 class File:
     """Minimal h5py.File look-alike (flat namespace of datasets + root attributes)."""
 
@@ -602,7 +616,7 @@ class File:
         self._datasets = {}  # name -> (shape, dtype, offset or None)
         self._chunked = {}   # name -> dict(chunks, filters, index, dirty, layout_pos)
         self._compact = {}   # name -> bytes (read only)
-        self.attrs = {}
+        self.attrs = _Attrs()
         self._closed = False
         self._base = 0
         if mode == "w":

@@ -151,6 +151,14 @@ int dsb_peer_open(const unsigned char *handle64, void **dev_ptr);
 int dsb_peer_close(void *dev_ptr);
 int dsb_peer_free(void *dev_ptr);
 
+/* Plumbing for the host side of BeamTransfer._generate_mfiles (drift/core/beamtransfer.py:632-663:
+ * the blocks a rank owns go from device memory -- its own, or the peer buffer above -- into the
+ * m-files): a stream-ordered copy (kind 0 = host to device, 1 = device to host, 2 = device to
+ * device; sync != 0 waits for the stream) and page-locked host staging memory. */
+int dsb_memcpy(void *dst, const void *src, size_t bytes, int kind, void *stream, int sync);
+int dsb_host_alloc(size_t bytes, void **host_ptr);
+int dsb_host_free(void *host_ptr);
+
 /* Size in elements (complex numbers) of an m-major buffer and the per-m block
  * offsets (mmax+2 entries, last = total). */
 int64_t dsb_mmajor_size(int n_out0, int n_out1, int npol, int lside, int mmax, int64_t *offsets);

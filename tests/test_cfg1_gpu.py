@@ -1,0 +1,116 @@
+"""GPU: BASELINE config 1 -- the reference's tests/testparams.yaml, VERBATIM (tests/golden/
+testparams.yaml is a byte copy of that input file) -- through ProductManager, checked like the
+reference's own functional tests (tests/test_functional.py:175-209: beam_m(14), the SVD spectrum,
+the KL and DoubleKL spectra) against the products the reference's classes generate from the same
+file (tests/golden/make_golden_cfg1.py; SHT = oracle at healpy iter = 2, the telescope default).
+
+`verbatim`: nothing added to the file, i.e. the shipped defaults: precision fp32x3, sht_iter 2.
+`fp64`    : the same file with `precision: fp64` in the telescope section (validation path).
+"""
+
+import filecmp
+import os
+
+import numpy as np
+import pytest
+import yaml
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "cfg1_products.npz"))
+
+
+@pytest.fixture(scope="module", params=["verbatim", "fp64"])
+def manager(request, tmp_path_factory, golden_dir):
+    from driftscan_b200.core import manager as dmanager
+
+    src = os.path.join(golden_dir, "testparams.yaml")
+    d = tmp_path_factory.mktemp("cfg1_" + request.param)
+    cfile = str(d / "testparams.yaml")
+    with open(src) as fh:
+        text = fh.read()
+    if request.param == "fp64":
+        conf = yaml.safe_load(text)
+        conf["telescope"]["precision"] = "fp64"
+        text = yaml.dump(conf)
+    with open(cfile, "w") as fh:
+        fh.write(text)
+    if request.param == "verbatim":
+        assert filecmp.cmp(src, cfile, shallow=False)
+    with pytest.warns(UserWarning, match="psfisher"):
+        pm = dmanager.ProductManager.from_config(cfile)
+    assert pm.telescope.precision == ("fp64" if request.param == "fp64" else "fp32x3") and pm.telescope.sht_iter == 2
+    pm.generate()
+    pm.mode = request.param
+    return pm
+
+
+def test_manager(manager):
+    # tests/test_functional.py:150-157
+    assert os.path.samefile(manager.directory, os.path.join(os.path.dirname(manager.directory), "testdir"))
+    tel = manager.telescope
+    assert (tel.nfeed, tel.nbase, tel.nfreq, tel.lmax, tel.mmax) == (20, 52, 8, 96, 94)
+    assert sorted(manager.kltransforms) == ["dk", "kl"]
+
+
+def test_beam_m(manager, gold):
+    # tests/test_functional.py:175-186 (rel 1e-4 / abs 1e-8 there)
+    tol = 1e-10 if manager.mode == "fp64" else 1e-6
+    for mi in (14, 60, 94):
+        bm, ref = manager.beamtransfer.beam_m(mi), gold[f"beam_m_{mi}"]
+        assert bm.shape == ref.shape
+        assert np.abs(bm - ref).max() <= tol * np.abs(ref).max(), mi
+        assert bm == pytest.approx(ref, rel=1e-4, abs=max(1e-8, tol * np.abs(ref).max()))
+
+
+def test_svd_spectrum(manager, gold):
+    # tests/test_functional.py:189-197 (rel 1e-3 / abs 400 there)
+    bt = manager.beamtransfer
+    assert bt.svd_len == int(gold["svd_len"]) and bt.ndofmax == int(gold["ndofmax"])
+    svd, ref = bt.svd_all(), gold["svd_all"]
+    assert svd.shape == ref.shape
+    tol = 1e-8 if manager.mode == "fp64" else 2e-6
+    assert np.abs(svd - ref).max() <= tol * ref.max()
+    assert svd == pytest.approx(ref, rel=1e-3, abs=400)
+    # modes a consumer keeps (svcut), per m and frequency, up to modes within a factor 2 of the cut
+    for mi in (0, 14, 60):
+        sv = bt.beam_singularvalues(mi)
+        num = (sv > sv.max() * bt.svcut).sum(axis=1)
+        assert ((ref[mi] > 2 * ref[mi].max() * bt.svcut).sum(axis=1) <= num).all()
+        assert (num <= (ref[mi] > 0.5 * ref[mi].max() * bt.svcut).sum(axis=1)).all()
+    # SVD mode subspace of m = 14 through the reconstruction B^H P B (vectors are defined up to phase)
+    sv, bsvd, bref = gold["sv_14"], bt.beam_svd(14), gold["beam_svd_14"]
+    scale = sv.max()
+    floor = 1e-6 if manager.mode == "fp64" else 1e-3
+    rtol = 1e-7 if manager.mode == "fp64" else 2e-5
+    for fi in range(sv.shape[0]):
+        k = int((sv[fi] > floor * scale).sum())
+        ra, rb = bsvd[fi, :k].reshape(k, -1), bref[fi, :k].reshape(k, -1)
+        want = rb.conj().T @ rb
+        assert np.abs(ra.conj().T @ ra - want).max() <= rtol * max(scale**2, np.abs(want).max())
+
+
+def test_kl_spectrum(manager, gold):
+    # tests/test_functional.py:200-209: the foregroundless KL filter
+    ev, ref = manager.kltransforms["kl"].evals_all(), gold["kl_evals_all"]
+    assert ev.shape == ref.shape
+    if manager.mode == "fp64":
+        assert ev == pytest.approx(ref, rel=1e-4, abs=1e-8 * ref.max())
+    else:
+        # without foregrounds the pencil is well conditioned: fp32x3 products move S/N by ~1e-6
+        assert ev == pytest.approx(ref, rel=1e-3, abs=1e-5 * ref.max())
+
+
+def test_dk_spectrum(manager, gold):
+    ev, ref = manager.kltransforms["dk"].evals_all(), gold["dk_evals_all"]
+    assert ev.shape == ref.shape
+    if manager.mode == "fp64":
+        assert ev == pytest.approx(ref, rel=1e-4, abs=1e-8 * ref.max())
+    else:
+        # foreground filter: 16 decades of noise covariance, see tests/test_kl_gpu.py
+        big = ref > 0.1
+        assert np.abs(ev - ref)[big].max() <= 0.1 * ref[big].max()
+        assert abs(int((ev > 0).sum()) - int((ref > 0).sum())) <= 0.02 * (ref > 0).sum() + 2
