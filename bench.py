@@ -315,6 +315,74 @@ def svd_section(tel, args, rank, world, dev, stream, with_cpu):
     return out
 
 
+def generate_section(args, rank, world, comm):
+    """The PRODUCT, not the kernel: BeamTransfer.generate() (drift/core/beamtransfer.py:447-480) wall
+    clock on a frequency subset of the workload -- host beams, transfer stage, the frequency -> m
+    exchange, m-files on disk, per-m SVD fed from the device-resident blocks, SVD files on disk,
+    svdspectrum.  `--generate-freqs` channels per GPU spanning the workload's band (the geometry,
+    lmax / mmax and nside mix of configs[2]; the full 64 channels would write 170 GB)."""
+    import shutil
+    import tempfile
+
+    import torch
+
+    from driftscan_b200.core import beamtransfer
+    from driftscan_b200.telescope import cylinder
+
+    nf = args.generate_freqs * world
+    out = {"frequencies": nf, "what": "BeamTransfer.generate(): beams + transfer + exchange + beam_m files + per-m SVD "
+           "+ svd files + svdspectrum, wall clock, max over ranks", "runs": {}}
+    base = [None]
+    if rank == 0:
+        base[0] = tempfile.mkdtemp(prefix="dsb_generate_", dir=args.generate_dir)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.broadcast_object_list(base, src=0)
+    base = base[0]
+    modes = [("contiguous", False)] + ([("lzf", True)] if args.generate_lzf else [])
+    for name, compress in modes:
+        tel = cylinder.PolarisedCylinderTelescope.from_config(dict(WORKLOAD, num_freq=nf, precision=args.precision))
+        if args.sht_iter is not None:
+            tel.sht_iter = args.sht_iter
+        bt = beamtransfer.BeamTransfer(os.path.join(base, name), telescope=tel)
+        bt.read_config(dict(compress_products=compress, mem_chunk=64.0))
+        comm.barrier()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        bt.generate()
+        torch.cuda.synchronize()
+        comm.barrier()
+        dt = time.time() - t0
+        tm = dict(bt.timing)
+        if world > 1:
+            t = torch.tensor([dt] + [tm.get(k, 0.0) for k in ("mfiles_compute_s", "mfiles_write_s", "svd_compute_s",
+                                                             "svd_write_s")], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+            tm = dict(zip(("mfiles_compute_s", "mfiles_write_s", "svd_compute_s", "svd_write_s"), t[1:].tolist()))
+        nbytes = 0
+        if rank == 0:
+            for root, _, files in os.walk(os.path.join(base, name)):
+                nbytes += sum(os.path.getsize(os.path.join(root, f)) for f in files)
+        units = tel.nbase * tel.nfreq
+        out["runs"][name] = {
+            "wall_s": dt, "units": int(units), "units_per_s": units / dt, "m_blocks": int(tel.mmax + 1),
+            "mfreq_blocks_per_s": (tel.mmax + 1) * tel.nfreq / dt, "bytes_on_disk": int(nbytes),
+            "exchange": bt.exchange_path, "seconds": tm, "sht_iter": int(tel.sht_iter),
+            "storage": "chunked + LZF (the reference's layout)" if compress else "contiguous (compress_products: false)",
+        }
+        tel.engine.close()
+        del bt, tel
+        torch.cuda.empty_cache()
+        comm.barrier()
+        if rank == 0:
+            shutil.rmtree(os.path.join(base, name), ignore_errors=True)
+    if rank == 0:
+        shutil.rmtree(base, ignore_errors=True)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -338,6 +406,11 @@ def main():
                     help="diagnostic: run the nside buckets of a step on separate streams (faults at present: two "
                          "Legendre launches in flight raise an illegal instruction, DESIGN.md section 7)")
     ap.add_argument("--no-svd", action="store_true", help="skip the per-m SVD measurement (second half of the metric)")
+    ap.add_argument("--no-generate", action="store_true", help="skip the BeamTransfer.generate() wall-clock leg")
+    ap.add_argument("--generate-freqs", type=int, default=2, help="channels per GPU in the generate() leg")
+    ap.add_argument("--generate-lzf", action="store_true", help="also time generate() with the reference's chunked + LZF storage")
+    ap.add_argument("--generate-dir", default=None, help="directory for the generate() leg's products (default: the system tmp)")
+    ap.add_argument("--no-check", action="store_true", help="N > 1: skip the bit-exact check of the multi-GPU product path")
     ap.add_argument("--svd-only", action="store_true", help="diagnostic: run only the per-m SVD measurement")
     ap.add_argument("--svd-ms", default="auto",
                     help="sample of m values the SVD stage is timed on (auto: 4 per GPU, evenly spread over 0..mmax)")
@@ -577,6 +650,9 @@ def main():
     prof_ms = (ctypes.c_double * 3)()
     prof_n = (ctypes.c_uint64 * 3)()
     _lib.lib.dsb_get_profile(prof_ms, prof_n)
+    refine_ms = ctypes.c_double()
+    refine_n = ctypes.c_uint64()
+    _lib.lib.dsb_get_profile_refine(ctypes.byref(refine_ms), ctypes.byref(refine_n))
     _lib.lib.dsb_set_profiling(0)
     # The kernels of a step are recorded once into a CUDA graph and replayed: one launch per step
     # from the host, so the measurement does not depend on how fast this process can enqueue ~50
@@ -896,6 +972,24 @@ def main():
         torch.cuda.empty_cache()
         svd = svd_section(tel, args, rank, world, dev, stream, with_cpu=(world == 1 and not args.no_cpu_baseline))
 
+    # ---- the product through the public API, wall clock; N > 1: the multi-GPU product path checked
+    # bit for bit against a single process on a small telescope (so a scaling run carries a
+    # correctness result next to its timings)
+    gen = check = None
+    if not args.no_generate:
+        gen = generate_section(args, rank, world, comm)
+    if world > 1 and not args.no_check:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import check_generate_multi
+
+        check = check_generate_multi.run_check(args.precision)
+
+    niter = int(tel.sht_iter)
+    refine = {"sht_iter": niter, "ms_per_step": refine_ms.value / max(args.steps, 1),
+              "ms_per_iteration": refine_ms.value / max(args.steps, 1) / max(niter, 1),
+              "what": "Jacobi refinement of the analysis (healpy map2alm iter): per pass one coefficient transpose, one "
+                      "synthesis contraction (tcgen05), the aliasing fold and one analysis contraction with the update "
+                      "fused into its epilogue; not part of the three stage times"}
     if stdout_fd is not None:
         sys.stdout.flush()
         os.dup2(stdout_fd, 1)
@@ -910,6 +1004,7 @@ def main():
             "launch_mode": ("CUDA graph of one step (%d kernels), replayed; stage times from a separate profiled "
                             "pass of direct launches" % graph["launches"]) if graph["g"] is not None
             else "direct launches", "cpu_baseline": cpu, "exchange": exchange, "svd": svd,
+            "refine": refine, "generate": gen, "multi_gpu_check": check,
         }
         print(json.dumps(line))
     if world > 1:

@@ -277,7 +277,7 @@ class BeamTransfer(config.Reader):
         # that owns (and writes) that m -- the transpose_blocks of beamtransfer.py:632 fused into the
         # kernel that produces the data (parallel.PeerScatter).  Without CUDA IPC: NCCL all-to-all.
         scatter = None
-        if comm.size > 1 and comm.is_nccl and not os.environ.get("DSB_NO_PEER_SCATTER"):
+        if comm.size > 1 and not os.environ.get("DSB_NO_PEER_SCATTER"):
             try:
                 scatter = parallel.PeerScatter(comm, comm.size * nf_chunk, nb_inc, np_inc, tel.lmax, tel.mmax,
                                                elem_bytes=elem, balance="count")

@@ -38,6 +38,7 @@
 // per stage) + 2 x 128 columns of correction accumulators (ping-pong per item).
 #include <cuda.h>
 #include <cstdlib>
+#include <mutex>
 
 #include "dsb_common.cuh"
 
@@ -553,8 +554,29 @@ int launch_contract_tc(const ContractDesc &d, int nitems, const WorkItem *items_
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(nitems, nsm);
-  legendre_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mA0, mA2, mB0, mB2, P);
-  DSB_LAUNCH_CHECK();
+  // Two launches of this kernel in flight at once (different streams) fault with an illegal
+  // instruction at the first tcgen05.mma of CTAs that start on a TPC the other launch is still
+  // leaving (not the shared-memory carve-out: DSB_TC_FIXED_SMEM does not help).
+  // Until that is understood the launches are chained through an event: every launch waits for the
+  // previous one, whichever stream it was on, so the entry points stay safe on several streams
+  // (everything else of a call -- ring FFT, fold, pack -- still overlaps across streams).  A stream
+  // that is being captured into a graph cannot wait on outside work: no chaining there.
+  {
+    static std::mutex mu;
+    static cudaEvent_t last = nullptr;
+    static const bool chain = getenv("DSB_TC_NO_CHAIN") == nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    DSB_CUDA(cudaStreamIsCapturing(stream, &cap));
+    const bool use = chain && cap == cudaStreamCaptureStatusNone;
+    if (use) {
+      if (!last) DSB_CUDA(cudaEventCreateWithFlags(&last, cudaEventDisableTiming));
+      else DSB_CUDA(cudaStreamWaitEvent(stream, last, 0));
+    }
+    legendre_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mA0, mA2, mB0, mB2, P);
+    DSB_LAUNCH_CHECK();
+    if (use) DSB_CUDA(cudaEventRecord(last, stream));
+  }
   return DSB_OK;
 }
 

@@ -245,6 +245,11 @@ class PeerScatter:
         if self.comm.size > 1:
             import torch
 
+            if not self.comm.is_nccl:
+                # host-side backends are not stream-ordered: drain the device, then meet
+                torch.cuda.synchronize()
+                self.comm.barrier()
+                return
             t = self.__dict__.get("_token")
             if t is None:
                 t = self._token = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
