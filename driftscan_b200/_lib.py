@@ -71,6 +71,7 @@ def _load():
         "dsb_get_profile_refine": (i32, [P(dbl), P(u64)]),
         "dsb_beam_upload": (i32, [vp, i32, vp, i32, i32, P(dbl), vp]),
         "dsb_beam_slots": (i32, [vp, i32]),
+        "dsb_beam_cylinder": (i32, [vp, i32, i32, vp, vp, dbl, i32, vp, vp, vp, P(dbl), vp]),
         "dsb_plan_build_tables": (i32, [vp, i32, i32, i32, i32, vp]),
         "dsb_transfer_units": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, P(i64), vp, i32, vp]),
         "dsb_transfer_units_scatter": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, P(i64), vp, vp]),
@@ -213,6 +214,19 @@ class Plan:
                 ctypes.byref(om), ctypes.c_void_p(stream or 0),
             )
         )
+        self.omega[slot] = om.value
+        return om.value
+
+    def cylinder_beam(self, slot, axes, dipole, alpha_ns, spline, stream=None):
+        """Analytic cylinder beam evaluated on the device (dsb_beam_cylinder).  ``axes``: (xhat, yhat,
+        zhat); ``dipole``: 3-vector or None (amplitude only); ``spline``: util.cubicspline.Interpolater."""
+        ax = np.ascontiguousarray(np.asarray(axes, dtype=np.float64).reshape(9))
+        dp = None if dipole is None else np.ascontiguousarray(dipole, dtype=np.float64)
+        kx, ky, km = (np.ascontiguousarray(a, dtype=np.float64) for a in (spline.x, spline.y, spline.m))
+        om = ctypes.c_double()
+        vp = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+        check(lib.dsb_beam_cylinder(self._h, slot, 1 if dipole is None else 2, vp(ax), vp(dp), float(alpha_ns),
+                                    len(kx), vp(kx), vp(ky), vp(km), ctypes.byref(om), ctypes.c_void_p(stream or 0)))
         self.omega[slot] = om.value
         return om.value
 

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdriftb200.so")
-SOURCES = ["plan.cu", "tables.cu", "ringfft.cu", "legendre_f64.cu", "legendre_tc.cu", "shtiter.cu", "pack.cu", "api.cu", "svd.cu", "kl.cu", "hostutil.cu"]
+SOURCES = ["plan.cu", "cylbeam.cu", "tables.cu", "ringfft.cu", "legendre_f64.cu", "legendre_tc.cu", "shtiter.cu", "pack.cu", "api.cu", "svd.cu", "kl.cu", "hostutil.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",

@@ -402,9 +402,17 @@ class BeamTransfer(config.Reader):
             logger.info(f"m's remaining in beam SVD computation: {m_list}")
         comm.barrier()
         lo, hi = comm.split_range(len(m_list))
-        for mi in m_list[lo:hi]:
-            logger.info(f"m index {mi}. Creating SVD file: {self._svdfile(mi)}")
-            self._generate_svdfile_m(mi, skip_svd_inv=skip_svd_inv)
+        mine = m_list[lo:hi]
+        # Several m per device call: every (m, frequency) block has the same shape (columns l < m are
+        # zero), so consecutive m -- similar cost -- are stacked until the batch holds ~64 matrices or
+        # the chain's scratch ([ntel, nsky + ntel] complex128 per matrix) reaches 8 GiB.  The chain is
+        # bound by launch latency on small batches (6000 launches per call at pathfinder scale).
+        per_matrix = 16 * self.ntel * (self.nsky + self.ntel)
+        group = max(1, min(64 // max(self.nfreq, 1), (8 << 30) // max(per_matrix * self.nfreq, 1)))
+        for g0 in range(0, len(mine), group):
+            ms = mine[g0 : g0 + group]
+            logger.info(f"m index {ms[0]}..{ms[-1]}. Creating SVD files: {self._svdfile(ms[0])} ...")
+            self._generate_svdfile_group(ms, skip_svd_inv=skip_svd_inv)
         comm.barrier()
         self._collect_svd_spectrum()
 
@@ -480,21 +488,45 @@ class BeamTransfer(config.Reader):
         return full
 
     def _generate_svdfile_m(self, mi, skip_svd_inv=False):
-        """SVD products of one m (beamtransfer.py:730-929); written to a dot-prefixed
-        temporary and renamed on success, as ``caput.misc.lock_file`` does."""
+        """SVD products of one m (beamtransfer.py:730-929)."""
+        self._generate_svdfile_group([mi], skip_svd_inv=skip_svd_inv)
+
+    def _generate_svdfile_group(self, ms, skip_svd_inv=False):
+        """SVD products of the m values ``ms`` from one device call; each file is written to a
+        dot-prefixed temporary and renamed on success, as ``caput.misc.lock_file`` does."""
+        import torch
+
         tel = self.telescope
         nfreq, npol, nl = tel.nfreq, tel.num_pol_sky, tel.lmax + 1
         t0 = time.time()
-        bf = self._resident_block(mi)
-        if bf is None:
-            bf = self.beam_m(mi)
-        bf = bf.reshape(nfreq, self.ntel, npol, nl)
+        blocks = []
+        for mi in ms:
+            bf = self._resident_block(mi)
+            if bf is None:
+                bf = self.beam_m(mi)
+            blocks.append(bf.reshape(nfreq, self.ntel, npol, nl))
+        if len(blocks) == 1:
+            bf_all = blocks[0]
+        elif isinstance(blocks[0], torch.Tensor):
+            bf_all = torch.cat(blocks, dim=0)
+        else:
+            bf_all = np.concatenate(blocks, axis=0)
+        del blocks
         noisew = tel.noisepower(np.arange(tel.npairs)[np.newaxis, :], np.arange(nfreq)[:, np.newaxis])
         noisew = noisew.reshape(nfreq, tel.npairs) ** (-0.5)
         noisew = np.concatenate([noisew, noisew], axis=1)
-        bsvd, but, ibs, sv, nmodes = self._svd_chain_device(bf, noisew, skip_svd_inv)
+        out = self._svd_chain_device(bf_all, np.tile(noisew, (len(ms), 1)), skip_svd_inv)
+        del bf_all
         t1 = time.time()
+        for gi, mi in enumerate(ms):
+            sl = slice(gi * nfreq, (gi + 1) * nfreq)
+            self._write_svdfile(mi, *(None if a is None else a[sl] for a in out[:4]), skip_svd_inv)
+        tm = self.__dict__.setdefault("timing", {})
+        tm["svd_compute_s"] = tm.get("svd_compute_s", 0.0) + (t1 - t0)
+        tm["svd_write_s"] = tm.get("svd_write_s", 0.0) + (time.time() - t1)
 
+    def _write_svdfile(self, mi, bsvd, but, ibs, sv, skip_svd_inv):
+        tel = self.telescope
         final = self._svdfile(mi)
         tmp = os.path.join(os.path.dirname(final), "." + os.path.basename(final))
         with h5lite.File(tmp, "w") as fs:
@@ -517,9 +549,6 @@ class BeamTransfer(config.Reader):
             except ValueError:
                 logger.warning("frequencies attribute too large for an HDF5 object header; omitted")
         os.replace(tmp, final)
-        tm = self.__dict__.setdefault("timing", {})
-        tm["svd_compute_s"] = tm.get("svd_compute_s", 0.0) + (t1 - t0)
-        tm["svd_write_s"] = tm.get("svd_write_s", 0.0) + (time.time() - t1)
 
     def _collect_svd_spectrum(self):
         """Gather all singular values into ``svdspectrum.hdf5`` (beamtransfer.py:931-947)."""

@@ -320,8 +320,8 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
   const size_t k2mul = f64 ? 2 : 1;
   size_t per_unit = nprob * lay.Kp * lay.cpu0 * es + (lay.has2 ? nprob * k2mul * lay.Kp * 8 * es : 0) +
                     nprob * t.NP * (lay.cpu0 + (lay.has2 ? 8 : 0)) * cs;
-  if (niter > 0)  // a(0), transposed coefficients (fp64 spin 2: both roles), synthesised ring functions
-    per_unit += nprob * t.NP * (lay.cpu0 + (lay.has2 ? 8 : 0)) * cs +
+  if (niter > 0)  // a(0) and A S a, transposed coefficients (fp64 spin 2: both roles), synthesised ring functions
+    per_unit += 2 * nprob * t.NP * (lay.cpu0 + (lay.has2 ? 8 : 0)) * cs +
                 nprob * t.NPk * (lay.cpu0 + (lay.has2 ? 8 * k2mul : 0)) * cs +
                 nprob * lay.Kp * (lay.cpu0 + (lay.has2 ? 8 : 0)) * es;
   const size_t plane_out = (size_t)npol_out * (lside + 1) * (2 * lside + 1) * 16;
@@ -423,7 +423,7 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
     const size_t ct2_bytes = (niter > 0 && lay.has2) ? nprob * k2mul * t.NPk * lay.ncols2 * cs : 0;
     const size_t g0_bytes = niter > 0 ? nprob * lay.ncols0 * lay.Kp * es : 0;
     const size_t g2_bytes = (niter > 0 && lay.has2) ? nprob * lay.ncols2 * lay.Kp * es : 0;
-    char *F0, *F2, *C0, *C2, *A0, *A2, *Ct0, *Ct2, *G0, *G2, *stage;
+    char *F0, *F2, *C0, *C2, *A0, *A2, *D0, *D2, *Ct0, *Ct2, *G0, *G2, *stage;
     UnitDev *ud_dev;
     int32_t *o0_dev, *o1_dev;
     WorkItem *items_dev, *sitems_dev;
@@ -436,6 +436,8 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
       C2 = cv.take<char>(c2_bytes);
       A0 = cv.take<char>(niter > 0 ? c0_bytes : 0);  // a(0) of the refinement
       A2 = cv.take<char>(niter > 0 ? c2_bytes : 0);
+      D0 = cv.take<char>(niter > 0 ? c0_bytes : 0);  // A S a of the current pass
+      D2 = cv.take<char>(niter > 0 ? c2_bytes : 0);
       Ct0 = cv.take<char>(ct0_bytes);
       Ct2 = cv.take<char>(ct2_bytes);
       G0 = cv.take<char>(g0_bytes);
@@ -526,6 +528,26 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
     da.has2 = lay.has2;
     int max_rows = 16;
     for (const auto &w : items) max_rows = std::max(max_rows, w.nrows);
+    // fp32 path: synthesis items whose rings cannot alias write the next analysis' operand directly
+    FusedFold ffold;
+    int fused_row0 = -1;
+    static const bool no_fused = getenv("DSB_FOLD_UNFUSED") != nullptr;  // diagnostic
+    if (niter > 0 && !f64 && !no_fused) {
+      fused_row0 = (int)round_up(fold_alias_rows(lay.mcap, plan->nfold), 128);  // whole work items
+      if (fused_row0 < plan->nfold) {
+        ffold.scale = plan->fold_scale;
+        ffold.F0 = (float *)F0;
+        ffold.F2 = (float *)F2;
+        ffold.units = ud_dev;
+        ffold.row0 = fused_row0;
+        ffold.nfold = plan->nfold;
+        ffold.nunits = nu;
+        ffold.cpu0 = lay.cpu0;
+        ffold.Kp = lay.Kp;
+      } else {
+        fused_row0 = -1;
+      }
+    }
     auto contract = [&](const ContractDesc &d, const std::vector<WorkItem> &its, const WorkItem *its_dev, int mrows,
                         const char *a0, const char *a2, bool synth, char *c0, char *c2) {
       if (f64)
@@ -534,7 +556,7 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
                                    (double *)c2, (const double *)A0, (const double *)A2, stream);
       return launch_contract_tc(d, (int)its.size(), its_dev, mrows, (const float *)a0, (const float *)a2,
                                 synth ? t.s0_bf : t.t0_bf, synth ? t.s2_bf : t.t2_bf, (float *)c0, (float *)c2,
-                                (const float *)A0, (const float *)A2, stream);
+                                (const float *)A0, (const float *)A2, stream, synth ? &ffold : nullptr);
     };
     if ((rc = contract(da, items, items_dev, max_rows, F0, F2, false, C0, C2)) != DSB_OK) break;
     timer.mark(2);
@@ -546,15 +568,18 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
       ContractDesc ds = da;  // synthesis: A = transposed coefficients, B = S tables, rows = fold rings
       ds.K = ds.kx = t.NPk;
       ds.pitch = t.Kp;
-      ContractDesc du = da;
-      du.update = 1;
       for (int it = 0; it < niter && rc == DSB_OK; ++it) {
-        if ((rc = launch_transpose_coeffs(lay, ud_dev, t.NP, t.NPk, precision, C0, C2, Ct0, Ct2, stream)) != DSB_OK)
+        // pass it > 0 starts by applying the previous pass' step a <- a(0) + a - A S a (fused into the transpose)
+        if ((rc = launch_transpose_coeffs(lay, ud_dev, t.NP, t.NPk, precision, C0, C2, A0, A2, it ? D0 : nullptr,
+                                          it ? D2 : nullptr, Ct0, Ct2, stream)) != DSB_OK)
           break;
         if ((rc = contract(ds, sitems, sitems_dev, std::min(128, plan->nfold), Ct0, Ct2, true, G0, G2)) != DSB_OK) break;
-        if ((rc = launch_alias_fold(plan, lay, ud_dev, precision, G0, G2, F0, F2, stream)) != DSB_OK) break;
-        rc = contract(du, items, items_dev, max_rows, F0, F2, false, C0, C2);
+        if ((rc = launch_alias_fold(plan, lay, ud_dev, precision, G0, G2, F0, F2, stream, fused_row0)) != DSB_OK) break;
+        rc = contract(da, items, items_dev, max_rows, F0, F2, false, D0, D2);
       }
+      if (rc == DSB_OK)  // the last step, no transpose
+        rc = launch_transpose_coeffs(lay, ud_dev, t.NP, t.NPk, precision, C0, C2, A0, A2, D0, D2, nullptr, nullptr,
+                                     stream);
       if (rc != DSB_OK) break;
     }
     timer.mark(3);
@@ -630,6 +655,7 @@ extern "C" int dsb_peer_alloc(size_t bytes, void **dev_ptr, unsigned char *handl
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   DSB_CUDA(cudaMalloc(dev_ptr, bytes ? bytes : 256));
   DSB_CUDA(cudaMemset(*dev_ptr, 0, bytes ? bytes : 256));
+  DSB_CUDA(cudaDeviceSynchronize());  // the fill runs on the legacy stream: done before anyone stores
   cudaIpcMemHandle_t h;
   DSB_CUDA(cudaIpcGetMemHandle(&h, *dev_ptr));
   memcpy(handle64, &h, 64);

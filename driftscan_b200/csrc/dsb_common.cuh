@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include <map>
 
 #include "../../include/driftscan_b200.h"
@@ -184,6 +185,7 @@ struct dsb_plan {
   // Jacobi refinement passes and optional ring weights (multiplicative, one per fold ring)
   int sht_iter = 0;
   std::vector<double> ring_weights;
+  float *fold_scale = nullptr;  // [nfold] 2 x nphi (nphi on the equator): scale of the fused fold
   // workspace (grown on demand, capped by dsb_set_workspace_limit)
   void *ws = nullptr;
   size_t ws_bytes = 0;
@@ -284,19 +286,34 @@ struct ContractDesc {
 int launch_contract_f64(const ContractDesc &d, int nitems, const WorkItem *items_dev, const double *A0,
                         const double *A2, const double *B0, const double *B2, double *C0, double *C2,
                         const double *base0, const double *base2, cudaStream_t stream);
+// Synthesis with the non-aliasing part of the fold fused into the epilogue (fp32 path): rows (fold
+// rings) >= row0 are written as ring spectra F[prob][ring][col] = scale[ring] * result.
+struct FusedFold {
+  const float *scale = nullptr;  // [nfold] 2 x pixels per ring (1 x on the equator); NULL = off
+  float *F0 = nullptr, *F2 = nullptr;
+  const UnitDev *units = nullptr;
+  int row0 = 0, nfold = 0, nunits = 0, cpu0 = 0, Kp = 0;
+};
 int launch_contract_tc(const ContractDesc &d, int nitems, const WorkItem *items_dev, int max_rows,
                        const float *A0, const float *A2, const __nv_bfloat16 *B0, const __nv_bfloat16 *B2,
-                       float *C0, float *C2, const float *base0, const float *base2, cudaStream_t stream);
+                       float *C0, float *C2, const float *base0, const float *base2, cudaStream_t stream,
+                       const FusedFold *fold = nullptr);
 
 // shtiter.cu -- the pieces of healpy's map2alm(iter > 0) that are not contractions
 // C[prob][col][NP] -> Ct[prob][n][col] (fp64 spin 2: both operand roles, X role at row NPk),
 // rows above a unit's own lmax zeroed
+// D0 != NULL: first apply the Jacobi step C <- A + C - D (A = a(0), D = A S a of the previous pass) and
+// write C back; Ct0 == NULL: that update only.
 int launch_transpose_coeffs(const BucketLayout &lay, const UnitDev *units_dev, int NP, int NPk, int precision,
-                            const void *C0, const void *C2, void *Ct0, void *Ct2, cudaStream_t stream);
+                            void *C0, void *C2, const void *A0, const void *A2, const void *D0, const void *D2,
+                            void *Ct0, void *Ct2, cudaStream_t stream);
 // G[prob][col][Kp] (synthesised ring functions) -> ring spectra of the pixelised map in the
 // operand layout of the analysis (F0 / F2 of ringfft.cu)
+// `fused_row0` >= 0: rings from there on were already written by the synthesis epilogue (FusedFold)
 int launch_alias_fold(dsb_plan *plan, const BucketLayout &lay, const UnitDev *units_dev, int precision,
-                      const void *G0, const void *G2, void *F0, void *F2, cudaStream_t stream);
+                      const void *G0, const void *G2, void *F0, void *F2, cudaStream_t stream, int fused_row0 = -1);
+// first fold ring that cannot alias for any unit of a bucket with the given largest m (multiple of 32)
+inline int fold_alias_rows(int mcap, int nfold) { return std::min((nfold + 31) / 32 * 32, (mcap / 2 + 31) / 32 * 32); }
 
 // pack.cu
 struct PackParams {

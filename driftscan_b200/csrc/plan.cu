@@ -41,7 +41,12 @@ int ensure_workspace(dsb_plan *plan, size_t bytes) {
     plan->ws_bytes = 0;
   }
   DSB_CUDA(cudaMalloc(&plan->ws, bytes));
+  // cudaMemset runs on the legacy default stream and returns before it is done; a caller on a
+  // non-blocking stream is not ordered behind it, so its descriptor copies into the new workspace
+  // could land first and be zeroed afterwards (work items with zero rows -> an illegal tcgen05.mma
+  // instruction descriptor: the "two streams" fault of round 1).  Wait for it.
   DSB_CUDA(cudaMemset(plan->ws, 0, bytes));
+  DSB_CUDA(cudaDeviceSynchronize());
   plan->ws_bytes = bytes;
   return DSB_OK;
 }
@@ -250,6 +255,13 @@ extern "C" int dsb_plan_create(int nside, const uint8_t *horizon_host, dsb_plan 
 
   DSB_CUDA(cudaMalloc(&plan->rings, sizeof(RingDesc) * nfold));
   DSB_CUDA(cudaMemcpy(plan->rings, plan->rings_h.data(), sizeof(RingDesc) * nfold, cudaMemcpyHostToDevice));
+  {
+    std::vector<float> fs(nfold);
+    for (int k = 0; k < nfold; ++k)
+      fs[k] = (float)((plan->rings_h[k].startS < 0 ? 1 : 2) * plan->rings_h[k].nphi);
+    DSB_CUDA(cudaMalloc(&plan->fold_scale, sizeof(float) * nfold));
+    DSB_CUDA(cudaMemcpy(plan->fold_scale, fs.data(), sizeof(float) * nfold, cudaMemcpyHostToDevice));
+  }
   DSB_CUDA(cudaMalloc(&plan->horizon, plan->npix));
   DSB_CUDA(cudaMemcpy(plan->horizon, horizon_host, plan->npix, cudaMemcpyHostToDevice));
   DSB_CUDA(cudaMalloc(&plan->trig, sizeof(double2) * ntrig));
@@ -332,6 +344,7 @@ extern "C" int dsb_plan_destroy(dsb_plan *plan) {
   }
   for (char *p : plan->graph_stage) cudaFreeHost(p);
   cudaFree(plan->rings);
+  cudaFree(plan->fold_scale);
   cudaFree(plan->horizon);
   cudaFree(plan->trig);
   cudaFree(plan->tw16_64);
@@ -363,15 +376,11 @@ extern "C" int dsb_beam_slots(dsb_plan *plan, int nslots) {
   return DSB_OK;
 }
 
-extern "C" int dsb_beam_upload(dsb_plan *plan, int slot, const double *beam_host, int ncomp,
-                               int is_complex, double *omega_out, void *stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  DSB_CHECK(plan && beam_host, DSB_ERR_INVALID, "dsb_beam_upload: NULL argument");
-  DSB_CHECK(ncomp == 1 || ncomp == 2, DSB_ERR_INVALID, "dsb_beam_upload: ncomp must be 1 or 2");
-  DSB_CHECK(!is_complex, DSB_ERR_UNSUPPORTED,
-            "dsb_beam_upload: complex primary beams are not supported by the device path yet");
-  DSB_CHECK(slot >= 0 && slot < kMaxBeamSlots, DSB_ERR_INVALID, "dsb_beam_upload: slot %d outside [0, %d)", slot,
-            kMaxBeamSlots);
+namespace dsb {
+// (re)allocate the fp64 / fp32 maps of a beam slot
+int beam_slot_storage(dsb_plan *plan, int slot, int ncomp) {
+  DSB_CHECK(ncomp == 1 || ncomp == 2, DSB_ERR_INVALID, "beam: ncomp must be 1 or 2");
+  DSB_CHECK(slot >= 0 && slot < kMaxBeamSlots, DSB_ERR_INVALID, "beam: slot %d outside [0, %d)", slot, kMaxBeamSlots);
   if ((int)plan->beams.size() <= slot) plan->beams.resize(slot + 1);
   BeamSlot &b = plan->beams[slot];
   const size_t n = (size_t)plan->npix * ncomp;
@@ -384,12 +393,16 @@ extern "C" int dsb_beam_upload(dsb_plan *plan, int slot, const double *beam_host
     DSB_CUDA(cudaMalloc(&b.d32, n * sizeof(float)));
     b.ncomp = ncomp;
   }
-  DSB_CUDA(cudaMemcpyAsync(b.d64, beam_host, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+  return DSB_OK;
+}
+
+// fp32 copy + solid angle of the fp64 map now in the slot; bumps the slot's generation
+int beam_finish_upload(dsb_plan *plan, int slot, int ncomp, double *omega_out, cudaStream_t stream) {
+  BeamSlot &b = plan->beams[slot];
   const int nblk = 128;
   double *partial = nullptr;
   DSB_CUDA(cudaMalloc(&partial, nblk * sizeof(double)));
-  beam_power_partial_kernel<<<nblk, 256, 0, stream>>>(b.d64, plan->horizon, plan->npix, ncomp, b.d32,
-                                                       partial);
+  beam_power_partial_kernel<<<nblk, 256, 0, stream>>>(b.d64, plan->horizon, plan->npix, ncomp, b.d32, partial);
   DSB_LAUNCH_CHECK();
   double hp[nblk];
   DSB_CUDA(cudaMemcpyAsync(hp, partial, sizeof(hp), cudaMemcpyDeviceToHost, stream));
@@ -402,4 +415,18 @@ extern "C" int dsb_beam_upload(dsb_plan *plan, int slot, const double *beam_host
   b.gen += 1;
   if (omega_out) *omega_out = b.omega;
   return DSB_OK;
+}
+}  // namespace dsb
+
+extern "C" int dsb_beam_upload(dsb_plan *plan, int slot, const double *beam_host, int ncomp,
+                               int is_complex, double *omega_out, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSB_CHECK(plan && beam_host, DSB_ERR_INVALID, "dsb_beam_upload: NULL argument");
+  DSB_CHECK(ncomp == 1 || ncomp == 2, DSB_ERR_INVALID, "dsb_beam_upload: ncomp must be 1 or 2");
+  DSB_CHECK(!is_complex, DSB_ERR_UNSUPPORTED,
+            "dsb_beam_upload: complex primary beams are not supported by the device path yet");
+  DSB_TRY(beam_slot_storage(plan, slot, ncomp));
+  DSB_CUDA(cudaMemcpyAsync(plan->beams[slot].d64, beam_host, (size_t)plan->npix * ncomp * sizeof(double),
+                           cudaMemcpyHostToDevice, stream));
+  return beam_finish_upload(plan, slot, ncomp, omega_out, stream);
 }

@@ -33,10 +33,17 @@ namespace dsb {
 //   rows [0, NPk)      W role:  (E | B) columns of the same problem
 //   rows [NPk, 2 NPk)  X role:  (-i B | +i E) of the problem with the opposite l - m parity
 // (the fp32 path stores the block once, the tensor-core kernel permutes while splitting).
-template <typename T, bool ROLE2>
+//
+// UPDATE: the Jacobi step a <- a(0) + a - (A S a) is applied on the way (base = a(0), D = A S a of
+// the previous pass) and the new coefficients are written back to C; Ct == nullptr: update only
+// (after the last pass).  Keeping this out of the contraction's epilogue matters: there the two
+// extra operands arrive as latency-bound strided loads on the tensor pipeline's critical path
+// (measured: the analysis with the update in its epilogue took 7.0 ms instead of 3.8).
+template <typename T, bool ROLE2, bool UPDATE>
 __global__ void __launch_bounds__(256)
-transpose_coeffs_kernel(const T *__restrict__ C, T *__restrict__ Ct, const UnitDev *__restrict__ units, int nunits,
-                        int cpu, int ncols, int NP, int NPk) {
+transpose_coeffs_kernel(  // (ROLE2 && UPDATE) is never instantiated, see transpose_t
+T *__restrict__ C, const T *__restrict__ base, const T *__restrict__ D, T *__restrict__ Ct,
+                        const UnitDev *__restrict__ units, int nunits, int cpu, int ncols, int NP, int NPk) {
   __shared__ T tile[32][33];
   const int prob = blockIdx.z;
   const int m = prob >> 1, p = prob & 1;
@@ -52,9 +59,17 @@ transpose_coeffs_kernel(const T *__restrict__ C, T *__restrict__ Ct, const UnitD
       const int c = col0 + ty + 8 * i, n = n0 + tx;
       const int u = c / cpu;
       T v = T(0);
-      if (u < nunits && n < NP && m + sp + 2 * n <= units[u].lmax) v = C[((size_t)sprob * ncols + c) * NP + n];
+      if (u < nunits && n < NP && m + sp + 2 * n <= units[u].lmax) {
+        const size_t at = ((size_t)sprob * ncols + c) * NP + n;
+        v = C[at];
+        if (UPDATE) {
+          v = (base[at] - D[at]) + v;
+          C[at] = v;  // UPDATE is only instantiated with a single role: read once, written once
+        }
+      }
       tile[ty + 8 * i][tx] = v;
     }
+    if (Ct == nullptr) continue;  // update only (uniform)
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -71,29 +86,50 @@ transpose_coeffs_kernel(const T *__restrict__ C, T *__restrict__ Ct, const UnitD
   }
 }
 
-int launch_transpose_coeffs(const BucketLayout &lay, const UnitDev *units_dev, int NP, int NPk, int precision,
-                            const void *C0, const void *C2, void *Ct0, void *Ct2, cudaStream_t stream) {
+template <typename T>
+static int transpose_t(const BucketLayout &lay, const UnitDev *units_dev, int NP, int NPk, void *C0, void *C2,
+                       const void *A0, const void *A2, const void *D0, const void *D2, void *Ct0, void *Ct2,
+                       cudaStream_t stream) {
   const int nprob = 2 * (lay.mcap + 1);
-  const bool f64 = precision == DSB_PREC_FP64;
-  dim3 g0(lay.ncols0 / 32, NPk / 32, nprob);
-  if (f64)
-    transpose_coeffs_kernel<double, false><<<g0, 256, 0, stream>>>((const double *)C0, (double *)Ct0, units_dev,
-                                                                   lay.nunits, lay.cpu0, lay.ncols0, NP, NPk);
+  const bool update = D0 != nullptr;
+  const bool role2 = sizeof(T) == 8;  // the fp64 spin-2 block stores both operand roles
+  dim3 g0(lay.ncols0 / 32, NPk / 32, nprob), g2(lay.ncols2 / 32, NPk / 32, nprob);
+  if (update)
+    transpose_coeffs_kernel<T, false, true><<<g0, 256, 0, stream>>>((T *)C0, (const T *)A0, (const T *)D0, (T *)Ct0,
+                                                                    units_dev, lay.nunits, lay.cpu0, lay.ncols0, NP, NPk);
   else
-    transpose_coeffs_kernel<float, false><<<g0, 256, 0, stream>>>((const float *)C0, (float *)Ct0, units_dev,
-                                                                  lay.nunits, lay.cpu0, lay.ncols0, NP, NPk);
+    transpose_coeffs_kernel<T, false, false><<<g0, 256, 0, stream>>>((T *)C0, nullptr, nullptr, (T *)Ct0, units_dev,
+                                                                     lay.nunits, lay.cpu0, lay.ncols0, NP, NPk);
   DSB_LAUNCH_CHECK();
-  if (lay.has2) {
-    dim3 g2(lay.ncols2 / 32, NPk / 32, nprob);
-    if (f64)
-      transpose_coeffs_kernel<double, true><<<g2, 256, 0, stream>>>((const double *)C2, (double *)Ct2, units_dev,
+  if (!lay.has2) return DSB_OK;
+  if (role2 && Ct2 != nullptr) {
+    // two roles read every coefficient twice (own problem, partner problem): an in-place update
+    // would race with the partner's read, so it runs as a pass of its own first
+    if (update) {
+      transpose_coeffs_kernel<T, false, true><<<g2, 256, 0, stream>>>((T *)C2, (const T *)A2, (const T *)D2, nullptr,
+                                                                      units_dev, lay.nunits, 8, lay.ncols2, NP, NPk);
+      DSB_LAUNCH_CHECK();
+    }
+    transpose_coeffs_kernel<T, true, false><<<g2, 256, 0, stream>>>((T *)C2, nullptr, nullptr, (T *)Ct2, units_dev,
                                                                     lay.nunits, 8, lay.ncols2, NP, NPk);
+  } else {
+    if (update)
+      transpose_coeffs_kernel<T, false, true><<<g2, 256, 0, stream>>>((T *)C2, (const T *)A2, (const T *)D2, (T *)Ct2,
+                                                                      units_dev, lay.nunits, 8, lay.ncols2, NP, NPk);
     else
-      transpose_coeffs_kernel<float, false><<<g2, 256, 0, stream>>>((const float *)C2, (float *)Ct2, units_dev,
-                                                                    lay.nunits, 8, lay.ncols2, NP, NPk);
-    DSB_LAUNCH_CHECK();
+      transpose_coeffs_kernel<T, false, false><<<g2, 256, 0, stream>>>((T *)C2, nullptr, nullptr, (T *)Ct2, units_dev,
+                                                                       lay.nunits, 8, lay.ncols2, NP, NPk);
   }
+  DSB_LAUNCH_CHECK();
   return DSB_OK;
+}
+
+int launch_transpose_coeffs(const BucketLayout &lay, const UnitDev *units_dev, int NP, int NPk, int precision,
+                            void *C0, void *C2, const void *A0, const void *A2, const void *D0, const void *D2,
+                            void *Ct0, void *Ct2, cudaStream_t stream) {
+  if (precision == DSB_PREC_FP64)
+    return transpose_t<double>(lay, units_dev, NP, NPk, C0, C2, A0, A2, D0, D2, Ct0, Ct2, stream);
+  return transpose_t<float>(lay, units_dev, NP, NPk, C0, C2, A0, A2, D0, D2, Ct0, Ct2, stream);
 }
 
 // ---- aliasing fold: G[prob][col][Kp] -> F[prob][k][col] ------------------------------------------
@@ -226,6 +262,77 @@ __device__ __forceinline__ void alias_fold_unit(const FoldParams &P, const RingD
   }
 }
 
+// The aliasing rings, production precision: one CTA stages the synthesised coefficients of one
+// (unit, Stokes map, tile of TK rings) -- every m', both fold parities -- in shared memory and
+// folds them through the n residues of each ring,
+//     B+[r] = sum_q s^q h_{r - q n},   B-[r] = sum_q s^q conj(h_{q n - r}),      r < n,
+//     F+-_m = s^j fn B+-[r]   for every m = r + j n <= mmax,
+// so a ring costs O(mmax) however short it is (the per-output gather of alias_fold_kernel costs
+// O(mmax^2 / n): 57 GB of L2 traffic per bucket for the rings next to the pole).
+struct BinsParams {
+  const RingDesc *rings;
+  const UnitDev *units;
+  int nunits, nfold, Kp, krows, TK;
+  int nmaps0, cpu0, ncols0, ncols2, has2;
+  const float *G0, *G2;
+  float *F0, *F2;
+};
+
+__global__ void __launch_bounds__(256) alias_fold_bins_kernel(const BinsParams P) {
+  extern __shared__ __align__(16) unsigned char bins_raw[];
+  float *s = reinterpret_cast<float *>(bins_raw);  // [prob][4 columns of the map][TK rings]
+  const int TK = P.TK, k0 = blockIdx.x * TK, map = blockIdx.y, tid = threadIdx.x;
+  const bool spin2 = map >= P.nmaps0;
+  const float *G = spin2 ? P.G2 : P.G0;
+  float *F = spin2 ? P.F2 : P.F0;
+  const size_t ncols = spin2 ? P.ncols2 : P.ncols0;
+  const int cpu = spin2 ? 8 : P.cpu0;
+  const int coff = 4 * (spin2 ? map - P.nmaps0 : map);
+  for (int u = blockIdx.z; u < P.nunits; u += gridDim.z) {
+    const int mm = P.units[u].mmax;
+    const size_t col0 = (size_t)u * cpu + coff;
+    __syncthreads();  // the previous unit's bins are done with the staging buffer
+    const int nload = 2 * (mm + 1) * 4 * TK;
+    for (int idx = tid; idx < nload; idx += 256) {
+      const int kk = idx % TK, pc = idx / TK;  // pc = prob * 4 + column
+      const int k = k0 + kk;
+      s[idx] = (k < P.krows) ? G[((size_t)(pc >> 2) * ncols + col0 + (pc & 3)) * P.Kp + k] : 0.f;
+    }
+    __syncthreads();
+    const int ntask = TK * 2 * (mm + 1);
+    for (int task = tid; task < ntask; task += 256) {
+      const int kk = task % TK, p = (task / TK) & 1, r = task / (2 * TK);
+      const int k = k0 + kk;
+      if (k >= P.krows) continue;
+      const RingDesc &rd = P.rings[k];
+      const int n = rd.nphi;
+      if (r >= n) continue;
+      const bool shifted = rd.shifted != 0, equator = rd.startS < 0;
+      float bpr = 0.f, bpi = 0.f, bmr = 0.f, bmi = 0.f;
+      const int qlo = -((mm - r) / n), qhi = (r + mm) / n;
+      for (int q = qlo; q <= qhi; ++q) {
+        const float sg = (shifted && (q & 1)) ? -1.f : 1.f;
+        const int m1 = r - q * n, a1 = m1 < 0 ? -m1 : m1;
+        const float *h1 = s + ((size_t)((2 * a1 + p) * 4 + (m1 < 0 ? 2 : 0))) * TK + kk;
+        bpr += sg * h1[0];
+        bpi += m1 < 0 ? -sg * h1[TK] : sg * h1[TK];
+        const int m2 = q * n - r, a2 = m2 < 0 ? -m2 : m2;
+        const float *h2 = s + ((size_t)((2 * a2 + p) * 4 + (m2 < 0 ? 2 : 0))) * TK + kk;
+        bmr += sg * h2[0];
+        bmi += m2 < 0 ? sg * h2[TK] : -sg * h2[TK];
+      }
+      float fn = (float)(equator ? n : 2 * n);
+      if (equator && p == 1) fn = 0.f;
+      int j = 0;
+      for (int m = r; m <= mm; m += n, ++j) {
+        const float f = (shifted && (j & 1)) ? -fn : fn;
+        const float out[4] = {f * bpr, f * bpi, f * bmr, f * bmi};
+        store4(F + ((size_t)(2 * m + p) * P.Kp + k) * ncols + col0, out);
+      }
+    }
+  }
+}
+
 // Rings with more than 2 mcap pixels do not alias (q = 0 only): the fold is a scaled transpose
 //   F+-_m = fn G+-_m   (m = 0: F-_0 = conj(F+_0)),
 // done through shared memory so that both the reads (contiguous in k) and the writes (contiguous
@@ -279,7 +386,7 @@ fold_identity_kernel(const RingDesc *__restrict__ rings, const UnitDev *__restri
 }
 
 int launch_alias_fold(dsb_plan *plan, const BucketLayout &lay, const UnitDev *units_dev, int precision,
-                      const void *G0, const void *G2, void *F0, void *F2, cudaStream_t stream) {
+                      const void *G0, const void *G2, void *F0, void *F2, cudaStream_t stream, int fused_row0) {
   FoldParams P;
   P.rings = plan->rings;
   P.units = units_dev;
@@ -299,9 +406,37 @@ int launch_alias_fold(dsb_plan *plan, const BucketLayout &lay, const UnitDev *un
   // rings k < mcap / 2 can alias for some unit of the bucket: general gather; the rest: transpose
   const int ktiles = (plan->nfold + 31) / 32;
   static const bool no_fast = getenv("DSB_FOLD_GENERAL") != nullptr;  // diagnostic: gather kernel everywhere
-  P.ktile0 = no_fast ? ktiles : std::min(ktiles, (lay.mcap / 2 + 31) / 32);
+  P.ktile0 = no_fast ? ktiles : fold_alias_rows(lay.mcap, plan->nfold) / 32;
   const bool f64 = precision == DSB_PREC_FP64;
-  if (P.ktile0 > 0) {
+  static const bool no_bins = getenv("DSB_FOLD_GATHER") != nullptr;  // diagnostic: per-output gather kernel
+  if (P.ktile0 > 0 && !f64 && !no_bins && !no_fast) {
+    BinsParams B;
+    B.rings = plan->rings;
+    B.units = units_dev;
+    B.nunits = lay.nunits;
+    B.nfold = plan->nfold;
+    B.Kp = lay.Kp;
+    B.krows = std::min(plan->nfold, P.ktile0 * 32);
+    B.nmaps0 = lay.nsp0;
+    B.cpu0 = lay.cpu0;
+    B.ncols0 = lay.ncols0;
+    B.ncols2 = lay.ncols2;
+    B.has2 = lay.has2;
+    B.G0 = (const float *)G0;
+    B.G2 = (const float *)G2;
+    B.F0 = (float *)F0;
+    B.F2 = (float *)F2;
+    int TK = 16;
+    const size_t per_ring = (size_t)2 * (lay.mcap + 1) * 4 * sizeof(float);
+    while (TK > 1 && per_ring * TK > 200 * 1024) TK >>= 1;
+    DSB_CHECK(per_ring * TK <= 220 * 1024, DSB_ERR_UNSUPPORTED, "alias fold: lmax %d does not fit shared memory", lay.mcap);
+    B.TK = TK;
+    const size_t smem = per_ring * TK;
+    DSB_CUDA(raise_dynamic_smem((const void *)alias_fold_bins_kernel, smem));
+    dim3 grid((B.krows + TK - 1) / TK, lay.nsp0 + (lay.has2 ? 2 : 0), std::min(lay.nunits, 65535));
+    alias_fold_bins_kernel<<<grid, 256, smem, stream>>>(B);
+    DSB_LAUNCH_CHECK();
+  } else if (P.ktile0 > 0) {
     dim3 grid(P.ktile0, (lay.mcap + 8) / 8, std::min(lay.nunits, 65535));
     if (f64)
       alias_fold_kernel<double><<<grid, 256, 0, stream>>>(P);
@@ -309,8 +444,9 @@ int launch_alias_fold(dsb_plan *plan, const BucketLayout &lay, const UnitDev *un
       alias_fold_kernel<float><<<grid, 256, 0, stream>>>(P);
     DSB_LAUNCH_CHECK();
   }
-  if (P.ktile0 < ktiles) {
-    const int nk = ktiles - P.ktile0;
+  const int kend = fused_row0 >= 0 ? std::min(ktiles, fused_row0 / 32) : ktiles;  // the rest came fused
+  if (P.ktile0 < kend) {
+    const int nk = kend - P.ktile0;
     dim3 g0(nk, lay.mcap + 1, lay.ncols0 / 32), g2(nk, lay.mcap + 1, lay.ncols2 / 32);
     if (f64) {
       fold_identity_kernel<double, false><<<g0, 256, 0, stream>>>(plan->rings, units_dev, lay.nunits, plan->nfold, lay.Kp,

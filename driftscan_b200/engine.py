@@ -11,6 +11,7 @@ There is no CPU path here: importing this module needs ``libdriftb200.so``.
 """
 
 import logging
+import os
 
 import numpy as np
 
@@ -29,6 +30,8 @@ class TransferEngine:
         self.beam_budget = int(getattr(telescope, "beam_cache_size", 200)) << 25  # bytes on device
         # healpy map2alm settings (see TransitTelescope.sht_iter)
         self.sht_iter = int(getattr(telescope, "sht_iter", 0) or 0)
+        # analytic cylinder beams are evaluated on the device (DSB_HOST_BEAMS=1: host maps + upload)
+        self.device_beams = not os.environ.get("DSB_HOST_BEAMS")
         self._plans = {}  # nside -> Plan
         self._slots = {}  # nside -> {(freq, beamclass): slot}
 
@@ -68,6 +71,13 @@ class TransferEngine:
         key = (int(freq), int(tel.beamclass[feed]))
         slots = self._slots[nside]
         if key not in slots:
+            spec = self._device_spec(feed, freq)
+            if spec is not None:
+                # built-in analytic beam: evaluated on the device, no host map, no upload
+                slot = len(slots)
+                self._plans[nside].cylinder_beam(slot, *spec)
+                slots[key] = slot
+                return slot
             if tel._nside != nside:
                 tel._init_trans(nside)
             beam = np.asarray(tel.beam(feed, freq))
@@ -79,6 +89,23 @@ class TransferEngine:
             self._plans[nside].upload_beam(slot, beam)
             slots[key] = slot
         return slots[key]
+
+    def _device_spec(self, feed, freq):
+        """Recipe of the beam of ``feed`` for the device, or None when the telescope's beam methods
+        are user code (then the host map is uploaded, as the reference's `_beam` cache holds it)."""
+        if not self.device_beams:
+            return None
+        tel = self.tel
+        fn = getattr(tel, "_device_beam_spec", None)
+        if fn is None:
+            return None
+        # the recipe only stands for the class that declares it: any override of the beam methods
+        # further down the MRO wins
+        owner = next(c for c in type(tel).__mro__ if "_device_beam_spec" in c.__dict__)
+        for name in ("beam", "beamx", "beamy"):
+            if hasattr(owner, name) and getattr(type(tel), name) is not getattr(owner, name):
+                return None
+        return fn(feed, freq)
 
     # ---- unit tables -----------------------------------------------------------
     def _npol_compute(self):

@@ -71,16 +71,31 @@ def _axes(zenith, rot):
     return rotate_ypr(rot, phat, -that, coord.sph_to_cart(np.asarray(zenith, dtype=np.float64)))
 
 
-def beam_amp(angpos, zenith, width, fwhm_x, fwhm_y, rot=(0.0, 0.0, 0.0)):
-    """Amplitude beam: diffraction pattern E-W times ExpTan N-S, zero below the horizon
-    (cylbeam.py:101-147)."""
-    xhat, yhat, zhat = _axes(zenith, rot)
+def ew_pattern_spline(fwhm_x, width):
+    """The East-West pattern of beam_amp as a spline object (cached per (fwhm, width))."""
     key = (fwhm_x, width)
     if key not in _pattern_cache:
         if len(_pattern_cache) >= 100:
             _pattern_cache.pop(next(iter(_pattern_cache)))
         _pattern_cache[key] = fraunhofer_cylinder(lambda t: beam_exptan(t, fwhm_x), width)
-    ew_pattern = _pattern_cache[key]
+    return _pattern_cache[key]
+
+
+def device_beam_spec(zenith, width, fwhm_x, fwhm_y, dipole_axis, rot=(0.0, 0.0, 0.0)):
+    """What the device needs to evaluate ``beam_amp(..., fwhm_x, fwhm_y) * polpattern(axis)`` itself
+    (dsb_beam_cylinder): the telescope axes, the dipole (``dipole_axis`` 'x', 'y' or None for the
+    amplitude alone), the North-South ExpTan constant and the East-West spline."""
+    xhat, yhat, zhat = _axes(zenith, rot)
+    dipole = {None: None, "x": xhat, "y": yhat}[dipole_axis]
+    alpha_ns = np.log(2.0) / (2.0 * np.tan(fwhm_y / 2.0) ** 2)
+    return (xhat, yhat, zhat), dipole, alpha_ns, ew_pattern_spline(fwhm_x, width)
+
+
+def beam_amp(angpos, zenith, width, fwhm_x, fwhm_y, rot=(0.0, 0.0, 0.0)):
+    """Amplitude beam: diffraction pattern E-W times ExpTan N-S, zero below the horizon
+    (cylbeam.py:101-147)."""
+    xhat, yhat, zhat = _axes(zenith, rot)
+    ew_pattern = ew_pattern_spline(fwhm_x, width)
 
     cvec = coord.sph_to_cart(angpos)
     above = (cvec @ coord.sph_to_cart(np.asarray(zenith, dtype=np.float64)) > 0.0).astype(np.float64)

@@ -86,6 +86,10 @@ class UnpolarisedCylinderTelescope(CylinderTelescope, telescope.SimpleUnpolarise
         # NB the reference passes the H-plane width for both planes (cylinder.py:188-194)
         return cylbeam.beam_amp(self._angpos, self.zenith, self._scaled_width(freq), self.fwhm_h, self.fwhm_h)
 
+    def _device_beam_spec(self, feed, freq):
+        """The same beam as a recipe the device evaluates itself (engine.TransferEngine._beam_slot)."""
+        return cylbeam.device_beam_spec(self.zenith, self._scaled_width(freq), self.fwhm_h, self.fwhm_h, None)
+
 
 class PolarisedCylinderTelescope(CylinderTelescope, telescope.SimplePolarisedTelescope):
     """Dual-polarisation feeds: X dipoles across, Y dipoles along the cylinder (cylinder.py:197-218)."""
@@ -95,3 +99,10 @@ class PolarisedCylinderTelescope(CylinderTelescope, telescope.SimplePolarisedTel
 
     def beamy(self, feed, freq):
         return cylbeam.beam_y(self._angpos, self.zenith, self._scaled_width(freq), self.fwhm_e, self.fwhm_h)
+
+    def _device_beam_spec(self, feed, freq):
+        """beamx / beamy as recipes the device evaluates itself (engine.TransferEngine._beam_slot)."""
+        w = self._scaled_width(freq)
+        if self.beamclass[feed] == 0:  # X dipole: beam_amp(fwhm_e, fwhm_h) * polpattern(xhat)
+            return cylbeam.device_beam_spec(self.zenith, w, self.fwhm_e, self.fwhm_h, "x")
+        return cylbeam.device_beam_spec(self.zenith, w, self.fwhm_h, self.fwhm_e, "y")

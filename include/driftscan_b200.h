@@ -84,6 +84,20 @@ int dsb_beam_upload(dsb_plan *plan, int slot, const double *beam_host, int ncomp
                     int is_complex, double *omega_out, void *stream);
 int dsb_beam_slots(dsb_plan *plan, int nslots); /* reserve `nslots` beam slots */
 
+/* The analytic cylinder beam evaluated on the device instead of uploaded: beam_amp / beam_x /
+ * beam_y of drift/telescope/cylbeam.py:101-212 with polpattern (:10-42) and beam_exptan
+ * (drift/util/_fast_tools.pyx:248-282),
+ *   amp(n) = S(n.xhat) exp(-alpha_ns tan^2(asin(n.yhat))) [n.zhat > 0],  E = amp * polpattern(dipole).
+ *   axes9   : xhat, yhat, zhat (Cartesian, 3 doubles each) -- cylbeam.py:127-130
+ *   dipole3 : dipole direction (ncomp = 2) or NULL (ncomp = 1: amplitude only, cylinder.py:188-194)
+ *   alpha_ns: ln2 / (2 tan^2(fwhm / 2)) of the North-South factor
+ *   knot_*  : the natural cubic spline S of the East-West Fraunhofer pattern (cylbeam.py:52-95):
+ *             abscissae, values and second derivatives, `nknot` each, ascending abscissae
+ * Fills `slot` exactly as dsb_beam_upload does (solid angle through omega_out). */
+int dsb_beam_cylinder(dsb_plan *plan, int slot, int ncomp, const double *axes9_host,
+                      const double *dipole3_host, double alpha_ns, int nknot, const double *knot_x_host,
+                      const double *knot_y_host, const double *knot_m_host, double *omega_out, void *stream);
+
 /* Legendre / spin-2 tables for l <= lmax, m <= mmax (the part of
  * healpy.map2alm that the reference reaches through cora.util.hputil,
  * drift/core/telescope.py:1189,1300,1310). */

@@ -50,10 +50,15 @@ def run_check(precision="fp32x3", mem_chunk=None, compress=False):
               "max_dev": 0.0, "files": 0}
     if comm.rank0:
         tel1 = cylinder.PolarisedCylinderTelescope.from_config(dict(CFG, precision=precision))
-        ref = beamtransfer.BeamTransfer(os.path.join(base, "single"), telescope=tel1)
-        ref.comm = parallel.Comm()  # a single process, whatever the process group says
-        ref.read_config(conf)
-        ref.generate()
+        # a single process, whatever the process group says (the constructor already meets a barrier)
+        real_current = parallel.Comm.current
+        parallel.Comm.current = classmethod(lambda cls: cls())
+        try:
+            ref = beamtransfer.BeamTransfer(os.path.join(base, "single"), telescope=tel1)
+            ref.read_config(conf)
+            ref.generate()
+        finally:
+            parallel.Comm.current = real_current
         for mi in range(tel.mmax + 1):
             pairs = [(bt.beam_m(mi), ref.beam_m(mi)), (bt.beam_singularvalues(mi), ref.beam_singularvalues(mi)),
                      (bt.beam_svd(mi), ref.beam_svd(mi)), (bt.beam_ut(mi), ref.beam_ut(mi))]
