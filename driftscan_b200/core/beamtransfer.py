@@ -60,6 +60,10 @@ class BeamTransfer(config.Reader):
     compress_products = config.Property(proptype=bool, default=True)
 
     noise_weight = True
+    # Benchmark hook (tools/run_cfg4.py): write only these m to disk.  A CHIME-scale product is 86 TiB
+    # (SURVEY section 8d); a streaming run computes and exchanges every m and stores a stated subset.
+    # The COMPLETED marker is not written for a partial product.
+    m_write_subset = None
 
     # ---- file names (beamtransfer.py:199-224) ------------------------------------
     @property
@@ -236,7 +240,9 @@ class BeamTransfer(config.Reader):
 
         # m ownership: contiguous ranges, first (nm % size) ranks get one more
         m_lo, m_hi = comm.split_range(nm)
-        for mi in range(m_lo, m_hi):
+        m_write = range(m_lo, m_hi) if self.m_write_subset is None else sorted(
+            m for m in set(int(x) for x in self.m_write_subset) if m_lo <= m < m_hi)
+        for mi in m_write:
             if os.path.exists(self._mfile(mi)) and not regen:
                 logger.info(f"m index {mi}. File: {self._mfile(mi)} exists. Skipping...")
                 continue
@@ -287,7 +293,7 @@ class BeamTransfer(config.Reader):
         self._resident = {}
         per_m = [2 * nb_inc * np_inc * (nl - mi) for mi in range(nm)]  # elements per frequency of block m
         nslots = (comm.size if scatter else 1) * nf_chunk
-        stage = _lib.PinnedBuffer(max(nslots * max(per_m[m_lo:m_hi], default=0) * elem, 64))
+        stage = _lib.PinnedBuffer(max(nslots * max((per_m[m] for m in m_write), default=0) * elem, 64))
         t_compute = t_write = 0.0
 
         def write_rows(f, mi, rows, src_ptr, nfr):
@@ -350,7 +356,7 @@ class BeamTransfer(config.Reader):
                     return buf.data_ptr() + int(moff[mi]) * elem
             t_compute += time.time() - t0
             t0 = time.time()
-            for mi in range(m_lo, m_hi):
+            for mi in m_write:
                 if not sources:
                     break
                 with h5lite.File(self._mfile(mi), "r+") as f:  # one open file per m and chunk
@@ -373,9 +379,11 @@ class BeamTransfer(config.Reader):
             scatter.close()
         self.timing = dict(getattr(self, "timing", {}), mfiles_compute_s=t_compute, mfiles_write_s=t_write)
 
+        self.timing["nchunks"] = nchunks
         comm.barrier()
         if comm.rank0:
-            open(self.directory + "/beam_m/COMPLETED", "a").close()
+            if self.m_write_subset is None:
+                open(self.directory + "/beam_m/COMPLETED", "a").close()
             logger.info(f"=== MPI transpose took {time.time() - st:f} s ===")
 
     def _release_resident(self):

@@ -531,8 +531,11 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
     // fp32 path: synthesis items whose rings cannot alias write the next analysis' operand directly
     FusedFold ffold;
     int fused_row0 = -1;
-    static const bool no_fused = getenv("DSB_FOLD_UNFUSED") != nullptr;  // diagnostic
-    if (niter > 0 && !f64 && !no_fused) {
+    // Measured (profiles/r02): the fused epilogue issues 64 four-byte stores per thread and item and
+    // costs the synthesis what the separate transpose kernel costs (4.3 vs 2.3 + 1.5 ms on the nside-128
+    // bucket of the bench): off by default, DSB_FOLD_FUSED=1 enables it.
+    static const bool fused = getenv("DSB_FOLD_FUSED") != nullptr;
+    if (niter > 0 && !f64 && fused) {
       fused_row0 = (int)round_up(fold_alias_rows(lay.mcap, plan->nfold), 128);  // whole work items
       if (fused_row0 < plan->nfold) {
         ffold.scale = plan->fold_scale;

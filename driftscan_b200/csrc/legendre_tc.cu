@@ -74,6 +74,8 @@ struct TcParams {
   int fold_row0, nfold, nunits, cpu0, Kp;
   int NB;            // table box rows (TMA box), multiple of 16, <= 256
   int nstages;
+  int diag;          // DSB_TC_DIAG (timing experiments, WRONG results): 1 = table tile loaded for the first
+                     // stage of an item only, 2 = converters skip the split arithmetic
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -239,15 +241,18 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
           unsigned char *sA = stages + (size_t)stage * stage_bytes;
           unsigned char *sR = sA + 3 * TC_A_PLANE;
           unsigned char *sB = sR + TC_A_RAW;
-          mbar_expect_tx(&full[stage], tx);
+          const bool load_b = !(P.diag & 1) || kc == 0;
+          mbar_expect_tx(&full[stage], load_b ? tx : (uint32_t)TC_A_RAW);
           // X role reads the spectra of the opposite fold parity
           const bool xrole = kc >= nkA;
           tma_load_3d(mA, &full[stage], sR, wi.coltile * TC_M, (xrole ? kc - nkA : kc) * TC_KC,
                       xrole ? (wi.prob ^ 1) : wi.prob);
+          if (load_b) {
 #pragma unroll
-          for (int pl = 0; pl < 3; ++pl)
-            tma_load_4d(mB, &full[stage], sB + pl * b_plane, xrole ? P.kx + (kc - nkA) * TC_KC : kc * TC_KC, wi.row0,
-                        wi.prob, pl);
+            for (int pl = 0; pl < 3; ++pl)
+              tma_load_4d(mB, &full[stage], sB + pl * b_plane, xrole ? P.kx + (kc - nkA) * TC_KC : kc * TC_KC, wi.row0,
+                          wi.prob, pl);
+          }
           if (++stage == P.nstages) {
             stage = 0;
             phase ^= 1;
@@ -443,7 +448,7 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         const float4 *sR = reinterpret_cast<const float4 *>(sA + 3 * TC_A_PLANE);
         // one (k row, 8-column group) per thread and step: 32 rows x 16 groups
 #pragma unroll
-        for (int e = ct; e < TC_KC * 16; e += 32 * TC_NCONV) {
+        for (int e = (P.diag & 2) ? TC_KC * 16 : ct; e < TC_KC * 16; e += 32 * TC_NCONV) {
           const int k = e >> 4, grp = e & 15;
           const float4 lo = sR[k * 32 + grp * 2], hi = sR[k * 32 + grp * 2 + 1];
           float v[8];
@@ -598,6 +603,8 @@ int launch_contract_tc(const ContractDesc &d, int nitems, const WorkItem *items_
     P.Kp = fold->Kp;
   }
   P.NB = NB;
+  static const int diag = getenv("DSB_TC_DIAG") ? atoi(getenv("DSB_TC_DIAG")) : 0;
+  P.diag = diag;
   const size_t stage_bytes = 3 * TC_A_PLANE + TC_A_RAW + (((size_t)3 * NB * 64 + 1023) & ~(size_t)1023);
   int nstages = (int)std::min<size_t>(8, (220 * 1024) / stage_bytes);
   DSB_CHECK(nstages >= 2, DSB_ERR_UNSUPPORTED, "pipeline does not fit shared memory");

@@ -280,23 +280,25 @@ struct BinsParams {
 
 __global__ void __launch_bounds__(256) alias_fold_bins_kernel(const BinsParams P) {
   extern __shared__ __align__(16) unsigned char bins_raw[];
-  float *s = reinterpret_cast<float *>(bins_raw);  // [prob][4 columns of the map][TK rings]
-  const int TK = P.TK, k0 = blockIdx.x * TK, map = blockIdx.y, tid = threadIdx.x;
-  const bool spin2 = map >= P.nmaps0;
+  float *s = reinterpret_cast<float *>(bins_raw);  // [prob][NC columns of the map group][TK rings]
+  // blockIdx.y = map group: the unit's spin-0 columns (I or I,V), then its spin-2 columns (Q,U).  A
+  // thread emits all maps of the group for its (ring, m): one full 32-byte sector per store pair
+  // (16-byte pieces written by different CTAs reach DRAM as partial sectors).
+  const int TK = P.TK, k0 = blockIdx.x * TK, tid = threadIdx.x;
+  const bool spin2 = blockIdx.y > 0;
   const float *G = spin2 ? P.G2 : P.G0;
   float *F = spin2 ? P.F2 : P.F0;
   const size_t ncols = spin2 ? P.ncols2 : P.ncols0;
-  const int cpu = spin2 ? 8 : P.cpu0;
-  const int coff = 4 * (spin2 ? map - P.nmaps0 : map);
+  const int NC = spin2 ? 8 : P.cpu0, nmap = NC >> 2;
   for (int u = blockIdx.z; u < P.nunits; u += gridDim.z) {
     const int mm = P.units[u].mmax;
-    const size_t col0 = (size_t)u * cpu + coff;
+    const size_t col0 = (size_t)u * NC;
     __syncthreads();  // the previous unit's bins are done with the staging buffer
-    const int nload = 2 * (mm + 1) * 4 * TK;
+    const int nload = 2 * (mm + 1) * NC * TK;
     for (int idx = tid; idx < nload; idx += 256) {
-      const int kk = idx % TK, pc = idx / TK;  // pc = prob * 4 + column
+      const int kk = idx % TK, pc = idx / TK;  // pc = prob * NC + column
       const int k = k0 + kk;
-      s[idx] = (k < P.krows) ? G[((size_t)(pc >> 2) * ncols + col0 + (pc & 3)) * P.Kp + k] : 0.f;
+      s[idx] = (k < P.krows) ? G[((size_t)(pc / NC) * ncols + col0 + (pc % NC)) * P.Kp + k] : 0.f;
     }
     __syncthreads();
     const int ntask = TK * 2 * (mm + 1);
@@ -308,26 +310,38 @@ __global__ void __launch_bounds__(256) alias_fold_bins_kernel(const BinsParams P
       const int n = rd.nphi;
       if (r >= n) continue;
       const bool shifted = rd.shifted != 0, equator = rd.startS < 0;
-      float bpr = 0.f, bpi = 0.f, bmr = 0.f, bmi = 0.f;
+      float b[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};  // per map: B+ re, im, B- re, im
       const int qlo = -((mm - r) / n), qhi = (r + mm) / n;
       for (int q = qlo; q <= qhi; ++q) {
         const float sg = (shifted && (q & 1)) ? -1.f : 1.f;
         const int m1 = r - q * n, a1 = m1 < 0 ? -m1 : m1;
-        const float *h1 = s + ((size_t)((2 * a1 + p) * 4 + (m1 < 0 ? 2 : 0))) * TK + kk;
-        bpr += sg * h1[0];
-        bpi += m1 < 0 ? -sg * h1[TK] : sg * h1[TK];
         const int m2 = q * n - r, a2 = m2 < 0 ? -m2 : m2;
-        const float *h2 = s + ((size_t)((2 * a2 + p) * 4 + (m2 < 0 ? 2 : 0))) * TK + kk;
-        bmr += sg * h2[0];
-        bmi += m2 < 0 ? sg * h2[TK] : -sg * h2[TK];
+        const float *h1 = s + ((size_t)((2 * a1 + p) * NC + (m1 < 0 ? 2 : 0))) * TK + kk;
+        const float *h2 = s + ((size_t)((2 * a2 + p) * NC + (m2 < 0 ? 2 : 0))) * TK + kk;
+#pragma unroll
+        for (int mp = 0; mp < 2; ++mp) {
+          if (mp < nmap) {
+            const float *g1 = h1 + 4 * mp * TK, *g2 = h2 + 4 * mp * TK;
+            b[mp][0] += sg * g1[0];
+            b[mp][1] += m1 < 0 ? -sg * g1[TK] : sg * g1[TK];
+            b[mp][2] += sg * g2[0];
+            b[mp][3] += m2 < 0 ? sg * g2[TK] : -sg * g2[TK];
+          }
+        }
       }
       float fn = (float)(equator ? n : 2 * n);
       if (equator && p == 1) fn = 0.f;
       int j = 0;
       for (int m = r; m <= mm; m += n, ++j) {
         const float f = (shifted && (j & 1)) ? -fn : fn;
-        const float out[4] = {f * bpr, f * bpi, f * bmr, f * bmi};
-        store4(F + ((size_t)(2 * m + p) * P.Kp + k) * ncols + col0, out);
+        float *dst = F + ((size_t)(2 * m + p) * P.Kp + k) * ncols + col0;
+#pragma unroll
+        for (int mp = 0; mp < 2; ++mp) {
+          if (mp < nmap) {
+            const float out[4] = {f * b[mp][0], f * b[mp][1], f * b[mp][2], f * b[mp][3]};
+            store4(dst + 4 * mp, out);
+          }
+        }
       }
     }
   }
@@ -426,14 +440,16 @@ int launch_alias_fold(dsb_plan *plan, const BucketLayout &lay, const UnitDev *un
     B.G2 = (const float *)G2;
     B.F0 = (float *)F0;
     B.F2 = (float *)F2;
+    // rings per CTA: the staging buffer is kept near 64 KB so that three CTAs share an SM (the
+    // kernel is a chain of load -> barrier -> fold -> store: it needs resident warps, not big tiles)
     int TK = 16;
-    const size_t per_ring = (size_t)2 * (lay.mcap + 1) * 4 * sizeof(float);
-    while (TK > 1 && per_ring * TK > 200 * 1024) TK >>= 1;
+    const size_t per_ring = (size_t)2 * (lay.mcap + 1) * 8 * sizeof(float);
+    while (TK > 1 && per_ring * TK > 64 * 1024) TK >>= 1;
     DSB_CHECK(per_ring * TK <= 220 * 1024, DSB_ERR_UNSUPPORTED, "alias fold: lmax %d does not fit shared memory", lay.mcap);
     B.TK = TK;
     const size_t smem = per_ring * TK;
     DSB_CUDA(raise_dynamic_smem((const void *)alias_fold_bins_kernel, smem));
-    dim3 grid((B.krows + TK - 1) / TK, lay.nsp0 + (lay.has2 ? 2 : 0), std::min(lay.nunits, 65535));
+    dim3 grid((B.krows + TK - 1) / TK, lay.has2 ? 2 : 1, std::min(lay.nunits, 65535));
     alias_fold_bins_kernel<<<grid, 256, smem, stream>>>(B);
     DSB_LAUNCH_CHECK();
   } else if (P.ktile0 > 0) {

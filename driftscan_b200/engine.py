@@ -119,26 +119,41 @@ class TransferEngine:
         plan = self.plan(nside)
         units = np.zeros(len(bl), dtype=_lib.UNIT_DTYPE)
         pairs = tel.uniquepairs[bl]
+        uv = tel.baselines[bl] / tel.wavelengths[fi][:, np.newaxis]
+        units["uvec"] = visibility.uv_vector(tel.zenith, uv)
+        # one beam slot per distinct (frequency, beam class), uploaded / evaluated in frequency order (so
+        # that the host beam cache of user telescopes is hit); everything per unit is array arithmetic
+        # (a CHIME-scale frequency has 7152 units, a product run 7.3 million)
+        fi = np.asarray(fi, dtype=np.int64)
+        cls_i, cls_j = tel.beamclass[pairs[:, 0]], tel.beamclass[pairs[:, 1]]
+        ncls = int(tel.beamclass.max()) + 1
+        keys = np.unique(np.concatenate([fi * ncls + cls_i, fi * ncls + cls_j]))
         # bound the device memory held by cached beams (fp64 + fp32 copy per map)
-        needed = {(int(f), int(c)) for f, c in zip(np.repeat(fi, 2), tel.beamclass[pairs].ravel())}
+        needed = {divmod(int(k), ncls) for k in keys}
         per_slot = 12 * nside * nside * (2 if tel._polarised_ else 1) * 12
         if len(needed | set(self._slots[nside])) * per_slot > self.beam_budget:
             self.drop_beams(nside)
-        uv = tel.baselines[bl] / tel.wavelengths[fi][:, np.newaxis]
-        units["uvec"] = visibility.uv_vector(tel.zenith, uv)
-        # upload in frequency order so that the host beam cache of user telescopes is hit
-        for i in np.argsort(fi, kind="stable"):
-            si = self._beam_slot(nside, pairs[i, 0], fi[i])
-            sj = self._beam_slot(nside, pairs[i, 1], fi[i])
-            units["beam_i"][i], units["beam_j"][i] = si, sj
-            units["prefactor"][i] = 1.0 / np.sqrt(plan.omega[si] * plan.omega[sj])
+        table = {}
+        for key in keys:  # ascending = frequency order
+            f, c = divmod(int(key), ncls)
+            feed = int(np.flatnonzero(tel.beamclass == c)[0])
+            table[int(key)] = self._beam_slot(nside, feed, f)
+        lut = np.array([table[int(k)] for k in keys], dtype=np.int32)
+        si = lut[np.searchsorted(keys, fi * ncls + cls_i)]
+        sj = lut[np.searchsorted(keys, fi * ncls + cls_j)]
+        omega = np.array([plan.omega[int(x)] for x in lut])
+        units["beam_i"], units["beam_j"] = si, sj
+        units["prefactor"] = 1.0 / np.sqrt(omega[np.searchsorted(keys, fi * ncls + cls_i)] *
+                                           omega[np.searchsorted(keys, fi * ncls + cls_j)])
         units["lmax"] = lmax
         units["out0"] = out0
         units["out1"] = out1
         return plan, units
 
     def _buckets(self, lmax):
-        nside = np.array([self.tel._unit_nside(int(l)) for l in lmax], dtype=np.int64)
+        lmax = np.asarray(lmax)
+        uniq, inv = np.unique(lmax, return_inverse=True)
+        nside = np.array([self.tel._unit_nside(int(l)) for l in uniq], dtype=np.int64)[inv]
         # ascending nside == ascending lmax order of the reference's unit loop
         return [(int(ns), np.flatnonzero(nside == ns)) for ns in np.unique(nside)]
 
