@@ -174,6 +174,7 @@ __device__ __forceinline__ void split3_bits(float v, uint32_t &h, uint32_t &m, u
 // (upper half of a, upper half of b) -> one 32-bit word, a in the low half
 __device__ __forceinline__ uint32_t hi2(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); }
 
+template <bool FUSED_FOLD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA2,
                    const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB2,
@@ -369,7 +370,7 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       // corrections, then store this thread's operand column contiguously in l
       mbar_wait(&cfull[cb], cb_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (P.fold_scale != nullptr && wi.row0 >= P.fold_row0) {
+      if (FUSED_FOLD && wi.row0 >= P.fold_row0) {
         // fused fold: this thread's operand column, rows = fold rings
         const int col = wi.coltile * TC_M + quarter * 32 + lane;
         const int cpu = s2 ? 8 : P.cpu0;
@@ -613,7 +614,9 @@ int launch_contract_tc(const ContractDesc &d, int nitems, const WorkItem *items_
   // diagnostic (two launches in flight): give every launch the same carve-out
   static const bool fixed_smem = getenv("DSB_TC_FIXED_SMEM") != nullptr;
   if (fixed_smem) smem = 226 * 1024;
-  DSB_CUDA(raise_dynamic_smem((const void *)legendre_tc_kernel, smem));
+  const bool fused = P.fold_scale != nullptr;
+  DSB_CUDA(raise_dynamic_smem(fused ? (const void *)legendre_tc_kernel<true> : (const void *)legendre_tc_kernel<false>,
+                              smem));
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
@@ -637,7 +640,10 @@ int launch_contract_tc(const ContractDesc &d, int nitems, const WorkItem *items_
       if (!last) DSB_CUDA(cudaEventCreateWithFlags(&last, cudaEventDisableTiming));
       else DSB_CUDA(cudaStreamWaitEvent(stream, last, 0));
     }
-    legendre_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mA0, mA2, mB0, mB2, P);
+    if (fused)
+      legendre_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(mA0, mA2, mB0, mB2, P);
+    else
+      legendre_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(mA0, mA2, mB0, mB2, P);
     DSB_LAUNCH_CHECK();
     if (use) DSB_CUDA(cudaEventRecord(last, stream));
   }
