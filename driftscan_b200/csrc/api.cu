@@ -323,7 +323,7 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
   if (niter > 0)  // a(0) and A S a, transposed coefficients (fp64 spin 2: both roles), synthesised ring functions
     per_unit += 2 * nprob * t.NP * (lay.cpu0 + (lay.has2 ? 8 : 0)) * cs +
                 nprob * t.NPk * (lay.cpu0 + (lay.has2 ? 8 * k2mul : 0)) * cs +
-                nprob * lay.Kp * (lay.cpu0 + (lay.has2 ? 8 : 0)) * es;
+                nprob * t.SR * (lay.cpu0 + (lay.has2 ? 8 : 0)) * es;
   const size_t plane_out = (size_t)npol_out * (lside + 1) * (2 * lside + 1) * 16;
   const size_t per_unit_tot = per_unit + ((tarray && out_is_host) ? plane_out : 0);
   size_t budget = workspace_limit();
@@ -390,9 +390,12 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
           }
     }
 
-    // Synthesis items of the Jacobi refinement: rows = fold rings, contraction over the l-index n of
-    // the tile's rows (the X role of spin 2 runs over the rows of the opposite l - m parity)
-    std::vector<WorkItem> sitems;
+    // Synthesis items of the Jacobi refinement: contraction over the l-index n of the tile's rows (the
+    // X role of spin 2 runs over the rows of the opposite l - m parity).  fp64: rows = all fold rings.
+    // Production precision: rows = the kc cap rings followed by the tile's rows of the precomputed
+    // (analysis o synthesis) product over the other rings (Tables::kc), cut into items of <= 128 rows;
+    // `citems` = the analysis over the cap rings only (contraction length kc).
+    std::vector<WorkItem> sitems, citems;
     if (niter > 0) {
       for (int s = 0; s <= (lay.has2 ? 2 : 0); s += 2) {
         const int cpu = s == 0 ? lay.cpu0 : 8;
@@ -404,12 +407,20 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
           for (int p = 0; p < 2; ++p)
             for (int ct = 0; ct < ntile; ++ct) {
               if (m > Lt[ct]) continue;
-              int nr = nrows_mp(Lt[ct], m, p);
+              const int nro = nrows_mp(Lt[ct], m, p);
+              int nr = nro;
               if (s == 2) nr = std::max(nr, nrows_mp(Lt[ct], m, 1 - p));
               const int klen = std::max(32, (int)round_up(nr, 32));
-              for (int r0 = 0; r0 < plan->nfold; r0 += 128)
-                sitems.push_back({2 * m + p, ct, std::min(128, plan->nfold - r0), s, r0, klen});
+              const int rows = f64 ? plan->nfold : t.kc + nro;
+              const int nit = (rows + 127) / 128;
+              const int per = (int)round_up((rows + nit - 1) / nit, 16);
+              for (int r0 = 0; r0 < rows; r0 += per)
+                sitems.push_back({2 * m + p, ct, std::min(per, rows - r0), s, r0, klen});
             }
+      }
+      if (!f64) {
+        citems = items;
+        for (auto &w : citems) w.klen = t.kc;
       }
     }
 
@@ -421,12 +432,12 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
     const size_t c2_bytes = lay.has2 ? nprob * lay.ncols2 * t.NP * cs : 0;
     const size_t ct0_bytes = niter > 0 ? nprob * t.NPk * lay.ncols0 * cs : 0;
     const size_t ct2_bytes = (niter > 0 && lay.has2) ? nprob * k2mul * t.NPk * lay.ncols2 * cs : 0;
-    const size_t g0_bytes = niter > 0 ? nprob * lay.ncols0 * lay.Kp * es : 0;
-    const size_t g2_bytes = (niter > 0 && lay.has2) ? nprob * lay.ncols2 * lay.Kp * es : 0;
+    const size_t g0_bytes = niter > 0 ? nprob * lay.ncols0 * t.SR * es : 0;
+    const size_t g2_bytes = (niter > 0 && lay.has2) ? nprob * lay.ncols2 * t.SR * es : 0;
     char *F0, *F2, *C0, *C2, *A0, *A2, *D0, *D2, *Ct0, *Ct2, *G0, *G2, *stage;
     UnitDev *ud_dev;
     int32_t *o0_dev, *o1_dev;
-    WorkItem *items_dev, *sitems_dev;
+    WorkItem *items_dev, *sitems_dev, *citems_dev;
     int64_t *moff_dev;
     auto carve = [&](void *base) {
       Carve cv(base);
@@ -447,6 +458,7 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
       o1_dev = cv.take<int32_t>(nu);
       items_dev = cv.take<WorkItem>(items.size());
       sitems_dev = cv.take<WorkItem>(sitems.size());
+      citems_dev = cv.take<WorkItem>(citems.size());
       moff_dev = cv.take<int64_t>(moff.size());
       stage = (tarray && out_is_host) ? cv.take<char>((size_t)nu * plane_out) : nullptr;
       return cv.off + 256;
@@ -468,10 +480,11 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
       // descriptors go through a pinned staging slot (see dsb_plan::stage_host): stream-ordered
       // copies, the host does not wait for the device
       const size_t b_ud = nu * sizeof(UnitDev), b_o = nu * sizeof(int32_t), b_it = items.size() * sizeof(WorkItem),
-                   b_mo = moff.size() * sizeof(int64_t), b_si = sitems.size() * sizeof(WorkItem);
+                   b_mo = moff.size() * sizeof(int64_t), b_si = sitems.size() * sizeof(WorkItem),
+                   b_ci = citems.size() * sizeof(WorkItem);
       auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
       const size_t o_ud = 0, o_o0 = al(b_ud), o_o1 = o_o0 + al(b_o), o_it = o_o1 + al(b_o), o_mo = o_it + al(b_it),
-                   o_si = o_mo + al(b_mo), total = o_si + al(b_si);
+                   o_si = o_mo + al(b_mo), o_ci = o_si + al(b_si), total = o_ci + al(b_ci);
       // A call recorded into a CUDA graph (the stream is capturing) is replayed with the copies
       // it recorded: its descriptors get a buffer of their own that lives as long as the plan.
       cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -502,12 +515,14 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
       memcpy(h + o_it, items.data(), b_it);
       memcpy(h + o_mo, moff.data(), b_mo);
       if (b_si) memcpy(h + o_si, sitems.data(), b_si);
+      if (b_ci) memcpy(h + o_ci, citems.data(), b_ci);
       DSB_CUDA(cudaMemcpyAsync(ud_dev, h + o_ud, b_ud, cudaMemcpyHostToDevice, stream));
       DSB_CUDA(cudaMemcpyAsync(o0_dev, h + o_o0, b_o, cudaMemcpyHostToDevice, stream));
       DSB_CUDA(cudaMemcpyAsync(o1_dev, h + o_o1, b_o, cudaMemcpyHostToDevice, stream));
       DSB_CUDA(cudaMemcpyAsync(items_dev, h + o_it, b_it, cudaMemcpyHostToDevice, stream));
       DSB_CUDA(cudaMemcpyAsync(moff_dev, h + o_mo, b_mo, cudaMemcpyHostToDevice, stream));
       if (b_si) DSB_CUDA(cudaMemcpyAsync(sitems_dev, h + o_si, b_si, cudaMemcpyHostToDevice, stream));
+      if (b_ci) DSB_CUDA(cudaMemcpyAsync(citems_dev, h + o_ci, b_ci, cudaMemcpyHostToDevice, stream));
       if (!capturing) DSB_CUDA(cudaEventRecord(plan->stage_ev[slot], stream));
     }
 
@@ -528,29 +543,6 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
     da.has2 = lay.has2;
     int max_rows = 16;
     for (const auto &w : items) max_rows = std::max(max_rows, w.nrows);
-    // fp32 path: synthesis items whose rings cannot alias write the next analysis' operand directly
-    FusedFold ffold;
-    int fused_row0 = -1;
-    // Measured (profiles/r02): the fused epilogue issues 64 four-byte stores per thread and item and
-    // costs the synthesis what the separate transpose kernel costs (4.3 vs 2.3 + 1.5 ms on the nside-128
-    // bucket of the bench): off by default, DSB_FOLD_FUSED=1 enables it.
-    static const bool fused = getenv("DSB_FOLD_FUSED") != nullptr;
-    if (niter > 0 && !f64 && fused) {
-      fused_row0 = (int)round_up(fold_alias_rows(lay.mcap, plan->nfold), 128);  // whole work items
-      if (fused_row0 < plan->nfold) {
-        ffold.scale = plan->fold_scale;
-        ffold.F0 = (float *)F0;
-        ffold.F2 = (float *)F2;
-        ffold.units = ud_dev;
-        ffold.row0 = fused_row0;
-        ffold.nfold = plan->nfold;
-        ffold.nunits = nu;
-        ffold.cpu0 = lay.cpu0;
-        ffold.Kp = lay.Kp;
-      } else {
-        fused_row0 = -1;
-      }
-    }
     auto contract = [&](const ContractDesc &d, const std::vector<WorkItem> &its, const WorkItem *its_dev, int mrows,
                         const char *a0, const char *a2, bool synth, char *c0, char *c2) {
       if (f64)
@@ -559,7 +551,7 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
                                    (double *)c2, (const double *)A0, (const double *)A2, stream);
       return launch_contract_tc(d, (int)its.size(), its_dev, mrows, (const float *)a0, (const float *)a2,
                                 synth ? t.s0_bf : t.t0_bf, synth ? t.s2_bf : t.t2_bf, (float *)c0, (float *)c2,
-                                (const float *)A0, (const float *)A2, stream, synth ? &ffold : nullptr);
+                                (const float *)A0, (const float *)A2, stream);
     };
     if ((rc = contract(da, items, items_dev, max_rows, F0, F2, false, C0, C2)) != DSB_OK) break;
     timer.mark(2);
@@ -568,21 +560,28 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
       // Jacobi refinement (healpy map2alm iter): a <- a(0) + a - A S a, S a on ring spectra
       DSB_CUDA(cudaMemcpyAsync(A0, C0, c0_bytes, cudaMemcpyDeviceToDevice, stream));
       if (c2_bytes) DSB_CUDA(cudaMemcpyAsync(A2, C2, c2_bytes, cudaMemcpyDeviceToDevice, stream));
-      ContractDesc ds = da;  // synthesis: A = transposed coefficients, B = S tables, rows = fold rings
+      ContractDesc ds = da;  // synthesis: A = transposed coefficients, B = S tables, rows = fold rings (+ product rows)
       ds.K = ds.kx = t.NPk;
-      ds.pitch = t.Kp;
+      ds.pitch = t.SR;
+      // production precision: (A S a) = D (cap rings, through the fold) + E (rows [kc, ..) of G)
+      const char *E0 = f64 ? nullptr : G0 + (size_t)t.kc * cs, *E2 = (f64 || !lay.has2) ? nullptr : G2 + (size_t)t.kc * cs;
+      int smax = 16;
+      for (const auto &w : sitems) smax = std::max(smax, w.nrows);
       for (int it = 0; it < niter && rc == DSB_OK; ++it) {
         // pass it > 0 starts by applying the previous pass' step a <- a(0) + a - A S a (fused into the transpose)
         if ((rc = launch_transpose_coeffs(lay, ud_dev, t.NP, t.NPk, precision, C0, C2, A0, A2, it ? D0 : nullptr,
-                                          it ? D2 : nullptr, Ct0, Ct2, stream)) != DSB_OK)
+                                          it ? D2 : nullptr, E0, E2, t.SR, Ct0, Ct2, stream)) != DSB_OK)
           break;
-        if ((rc = contract(ds, sitems, sitems_dev, std::min(128, plan->nfold), Ct0, Ct2, true, G0, G2)) != DSB_OK) break;
-        if ((rc = launch_alias_fold(plan, lay, ud_dev, precision, G0, G2, F0, F2, stream, fused_row0)) != DSB_OK) break;
-        rc = contract(da, items, items_dev, max_rows, F0, F2, false, D0, D2);
+        if ((rc = contract(ds, sitems, sitems_dev, smax, Ct0, Ct2, true, G0, G2)) != DSB_OK) break;
+        if ((rc = launch_alias_fold(plan, lay, ud_dev, precision, G0, G2, F0, F2, stream, f64 ? -1 : t.kc, t.SR)) !=
+            DSB_OK)
+          break;
+        rc = f64 ? contract(da, items, items_dev, max_rows, F0, F2, false, D0, D2)
+                 : contract(da, citems, citems_dev, max_rows, F0, F2, false, D0, D2);
       }
       if (rc == DSB_OK)  // the last step, no transpose
-        rc = launch_transpose_coeffs(lay, ud_dev, t.NP, t.NPk, precision, C0, C2, A0, A2, D0, D2, nullptr, nullptr,
-                                     stream);
+        rc = launch_transpose_coeffs(lay, ud_dev, t.NP, t.NPk, precision, C0, C2, A0, A2, D0, D2, E0, E2, t.SR, nullptr,
+                                     nullptr, stream);
       if (rc != DSB_OK) break;
     }
     timer.mark(3);

@@ -131,10 +131,23 @@ struct Tables {
   // table:  S0[prob][k][n] = lambda_lm(theta_k);  S2[prob][k][n | NPk + n'] = [-W_lm | -X_l'm],
   // l = m + p + 2n, l' = m + (1 - p) + 2n' (the X role pairs a problem with the rows of the
   // opposite l - m parity).  Row pitch Kp, NPk = NP rounded up to the k-tile.
+  //
+  // Production precision (bf16 x3): only the first `kc` fold rings -- the ones next to the pole on
+  // which coefficients of different m can alias onto each other above rounding level, see
+  // alias_cap_rows() in tables.cu -- are synthesised as ring functions.  On every other ring the
+  // map sampled from the synthesis has the ring spectrum n h_m exactly (to 1e-14), analysis after
+  // synthesis is block diagonal in m there, and the product of the two tables over those rings
+  // is precomputed (fp64) and appended to the synthesis table as NP more rows per problem:
+  //   PE0[prob][n][n']        = sum_{k >= kc} T0[prob][n][k] fs_k S0[prob][k][n']
+  //   PE2[prob][n][n' | NPk + n''] likewise with both operand roles (tables.cu: pe_kernel)
+  // so one contraction with the transposed coefficients yields, per problem, the kc ring functions
+  // of the cap (rows [0, kc)) and (A S a) restricted to the other rings (rows [kc, kc + NP)).
+  // Row pitch SR = kc + NP.  fp64 (validation): kc = nfold, SR = Kp, every ring synthesised.
   int synth = 0;
   int NPk = 0;
+  int kc = 0, SR = 0;
   double *s0_f64 = nullptr, *s2_f64 = nullptr;
-  __nv_bfloat16 *s0_bf = nullptr, *s2_bf = nullptr;  // [3][nprob][Kp][NPk or 2 NPk]
+  __nv_bfloat16 *s0_bf = nullptr, *s2_bf = nullptr;  // [3][nprob][SR][NPk or 2 NPk]
   size_t splane0 = 0, splane2 = 0;
 };
 
@@ -286,32 +299,25 @@ struct ContractDesc {
 int launch_contract_f64(const ContractDesc &d, int nitems, const WorkItem *items_dev, const double *A0,
                         const double *A2, const double *B0, const double *B2, double *C0, double *C2,
                         const double *base0, const double *base2, cudaStream_t stream);
-// Synthesis with the non-aliasing part of the fold fused into the epilogue (fp32 path): rows (fold
-// rings) >= row0 are written as ring spectra F[prob][ring][col] = scale[ring] * result.
-struct FusedFold {
-  const float *scale = nullptr;  // [nfold] 2 x pixels per ring (1 x on the equator); NULL = off
-  float *F0 = nullptr, *F2 = nullptr;
-  const UnitDev *units = nullptr;
-  int row0 = 0, nfold = 0, nunits = 0, cpu0 = 0, Kp = 0;
-};
 int launch_contract_tc(const ContractDesc &d, int nitems, const WorkItem *items_dev, int max_rows,
                        const float *A0, const float *A2, const __nv_bfloat16 *B0, const __nv_bfloat16 *B2,
-                       float *C0, float *C2, const float *base0, const float *base2, cudaStream_t stream,
-                       const FusedFold *fold = nullptr);
+                       float *C0, float *C2, const float *base0, const float *base2, cudaStream_t stream);
 
 // shtiter.cu -- the pieces of healpy's map2alm(iter > 0) that are not contractions
 // C[prob][col][NP] -> Ct[prob][n][col] (fp64 spin 2: both operand roles, X role at row NPk),
 // rows above a unit's own lmax zeroed
 // D0 != NULL: first apply the Jacobi step C <- A + C - D (A = a(0), D = A S a of the previous pass) and
-// write C back; Ct0 == NULL: that update only.
+// write C back; Ct0 == NULL: that update only.  Production precision: A S a = D + E, E with row
+// pitch `epitch` (see Tables::kc).
 int launch_transpose_coeffs(const BucketLayout &lay, const UnitDev *units_dev, int NP, int NPk, int precision,
                             void *C0, void *C2, const void *A0, const void *A2, const void *D0, const void *D2,
-                            void *Ct0, void *Ct2, cudaStream_t stream);
-// G[prob][col][Kp] (synthesised ring functions) -> ring spectra of the pixelised map in the
-// operand layout of the analysis (F0 / F2 of ringfft.cu)
-// `fused_row0` >= 0: rings from there on were already written by the synthesis epilogue (FusedFold)
+                            const void *E0, const void *E2, int epitch, void *Ct0, void *Ct2, cudaStream_t stream);
+// G[prob][col][pitch] (synthesised ring functions) -> ring spectra of the pixelised map in the
+// operand layout of the analysis (F0 / F2 of ringfft.cu).  fp64: every ring (kc < 0, pitch Kp);
+// production precision: the kc cap rings, G pitch `gpitch`.
 int launch_alias_fold(dsb_plan *plan, const BucketLayout &lay, const UnitDev *units_dev, int precision,
-                      const void *G0, const void *G2, void *F0, void *F2, cudaStream_t stream, int fused_row0 = -1);
+                      const void *G0, const void *G2, void *F0, void *F2, cudaStream_t stream, int kc = -1,
+                      int gpitch = 0);
 // first fold ring that cannot alias for any unit of a bucket with the given largest m (multiple of 32)
 inline int fold_alias_rows(int mcap, int nfold) { return std::min((nfold + 31) / 32 * 32, (mcap / 2 + 31) / 32 * 32); }
 

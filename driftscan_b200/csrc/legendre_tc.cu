@@ -64,14 +64,6 @@ struct TcParams {
   float *C0, *C2;
   const float *base0, *base2;  // update mode: C = base + C - result
   int update;
-  // synthesis with the fold fused in (Jacobi refinement, shtiter.cu): work items whose rows (fold
-  // rings) start at fold_row0 or later cannot alias for any unit of the bucket, so the ring
-  // spectra of the pixelised map are the scaled synthesis itself and go straight into the operand
-  // layout of the next analysis, F[prob][ring][col] -- no round trip through G for them
-  float *F0, *F2;
-  const float *fold_scale;  // [nfold] pixels per ring x 2 (x 1 on the equator)
-  const UnitDev *units;
-  int fold_row0, nfold, nunits, cpu0, Kp;
   int NB;            // table box rows (TMA box), multiple of 16, <= 256
   int nstages;
   int diag;          // DSB_TC_DIAG (timing experiments, WRONG results): 1 = table tile loaded for the first
@@ -174,7 +166,6 @@ __device__ __forceinline__ void split3_bits(float v, uint32_t &h, uint32_t &m, u
 // (upper half of a, upper half of b) -> one 32-bit word, a in the low half
 __device__ __forceinline__ uint32_t hi2(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); }
 
-template <bool FUSED_FOLD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA2,
                    const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB2,
@@ -370,39 +361,6 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       // corrections, then store this thread's operand column contiguously in l
       mbar_wait(&cfull[cb], cb_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (FUSED_FOLD && wi.row0 >= P.fold_row0) {
-        // fused fold: this thread's operand column, rows = fold rings
-        const int col = wi.coltile * TC_M + quarter * 32 + lane;
-        const int cpu = s2 ? 8 : P.cpu0;
-        const int u = col / cpu, m = wi.prob >> 1, par = wi.prob & 1;
-        const bool live = u < P.nunits && m <= P.units[min(u, P.nunits - 1)].mmax;
-        const int j4 = col & 3;
-        float *F = (s2 ? P.F2 : P.F0) + (size_t)wi.prob * P.Kp * ncols + col;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (half * 64 + g * 16 < N) {  // warp-uniform
-            uint32_t v[16];
-            tmem_ld16(lane_base + 256 + (uint32_t)cb * 128 + g * 16, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              const int row = wi.row0 + half * 64 + g * 16 + q;
-              float val = sums[g * 16 + q] + __uint_as_float(v[q]);
-              // m = 0: F-_0 = conj(F+_0), the (-re, -im) columns mirror the (+re, +im) ones two lanes down
-              const float below = __shfl_up_sync(0xffffffffu, val, 2);
-              if (m == 0 && j4 >= 2) val = j4 == 2 ? below : -below;
-              if (live && row < P.nfold) {
-                const float fs = (par == 1 && row == P.nfold - 1) ? 0.f : P.fold_scale[row];
-                F[(size_t)row * ncols] = fs * val;
-              }
-            }
-          }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&cfree[cb]);
-        continue;
-      }
       const size_t cidx =
           ((size_t)wi.prob * ncols + (size_t)wi.coltile * TC_M + quarter * 32 + lane) * P.NP + wi.row0 + half * 64;
       float *C = (s2 ? P.C2 : P.C0) + cidx;
@@ -547,8 +505,7 @@ static int encode4(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1,
 
 int launch_contract_tc(const ContractDesc &d, int nitems, const WorkItem *items_dev, int max_rows,
                        const float *A0, const float *A2, const __nv_bfloat16 *B0, const __nv_bfloat16 *B2,
-                       float *C0, float *C2, const float *base0, const float *base2, cudaStream_t stream,
-                       const FusedFold *fold) {
+                       float *C0, float *C2, const float *base0, const float *base2, cudaStream_t stream) {
   if (nitems == 0) return DSB_OK;
   DSB_CHECK(d.K % TC_KC == 0 && d.kx % TC_KC == 0, DSB_ERR_INVALID, "contraction length must be a multiple of %d",
             TC_KC);
@@ -588,21 +545,6 @@ int launch_contract_tc(const ContractDesc &d, int nitems, const WorkItem *items_
   P.base0 = base0;
   P.base2 = base2;
   P.update = d.update;
-  P.fold_scale = nullptr;
-  P.F0 = P.F2 = nullptr;
-  P.units = nullptr;
-  P.fold_row0 = P.nfold = P.nunits = P.cpu0 = P.Kp = 0;
-  if (fold && fold->scale) {
-    P.fold_scale = fold->scale;
-    P.F0 = fold->F0;
-    P.F2 = fold->F2;
-    P.units = fold->units;
-    P.fold_row0 = fold->row0;
-    P.nfold = fold->nfold;
-    P.nunits = fold->nunits;
-    P.cpu0 = fold->cpu0;
-    P.Kp = fold->Kp;
-  }
   P.NB = NB;
   static const int diag = getenv("DSB_TC_DIAG") ? atoi(getenv("DSB_TC_DIAG")) : 0;
   P.diag = diag;
@@ -614,9 +556,7 @@ int launch_contract_tc(const ContractDesc &d, int nitems, const WorkItem *items_
   // diagnostic (two launches in flight): give every launch the same carve-out
   static const bool fixed_smem = getenv("DSB_TC_FIXED_SMEM") != nullptr;
   if (fixed_smem) smem = 226 * 1024;
-  const bool fused = P.fold_scale != nullptr;
-  DSB_CUDA(raise_dynamic_smem(fused ? (const void *)legendre_tc_kernel<true> : (const void *)legendre_tc_kernel<false>,
-                              smem));
+  DSB_CUDA(raise_dynamic_smem((const void *)legendre_tc_kernel, smem));
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
@@ -640,10 +580,7 @@ int launch_contract_tc(const ContractDesc &d, int nitems, const WorkItem *items_
       if (!last) DSB_CUDA(cudaEventCreateWithFlags(&last, cudaEventDisableTiming));
       else DSB_CUDA(cudaStreamWaitEvent(stream, last, 0));
     }
-    if (fused)
-      legendre_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(mA0, mA2, mB0, mB2, P);
-    else
-      legendre_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(mA0, mA2, mB0, mB2, P);
+    legendre_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mA0, mA2, mB0, mB2, P);
     DSB_LAUNCH_CHECK();
     if (use) DSB_CUDA(cudaEventRecord(last, stream));
   }
@@ -683,8 +620,7 @@ extern "C" int dsb_debug_gemm_tc(int nprob, int K, int NP, int ncols, int nitems
   d.K = d.kx = K;
   d.pitch = NP;
   d.ncols0 = d.ncols2 = ncols;
-  int rc = launch_contract_tc(d, nitems, items, max_rows, F, nullptr, T, nullptr, C, nullptr, nullptr, nullptr, 0,
-                              nullptr);
+  int rc = launch_contract_tc(d, nitems, items, max_rows, F, nullptr, T, nullptr, C, nullptr, nullptr, nullptr, 0);
   if (rc == DSB_OK) {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {

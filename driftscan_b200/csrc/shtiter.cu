@@ -19,8 +19,10 @@
 // fold parity: lambda_lm(pi - theta) = (-1)^(l+m) lambda_lm(theta) gives the even (odd) l - m
 // rows the parity of the even (odd) north/south combination for every m.
 //
-// This file holds the two data-movement kernels of an iteration; the contractions are
-// launch_contract_{tc,f64}, the update a(0) + a - (A S) a is fused into their epilogue.
+// This file holds the data-movement kernels of an iteration; the contractions are
+// launch_contract_{tc,f64}.  In the production precision only the kc rings next to the pole are
+// synthesised and folded at all (Tables::kc, tables.cu): on every other ring aliasing is below 1e-14
+// and (A S a) restricted to those rings comes from a precomputed per-m product table.
 #include <algorithm>
 #include <cstdlib>
 
@@ -39,17 +41,28 @@ namespace dsb {
 // (after the last pass).  Keeping this out of the contraction's epilogue matters: there the two
 // extra operands arrive as latency-bound strided loads on the tensor pipeline's critical path
 // (measured: the analysis with the update in its epilogue took 7.0 ms instead of 3.8).
+//
+// split != 0 (production precision): (A S a) arrives in two parts, D = the cap rings' share and
+// E[prob][col][epitch] = the share of all other rings (rows [kc, kc + NP) of the contraction with the
+// extended synthesis table, Tables::kc); and the transposed operand gets the m = 0 symmetry
+// a-_l0 = conj(a+_l0) imposed (the ring spectra of a map satisfy F-_0 = conj(F+_0); the fold of the
+// cap rings takes F-_0 from the + slot, the precomputed product needs it in its input).
+// lmax_b = largest unit lmax of the bucket: tiles above it hold nothing and are skipped.
 template <typename T, bool ROLE2, bool UPDATE>
 __global__ void __launch_bounds__(256)
 transpose_coeffs_kernel(  // (ROLE2 && UPDATE) is never instantiated, see transpose_t
-T *__restrict__ C, const T *__restrict__ base, const T *__restrict__ D, T *__restrict__ Ct,
-                        const UnitDev *__restrict__ units, int nunits, int cpu, int ncols, int NP, int NPk) {
+T *__restrict__ C, const T *__restrict__ base, const T *__restrict__ D, const T *__restrict__ E, int epitch,
+                        T *__restrict__ Ct, const UnitDev *__restrict__ units, int nunits, int cpu, int ncols, int NP,
+                        int NPk, int lmax_b, int split) {
   __shared__ T tile[32][33];
   const int prob = blockIdx.z;
   const int m = prob >> 1, p = prob & 1;
   const int col0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int nrole = ROLE2 ? 2 : 1;
+  // rows of this tile that any contraction reads: below klen_rows(m) = the k-tile-rounded row count of
+  // the longer of the two l - m parities at the bucket's lmax (klen of the synthesis items)
+  if (split && n0 >= (int)((nrows_mp(lmax_b, m, 0) + 31) & ~31)) return;
   for (int role = 0; role < nrole; ++role) {
     const int sprob = role ? (prob ^ 1) : prob;  // source problem
     const int sp = role ? 1 - p : p;
@@ -63,7 +76,9 @@ T *__restrict__ C, const T *__restrict__ base, const T *__restrict__ D, T *__res
         const size_t at = ((size_t)sprob * ncols + c) * NP + n;
         v = C[at];
         if (UPDATE) {
-          v = (base[at] - D[at]) + v;
+          T d = D[at];
+          if (E) d += E[((size_t)sprob * ncols + c) * epitch + n];
+          v = (base[at] - d) + v;
           C[at] = v;  // UPDATE is only instantiated with a single role: read once, written once
         }
       }
@@ -71,6 +86,14 @@ T *__restrict__ C, const T *__restrict__ base, const T *__restrict__ D, T *__res
     }
     if (Ct == nullptr) continue;  // update only (uniform)
     __syncthreads();
+    if (split && m == 0) {  // (+re, +im, -re, -im) per map: - slot <- conj(+ slot)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = ty + 8 * i;
+        if ((c & 3) >= 2) tile[c][tx] = (c & 3) == 2 ? tile[c - 2][tx] : -tile[c - 2][tx];
+      }
+      __syncthreads();
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int n = n0 + ty + 8 * i;
@@ -88,37 +111,43 @@ T *__restrict__ C, const T *__restrict__ base, const T *__restrict__ D, T *__res
 
 template <typename T>
 static int transpose_t(const BucketLayout &lay, const UnitDev *units_dev, int NP, int NPk, void *C0, void *C2,
-                       const void *A0, const void *A2, const void *D0, const void *D2, void *Ct0, void *Ct2,
-                       cudaStream_t stream) {
+                       const void *A0, const void *A2, const void *D0, const void *D2, const void *E0, const void *E2,
+                       int epitch, int split, void *Ct0, void *Ct2, cudaStream_t stream) {
   const int nprob = 2 * (lay.mcap + 1);
   const bool update = D0 != nullptr;
   const bool role2 = sizeof(T) == 8;  // the fp64 spin-2 block stores both operand roles
   dim3 g0(lay.ncols0 / 32, NPk / 32, nprob), g2(lay.ncols2 / 32, NPk / 32, nprob);
+  const int L = lay.lmax_b;
   if (update)
-    transpose_coeffs_kernel<T, false, true><<<g0, 256, 0, stream>>>((T *)C0, (const T *)A0, (const T *)D0, (T *)Ct0,
-                                                                    units_dev, lay.nunits, lay.cpu0, lay.ncols0, NP, NPk);
+    transpose_coeffs_kernel<T, false, true><<<g0, 256, 0, stream>>>((T *)C0, (const T *)A0, (const T *)D0, (const T *)E0,
+                                                                    epitch, (T *)Ct0, units_dev, lay.nunits, lay.cpu0,
+                                                                    lay.ncols0, NP, NPk, L, split);
   else
-    transpose_coeffs_kernel<T, false, false><<<g0, 256, 0, stream>>>((T *)C0, nullptr, nullptr, (T *)Ct0, units_dev,
-                                                                     lay.nunits, lay.cpu0, lay.ncols0, NP, NPk);
+    transpose_coeffs_kernel<T, false, false><<<g0, 256, 0, stream>>>((T *)C0, nullptr, nullptr, nullptr, 0, (T *)Ct0,
+                                                                     units_dev, lay.nunits, lay.cpu0, lay.ncols0, NP, NPk,
+                                                                     L, split);
   DSB_LAUNCH_CHECK();
   if (!lay.has2) return DSB_OK;
   if (role2 && Ct2 != nullptr) {
     // two roles read every coefficient twice (own problem, partner problem): an in-place update
     // would race with the partner's read, so it runs as a pass of its own first
     if (update) {
-      transpose_coeffs_kernel<T, false, true><<<g2, 256, 0, stream>>>((T *)C2, (const T *)A2, (const T *)D2, nullptr,
-                                                                      units_dev, lay.nunits, 8, lay.ncols2, NP, NPk);
+      transpose_coeffs_kernel<T, false, true><<<g2, 256, 0, stream>>>((T *)C2, (const T *)A2, (const T *)D2,
+                                                                      (const T *)E2, epitch, nullptr, units_dev,
+                                                                      lay.nunits, 8, lay.ncols2, NP, NPk, L, split);
       DSB_LAUNCH_CHECK();
     }
-    transpose_coeffs_kernel<T, true, false><<<g2, 256, 0, stream>>>((T *)C2, nullptr, nullptr, (T *)Ct2, units_dev,
-                                                                    lay.nunits, 8, lay.ncols2, NP, NPk);
+    transpose_coeffs_kernel<T, true, false><<<g2, 256, 0, stream>>>((T *)C2, nullptr, nullptr, nullptr, 0, (T *)Ct2,
+                                                                    units_dev, lay.nunits, 8, lay.ncols2, NP, NPk, L, split);
   } else {
     if (update)
-      transpose_coeffs_kernel<T, false, true><<<g2, 256, 0, stream>>>((T *)C2, (const T *)A2, (const T *)D2, (T *)Ct2,
-                                                                      units_dev, lay.nunits, 8, lay.ncols2, NP, NPk);
+      transpose_coeffs_kernel<T, false, true><<<g2, 256, 0, stream>>>((T *)C2, (const T *)A2, (const T *)D2,
+                                                                      (const T *)E2, epitch, (T *)Ct2, units_dev,
+                                                                      lay.nunits, 8, lay.ncols2, NP, NPk, L, split);
     else
-      transpose_coeffs_kernel<T, false, false><<<g2, 256, 0, stream>>>((T *)C2, nullptr, nullptr, (T *)Ct2, units_dev,
-                                                                       lay.nunits, 8, lay.ncols2, NP, NPk);
+      transpose_coeffs_kernel<T, false, false><<<g2, 256, 0, stream>>>((T *)C2, nullptr, nullptr, nullptr, 0, (T *)Ct2,
+                                                                       units_dev, lay.nunits, 8, lay.ncols2, NP, NPk, L,
+                                                                       split);
   }
   DSB_LAUNCH_CHECK();
   return DSB_OK;
@@ -126,10 +155,11 @@ static int transpose_t(const BucketLayout &lay, const UnitDev *units_dev, int NP
 
 int launch_transpose_coeffs(const BucketLayout &lay, const UnitDev *units_dev, int NP, int NPk, int precision,
                             void *C0, void *C2, const void *A0, const void *A2, const void *D0, const void *D2,
-                            void *Ct0, void *Ct2, cudaStream_t stream) {
+                            const void *E0, const void *E2, int epitch, void *Ct0, void *Ct2, cudaStream_t stream) {
   if (precision == DSB_PREC_FP64)
-    return transpose_t<double>(lay, units_dev, NP, NPk, C0, C2, A0, A2, D0, D2, Ct0, Ct2, stream);
-  return transpose_t<float>(lay, units_dev, NP, NPk, C0, C2, A0, A2, D0, D2, Ct0, Ct2, stream);
+    return transpose_t<double>(lay, units_dev, NP, NPk, C0, C2, A0, A2, D0, D2, nullptr, nullptr, 0, 0, Ct0, Ct2,
+                               stream);
+  return transpose_t<float>(lay, units_dev, NP, NPk, C0, C2, A0, A2, D0, D2, E0, E2, epitch, 1, Ct0, Ct2, stream);
 }
 
 // ---- aliasing fold: G[prob][col][Kp] -> F[prob][k][col] ------------------------------------------
@@ -272,7 +302,7 @@ __device__ __forceinline__ void alias_fold_unit(const FoldParams &P, const RingD
 struct BinsParams {
   const RingDesc *rings;
   const UnitDev *units;
-  int nunits, nfold, Kp, krows, TK;
+  int nunits, nfold, Kp, Gp, krows, TK;  // Kp / Gp: row pitch of F / G
   int nmaps0, cpu0, ncols0, ncols2, has2;
   const float *G0, *G2;
   float *F0, *F2;
@@ -298,7 +328,7 @@ __global__ void __launch_bounds__(256) alias_fold_bins_kernel(const BinsParams P
     for (int idx = tid; idx < nload; idx += 256) {
       const int kk = idx % TK, pc = idx / TK;  // pc = prob * NC + column
       const int k = k0 + kk;
-      s[idx] = (k < P.krows) ? G[((size_t)(pc / NC) * ncols + col0 + (pc % NC)) * P.Kp + k] : 0.f;
+      s[idx] = (k < P.krows) ? G[((size_t)(pc / NC) * ncols + col0 + (pc % NC)) * P.Gp + k] : 0.f;
     }
     __syncthreads();
     const int ntask = TK * 2 * (mm + 1);
@@ -399,38 +429,23 @@ fold_identity_kernel(const RingDesc *__restrict__ rings, const UnitDev *__restri
   }
 }
 
+// kc < 0 (fp64): G holds every fold ring (pitch Kp); rings that can alias for some unit of the bucket go
+// through the gather kernel, the rest through the scaled transpose.
+// kc >= 0 (production precision): G holds the kc cap rings only (pitch gpitch, Tables::kc); the other
+// rings never come back as ring spectra (their share of A S a is rows [kc, ..) of the same G).
 int launch_alias_fold(dsb_plan *plan, const BucketLayout &lay, const UnitDev *units_dev, int precision,
-                      const void *G0, const void *G2, void *F0, void *F2, cudaStream_t stream, int fused_row0) {
-  FoldParams P;
-  P.rings = plan->rings;
-  P.units = units_dev;
-  P.nunits = lay.nunits;
-  P.nfold = plan->nfold;
-  P.Kp = lay.Kp;
-  P.mcap = lay.mcap;
-  P.nsp0 = lay.nsp0;
-  P.has2 = lay.has2;
-  P.cpu0 = lay.cpu0;
-  P.ncols0 = lay.ncols0;
-  P.ncols2 = lay.ncols2;
-  P.G0 = G0;
-  P.G2 = G2;
-  P.F0 = F0;
-  P.F2 = F2;
-  // rings k < mcap / 2 can alias for some unit of the bucket: general gather; the rest: transpose
-  const int ktiles = (plan->nfold + 31) / 32;
-  static const bool no_fast = getenv("DSB_FOLD_GENERAL") != nullptr;  // diagnostic: gather kernel everywhere
-  P.ktile0 = no_fast ? ktiles : fold_alias_rows(lay.mcap, plan->nfold) / 32;
+                      const void *G0, const void *G2, void *F0, void *F2, cudaStream_t stream, int kc, int gpitch) {
   const bool f64 = precision == DSB_PREC_FP64;
-  static const bool no_bins = getenv("DSB_FOLD_GATHER") != nullptr;  // diagnostic: per-output gather kernel
-  if (P.ktile0 > 0 && !f64 && !no_bins && !no_fast) {
+  if (!f64) {
+    DSB_CHECK(kc >= 0 && kc % 32 == 0 && gpitch >= kc, DSB_ERR_INVALID, "alias fold: bad cap row count %d", kc);
     BinsParams B;
     B.rings = plan->rings;
     B.units = units_dev;
     B.nunits = lay.nunits;
     B.nfold = plan->nfold;
     B.Kp = lay.Kp;
-    B.krows = std::min(plan->nfold, P.ktile0 * 32);
+    B.Gp = gpitch;
+    B.krows = std::min(plan->nfold, kc);
     B.nmaps0 = lay.nsp0;
     B.cpu0 = lay.cpu0;
     B.ncols0 = lay.ncols0;
@@ -452,35 +467,42 @@ int launch_alias_fold(dsb_plan *plan, const BucketLayout &lay, const UnitDev *un
     dim3 grid((B.krows + TK - 1) / TK, lay.has2 ? 2 : 1, std::min(lay.nunits, 65535));
     alias_fold_bins_kernel<<<grid, 256, smem, stream>>>(B);
     DSB_LAUNCH_CHECK();
-  } else if (P.ktile0 > 0) {
+    return DSB_OK;
+  }
+  FoldParams P;
+  P.rings = plan->rings;
+  P.units = units_dev;
+  P.nunits = lay.nunits;
+  P.nfold = plan->nfold;
+  P.Kp = lay.Kp;
+  P.mcap = lay.mcap;
+  P.nsp0 = lay.nsp0;
+  P.has2 = lay.has2;
+  P.cpu0 = lay.cpu0;
+  P.ncols0 = lay.ncols0;
+  P.ncols2 = lay.ncols2;
+  P.G0 = G0;
+  P.G2 = G2;
+  P.F0 = F0;
+  P.F2 = F2;
+  const int ktiles = (plan->nfold + 31) / 32;
+  static const bool no_fast = getenv("DSB_FOLD_GENERAL") != nullptr;  // diagnostic: gather kernel everywhere
+  P.ktile0 = no_fast ? ktiles : fold_alias_rows(lay.mcap, plan->nfold) / 32;
+  if (P.ktile0 > 0) {
     dim3 grid(P.ktile0, (lay.mcap + 8) / 8, std::min(lay.nunits, 65535));
-    if (f64)
-      alias_fold_kernel<double><<<grid, 256, 0, stream>>>(P);
-    else
-      alias_fold_kernel<float><<<grid, 256, 0, stream>>>(P);
+    alias_fold_kernel<double><<<grid, 256, 0, stream>>>(P);
     DSB_LAUNCH_CHECK();
   }
-  const int kend = fused_row0 >= 0 ? std::min(ktiles, fused_row0 / 32) : ktiles;  // the rest came fused
-  if (P.ktile0 < kend) {
-    const int nk = kend - P.ktile0;
+  if (P.ktile0 < ktiles) {
+    const int nk = ktiles - P.ktile0;
     dim3 g0(nk, lay.mcap + 1, lay.ncols0 / 32), g2(nk, lay.mcap + 1, lay.ncols2 / 32);
-    if (f64) {
-      fold_identity_kernel<double, false><<<g0, 256, 0, stream>>>(plan->rings, units_dev, lay.nunits, plan->nfold, lay.Kp,
-                                                                  P.ktile0, lay.cpu0, lay.ncols0, (const double *)G0,
-                                                                  (double *)F0);
-      if (lay.has2)
-        fold_identity_kernel<double, true><<<g2, 256, 0, stream>>>(plan->rings, units_dev, lay.nunits, plan->nfold,
-                                                                   lay.Kp, P.ktile0, 8, lay.ncols2, (const double *)G2,
-                                                                   (double *)F2);
-    } else {
-      fold_identity_kernel<float, false><<<g0, 256, 0, stream>>>(plan->rings, units_dev, lay.nunits, plan->nfold, lay.Kp,
-                                                                 P.ktile0, lay.cpu0, lay.ncols0, (const float *)G0,
-                                                                 (float *)F0);
-      if (lay.has2)
-        fold_identity_kernel<float, false><<<g2, 256, 0, stream>>>(plan->rings, units_dev, lay.nunits, plan->nfold,
-                                                                   lay.Kp, P.ktile0, 8, lay.ncols2, (const float *)G2,
-                                                                   (float *)F2);
-    }
+    fold_identity_kernel<double, false><<<g0, 256, 0, stream>>>(plan->rings, units_dev, lay.nunits, plan->nfold, lay.Kp,
+                                                                P.ktile0, lay.cpu0, lay.ncols0, (const double *)G0,
+                                                                (double *)F0);
+    if (lay.has2)
+      fold_identity_kernel<double, true><<<g2, 256, 0, stream>>>(plan->rings, units_dev, lay.nunits, plan->nfold, lay.Kp,
+                                                                 P.ktile0, 8, lay.ncols2, (const double *)G2,
+                                                                 (double *)F2);
     DSB_LAUNCH_CHECK();
   }
   return DSB_OK;

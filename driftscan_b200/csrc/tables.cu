@@ -12,6 +12,9 @@
 // with s lambda_lm = sqrt((2l+1)/4pi) d^l_{m,-s}, W = (2lam + -2lam)/2, X = (2lam - -2lam)/2.
 // The Wigner-d functions come from the three-term recurrence in l, carried with a
 // power-of-two scale so that sin^m(theta/2) underflow near the poles is harmless.
+#include <cmath>
+#include <cstdlib>
+
 #include "dsb_common.cuh"
 
 namespace dsb {
@@ -107,26 +110,32 @@ __device__ __forceinline__ void split3(double v, __nv_bfloat16 &h, __nv_bfloat16
 // SYN = true : synthesis tables (no weight), [prob][k][n | NPk + n'], pitch Kp rows per problem;
 //              NP is then NPk and the X value of degree l goes to the problem of the opposite
 //              l - m parity (see Tables in dsb_common.cuh)
+//              `srows` = row pitch per problem (Kp, or kc + NP when only the cap rings are
+//              synthesised), rings k >= kcut are not emitted
+// amp != NULL: amp[m][k] = max over l of |unweighted table value| (both roles for spin 2)
 template <bool SPIN2, bool BF16, bool SYN>
 __global__ void tables_kernel(const RingDesc *__restrict__ rings, int nfold, int Kp, int lmax, int NP,
-                              double *__restrict__ tf64, __nv_bfloat16 *__restrict__ tbf, size_t plane) {
+                              double *__restrict__ tf64, __nv_bfloat16 *__restrict__ tbf, size_t plane, int srows,
+                              int kcut, double *__restrict__ amp) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = blockIdx.y;
-  if (k >= nfold) return;
+  if (k >= nfold || (SYN && k >= kcut)) return;
   RingDesc rd = rings[k];
   if (SYN) rd.quad = 1.0;
   const int K = SPIN2 ? 2 * Kp : Kp;
   const double x = rd.cth;
   const double norm0 = 0.28209479177387814;  // 1/sqrt(4 pi)
+  double vmax = 0.0;
 
   auto store = [&](int l, double v, int kk) {
     const int p = (l - m) & 1;
     const int n = (l - m) >> 1;
+    vmax = fmax(vmax, fabs(v));
     size_t idx = ((size_t)(2 * m + p) * NP + n) * K + kk;
     if (SYN) {
       const bool xrole = kk >= Kp;
       const int W = SPIN2 ? 2 * NP : NP;
-      idx = ((size_t)(2 * m + (xrole ? 1 - p : p)) * Kp + (xrole ? kk - Kp : kk)) * W + (xrole ? NP : 0) + n;
+      idx = ((size_t)(2 * m + (xrole ? 1 - p : p)) * srows + (xrole ? kk - Kp : kk)) * W + (xrole ? NP : 0) + n;
     }
     if (BF16) {
       __nv_bfloat16 h, mm, lo;
@@ -169,6 +178,63 @@ __global__ void tables_kernel(const RingDesc *__restrict__ rings, int nfold, int
       }
     }
   }
+  if (amp) amp[(size_t)m * nfold + k] = vmax / rd.quad;
+}
+
+// ---- (analysis o synthesis) over the rings that cannot alias, as a table -----------------------
+//   out[prob][row0 + n][col0 + j] = sum_{k0 <= k < k1} ( A1[prob][n][k] B1[prob ^ bx][j][k] c[p][k]
+//                                                        + A2[prob][n][k] B2[prob ^ bx][j][k] c[1 - p][k] )
+// A*, B* point into the fp64 ANALYSIS tables (row pitch ld, NP rows per problem), c[p][k] =
+// fs_k(p) / quad_k turns the second factor into (fold scale) x (synthesis table); the second term
+// is the X role of the spin-2 block (fold parity 1 - p).  Result split into three bf16 planes.
+__global__ void __launch_bounds__(256)
+pe_kernel(const double *__restrict__ A1, const double *__restrict__ B1, const double *__restrict__ A2,
+          const double *__restrict__ B2, int bx, int ld, int NP, const double *__restrict__ coef, int nfold, int k0,
+          int k1, __nv_bfloat16 *__restrict__ out, size_t plane, int srows, int W, int row0, int col0) {
+  __shared__ double As[2][16][65], Bs[2][16][65];
+  const int prob = blockIdx.z, p = prob & 1;
+  const int n0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const size_t pa = (size_t)prob * NP * ld, pb = (size_t)(prob ^ bx) * NP * ld;
+  const int nterm = A2 ? 2 : 1;
+  double acc[4][4] = {};
+  for (int kb = k0; kb < k1; kb += 16) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      const int r = e >> 4, kk = e & 15, k = kb + kk;
+      for (int t = 0; t < nterm; ++t) {
+        const double *A = t ? A2 : A1, *B = t ? B2 : B1;
+        const double c = k < k1 ? coef[(size_t)(t ? 1 - p : p) * nfold + k] : 0.0;
+        As[t][kk][r] = (k < k1 && n0 + r < NP) ? A[pa + (size_t)(n0 + r) * ld + k] * c : 0.0;
+        Bs[t][kk][r] = (k < k1 && j0 + r < NP) ? B[pb + (size_t)(j0 + r) * ld + k] : 0.0;
+      }
+    }
+    __syncthreads();
+    for (int t = 0; t < nterm; ++t)
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[t][kk][ty + 16 * i], b[i] = Bs[t][kk][tx + 16 * i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + ty + 16 * i, jj = j0 + tx + 16 * j;
+      if (n >= NP || jj >= NP) continue;
+      const size_t idx = ((size_t)prob * srows + row0 + n) * W + col0 + jj;
+      __nv_bfloat16 h, mm, lo;
+      split3(acc[i][j], h, mm, lo);
+      out[idx] = h;
+      out[plane + idx] = mm;
+      out[2 * plane + idx] = lo;
+    }
 }
 
 const Tables *find_tables(const dsb_plan *plan, int lmax, int mmax, int spin2, int precision, int synth) {
@@ -192,22 +258,49 @@ void free_tables(Tables &t) {
 
 template <bool SPIN2, bool SYN>
 static int build_one(dsb_plan *plan, const Tables &t, int precision, size_t plane, double **f64,
-                     __nv_bfloat16 **bf, cudaStream_t stream) {
+                     __nv_bfloat16 **bf, cudaStream_t stream, double *amp = nullptr) {
   dim3 block(128), grid((plan->nfold + 127) / 128, t.mmax + 1);
   const int np = SYN ? t.NPk : t.NP;
+  const int srows = SYN ? t.SR : 0, kcut = SYN ? t.kc : plan->nfold;
   if (precision == DSB_PREC_FP64) {
     DSB_CUDA(cudaMalloc(f64, plane * sizeof(double)));
     DSB_CUDA(cudaMemsetAsync(*f64, 0, plane * sizeof(double), stream));
     tables_kernel<SPIN2, false, SYN><<<grid, block, 0, stream>>>(plan->rings, plan->nfold, t.Kp, t.lmax, np, *f64,
-                                                                 nullptr, 0);
+                                                                 nullptr, 0, srows, kcut, amp);
   } else {
     DSB_CUDA(cudaMalloc(bf, 3 * plane * sizeof(__nv_bfloat16)));
     DSB_CUDA(cudaMemsetAsync(*bf, 0, 3 * plane * sizeof(__nv_bfloat16), stream));
     tables_kernel<SPIN2, true, SYN><<<grid, block, 0, stream>>>(plan->rings, plan->nfold, t.Kp, t.lmax, np,
-                                                                nullptr, *bf, plane);
+                                                                nullptr, *bf, plane, srows, kcut, amp);
   }
   DSB_LAUNCH_CHECK();
   return DSB_OK;
+}
+
+// Fold rings on which aliasing is above rounding level.  A ring of n pixels maps the synthesised
+// coefficient m' onto every m = m' (mod n); through the analysis this adds
+//   quad_k fs_k lambda_lm(theta_k) lambda_l'm'(theta_k)
+// to the (l m, l' m') entry of A S.  Next to the pole |lambda_lm| falls off like (l theta / 2)^m / m!,
+// and an aliased pair has |m| + |m'| >= n = 4 (k + 1): beyond the first few rings the product is far
+// below fp64 rounding (1e-20 at ring 16 of nside 256, lmax 233).  amp[m][k] = max_l |lambda_lm(theta_k)|
+// (spin 0 and spin 2); a ring is kept when the bound, times the number of terms of a row, reaches eps.
+static int alias_cap_rows(const dsb_plan *plan, const Tables &t, const std::vector<double> &amp, double eps) {
+  const int nfold = plan->nfold, M = t.mmax;
+  int last = -1;
+  for (int k = 0; k < nfold; ++k) {
+    const RingDesc &rd = plan->rings_h[k];
+    const int n = rd.nphi;
+    if (n > 2 * M) break;  // cannot alias at all (ring lengths do not decrease)
+    double b = 0.0;
+    for (int m = 0; m <= M; ++m)
+      for (int q = -((M + m) / n); q <= (M + m) / n; ++q) {
+        if (q == 0) continue;
+        const int m1 = std::abs(m - q * n);
+        if (m1 <= M) b = std::max(b, amp[(size_t)m * nfold + k] * amp[(size_t)m1 * nfold + k]);
+      }
+    if (b * rd.quad * 2.0 * n * 2.0 * (t.lmax + 1) >= eps) last = k;
+  }
+  return (int)std::min<int64_t>(round_up(nfold, 32), round_up(std::max(last + 1, 1), 32));
 }
 
 int build_tables(dsb_plan *plan, Tables &t, cudaStream_t stream) {
@@ -217,15 +310,80 @@ int build_tables(dsb_plan *plan, Tables &t, cudaStream_t stream) {
   t.NPk = (int)round_up(t.NP, 32);
   t.plane0 = (size_t)nprob * t.NP * t.Kp;
   t.plane2 = (size_t)nprob * t.NP * 2 * t.Kp;
-  t.splane0 = (size_t)nprob * t.Kp * t.NPk;
-  t.splane2 = (size_t)nprob * t.Kp * 2 * t.NPk;
   DSB_TRY((build_one<false, false>(plan, t, t.precision, t.plane0, &t.t0_f64, &t.t0_bf, stream)));
   if (t.spin2) DSB_TRY((build_one<true, false>(plan, t, t.precision, t.plane2, &t.t2_f64, &t.t2_bf, stream)));
-  if (t.synth) {
+  if (!t.synth) return DSB_OK;
+  if (t.precision == DSB_PREC_FP64) {
+    t.kc = plan->nfold;
+    t.SR = t.Kp;
+    t.splane0 = (size_t)nprob * t.SR * t.NPk;
+    t.splane2 = (size_t)nprob * t.SR * 2 * t.NPk;
     DSB_TRY((build_one<false, true>(plan, t, t.precision, t.splane0, &t.s0_f64, &t.s0_bf, stream)));
     if (t.spin2) DSB_TRY((build_one<true, true>(plan, t, t.precision, t.splane2, &t.s2_f64, &t.s2_bf, stream)));
+    return DSB_OK;
   }
-  return DSB_OK;
+  // production precision: cap rings as ring functions + the precomputed product over all other rings
+  const int nfold = plan->nfold;
+  double *f0 = nullptr, *f2 = nullptr, *amp_dev = nullptr, *coef_dev = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(f0);
+    cudaFree(f2);
+    cudaFree(amp_dev);
+    cudaFree(coef_dev);
+  };
+  const size_t namp = (size_t)(t.mmax + 1) * nfold;
+  int rc = DSB_OK;
+  auto body = [&]() -> int {
+    DSB_CUDA(cudaMalloc(&amp_dev, 2 * namp * sizeof(double)));
+    DSB_CUDA(cudaMemsetAsync(amp_dev, 0, 2 * namp * sizeof(double), stream));
+    __nv_bfloat16 *none = nullptr;
+    DSB_TRY((build_one<false, false>(plan, t, DSB_PREC_FP64, t.plane0, &f0, &none, stream, amp_dev)));
+    if (t.spin2) DSB_TRY((build_one<true, false>(plan, t, DSB_PREC_FP64, t.plane2, &f2, &none, stream, amp_dev + namp)));
+    std::vector<double> amp(2 * namp);
+    DSB_CUDA(cudaMemcpyAsync(amp.data(), amp_dev, 2 * namp * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    DSB_CUDA(cudaStreamSynchronize(stream));
+    for (size_t i = 0; i < namp; ++i) amp[i] = std::max(amp[i], amp[namp + i]);
+    static const char *eps_env = getenv("DSB_ALIAS_EPS");  // diagnostic: 0 keeps every ring that can alias
+    const double eps = eps_env ? atof(eps_env) : 1e-14;
+    t.kc = alias_cap_rows(plan, t, amp, eps);
+    t.SR = t.kc + t.NP;
+    t.splane0 = (size_t)nprob * t.SR * t.NPk;
+    t.splane2 = (size_t)nprob * t.SR * 2 * t.NPk;
+    // c[p][k] = fs_k(p) / quad_k: ring spectrum of the sampled synthesis (2 n_k, n_k on the equator,
+    // whose odd fold is empty) over the weight the analysis table carries
+    std::vector<double> coef(2 * (size_t)nfold);
+    for (int k = 0; k < nfold; ++k) {
+      const RingDesc &rd = plan->rings_h[k];
+      const bool equator = rd.startS < 0;
+      coef[k] = (equator ? 1.0 : 2.0) * rd.nphi / rd.quad;
+      coef[nfold + k] = equator ? 0.0 : coef[k];
+    }
+    DSB_CUDA(cudaMalloc(&coef_dev, coef.size() * sizeof(double)));
+    DSB_CUDA(cudaMemcpyAsync(coef_dev, coef.data(), coef.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+    DSB_TRY((build_one<false, true>(plan, t, t.precision, t.splane0, &t.s0_f64, &t.s0_bf, stream)));
+    if (t.spin2) DSB_TRY((build_one<true, true>(plan, t, t.precision, t.splane2, &t.s2_f64, &t.s2_bf, stream)));
+    if (t.kc < nfold) {
+      const dim3 grid((t.NP + 63) / 64, (t.NP + 63) / 64, nprob);
+      pe_kernel<<<grid, 256, 0, stream>>>(f0, f0, nullptr, nullptr, 0, t.Kp, t.NP, coef_dev, nfold, t.kc, nfold, t.s0_bf,
+                                          t.splane0, t.SR, t.NPk, t.kc, 0);
+      DSB_LAUNCH_CHECK();
+      if (t.spin2) {
+        const double *w = f2, *x = f2 + t.Kp;  // [-W | -X] halves of a table row
+        // W role columns: rows of the same problem;  X role columns: rows of the partner problem
+        pe_kernel<<<grid, 256, 0, stream>>>(w, w, x, x, 0, 2 * t.Kp, t.NP, coef_dev, nfold, t.kc, nfold, t.s2_bf,
+                                            t.splane2, t.SR, 2 * t.NPk, t.kc, 0);
+        DSB_LAUNCH_CHECK();
+        pe_kernel<<<grid, 256, 0, stream>>>(w, x, x, w, 1, 2 * t.Kp, t.NP, coef_dev, nfold, t.kc, nfold, t.s2_bf,
+                                            t.splane2, t.SR, 2 * t.NPk, t.kc, t.NPk);
+        DSB_LAUNCH_CHECK();
+      }
+    }
+    DSB_CUDA(cudaStreamSynchronize(stream));
+    return DSB_OK;
+  };
+  rc = body();
+  cleanup();
+  return rc;
 }
 
 }  // namespace dsb
