@@ -361,6 +361,8 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
     lay.ncols0 = (int)round_up((int64_t)nu * lay.cpu0, 128);
     lay.ncols2 = lay.has2 ? (int)round_up((int64_t)nu * 8, 128) : 0;
 
+    // production precision with refinement: coefficients live in the operand layout [prob][n][col]
+    const bool tflow = !f64 && niter > 0;
     // work items
     std::vector<WorkItem> items;
     std::vector<UnitDev> ud(nu);
@@ -385,7 +387,13 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
         for (int p = 0; p < 2; ++p)
           for (int ct = 0; ct < ntile; ++ct) {
             if (m > Lt[ct]) continue;
-            const int nr = nrows_mp(Lt[ct], m, p);
+            int nr = nrows_mp(Lt[ct], m, p);
+            if (tflow) {
+              // the result is the operand of the refinement's first contraction: every row that
+              // contraction reads (its klen, both l - m parities for spin 2) has to be written
+              if (s == 2) nr = std::max(nr, nrows_mp(Lt[ct], m, 1 - p));
+              nr = std::min(t.NP, std::max(32, (int)round_up(nr, 32)));
+            }
             for (int r0 = 0; r0 < nr; r0 += 128) items.push_back({2 * m + p, ct, std::min(128, nr - r0), s, r0});
           }
     }
@@ -418,7 +426,7 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
                 sitems.push_back({2 * m + p, ct, std::min(per, rows - r0), s, r0, klen});
             }
       }
-      if (!f64) {
+      if (tflow) {
         citems = items;
         for (auto &w : citems) w.klen = t.kc;
       }
@@ -550,39 +558,66 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
                                    synth ? t.s0_f64 : t.t0_f64, synth ? t.s2_f64 : t.t2_f64, (double *)c0,
                                    (double *)c2, (const double *)A0, (const double *)A2, stream);
       return launch_contract_tc(d, (int)its.size(), its_dev, mrows, (const float *)a0, (const float *)a2,
-                                synth ? t.s0_bf : t.t0_bf, synth ? t.s2_bf : t.t2_bf, (float *)c0, (float *)c2,
-                                (const float *)A0, (const float *)A2, stream);
+                                synth ? t.s0_bf : t.t0_bf, synth ? t.s2_bf : t.t2_bf, (float *)c0, (float *)c2, ud_dev,
+                                stream);
     };
-    if ((rc = contract(da, items, items_dev, max_rows, F0, F2, false, C0, C2)) != DSB_OK) break;
-    timer.mark(2);
-    hc.lap(6);
-    if (niter > 0) {
-      // Jacobi refinement (healpy map2alm iter): a <- a(0) + a - A S a, S a on ring spectra
-      DSB_CUDA(cudaMemcpyAsync(A0, C0, c0_bytes, cudaMemcpyDeviceToDevice, stream));
-      if (c2_bytes) DSB_CUDA(cudaMemcpyAsync(A2, C2, c2_bytes, cudaMemcpyDeviceToDevice, stream));
-      ContractDesc ds = da;  // synthesis: A = transposed coefficients, B = S tables, rows = fold rings (+ product rows)
-      ds.K = ds.kx = t.NPk;
-      ds.pitch = t.SR;
-      // production precision: (A S a) = D (cap rings, through the fold) + E (rows [kc, ..) of G)
-      const char *E0 = f64 ? nullptr : G0 + (size_t)t.kc * cs, *E2 = (f64 || !lay.has2) ? nullptr : G2 + (size_t)t.kc * cs;
-      int smax = 16;
-      for (const auto &w : sitems) smax = std::max(smax, w.nrows);
+    ContractDesc ds = da;  // synthesis: A = transposed coefficients, B = S tables, rows = fold rings (+ product rows)
+    ds.K = ds.kx = t.NPk;
+    ds.pitch = t.SR;
+    int smax = 16;
+    for (const auto &w : sitems) smax = std::max(smax, w.nrows);
+    if (tflow) {
+      // a(0), masked to each unit's lmax, straight into the operand layout
+      ContractDesc dt = da;
+      dt.tpitch = t.NP;
+      dt.tmask = 1;
+      dt.nunits = nu;
+      dt.cpu0 = lay.cpu0;
+      if ((rc = contract(dt, items, items_dev, max_rows, F0, F2, false, A0, A2)) != DSB_OK) break;
+      timer.mark(2);
+      hc.lap(6);
+      // Jacobi refinement (healpy map2alm iter): a <- a(0) + a - A S a;  A S a = D + E with
+      //   Gt = (cap-ring functions | E) from one contraction with the extended synthesis table,
+      //   D  = analysis of the folded cap rings (contraction length kc)
+      ds.tpitch = t.SR;
+      ContractDesc dc = da;
+      dc.tpitch = t.NP;
+      const char *cur0 = A0, *cur2 = A2;
       for (int it = 0; it < niter && rc == DSB_OK; ++it) {
-        // pass it > 0 starts by applying the previous pass' step a <- a(0) + a - A S a (fused into the transpose)
-        if ((rc = launch_transpose_coeffs(lay, ud_dev, t.NP, t.NPk, precision, C0, C2, A0, A2, it ? D0 : nullptr,
-                                          it ? D2 : nullptr, E0, E2, t.SR, Ct0, Ct2, stream)) != DSB_OK)
-          break;
-        if ((rc = contract(ds, sitems, sitems_dev, smax, Ct0, Ct2, true, G0, G2)) != DSB_OK) break;
-        if ((rc = launch_alias_fold(plan, lay, ud_dev, precision, G0, G2, F0, F2, stream, f64 ? -1 : t.kc, t.SR)) !=
-            DSB_OK)
-          break;
-        rc = f64 ? contract(da, items, items_dev, max_rows, F0, F2, false, D0, D2)
-                 : contract(da, citems, citems_dev, max_rows, F0, F2, false, D0, D2);
+        if ((rc = contract(ds, sitems, sitems_dev, smax, cur0, cur2, true, G0, G2)) != DSB_OK) break;
+        if ((rc = launch_alias_fold(plan, lay, ud_dev, precision, G0, G2, F0, F2, stream, t.kc, t.SR)) != DSB_OK) break;
+        if ((rc = contract(dc, citems, citems_dev, max_rows, F0, F2, false, D0, D2)) != DSB_OK) break;
+        const bool last = it == niter - 1;
+        rc = launch_refine_update(lay, ud_dev, t.NP, t.kc, t.SR, (const float *)A0, (const float *)A2,
+                                  (const float *)cur0, (const float *)cur2, (const float *)D0, (const float *)D2,
+                                  (const float *)G0, (const float *)G2, (float *)(last ? C0 : Ct0),
+                                  (float *)(last ? C2 : Ct2), last, stream);
+        cur0 = Ct0;
+        cur2 = Ct2;
       }
-      if (rc == DSB_OK)  // the last step, no transpose
-        rc = launch_transpose_coeffs(lay, ud_dev, t.NP, t.NPk, precision, C0, C2, A0, A2, D0, D2, E0, E2, t.SR, nullptr,
-                                     nullptr, stream);
       if (rc != DSB_OK) break;
+    } else {
+      if ((rc = contract(da, items, items_dev, max_rows, F0, F2, false, C0, C2)) != DSB_OK) break;
+      timer.mark(2);
+      hc.lap(6);
+      if (niter > 0) {
+        // fp64 validation path: every ring synthesised, folded and analysed again
+        DSB_CUDA(cudaMemcpyAsync(A0, C0, c0_bytes, cudaMemcpyDeviceToDevice, stream));
+        if (c2_bytes) DSB_CUDA(cudaMemcpyAsync(A2, C2, c2_bytes, cudaMemcpyDeviceToDevice, stream));
+        for (int it = 0; it < niter && rc == DSB_OK; ++it) {
+          // pass it > 0 starts by applying the previous pass' step a <- a(0) + a - A S a (fused into the transpose)
+          if ((rc = launch_transpose_coeffs(lay, ud_dev, t.NP, t.NPk, precision, C0, C2, A0, A2, it ? D0 : nullptr,
+                                            it ? D2 : nullptr, Ct0, Ct2, stream)) != DSB_OK)
+            break;
+          if ((rc = contract(ds, sitems, sitems_dev, smax, Ct0, Ct2, true, G0, G2)) != DSB_OK) break;
+          if ((rc = launch_alias_fold(plan, lay, ud_dev, precision, G0, G2, F0, F2, stream)) != DSB_OK) break;
+          rc = contract(da, items, items_dev, max_rows, F0, F2, false, D0, D2);
+        }
+        if (rc == DSB_OK)  // the last step, no transpose
+          rc = launch_transpose_coeffs(lay, ud_dev, t.NP, t.NPk, precision, C0, C2, A0, A2, D0, D2, nullptr, nullptr,
+                                       stream);
+        if (rc != DSB_OK) break;
+      }
     }
     timer.mark(3);
 

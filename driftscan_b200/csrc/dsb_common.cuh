@@ -119,7 +119,7 @@ struct BeamSlot {
 // spin-0 table: [prob][NP rows][K0 = Kp] ; spin-2 table: [prob][NP rows][2*Kp] = [-W | -X].
 struct Tables {
   int lmax = -1, mmax = -1, spin2 = 0, precision = -1;
-  int NP = 0;        // padded row pitch (max rows per problem, multiple of 16)
+  int NP = 0;        // padded row pitch (max rows per problem, multiple of 32)
   int Kp = 0;        // padded fold-ring count (multiple of 32)
   // fp64
   double *t0_f64 = nullptr, *t2_f64 = nullptr;
@@ -294,27 +294,34 @@ struct ContractDesc {
   int kx = 0;        // offset of the X role in the table (and in the fp64 A buffer)
   int pitch = 0;     // row pitch of C and number of table rows per problem
   int ncols0 = 0, ncols2 = 0, has2 = 0;
-  int update = 0;    // 0: C = r;  1: C = base + C - r  (Jacobi refinement step)
+  int update = 0;    // fp64 kernel only: 0: C = r;  1: C = base + C - r
+  // tensor-core kernel only: tpitch > 0 writes the result transposed, Ct[prob][row][col] with tpitch
+  // rows per problem; tmask also zeroes rows above each column's unit lmax and imposes the m = 0
+  // symmetry (the output is then an operand of the next contraction as it stands)
+  int tpitch = 0, tmask = 0, nunits = 0, cpu0 = 0;
 };
 int launch_contract_f64(const ContractDesc &d, int nitems, const WorkItem *items_dev, const double *A0,
                         const double *A2, const double *B0, const double *B2, double *C0, double *C2,
                         const double *base0, const double *base2, cudaStream_t stream);
 int launch_contract_tc(const ContractDesc &d, int nitems, const WorkItem *items_dev, int max_rows,
                        const float *A0, const float *A2, const __nv_bfloat16 *B0, const __nv_bfloat16 *B2,
-                       float *C0, float *C2, const float *base0, const float *base2, cudaStream_t stream);
+                       float *C0, float *C2, const UnitDev *units_dev, cudaStream_t stream);
 
 // shtiter.cu -- the pieces of healpy's map2alm(iter > 0) that are not contractions
-// C[prob][col][NP] -> Ct[prob][n][col] (fp64 spin 2: both operand roles, X role at row NPk),
-// rows above a unit's own lmax zeroed
-// D0 != NULL: first apply the Jacobi step C <- A + C - D (A = a(0), D = A S a of the previous pass) and
-// write C back; Ct0 == NULL: that update only.  Production precision: A S a = D + E, E with row
-// pitch `epitch` (see Tables::kc).
+// fp64 (validation) path: C[prob][col][NP] -> Ct[prob][n][col] (spin 2: both operand roles, X role at
+// row NPk), rows above a unit's own lmax zeroed.  D0 != NULL: first apply the Jacobi step C <- A + C - D
+// (A = a(0), D = A S a of the previous pass) and write C back; Ct0 == NULL: that update only.
 int launch_transpose_coeffs(const BucketLayout &lay, const UnitDev *units_dev, int NP, int NPk, int precision,
                             void *C0, void *C2, const void *A0, const void *A2, const void *D0, const void *D2,
-                            const void *E0, const void *E2, int epitch, void *Ct0, void *Ct2, cudaStream_t stream);
+                            void *Ct0, void *Ct2, cudaStream_t stream);
+// Production precision: the Jacobi step in the operand layout [prob][NP][ncols] (a0, a, D), E = rows
+// [kc, kc + NP) of Gt[prob][SR][ncols]; out = a' in the same layout, or (final) C[prob][col][NP]
+int launch_refine_update(const BucketLayout &lay, const UnitDev *units_dev, int NP, int kc, int SR, const float *A0t,
+                         const float *A2t, const float *a0, const float *a2, const float *D0, const float *D2,
+                         const float *G0, const float *G2, float *out0, float *out2, bool final, cudaStream_t stream);
 // G[prob][col][pitch] (synthesised ring functions) -> ring spectra of the pixelised map in the
 // operand layout of the analysis (F0 / F2 of ringfft.cu).  fp64: every ring (kc < 0, pitch Kp);
-// production precision: the kc cap rings, G pitch `gpitch`.
+// production precision: the kc cap rings of the transposed Gt[prob][gpitch][col].
 int launch_alias_fold(dsb_plan *plan, const BucketLayout &lay, const UnitDev *units_dev, int precision,
                       const void *G0, const void *G2, void *F0, void *F2, cudaStream_t stream, int kc = -1,
                       int gpitch = 0);

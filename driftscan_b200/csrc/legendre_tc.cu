@@ -62,8 +62,13 @@ struct TcParams {
   int ncols0, ncols2;
   int NP;            // row pitch of C
   float *C0, *C2;
-  const float *base0, *base2;  // update mode: C = base + C - result
-  int update;
+  // transposed output (Jacobi refinement, shtiter.cu): tpitch > 0 writes Ct[prob][row][col] with
+  // tpitch rows per problem -- the operand layout of the next contraction -- instead of
+  // C[prob][col][row]; tmask: rows above the column's own unit lmax are written as zeros and the
+  // m = 0 problems get a-_l0 = conj(a+_l0) (the result is used as an operand as it stands)
+  int tpitch, tmask;
+  const UnitDev *units;
+  int nunits, cpu0;
   int NB;            // table box rows (TMA box), multiple of 16, <= 256
   int nstages;
   int diag;          // DSB_TC_DIAG (timing experiments, WRONG results): 1 = table tile loaded for the first
@@ -166,6 +171,7 @@ __device__ __forceinline__ void split3_bits(float v, uint32_t &h, uint32_t &m, u
 // (upper half of a, upper half of b) -> one 32-bit word, a in the low half
 __device__ __forceinline__ uint32_t hi2(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); }
 
+template <bool TMODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA2,
                    const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB2,
@@ -361,10 +367,47 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       // corrections, then store this thread's operand column contiguously in l
       mbar_wait(&cfull[cb], cb_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if constexpr (TMODE) {
+        // transposed store: lane = operand column, one 128-byte line per warp and row
+        const int col = wi.coltile * TC_M + quarter * 32 + lane;
+        const int m = wi.prob >> 1;
+        int nkeep = 1 << 30;  // rows (from row0) at or below the unit's lmax
+        if (P.tmask) {
+          const int u = col / (s2 ? 8 : P.cpu0);
+          const int lm = u < P.nunits ? P.units[u].lmax : -1;
+          nkeep = lm < m + (wi.prob & 1) ? 0 : (lm - m - (wi.prob & 1)) / 2 + 1;
+          nkeep -= wi.row0 + half * 64;
+        }
+        const bool sym = P.tmask && m == 0;  // warp-uniform
+        const int j4 = col & 3;
+        float *o = (s2 ? P.C2 : P.C0) + ((size_t)wi.prob * P.tpitch + wi.row0 + half * 64) * ncols + col;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (half * 64 + g * 16 < N) {  // warp-uniform
+            uint32_t v[16];
+            tmem_ld16(lane_base + 256 + (uint32_t)cb * 128 + g * 16, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              float val = sums[g * 16 + q] + __uint_as_float(v[q]);
+              if (sym) {  // (+re, +im, -re, -im) per map: - slot <- conj(+ slot)
+                const float below = __shfl_up_sync(0xffffffffu, val, 2);
+                if (j4 >= 2) val = j4 == 2 ? below : -below;
+              }
+              o[(size_t)(g * 16 + q) * ncols] = (g * 16 + q < nkeep) ? val : 0.f;
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&cfree[cb]);
+        continue;
+      }
+      if constexpr (TMODE) {
+      } else {
       const size_t cidx =
           ((size_t)wi.prob * ncols + (size_t)wi.coltile * TC_M + quarter * 32 + lane) * P.NP + wi.row0 + half * 64;
       float *C = (s2 ? P.C2 : P.C0) + cidx;
-      const float *base = P.update ? (s2 ? P.base2 : P.base0) + cidx : nullptr;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         if (half * 64 + g * 16 < N) {
@@ -373,18 +416,13 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           float4 *dst = reinterpret_cast<float4 *>(C + g * 16);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 r = make_float4(sums[g * 16 + 4 * q] + __uint_as_float(v[4 * q]),
-                                   sums[g * 16 + 4 * q + 1] + __uint_as_float(v[4 * q + 1]),
-                                   sums[g * 16 + 4 * q + 2] + __uint_as_float(v[4 * q + 2]),
-                                   sums[g * 16 + 4 * q + 3] + __uint_as_float(v[4 * q + 3]));
-            if (P.update) {  // Jacobi refinement: a <- a0 + a - (A S a)
-              const float4 b = reinterpret_cast<const float4 *>(base + g * 16)[q], c = dst[q];
-              r = make_float4((b.x - r.x) + c.x, (b.y - r.y) + c.y, (b.z - r.z) + c.z, (b.w - r.w) + c.w);
-            }
-            dst[q] = r;
-          }
+          for (int q = 0; q < 4; ++q)
+            dst[q] = make_float4(sums[g * 16 + 4 * q] + __uint_as_float(v[4 * q]),
+                                 sums[g * 16 + 4 * q + 1] + __uint_as_float(v[4 * q + 1]),
+                                 sums[g * 16 + 4 * q + 2] + __uint_as_float(v[4 * q + 2]),
+                                 sums[g * 16 + 4 * q + 3] + __uint_as_float(v[4 * q + 3]));
         }
+      }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -505,7 +543,7 @@ static int encode4(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1,
 
 int launch_contract_tc(const ContractDesc &d, int nitems, const WorkItem *items_dev, int max_rows,
                        const float *A0, const float *A2, const __nv_bfloat16 *B0, const __nv_bfloat16 *B2,
-                       float *C0, float *C2, const float *base0, const float *base2, cudaStream_t stream) {
+                       float *C0, float *C2, const UnitDev *units_dev, cudaStream_t stream) {
   if (nitems == 0) return DSB_OK;
   DSB_CHECK(d.K % TC_KC == 0 && d.kx % TC_KC == 0, DSB_ERR_INVALID, "contraction length must be a multiple of %d",
             TC_KC);
@@ -513,7 +551,7 @@ int launch_contract_tc(const ContractDesc &d, int nitems, const WorkItem *items_
             "column counts must be multiples of 128");
   DSB_CHECK(d.pitch % 16 == 0, DSB_ERR_INVALID, "row pitch must be a multiple of 16");
   DSB_CHECK(max_rows <= TC_MAXROWS, DSB_ERR_INVALID, "work items hold at most %d rows", TC_MAXROWS);
-  DSB_CHECK(!d.update || (base0 && (!d.has2 || base2)), DSB_ERR_INVALID, "update mode needs the base coefficients");
+  DSB_CHECK(!d.tmask || (d.tpitch > 0 && units_dev), DSB_ERR_INVALID, "masked output needs the transposed layout and the units");
   int NB = (int)round_up(std::min(std::max(max_rows, 16), TC_MAXROWS), 16);
 
   CUtensorMap mA0, mA2, mB0, mB2;
@@ -542,9 +580,11 @@ int launch_contract_tc(const ContractDesc &d, int nitems, const WorkItem *items_
   P.NP = d.pitch;
   P.C0 = C0;
   P.C2 = C2;
-  P.base0 = base0;
-  P.base2 = base2;
-  P.update = d.update;
+  P.tpitch = d.tpitch;
+  P.tmask = d.tmask;
+  P.units = units_dev;
+  P.nunits = d.nunits;
+  P.cpu0 = d.cpu0;
   P.NB = NB;
   static const int diag = getenv("DSB_TC_DIAG") ? atoi(getenv("DSB_TC_DIAG")) : 0;
   P.diag = diag;
@@ -556,7 +596,8 @@ int launch_contract_tc(const ContractDesc &d, int nitems, const WorkItem *items_
   // diagnostic (two launches in flight): give every launch the same carve-out
   static const bool fixed_smem = getenv("DSB_TC_FIXED_SMEM") != nullptr;
   if (fixed_smem) smem = 226 * 1024;
-  DSB_CUDA(raise_dynamic_smem((const void *)legendre_tc_kernel, smem));
+  const bool tmode = P.tpitch > 0;
+  DSB_CUDA(raise_dynamic_smem(tmode ? (const void *)legendre_tc_kernel<true> : (const void *)legendre_tc_kernel<false>, smem));
   int dev = 0, nsm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
@@ -580,7 +621,10 @@ int launch_contract_tc(const ContractDesc &d, int nitems, const WorkItem *items_
       if (!last) DSB_CUDA(cudaEventCreateWithFlags(&last, cudaEventDisableTiming));
       else DSB_CUDA(cudaStreamWaitEvent(stream, last, 0));
     }
-    legendre_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mA0, mA2, mB0, mB2, P);
+    if (tmode)
+      legendre_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(mA0, mA2, mB0, mB2, P);
+    else
+      legendre_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(mA0, mA2, mB0, mB2, P);
     DSB_LAUNCH_CHECK();
     if (use) DSB_CUDA(cudaEventRecord(last, stream));
   }
@@ -620,7 +664,7 @@ extern "C" int dsb_debug_gemm_tc(int nprob, int K, int NP, int ncols, int nitems
   d.K = d.kx = K;
   d.pitch = NP;
   d.ncols0 = d.ncols2 = ncols;
-  int rc = launch_contract_tc(d, nitems, items, max_rows, F, nullptr, T, nullptr, C, nullptr, nullptr, nullptr, 0);
+  int rc = launch_contract_tc(d, nitems, items, max_rows, F, nullptr, T, nullptr, C, nullptr, nullptr, 0);
   if (rc == DSB_OK) {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {

@@ -155,11 +155,74 @@ static int transpose_t(const BucketLayout &lay, const UnitDev *units_dev, int NP
 
 int launch_transpose_coeffs(const BucketLayout &lay, const UnitDev *units_dev, int NP, int NPk, int precision,
                             void *C0, void *C2, const void *A0, const void *A2, const void *D0, const void *D2,
-                            const void *E0, const void *E2, int epitch, void *Ct0, void *Ct2, cudaStream_t stream) {
-  if (precision == DSB_PREC_FP64)
-    return transpose_t<double>(lay, units_dev, NP, NPk, C0, C2, A0, A2, D0, D2, nullptr, nullptr, 0, 0, Ct0, Ct2,
-                               stream);
-  return transpose_t<float>(lay, units_dev, NP, NPk, C0, C2, A0, A2, D0, D2, E0, E2, epitch, 1, Ct0, Ct2, stream);
+                            void *Ct0, void *Ct2, cudaStream_t stream) {
+  DSB_CHECK(precision == DSB_PREC_FP64, DSB_ERR_INVALID, "transpose_coeffs is the fp64 (validation) refinement path");
+  return transpose_t<double>(lay, units_dev, NP, NPk, C0, C2, A0, A2, D0, D2, nullptr, nullptr, 0, 0, Ct0, Ct2, stream);
+}
+
+// ---- production precision: the Jacobi step in the operand layout -------------------------------
+//   a'[prob][n][col] = a0 + a - D - E      (rows above the column's unit lmax: 0; m = 0: a-_l0 = conj(a+_l0))
+// a0, a, D: [prob][NP][ncols];  E: rows [kc, kc + NP) of the contraction with the extended synthesis
+// table, Gt[prob][SR][ncols] (Tables::kc).  Everything is contiguous in the operand columns: pure
+// streaming.  FINAL: the result leaves in the layout of the pack kernel, C[prob][col][NP].
+template <bool FINAL>
+__global__ void __launch_bounds__(256)
+refine_update_kernel(const float *__restrict__ a0, const float *__restrict__ a, const float *__restrict__ D,
+                     const float *__restrict__ E, int epitch, float *__restrict__ out, const UnitDev *__restrict__ units,
+                     int nunits, int cpu, int ncols, int NP, int lmax_b) {
+  __shared__ float tile[32][33];
+  const int prob = blockIdx.z;
+  const int m = prob >> 1, p = prob & 1;
+  const int col0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  if (n0 >= (int)((nrows_mp(lmax_b, m, 0) + 31) & ~31)) return;  // nothing of this problem up there
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = col0 + tx;
+  const int u = c / cpu;
+  const int lm = u < nunits ? units[u].lmax : -1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty + 8 * i;
+    float v = 0.f;
+    if (n < NP && m + p + 2 * n <= lm) {
+      const size_t at = ((size_t)prob * NP + n) * ncols + c;
+      v = (a0[at] - (D[at] + E[((size_t)prob * epitch + n) * ncols + c])) + a[at];
+    }
+    if (m == 0) {  // warp-uniform; (+re, +im, -re, -im) per map
+      const float below = __shfl_up_sync(0xffffffffu, v, 2);
+      if ((tx & 3) >= 2) v = (tx & 3) == 2 ? below : -below;
+    }
+    if (FINAL) tile[ty + 8 * i][tx] = v;
+    else if (n < NP) out[((size_t)prob * NP + n) * ncols + c] = v;
+  }
+  if (FINAL) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int cc = col0 + ty + 8 * i, n = n0 + tx;
+      if (n < NP) out[((size_t)prob * ncols + cc) * NP + n] = tile[tx][ty + 8 * i];
+    }
+  }
+}
+
+int launch_refine_update(const BucketLayout &lay, const UnitDev *units_dev, int NP, int kc, int SR, const float *A0t,
+                         const float *A2t, const float *a0, const float *a2, const float *D0, const float *D2,
+                         const float *G0, const float *G2, float *out0, float *out2, bool final, cudaStream_t stream) {
+  const int nprob = 2 * (lay.mcap + 1);
+  for (int s = 0; s <= (lay.has2 ? 2 : 0); s += 2) {
+    const int ncols = s ? lay.ncols2 : lay.ncols0, cpu = s ? 8 : lay.cpu0;
+    const float *b = s ? A2t : A0t, *a = s ? a2 : a0, *D = s ? D2 : D0, *G = s ? G2 : G0;
+    float *o = s ? out2 : out0;
+    const float *E = G + (size_t)kc * ncols;
+    dim3 grid(ncols / 32, NP / 32, nprob);
+    if (final)
+      refine_update_kernel<true><<<grid, 256, 0, stream>>>(b, a, D, E, SR, o, units_dev, lay.nunits, cpu, ncols, NP,
+                                                          lay.lmax_b);
+    else
+      refine_update_kernel<false><<<grid, 256, 0, stream>>>(b, a, D, E, SR, o, units_dev, lay.nunits, cpu, ncols, NP,
+                                                           lay.lmax_b);
+    DSB_LAUNCH_CHECK();
+  }
+  return DSB_OK;
 }
 
 // ---- aliasing fold: G[prob][col][Kp] -> F[prob][k][col] ------------------------------------------
@@ -324,11 +387,14 @@ __global__ void __launch_bounds__(256) alias_fold_bins_kernel(const BinsParams P
     const int mm = P.units[u].mmax;
     const size_t col0 = (size_t)u * NC;
     __syncthreads();  // the previous unit's bins are done with the staging buffer
+    // G arrives transposed, Gt[prob][ring][col] (Gp rows per problem): the NC columns of the group
+    // are one or two 32-byte sectors per (problem, ring)
     const int nload = 2 * (mm + 1) * NC * TK;
     for (int idx = tid; idx < nload; idx += 256) {
-      const int kk = idx % TK, pc = idx / TK;  // pc = prob * NC + column
+      const int cc = idx % NC, pk = idx / NC;  // pk = prob * TK + ring
+      const int kk = pk % TK, prob = pk / TK;
       const int k = k0 + kk;
-      s[idx] = (k < P.krows) ? G[((size_t)(pc / NC) * ncols + col0 + (pc % NC)) * P.Gp + k] : 0.f;
+      s[(prob * NC + cc) * TK + kk] = (k < P.krows) ? G[((size_t)prob * P.Gp + k) * ncols + col0 + cc] : 0.f;
     }
     __syncthreads();
     const int ntask = TK * 2 * (mm + 1);

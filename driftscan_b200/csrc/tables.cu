@@ -306,8 +306,8 @@ static int alias_cap_rows(const dsb_plan *plan, const Tables &t, const std::vect
 int build_tables(dsb_plan *plan, Tables &t, cudaStream_t stream) {
   const int nprob = 2 * (t.mmax + 1);
   t.Kp = plan->Kp;
-  t.NP = (int)round_up(nrows_mp(t.lmax, 0, 0), 16);
-  t.NPk = (int)round_up(t.NP, 32);
+  t.NP = (int)round_up(nrows_mp(t.lmax, 0, 0), 32);  // also the k-tile of the synthesis direction
+  t.NPk = t.NP;
   t.plane0 = (size_t)nprob * t.NP * t.Kp;
   t.plane2 = (size_t)nprob * t.NP * 2 * t.Kp;
   DSB_TRY((build_one<false, false>(plan, t, t.precision, t.plane0, &t.t0_f64, &t.t0_bf, stream)));
