@@ -518,6 +518,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? DSB_RING_MINBLOCKS : 1)
   using F = Fft16<LOG2L>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ GroupUnit us[kMaxGroup];
+  __shared__ cplx<T> rot_s[kMaxGroup];  // fringe(south) / fringe(north) of the ring pair, per unit
   RingCtx<T> c;
   c.P = &P;
   c.k = P.ring_list[blockIdx.x];
@@ -603,25 +604,33 @@ __global__ void __launch_bounds__(256, sizeof(T) == 4 ? DSB_RING_MINBLOCKS : 1)
       x.deadV = ud.beam_j;
       x.pad = 0;
       us[tid] = x;
+      double sn, cs;
+      const double tz = 2.0 * ud.az * rd.cth;  // turns between the mirror rings
+      sincospi(-2.0 * (tz - rint(tz)), &sn, &cs);
+      rot_s[tid] = {(T)cs, (T)sn};
     }
     __syncthreads();
 
     // ---- A: fringe of every pixel of the live rings ------------------------------------
-    for (int idx = tid; idx < Gn * nlive * n; idx += blockDim.x) {
-      const int sq = (int)__umulhi((unsigned)idx, nmagic), j = idx - sq * n;
-      const int gi = nlive == 2 ? sq >> 1 : sq, lr = nlive == 2 ? sq & 1 : 0;
-      const int ring = (liveN && lr == 0) ? 0 : 1;
+    // The southern mirror ring has the same sin(theta) and the same phi_j: its fringe is the northern
+    // one times the constant e^{-4 pi i az cos(theta)} (us[].rot), one complex multiply instead of a
+    // second fp64 phase reduction and sincospi.
+#pragma unroll 2
+    for (int idx = tid; idx < Gn * n; idx += blockDim.x) {
+      const int gi = (int)__umulhi((unsigned)idx, nmagic), j = idx - gi * n;
       const double2 tr = trig[j];
-      const double zc = ring ? -rd.cth : rd.cth;
       // n . (u uhat + v vhat) in wavelengths, reduced to a fraction of a turn in fp64
-      double du = us[gi].axs * tr.x + us[gi].ays * tr.y + us[gi].az * zc;
+      const double dxy = us[gi].axs * tr.x + us[gi].ays * tr.y;
+      const double dz = us[gi].az * rd.cth;
+      double du = liveN ? dxy + dz : dxy - dz;
       du -= rint(du);
       T fs, fc;
       sincospi_t((T)(2.0 * du), &fs, &fc);
       const T pref = (T)us[gi].pref;
       cplx<T> v = {pref * fc, pref * fs};
       if (KIND == KIND_BLUESTEIN) v = cmul(v, ch_s[j]);
-      fr_s[idx] = v;
+      fr_s[gi * nlive * n + j] = v;
+      if (nlive == 2) fr_s[(gi * 2 + 1) * n + j] = cmul(v, rot_s[gi]);
     }
     __syncthreads();
 

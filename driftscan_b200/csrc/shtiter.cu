@@ -365,7 +365,7 @@ __device__ __forceinline__ void alias_fold_unit(const FoldParams &P, const RingD
 struct BinsParams {
   const RingDesc *rings;
   const UnitDev *units;
-  int nunits, nfold, Kp, Gp, krows, TK;  // Kp / Gp: row pitch of F / G
+  int nunits, nfold, Kp, Gp, krows, TK, UG;  // Kp / Gp: row pitch of F / G; UG units per CTA
   int nmaps0, cpu0, ncols0, ncols2, has2;
   const float *G0, *G2;
   float *F0, *F2;
@@ -373,71 +373,70 @@ struct BinsParams {
 
 __global__ void __launch_bounds__(256) alias_fold_bins_kernel(const BinsParams P) {
   extern __shared__ __align__(16) unsigned char bins_raw[];
-  float *s = reinterpret_cast<float *>(bins_raw);  // [prob][NC columns of the map group][TK rings]
-  // blockIdx.y = map group: the unit's spin-0 columns (I or I,V), then its spin-2 columns (Q,U).  A
-  // thread emits all maps of the group for its (ring, m): one full 32-byte sector per store pair
-  // (16-byte pieces written by different CTAs reach DRAM as partial sectors).
-  const int TK = P.TK, k0 = blockIdx.x * TK, tid = threadIdx.x;
+  float *s = reinterpret_cast<float *>(bins_raw);  // [prob][UG units x NC columns of the map group][TK rings]
+  // blockIdx.y = map group: the units' spin-0 columns (I or I,V), then their spin-2 columns (Q,U).  A CTA
+  // takes UG consecutive units: their columns of a (problem, ring) are one contiguous 128-byte line of
+  // Gt.  A thread emits all maps of the group for its (unit, ring, m): one full 32-byte sector per store
+  // pair (16-byte pieces written by different CTAs reach DRAM as partial sectors).
+  const int TK = P.TK, UG = P.UG, k0 = blockIdx.x * TK, tid = threadIdx.x;
   const bool spin2 = blockIdx.y > 0;
   const float *G = spin2 ? P.G2 : P.G0;
   float *F = spin2 ? P.F2 : P.F0;
   const size_t ncols = spin2 ? P.ncols2 : P.ncols0;
   const int NC = spin2 ? 8 : P.cpu0, nmap = NC >> 2;
-  for (int u = blockIdx.z; u < P.nunits; u += gridDim.z) {
-    const int mm = P.units[u].mmax;
-    const size_t col0 = (size_t)u * NC;
-    __syncthreads();  // the previous unit's bins are done with the staging buffer
-    // G arrives transposed, Gt[prob][ring][col] (Gp rows per problem): the NC columns of the group
-    // are one or two 32-byte sectors per (problem, ring)
-    const int nload = 2 * (mm + 1) * NC * TK;
+  const int NCt = NC * UG;
+  for (int ug = blockIdx.z * UG; ug < P.nunits; ug += gridDim.z * UG) {
+    const int nu = min(UG, P.nunits - ug);
+    int mmg = 0;  // largest m of the group (units are ordered by decreasing lmax)
+    for (int i = 0; i < nu; ++i) mmg = max(mmg, P.units[ug + i].mmax);
+    const size_t col0 = (size_t)ug * NC;
+    __syncthreads();  // the previous group's bins are done with the staging buffer
+    // NCt is a power of two (NC = 4 or 8 columns, UG = 1, 2 or 4 units); one ring per CTA
+    const int nload = 2 * (mmg + 1) * NCt;
+    const int lNCt = 31 - __clz(NCt);
+    const float *Gk = G + (size_t)k0 * ncols + col0;
+    const size_t gstride = (size_t)P.Gp * ncols;
+#pragma unroll 8
     for (int idx = tid; idx < nload; idx += 256) {
-      const int cc = idx % NC, pk = idx / NC;  // pk = prob * TK + ring
-      const int kk = pk % TK, prob = pk / TK;
-      const int k = k0 + kk;
-      s[(prob * NC + cc) * TK + kk] = (k < P.krows) ? G[((size_t)prob * P.Gp + k) * ncols + col0 + cc] : 0.f;
+      const int cc = idx & (NCt - 1), prob = idx >> lNCt;
+      s[idx] = (cc < nu * NC) ? Gk[prob * gstride + cc] : 0.f;
     }
     __syncthreads();
-    const int ntask = TK * 2 * (mm + 1);
-    for (int task = tid; task < ntask; task += 256) {
-      const int kk = task % TK, p = (task / TK) & 1, r = task / (2 * TK);
-      const int k = k0 + kk;
-      if (k >= P.krows) continue;
-      const RingDesc &rd = P.rings[k];
-      const int n = rd.nphi;
-      if (r >= n) continue;
-      const bool shifted = rd.shifted != 0, equator = rd.startS < 0;
-      float b[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};  // per map: B+ re, im, B- re, im
+    // one thread per (residue r, fold parity, unit, complex slot of the group): the 16 threads of a
+    // (r, parity) read one 128-byte line of the staging buffer per term and store one line per m
+    const int k = k0;  // TK = 1
+    const RingDesc &rd = P.rings[k];
+    const int n = rd.nphi;
+    const bool shifted = rd.shifted != 0, equator = rd.startS < 0;
+    const int CQ = NC >> 1, lanes = UG * CQ;
+    const int lCQ = 31 - __clz(CQ), llanes = 31 - __clz(lanes);
+    const int rmax = min(n, mmg + 1);
+    for (int task = tid; task < 2 * rmax * lanes; task += 256) {
+      const int l = task & (lanes - 1), rp = task >> llanes;
+      const int p = rp & 1, r = rp >> 1;
+      const int ui = l >> lCQ, cq = l & (CQ - 1);
+      if (ui >= nu) continue;
+      const int mm = P.units[ug + ui].mmax;
+      if (r > mm) continue;
+      const int pm = cq & 1;  // 0: B+[r] = sum_q s^q h_{r - q n};  1: B-[r] = sum_q s^q conj(h_{q n - r})
+      const float *su = s + ui * NC + 4 * (cq >> 1);  // this map's (+re, +im, -re, -im); TK = 1
+      float br = 0.f, bi = 0.f;
       const int qlo = -((mm - r) / n), qhi = (r + mm) / n;
       for (int q = qlo; q <= qhi; ++q) {
         const float sg = (shifted && (q & 1)) ? -1.f : 1.f;
-        const int m1 = r - q * n, a1 = m1 < 0 ? -m1 : m1;
-        const int m2 = q * n - r, a2 = m2 < 0 ? -m2 : m2;
-        const float *h1 = s + ((size_t)((2 * a1 + p) * NC + (m1 < 0 ? 2 : 0))) * TK + kk;
-        const float *h2 = s + ((size_t)((2 * a2 + p) * NC + (m2 < 0 ? 2 : 0))) * TK + kk;
-#pragma unroll
-        for (int mp = 0; mp < 2; ++mp) {
-          if (mp < nmap) {
-            const float *g1 = h1 + 4 * mp * TK, *g2 = h2 + 4 * mp * TK;
-            b[mp][0] += sg * g1[0];
-            b[mp][1] += m1 < 0 ? -sg * g1[TK] : sg * g1[TK];
-            b[mp][2] += sg * g2[0];
-            b[mp][3] += m2 < 0 ? sg * g2[TK] : -sg * g2[TK];
-          }
-        }
+        const int m1 = pm ? q * n - r : r - q * n;
+        const bool neg = m1 < 0;
+        const float *g = su + (size_t)(2 * (neg ? -m1 : m1) + p) * NCt + (neg ? 2 : 0);
+        br += sg * g[0];
+        bi += (neg != (pm != 0)) ? -sg * g[1] : sg * g[1];
       }
       float fn = (float)(equator ? n : 2 * n);
       if (equator && p == 1) fn = 0.f;
       int j = 0;
       for (int m = r; m <= mm; m += n, ++j) {
         const float f = (shifted && (j & 1)) ? -fn : fn;
-        float *dst = F + ((size_t)(2 * m + p) * P.Kp + k) * ncols + col0;
-#pragma unroll
-        for (int mp = 0; mp < 2; ++mp) {
-          if (mp < nmap) {
-            const float out[4] = {f * b[mp][0], f * b[mp][1], f * b[mp][2], f * b[mp][3]};
-            store4(dst + 4 * mp, out);
-          }
-        }
+        float2 *dst = reinterpret_cast<float2 *>(F + ((size_t)(2 * m + p) * P.Kp + k) * ncols + col0 + ui * NC + 2 * cq);
+        *dst = make_float2(f * br, f * bi);
       }
     }
   }
@@ -521,16 +520,20 @@ int launch_alias_fold(dsb_plan *plan, const BucketLayout &lay, const UnitDev *un
     B.G2 = (const float *)G2;
     B.F0 = (float *)F0;
     B.F2 = (float *)F2;
-    // rings per CTA: the staging buffer is kept near 64 KB so that three CTAs share an SM (the
-    // kernel is a chain of load -> barrier -> fold -> store: it needs resident warps, not big tiles)
-    int TK = 16;
-    const size_t per_ring = (size_t)2 * (lay.mcap + 1) * 8 * sizeof(float);
-    while (TK > 1 && per_ring * TK > 64 * 1024) TK >>= 1;
-    DSB_CHECK(per_ring * TK <= 220 * 1024, DSB_ERR_UNSUPPORTED, "alias fold: lmax %d does not fit shared memory", lay.mcap);
+    // units x rings per CTA: four units make the loads whole 128-byte lines; the staging buffer is
+    // kept near 64 KB so that three CTAs share an SM (the kernel is a chain of load -> barrier ->
+    // fold -> store: it needs resident warps, not big tiles)
+    const size_t per_ring = (size_t)2 * (lay.mcap + 1) * 8 * sizeof(float);  // one unit, one ring
+    int UG = 4;
+    const int TK = 1;
+    while (UG > 1 && per_ring * UG > 64 * 1024) UG >>= 1;
+    DSB_CHECK(per_ring * UG * TK <= 220 * 1024, DSB_ERR_UNSUPPORTED, "alias fold: lmax %d does not fit shared memory",
+              lay.mcap);
     B.TK = TK;
-    const size_t smem = per_ring * TK;
+    B.UG = UG;
+    const size_t smem = per_ring * UG * TK;
     DSB_CUDA(raise_dynamic_smem((const void *)alias_fold_bins_kernel, smem));
-    dim3 grid((B.krows + TK - 1) / TK, lay.has2 ? 2 : 1, std::min(lay.nunits, 65535));
+    dim3 grid((B.krows + TK - 1) / TK, lay.has2 ? 2 : 1, std::min((lay.nunits + UG - 1) / UG, 65535));
     alias_fold_bins_kernel<<<grid, 256, smem, stream>>>(B);
     DSB_LAUNCH_CHECK();
     return DSB_OK;
