@@ -27,10 +27,11 @@
 // Accumulation.  The tensor core adds each K=16 partial product into the fp32 TMEM
 // accumulator with truncation, a bias of ~2^-24 of the accumulator per MMA that grows
 // linearly with the number of chained MMAs (measured: 6e-6 of max|B| at nside 256, where a
-// series chains 192 of them).  So the leading product a1 b1 never accumulates across pipeline
-// stages: each stage (K = 32, two MMAs) writes a fresh TMEM chunk that the epilogue warps
-// drain and add to fp32 register sums (round to nearest); the five correction products, 2^-8
-// and smaller, accumulate in their own TMEM block, where the same truncation is harmless.
+// series chains 192 of them).  So the leading product a1 b1 only accumulates over TC_DRAIN
+// pipeline stages (K = 32, two MMAs each): every such group writes a fresh TMEM chunk that the
+// epilogue warps drain and add to fp32 register sums (round to nearest); the five correction
+// products, 2^-8 and smaller, accumulate in their own TMEM block, where the same truncation is
+// harmless.
 //
 // Warp roles:  warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 =
 // epilogue (two per TMEM lane quarter, 64 rows each), warps 10.. = converters.  Persistent
@@ -45,6 +46,7 @@
 namespace dsb {
 
 constexpr int TC_KC = 32;          // k per pipeline stage
+constexpr int TC_DRAIN = 2;        // pipeline stages whose leading product shares one TMEM chunk
 constexpr int TC_M = 128;          // operand columns per tile
 constexpr int TC_NCONV = 6;        // converter warps
 constexpr int TC_NEPI = 8;         // epilogue warps
@@ -171,6 +173,23 @@ __device__ __forceinline__ void split3_bits(float v, uint32_t &h, uint32_t &m, u
 // (upper half of a, upper half of b) -> one 32-bit word, a in the low half
 __device__ __forceinline__ uint32_t hi2(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); }
 
+// Two values at once: (v0, v1) = h + m + l with h, m, l pairs of bf16 (v0 in the low half of each
+// word -- the order of two neighbouring operand columns in a plane).  One packed conversion per
+// plane instead of integer rounding per value.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ void split3_pair(float v0, float v1, uint32_t &h, uint32_t &m, uint32_t &l) {
+  h = pack_bf16x2(v0, v1);
+  float r0 = v0 - __uint_as_float(h << 16), r1 = v1 - __uint_as_float(h & 0xFFFF0000u);
+  m = pack_bf16x2(r0, r1);
+  r0 -= __uint_as_float(m << 16);
+  r1 -= __uint_as_float(m & 0xFFFF0000u);
+  l = pack_bf16x2(r0, r1);
+}
+
 template <bool TMODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA2,
@@ -280,11 +299,12 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_corr = tmem_base + 256 + (uint32_t)cb * 128;
         uint32_t accum_c = 0;
-        for (int kc = 0; kc < nk; ++kc, ++chunk) {
+        for (int kc = 0; kc < nk; ++kc) {
           const uint32_t mb = chunk & 1;
+          const bool first = kc % TC_DRAIN == 0, last = (kc % TC_DRAIN == TC_DRAIN - 1) || kc == nk - 1;
           mbar_wait(&full[stage], phase);  // B planes (TMA)
           mbar_wait(&conv[stage], phase);  // A planes (converters)
-          mbar_wait(&mfree[mb], ((chunk >> 1) & 1) ^ 1);
+          if (first) mbar_wait(&mfree[mb], ((chunk >> 1) & 1) ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sA = smem_u32(stages + (size_t)stage * stage_bytes);
           const uint32_t sB = sA + 3 * TC_A_PLANE + TC_A_RAW;
@@ -304,13 +324,16 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
               umma_bf16(d_corr, da, db, idesc, accum_c);
               accum_c = 1;
             }
-            // leading product a1 b1 into this stage's fresh chunk
+            // leading product a1 b1 into the chunk of this group of stages
             const uint64_t da = make_desc(sA + ks * 2048, TC_A_PLANE / 2, 1024, 2);
             const uint64_t db = make_desc(sB + ks * 32, 16, 512, 4);
-            umma_bf16(d_main, da, db, idesc, ks > 0 ? 1u : 0u);
+            umma_bf16(d_main, da, db, idesc, (first && ks == 0) ? 0u : 1u);
           }
           umma_commit(&empty[stage]);
-          umma_commit(&mfull[mb]);
+          if (last) {
+            umma_commit(&mfull[mb]);
+            ++chunk;
+          }
           if (++stage == P.nstages) {
             stage = 0;
             phase ^= 1;
@@ -338,7 +361,7 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       float sums[64];
 #pragma unroll
       for (int i = 0; i < 64; ++i) sums[i] = 0.f;
-      for (int kc = 0; kc < nk; ++kc, ++chunk) {
+      for (int kc = 0; kc < nk; kc += TC_DRAIN, ++chunk) {
         const uint32_t mb = chunk & 1;
         mbar_wait(&mfull[mb], (chunk >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -457,18 +480,15 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
             v[0] = hi.y, v[1] = -hi.x, v[2] = hi.w, v[3] = -hi.z;
             v[4] = -lo.y, v[5] = lo.x, v[6] = -lo.w, v[7] = lo.z;
           }
-          uint32_t h[8], m[8], l[8];
+          uint32_t h[4], m[4], l[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) split3_bits(v[i], h[i], m[i], l[i]);
+          for (int i = 0; i < 4; ++i) split3_pair(v[2 * i], v[2 * i + 1], h[i], m[i], l[i]);
           // MN-major SW128: box (64 columns) -> k row of 128 B -> 16-byte chunk ^ (k & 7)
           const uint32_t off = (uint32_t)(grp >> 3) * (TC_A_PLANE / 2) + (uint32_t)k * 128 +
                                ((uint32_t)((grp & 7) ^ (k & 7)) << 4);
-          *reinterpret_cast<uint4 *>(sA + off) =
-              make_uint4(hi2(h[0], h[1]), hi2(h[2], h[3]), hi2(h[4], h[5]), hi2(h[6], h[7]));
-          *reinterpret_cast<uint4 *>(sA + TC_A_PLANE + off) =
-              make_uint4(hi2(m[0], m[1]), hi2(m[2], m[3]), hi2(m[4], m[5]), hi2(m[6], m[7]));
-          *reinterpret_cast<uint4 *>(sA + 2 * TC_A_PLANE + off) =
-              make_uint4(hi2(l[0], l[1]), hi2(l[2], l[3]), hi2(l[4], l[5]), hi2(l[6], l[7]));
+          *reinterpret_cast<uint4 *>(sA + off) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4 *>(sA + TC_A_PLANE + off) = make_uint4(m[0], m[1], m[2], m[3]);
+          *reinterpret_cast<uint4 *>(sA + 2 * TC_A_PLANE + off) = make_uint4(l[0], l[1], l[2], l[3]);
         }
         // make the generic-proxy writes visible to the tensor core (async proxy), then signal
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
