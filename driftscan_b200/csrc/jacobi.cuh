@@ -32,7 +32,15 @@ int jacobi_pass(zc *R, int ldr, int ncols, const int32_t *idx, const int32_t *na
 // Unitary row operations (Householder reflections) that bring columns [ip0, ip1) of the active
 // rows to upper-triangular form before a Jacobi pass: cuts the sweep count of graded matrices
 // from ~25 to ~5.  Every column is carried along, exactly as in jacobi_pass.
+// `keep` != NULL: the reflectors are handed to the caller (stream-ordered allocations it frees with
+// cudaFreeAsync) instead of being released: H_k = I - tau_k v_k v_k^H, v_k = Vh[b][k][position],
+// positions = the order of idx at the time of the call.
+struct HHKeep {
+  zc *Vh = nullptr;        // [batch][steps][ldr]
+  double *tauh = nullptr;  // [batch][steps]
+  int steps = 0, nmax = 0;
+};
 int householder_precondition(zc *R, int ldr, int ncols, const int32_t *idx, const int32_t *nact, int batch, int ip0,
-                             int ip1, int nmax, JacobiScratch &js, cudaStream_t stream);
+                             int ip1, int nmax, JacobiScratch &js, cudaStream_t stream, HHKeep *keep = nullptr);
 
 }  // namespace dsb

@@ -876,11 +876,13 @@ hh_T_kernel(const zc *__restrict__ Vh_all, const double *__restrict__ tauh_all, 
 }
 
 // C <- (I - V T V^H)^H C = C - V T^H (V^H C) for the columns OUTSIDE [ip0, ip1): the reflectors of
-// a block are applied together, two passes over the rows per kHB reflectors instead of two each
+// a block are applied together, two passes over the rows per kHB reflectors instead of two each.
+// fwd: C <- (I - V T V^H) C instead (the block of Q itself rather than of Q^H: used to carry the
+// compact left vectors of the SVD chain back to telescope space)
 __global__ void __launch_bounds__(256)
 hh_block_apply_kernel(zc *__restrict__ Rall, int ldr, int ncols, const int32_t *__restrict__ idx_all,
                       const int32_t *__restrict__ nact_all, const zc *__restrict__ Vh_all, int steps, int k0, int nb,
-                      const zc *__restrict__ T_all, int ip0, int ip1) {
+                      const zc *__restrict__ T_all, int ip0, int ip1, int fwd) {
   const int b = blockIdx.y;
   const int n = nact_all[b];
   if (k0 >= n - 1) return;
@@ -927,16 +929,30 @@ hh_block_apply_kernel(zc *__restrict__ Rall, int ldr, int ncols, const int32_t *
     w[j] = {re, im};
   }
   zc wp[kHB];
+  if (!fwd) {
 #pragma unroll
-  for (int i = 0; i < kHB; ++i) {
-    double re = 0.0, im = 0.0;
+    for (int i = 0; i < kHB; ++i) {
+      double re = 0.0, im = 0.0;
 #pragma unroll
-    for (int j = 0; j <= i; ++j) {
-      const zc t = s_T[j][i];
-      re += t.x * w[j].x + t.y * w[j].y;  // conj(t) w
-      im += t.x * w[j].y - t.y * w[j].x;
+      for (int j = 0; j <= i; ++j) {
+        const zc t = s_T[j][i];
+        re += t.x * w[j].x + t.y * w[j].y;  // conj(t) w
+        im += t.x * w[j].y - t.y * w[j].x;
+      }
+      wp[i] = {re, im};
     }
-    wp[i] = {re, im};
+  } else {  // C <- (I - V T V^H) C:  w' = T w  (T upper triangular; entries beyond nb are zero)
+#pragma unroll
+    for (int i = 0; i < kHB; ++i) {
+      double re = 0.0, im = 0.0;
+#pragma unroll
+      for (int j = i; j < kHB; ++j) {
+        const zc t = s_T[i][j];
+        re += t.x * w[j].x - t.y * w[j].y;
+        im += t.x * w[j].y + t.y * w[j].x;
+      }
+      wp[i] = {re, im};
+    }
   }
   for (int r = k0 + slice; r < n; r += 4) {
     zc *x = R + (size_t)idx[r] * ncols + col;
@@ -955,7 +971,7 @@ hh_block_apply_kernel(zc *__restrict__ Rall, int ldr, int ncols, const int32_t *
 
 // Triangularise columns [ip0, ip1) of the active rows of every matrix (see above).
 int householder_precondition(zc *R, int ldr, int ncols, const int32_t *idx, const int32_t *nact, int batch, int ip0,
-                             int ip1, int nmax, JacobiScratch &js, cudaStream_t stream) {
+                             int ip1, int nmax, JacobiScratch &js, cudaStream_t stream, HHKeep *keep) {
   static const bool off = getenv("DSB_SVD_NOQR") != nullptr;
   const int ipw = ip1 - ip0;
   if (off || ipw <= 0) return DSB_OK;
@@ -967,6 +983,7 @@ int householder_precondition(zc *R, int ldr, int ncols, const int32_t *idx, cons
     DSB_CUDA(cudaStreamSynchronize(stream));
     nmax = js.h_flag[1];
   }
+  if (keep) keep->nmax = nmax;
   if (nmax < 2) return DSB_OK;
   const int steps = std::min(nmax - 1, ipw);
   if (steps <= 0) return DSB_OK;
@@ -1010,7 +1027,7 @@ int householder_precondition(zc *R, int ldr, int ncols, const int32_t *idx, cons
     for (int k0 = 0; k0 < steps; k0 += kHB) {
       const int nb = std::min(kHB, steps - k0);
       hh_T_kernel<<<batch, 256, 0, stream>>>(Vh, tauh, steps, ldr, nact, k0, nb, T);
-      hh_block_apply_kernel<<<gblock, 256, 0, stream>>>(R, ldr, ncols, idx, nact, Vh, steps, k0, nb, T, ip0, ip1);
+      hh_block_apply_kernel<<<gblock, 256, 0, stream>>>(R, ldr, ncols, idx, nact, Vh, steps, k0, nb, T, ip0, ip1, 0);
     }
     count_launch(2 * ((steps + kHB - 1) / kHB) - 1);
     DSB_LAUNCH_CHECK();
@@ -1026,8 +1043,15 @@ int householder_precondition(zc *R, int ldr, int ncols, const int32_t *idx, cons
   }
   cudaFreeAsync(clist, stream);
   cudaFreeAsync(ncl, stream);
-  cudaFreeAsync(Vh, stream);
-  cudaFreeAsync(tauh, stream);
+  if (keep) {
+    keep->Vh = Vh;
+    keep->tauh = tauh;
+    keep->steps = steps;
+    keep->nmax = nmax;
+  } else {
+    cudaFreeAsync(Vh, stream);
+    cudaFreeAsync(tauh, stream);
+  }
   cudaFreeAsync(T, stream);
   cudaFreeAsync(cn2, stream);
   cudaFreeAsync(piv0, stream);
@@ -1277,8 +1301,10 @@ __global__ void svd_emit_kernel(const zc *__restrict__ R, const double *__restri
 // pinv(beam) from the row-orthogonalised scratch S = [ Sigma Q | W^H ] :
 //   pinv[c][j] = sum_k conj(S[k][c]) / sigma_k^2 * S[k][nsky + j],  sigma_k > rcond * sigma_max
 // written as invbeam[b][c][j] with row pitch svd_len (columns >= nmodes zero).
+// S may hold the sky columns compactly, [pol][l - l0] with l0 leading l of every polarisation
+// dropped (they are identically zero in the block): nl_full > 0 expands them again on output.
 __global__ void svd_pinv_kernel(const zc *__restrict__ S, const int32_t *__restrict__ snact, int nsky, int svd_len,
-                                zc *__restrict__ invbeam, double rcond_in) {
+                                zc *__restrict__ invbeam, double rcond_in, int nl_full = 0, int l0 = 0) {
   const int b = blockIdx.y;
   const int nm = snact[b];
   const int scols = nsky + svd_len;
@@ -1309,11 +1335,19 @@ __global__ void svd_pinv_kernel(const zc *__restrict__ S, const int32_t *__restr
     s_inv[k] = (k < nm && a > rcond * rcond * s_max2 && a > 0.0) ? 1.0 / a : 0.0;
   }
   __syncthreads();
-  const size_t total = (size_t)nsky * svd_len;
+  const int nle = nl_full > 0 ? nl_full - l0 : 0;
+  const size_t total = (size_t)(nl_full > 0 ? (nsky / nle) * nl_full : nsky) * svd_len;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i / svd_len), j = (int)(i % svd_len);
+    int c = (int)(i / svd_len);
+    const int j = (int)(i % svd_len);
+    bool zero_col = false;
+    if (nl_full > 0) {
+      const int pol = c / nl_full, l = c - pol * nl_full;
+      zero_col = l < l0;
+      c = pol * nle + l - l0;
+    }
     double re = 0.0, im = 0.0;
-    if (j < nm) {
+    if (j < nm && !zero_col) {
       for (int k = 0; k < nm; ++k) {
         const zc a = Sb[(size_t)k * scols + c];
         const zc w = Sb[(size_t)k * scols + nsky + j];
@@ -1325,6 +1359,148 @@ __global__ void svd_pinv_kernel(const zc *__restrict__ S, const int32_t *__restr
     }
     invbeam[(size_t)b * total + i] = {re, im};
   }
+}
+
+
+// ---- compact form of the chain ----------------------------------------------------------------
+// l0[0] = smallest l with a non-zero entry anywhere in bf[batch][ntel][npol][nl] (columns l < m of a
+// beam-transfer block are identically zero, beamtransfer.py:610-624)
+__global__ void leading_zero_kernel(const zc *__restrict__ bf, size_t total, int nl, int32_t *__restrict__ l0) {
+  int best = nl;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const zc v = bf[i];
+    if (v.x != 0.0 || v.y != 0.0) best = min(best, (int)(i % nl));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0 && best < nl) atomicMin(l0, best);
+}
+
+// M1 = diag(w) B with the sky columns [pol][l - l0], l >= l0 (no accumulator)
+__global__ void svd_prepare_compact_kernel(const zc *__restrict__ bf, const double *__restrict__ noisew,
+                                           zc *__restrict__ M, int ntel, int npol, int nl, int l0,
+                                           int32_t *__restrict__ idx, int32_t *__restrict__ nact) {
+  const int b = blockIdx.y;
+  const int nle = nl - l0, ncols = npol * nle;
+  const size_t total = (size_t)ntel * ncols;
+  const zc *B = bf + (size_t)b * ntel * npol * nl;
+  zc *Mb = M + (size_t)b * total;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ncols), c = (int)(i % ncols);
+    const int pol = c / nle, l = c - pol * nle + l0;
+    const double w = noisew ? noisew[(size_t)b * ntel + r] : 1.0;
+    const zc s = B[((size_t)r * npol + pol) * nl + l];
+    Mb[i] = {s.x * w, s.y * w};
+  }
+  if (blockIdx.x == 0) {
+    for (int r = threadIdx.x; r < ntel; r += blockDim.x) idx[(size_t)b * ntel + r] = r;
+    if (threadIdx.x == 0) nact[b] = ntel;
+  }
+}
+
+// M2[b][i] = [ R1 row at position i | e_i ], i < rc: the triangular factor left in the first rows (by
+// position in idx1) of the reflected M1, with a fresh accumulator of its own width
+__global__ void svd_compact_copy_kernel(const zc *__restrict__ M1, const int32_t *__restrict__ idx1,
+                                        const int32_t *__restrict__ nact1, int ntel, int nsky, int rc,
+                                        zc *__restrict__ M2, int32_t *__restrict__ idx2, int32_t *__restrict__ nact2) {
+  const int b = blockIdx.y;
+  const int ncols2 = nsky + rc;
+  const int n2 = min(nact1[b], rc);
+  const size_t total = (size_t)rc * ncols2;
+  const zc *A = M1 + (size_t)b * ntel * nsky;
+  zc *O = M2 + (size_t)b * total;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ncols2), c = (int)(i % ncols2);
+    zc v = {0.0, 0.0};
+    if (r < n2) {
+      if (c < nsky) v = A[(size_t)idx1[(size_t)b * ntel + r] * nsky + c];
+      else if (c - nsky == r) v = {1.0, 0.0};
+    }
+    O[i] = v;
+  }
+  if (blockIdx.x == 0) {
+    for (int r = threadIdx.x; r < rc; r += blockDim.x) idx2[(size_t)b * rc + r] = r;
+    if (threadIdx.x == 0) nact2[b] = n2;
+  }
+}
+
+// beam_svd[b][k][pol][l] = M2[idx2[k]][pol][l - l0];  Z[b][pos][k] = conj(M2[idx2[k]][nsky + pos]) -- the
+// adjoint of the compact left vectors, one row per position of stage 1, ready for the reflectors --
+// and the pseudo-inverse scratch  S[b][k] = [ beam_k (compact) | e_k ].
+__global__ void svd_emit_compact_kernel(const zc *__restrict__ M2, const int32_t *__restrict__ idx2,
+                                        const int32_t *__restrict__ nact2, int rc, int nsky, int npol, int nl, int l0,
+                                        int ntel, int svd_len, zc *__restrict__ beam_svd, zc *__restrict__ Z,
+                                        zc *__restrict__ S, int32_t *__restrict__ sidx, int32_t *__restrict__ snact,
+                                        int32_t *__restrict__ nmodes_out) {
+  const int b = blockIdx.y;
+  const int ncols2 = nsky + rc, nle = nl - l0;
+  const int nm = min(nact2[b], svd_len);
+  const zc zero = {0.0, 0.0};
+  const zc *Mb = M2 + (size_t)b * rc * ncols2;
+  const int32_t *idx = idx2 + (size_t)b * rc;
+  const size_t tot1 = (size_t)svd_len * npol * nl, tot2 = (size_t)ntel * svd_len;
+  const int scols = nsky + svd_len;
+  const size_t tot3 = S ? (size_t)svd_len * scols : 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tot1 + tot2 + tot3;
+       i += (size_t)gridDim.x * blockDim.x) {
+    if (i < tot1) {
+      const int k = (int)(i / ((size_t)npol * nl)), c = (int)(i % ((size_t)npol * nl));
+      const int pol = c / nl, l = c - pol * nl;
+      beam_svd[(size_t)b * tot1 + i] = (k < nm && l >= l0) ? Mb[(size_t)idx[k] * ncols2 + pol * nle + l - l0] : zero;
+    } else if (i < tot1 + tot2) {
+      const size_t j = i - tot1;
+      const int pos = (int)(j / svd_len), k = (int)(j % svd_len);
+      zc v = zero;
+      if (k < nm && pos < rc) {
+        v = Mb[(size_t)idx[k] * ncols2 + nsky + pos];
+        v.y = -v.y;
+      }
+      Z[(size_t)b * tot2 + j] = v;
+    } else {
+      const size_t j = i - tot1 - tot2;
+      const int k = (int)(j / scols), c = (int)(j % scols);
+      zc v = zero;
+      if (k < nm) {
+        if (c < nsky) v = Mb[(size_t)idx[k] * ncols2 + c];
+        else v = {(c - nsky == k) ? 1.0 : 0.0, 0.0};
+      }
+      S[(size_t)b * tot3 + j] = v;
+    }
+  }
+  if (blockIdx.x == 0) {
+    if (sidx)
+      for (int r = threadIdx.x; r < svd_len; r += blockDim.x) sidx[(size_t)b * svd_len + r] = r;
+    if (threadIdx.x == 0) {
+      if (snact) snact[b] = nm;
+      if (nmodes_out) nmodes_out[b] = nm;
+    }
+  }
+}
+
+// beam_ut[b][k][t] = conj(Z[b][pos][k]) w[t],  t = idx1[pos];  rows outside stage 1's active set
+// (identically zero rows of the block) get zeros
+__global__ void svd_ut_final_kernel(const zc *__restrict__ Z, const int32_t *__restrict__ idx1,
+                                    const int32_t *__restrict__ nact1, const double *__restrict__ noisew, int ntel,
+                                    int svd_len, zc *__restrict__ beam_ut) {
+  const int b = blockIdx.y;
+  const size_t total = (size_t)ntel * svd_len;
+  const int n1 = nact1[b];
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int pos = (int)(i / svd_len), k = (int)(i % svd_len);
+    const int t = idx1[(size_t)b * ntel + pos];
+    zc v = {0.0, 0.0};
+    if (pos < n1) {
+      const zc z = Z[(size_t)b * total + i];
+      const double w = noisew[(size_t)b * ntel + t];
+      v = {z.x * w, -z.y * w};
+    }
+    beam_ut[((size_t)b * svd_len + k) * ntel + t] = v;
+  }
+}
+
+__global__ void iota_rows_kernel(int32_t *__restrict__ idx, int n) {
+  const int b = blockIdx.y;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) idx[(size_t)b * n + r] = r;
 }
 
 // out[svbounds[f] + k][r] = sum_{pol < npol_use} sum_l beam_svd[f][k][pol][l] vec[f][pol][l][r]
@@ -1376,88 +1552,151 @@ static int svd_chain_impl(const void *bf_dev, const double *noisew_dev, int batc
     set_error("dsb_svd_chain: no CUDA device available (there is no CPU fallback)");
     return DSB_ERR_CUDA;
   }
-  const int nsky = npol * nl;
-  const int ncols = nsky + ntel;
-  const int scols = nsky + svd_len;
   const bool want_inv = invbeam_dev != nullptr;
+  const int max_sweeps = 60;
+  const double tol = 0.0;  // derive from the inner-product length
 
-  // scratch
-  zc *R = nullptr, *S = nullptr;
-  int32_t *idx = nullptr, *tmp = nullptr, *nact = nullptr, *sidx = nullptr, *snact = nullptr, *sweeps = nullptr;
+  JacobiScratch js;
+  DSB_TRY(js.alloc(batch, ntel, stream));
+
+  // ---- leading zero columns: l < m of a beam-transfer block (every polarisation) --------------------
+  int l0 = 0;
+  {
+    int32_t *l0_dev = js.flag;  // scratch int
+    const int32_t init = nl;
+    DSB_CUDA(cudaMemcpyAsync(l0_dev, &init, sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+    const size_t total = (size_t)batch * ntel * npol * nl;
+    leading_zero_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
+        (const zc *)bf_dev, total, nl, l0_dev);
+    DSB_LAUNCH_CHECK();
+    DSB_CUDA(cudaMemcpyAsync(js.h_flag, l0_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    DSB_CUDA(cudaStreamSynchronize(stream));
+    l0 = js.h_flag[0] >= nl ? 0 : js.h_flag[0];
+    static const bool no_trim = getenv("DSB_SVD_NOTRIM") != nullptr;  // diagnostic
+    if (no_trim) l0 = 0;
+  }
+  const int nle = nl - l0;       // l columns kept per polarisation
+  const int nsky = npol * nle;   // compact sky columns
+  const int scols = nsky + svd_len;
+
+  // ---- stage 1: Q^H A = R1 by pivoted reflections on the whitened block alone ------------------------
+  // (no accumulator: the reflectors are kept and applied to the final, at most svd_len, left vectors)
+  zc *M1 = nullptr, *M2 = nullptr, *S = nullptr, *Z = nullptr, *Tw = nullptr;
+  int32_t *idx1 = nullptr, *tmp = nullptr, *nact1 = nullptr, *idx2 = nullptr, *nact2 = nullptr, *idxz = nullptr;
+  int32_t *sidx = nullptr, *snact = nullptr, *sweeps = nullptr;
   double *sig = nullptr;
-  DSB_CUDA(cudaMallocAsync((void **)&R, sizeof(zc) * (size_t)batch * ntel * ncols, stream));
-  DSB_CUDA(cudaMallocAsync((void **)&idx, sizeof(int32_t) * (size_t)batch * ntel, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&M1, sizeof(zc) * (size_t)batch * ntel * nsky, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&idx1, sizeof(int32_t) * (size_t)batch * ntel, stream));
   DSB_CUDA(cudaMallocAsync((void **)&tmp, sizeof(int32_t) * (size_t)batch * ntel, stream));
   DSB_CUDA(cudaMallocAsync((void **)&sig, sizeof(double) * (size_t)batch * ntel, stream));
-  DSB_CUDA(cudaMallocAsync((void **)&nact, sizeof(int32_t) * batch, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&nact1, sizeof(int32_t) * batch, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&nact2, sizeof(int32_t) * batch, stream));
   DSB_CUDA(cudaMallocAsync((void **)&sweeps, sizeof(int32_t) * 4 * batch, stream));
+  DSB_CUDA(cudaMemsetAsync(sweeps, 0, sizeof(int32_t) * 4 * batch, stream));
+  dim3 gprep(64, batch);
+  svd_prepare_compact_kernel<<<gprep, 256, 0, stream>>>((const zc *)bf_dev, noisew_dev, M1, ntel, npol, nl, l0, idx1,
+                                                        nact1);
+  DSB_LAUNCH_CHECK();
+  // rows ordered by norm; exactly zero rows -- e.g. the m = 0 negative-m half -- leave the active set
+  // (they cannot be in the image)
+  rank_select_kernel<<<batch, 256, 0, stream>>>(M1, ntel, nsky, idx1, nact1, 0, nsky, 0, 0.0, ntel, sig, tmp, nullptr,
+                                                0);
+  DSB_LAUNCH_CHECK();
+  HHKeep hk;
+  DSB_TRY(householder_precondition(M1, ntel, nsky, idx1, nact1, batch, 0, nsky, -1, js, stream, &hk));
+  // rows that can be non-zero after the reflections: positions [0, rc)
+  // (reflections switched off, DSB_SVD_NOQR: nothing was compressed, every row stays)
+  const int rc = hk.nmax > 0 ? std::max(1, std::min(hk.nmax, hk.steps > 0 ? nsky : ntel)) : ntel;
+  const int ncols = nsky + rc;
+  DSB_CUDA(cudaMallocAsync((void **)&M2, sizeof(zc) * (size_t)batch * rc * ncols, stream));
+  DSB_CUDA(cudaMallocAsync((void **)&idx2, sizeof(int32_t) * (size_t)batch * rc, stream));
+  svd_compact_copy_kernel<<<gprep, 256, 0, stream>>>(M1, idx1, nact1, ntel, nsky, rc, M2, idx2, nact2);
+  DSB_LAUNCH_CHECK();
+  cudaFreeAsync(M1, stream);
+  M1 = nullptr;
+
+  // ---- stage 2: the chain on the rows of [ R1 | I_rc ] ------------------------------------------------
+  if (chain) {
+    // SVD 1: image of the whole whitened matrix
+    DSB_TRY(jacobi_pass(M2, rc, ncols, idx2, nact2, batch, 0, nsky, -1, max_sweeps, tol, sweeps, js, stream));
+    rank_select_kernel<<<batch, 256, 0, stream>>>(M2, rc, ncols, idx2, nact2, 0, nsky, 0, rtol1, rc, sig, tmp, nullptr,
+                                                  0);
+    DSB_LAUNCH_CHECK();
+    // SVD 2: null space of the polarised columns
+    rank_select_kernel<<<batch, 256, 0, stream>>>(M2, rc, ncols, idx2, nact2, nle, nsky, 3, 0.0, rc, sig, tmp, nullptr,
+                                                  0);
+    DSB_LAUNCH_CHECK();
+    DSB_TRY(householder_precondition(M2, rc, ncols, idx2, nact2, batch, nle, nsky, -1, js, stream));
+    DSB_TRY(jacobi_pass(M2, rc, ncols, idx2, nact2, batch, nle, nsky, -1, max_sweeps, tol, sweeps + batch, js, stream));
+    rank_select_kernel<<<batch, 256, 0, stream>>>(M2, rc, ncols, idx2, nact2, nle, nsky, 1, polsvcut, nsky - nle, sig,
+                                                  tmp, nullptr, 0);
+    DSB_LAUNCH_CHECK();
+  }
+  // SVD 3: temperature columns of the surviving rows
+  DSB_CUDA(cudaMemsetAsync(sv_dev, 0, sizeof(double) * (size_t)batch * svd_len, stream));
+  rank_select_kernel<<<batch, 256, 0, stream>>>(M2, rc, ncols, idx2, nact2, 0, nle, 3, 0.0, rc, sig, tmp, nullptr, 0);
+  DSB_LAUNCH_CHECK();
+  DSB_TRY(householder_precondition(M2, rc, ncols, idx2, nact2, batch, 0, nle, -1, js, stream));
+  DSB_TRY(jacobi_pass(M2, rc, ncols, idx2, nact2, batch, 0, nle, -1, max_sweeps, tol, sweeps + 2 * batch, js, stream));
+  rank_select_kernel<<<batch, 256, 0, stream>>>(M2, rc, ncols, idx2, nact2, 0, nle, 2, 0.0, nl, sig, tmp, sv_dev,
+                                                svd_len);
+  DSB_LAUNCH_CHECK();
+
+  // ---- stage 3: products; the compact left vectors go back through the stage-1 reflectors ------------
+  DSB_CUDA(cudaMallocAsync((void **)&Z, sizeof(zc) * (size_t)batch * ntel * svd_len, stream));
   if (want_inv) {
     DSB_CUDA(cudaMallocAsync((void **)&S, sizeof(zc) * (size_t)batch * svd_len * scols, stream));
     DSB_CUDA(cudaMallocAsync((void **)&sidx, sizeof(int32_t) * (size_t)batch * svd_len, stream));
     DSB_CUDA(cudaMallocAsync((void **)&snact, sizeof(int32_t) * batch, stream));
   }
-
-  JacobiScratch js;
-  DSB_TRY(js.alloc(batch, ntel, stream));
-
-  const int max_sweeps = 60;
-  const double tol = 0.0;  // derive from the inner-product length
-  dim3 gprep(64, batch);
-  svd_prepare_kernel<<<gprep, 256, 0, stream>>>((const zc *)bf_dev, noisew_dev, R, ntel, nsky, idx, nact);
+  dim3 gemit(64, batch);
+  svd_emit_compact_kernel<<<gemit, 256, 0, stream>>>(M2, idx2, nact2, rc, nsky, npol, nl, l0, ntel, svd_len,
+                                                     (zc *)beam_svd_dev, Z, S, sidx, snact, nmodes_dev);
   DSB_LAUNCH_CHECK();
-  if (chain) {
-    // SVD 1: image of the whole whitened matrix (rows ordered by norm, exactly zero rows -- e.g. the
-    // m = 0 negative-m half -- leave the active set: they cannot be in the image)
-    rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, 0, nsky, 0, 0.0, ntel, sig, tmp,
-                                                  nullptr, 0);
+  if (hk.steps > 0) {
+    // Z <- Q Z = B_0 (B_1 ( ... B_last Z)),  B_j = H_8j ... H_8j+7 = I - V T V^H
+    DSB_CUDA(cudaMallocAsync((void **)&Tw, sizeof(zc) * (size_t)batch * kHB * kHB, stream));
+    DSB_CUDA(cudaMallocAsync((void **)&idxz, sizeof(int32_t) * (size_t)batch * ntel, stream));
+    iota_rows_kernel<<<dim3((ntel + 255) / 256, batch), 256, 0, stream>>>(idxz, ntel);
     DSB_LAUNCH_CHECK();
-    DSB_TRY(householder_precondition(R, ntel, ncols, idx, nact, batch, 0, nsky, -1, js, stream));
-    DSB_TRY(jacobi_pass(R, ntel, ncols, idx, nact, batch, 0, nsky, -1, max_sweeps, tol, sweeps, js, stream));
-    rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, 0, nsky, 0, rtol1, ntel, sig, tmp,
-                                                  nullptr, 0);
-    DSB_LAUNCH_CHECK();
-    // SVD 2: null space of the polarised columns
-    rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, nl, nsky, 3, 0.0, ntel, sig, tmp,
-                                                  nullptr, 0);
-    DSB_LAUNCH_CHECK();
-    DSB_TRY(householder_precondition(R, ntel, ncols, idx, nact, batch, nl, nsky, -1, js, stream));
-    DSB_TRY(jacobi_pass(R, ntel, ncols, idx, nact, batch, nl, nsky, -1, max_sweeps, tol, sweeps + batch, js, stream));
-    rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, nl, nsky, 1, polsvcut, nsky - nl,
-                                                  sig, tmp, nullptr, 0);
+    const dim3 gblock((svd_len + 63) / 64, batch);
+    for (int k0 = (hk.steps - 1) / kHB * kHB; k0 >= 0; k0 -= kHB) {
+      const int nb = std::min(kHB, hk.steps - k0);
+      hh_T_kernel<<<batch, 256, 0, stream>>>(hk.Vh, hk.tauh, hk.steps, ntel, nact1, k0, nb, Tw);
+      hh_block_apply_kernel<<<gblock, 256, 0, stream>>>(Z, ntel, svd_len, idxz, nact1, hk.Vh, hk.steps, k0, nb, Tw, 0, 0,
+                                                        1);
+    }
+    count_launch(2 * ((hk.steps + kHB - 1) / kHB) - 1);
     DSB_LAUNCH_CHECK();
   }
-  // SVD 3: temperature columns of the surviving rows
-  DSB_CUDA(cudaMemsetAsync(sv_dev, 0, sizeof(double) * (size_t)batch * svd_len, stream));
-  rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, 0, nl, 3, 0.0, ntel, sig, tmp, nullptr, 0);
-  DSB_LAUNCH_CHECK();
-  DSB_TRY(householder_precondition(R, ntel, ncols, idx, nact, batch, 0, nl, chain ? -1 : ntel, js, stream));
-  DSB_TRY(jacobi_pass(R, ntel, ncols, idx, nact, batch, 0, nl, chain ? -1 : ntel, max_sweeps, tol,
-                      sweeps + 2 * batch, js, stream));
-  rank_select_kernel<<<batch, 256, 0, stream>>>(R, ntel, ncols, idx, nact, 0, nl, 2, 0.0, nl, sig, tmp, sv_dev,
-                                                svd_len);
-  DSB_LAUNCH_CHECK();
-  dim3 gemit(64, batch);
-  svd_emit_kernel<<<gemit, 256, 0, stream>>>(R, noisew_dev, idx, nact, ntel, nsky, svd_len, (zc *)beam_svd_dev,
-                                             (zc *)beam_ut_dev, S, sidx, snact, nmodes_dev);
+  svd_ut_final_kernel<<<gemit, 256, 0, stream>>>(Z, idx1, nact1, noisew_dev, ntel, svd_len, (zc *)beam_ut_dev);
   DSB_LAUNCH_CHECK();
   if (want_inv) {
     DSB_TRY(householder_precondition(S, svd_len, scols, sidx, snact, batch, 0, nsky, -1, js, stream));
     DSB_TRY(jacobi_pass(S, svd_len, scols, sidx, snact, batch, 0, nsky, -1, max_sweeps, tol, sweeps + 3 * batch, js,
                         stream));
     dim3 gp(32, batch);
-    svd_pinv_kernel<<<gp, 256, sizeof(double) * svd_len, stream>>>(S, snact, nsky, svd_len, (zc *)invbeam_dev, -1.0);
+    svd_pinv_kernel<<<gp, 256, sizeof(double) * svd_len, stream>>>(S, snact, nsky, svd_len, (zc *)invbeam_dev, -1.0, nl,
+                                                                   l0);
     DSB_LAUNCH_CHECK();
   }
   // convergence check
   std::vector<int32_t> hs(4 * batch, 0);
   DSB_CUDA(cudaMemcpyAsync(hs.data(), sweeps, sizeof(int32_t) * 4 * batch, cudaMemcpyDeviceToHost, stream));
   DSB_CUDA(cudaStreamSynchronize(stream));
-  cudaFreeAsync(R, stream);
-  cudaFreeAsync(idx, stream);
+  cudaFreeAsync(M2, stream);
+  cudaFreeAsync(idx1, stream);
+  cudaFreeAsync(idx2, stream);
   cudaFreeAsync(tmp, stream);
   cudaFreeAsync(sig, stream);
-  cudaFreeAsync(nact, stream);
+  cudaFreeAsync(nact1, stream);
+  cudaFreeAsync(nact2, stream);
   cudaFreeAsync(sweeps, stream);
+  cudaFreeAsync(Z, stream);
+  if (hk.Vh) cudaFreeAsync(hk.Vh, stream);
+  if (hk.tauh) cudaFreeAsync(hk.tauh, stream);
+  if (Tw) cudaFreeAsync(Tw, stream);
+  if (idxz) cudaFreeAsync(idxz, stream);
   js.release(stream);
   if (want_inv) {
     cudaFreeAsync(S, stream);
