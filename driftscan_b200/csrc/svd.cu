@@ -1363,17 +1363,19 @@ __global__ void svd_pinv_kernel(const zc *__restrict__ S, const int32_t *__restr
 
 
 // ---- compact form of the chain ----------------------------------------------------------------
-// l0[0] = smallest l with a non-zero entry anywhere in bf[batch][ntel][npol][nl] (columns l < m of a
-// beam-transfer block are identically zero, beamtransfer.py:610-624)
-__global__ void leading_zero_kernel(const zc *__restrict__ bf, size_t total, int nl, int32_t *__restrict__ l0) {
+// l0[b] = smallest l with a non-zero entry in bf[b][ntel][npol][nl] (columns l < m of a beam-transfer
+// block are identically zero, beamtransfer.py:610-624)
+// per matrix: blockIdx.y = matrix, l0[b] initialised to nl by the caller
+__global__ void leading_zero_kernel(const zc *__restrict__ bf, size_t per_matrix, int nl, int32_t *__restrict__ l0) {
+  const zc *B = bf + (size_t)blockIdx.y * per_matrix;
   int best = nl;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const zc v = bf[i];
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < per_matrix; i += (size_t)gridDim.x * blockDim.x) {
+    const zc v = B[i];
     if (v.x != 0.0 || v.y != 0.0) best = min(best, (int)(i % nl));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-  if ((threadIdx.x & 31) == 0 && best < nl) atomicMin(l0, best);
+  if ((threadIdx.x & 31) == 0 && best < nl) atomicMin(&l0[blockIdx.y], best);
 }
 
 // M1 = diag(w) B with the sky columns [pol][l - l0], l >= l0 (no accumulator)
@@ -1534,47 +1536,17 @@ __global__ void project_sky_to_svd_kernel(const zc *__restrict__ beam_svd, const
 
 using namespace dsb;
 
-// temp_only: the single-SVD variant of BeamTransferTempSVD (beamtransfer.py:1549-1581): no image /
-// null-space passes, left singular vectors of the temperature columns of the whole whitened block.
-static int svd_chain_impl(const void *bf_dev, const double *noisew_dev, int batch, int ntel, int npol, int nl,
-                          int svd_len, double rtol1, double polsvcut, void *beam_svd_dev, void *beam_ut_dev,
-                          void *invbeam_dev, double *sv_dev, int32_t *nmodes_dev, bool temp_only,
-                          void *stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  const bool chain = npol > 1 && !temp_only;
-  DSB_CHECK(bf_dev && noisew_dev && beam_svd_dev && beam_ut_dev && sv_dev, DSB_ERR_INVALID,
-            "dsb_svd_chain: NULL argument");
-  DSB_CHECK(batch >= 0 && ntel > 0 && npol > 0 && nl > 0 && svd_len > 0 && svd_len <= ntel, DSB_ERR_INVALID,
-            "dsb_svd_chain: bad dimensions");
-  if (batch == 0) return DSB_OK;
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-    set_error("dsb_svd_chain: no CUDA device available (there is no CPU fallback)");
-    return DSB_ERR_CUDA;
-  }
+// One group of matrices that share their number l0 of leading zero l columns (one m of a stacked call).
+static int svd_chain_group(const void *bf_dev, const double *noisew_dev, int batch, int ntel, int npol, int nl,
+                           int svd_len, double rtol1, double polsvcut, void *beam_svd_dev, void *beam_ut_dev,
+                           void *invbeam_dev, double *sv_dev, int32_t *nmodes_dev, bool chain, int l0,
+                           cudaStream_t stream) {
   const bool want_inv = invbeam_dev != nullptr;
   const int max_sweeps = 60;
   const double tol = 0.0;  // derive from the inner-product length
 
   JacobiScratch js;
   DSB_TRY(js.alloc(batch, ntel, stream));
-
-  // ---- leading zero columns: l < m of a beam-transfer block (every polarisation) --------------------
-  int l0 = 0;
-  {
-    int32_t *l0_dev = js.flag;  // scratch int
-    const int32_t init = nl;
-    DSB_CUDA(cudaMemcpyAsync(l0_dev, &init, sizeof(int32_t), cudaMemcpyHostToDevice, stream));
-    const size_t total = (size_t)batch * ntel * npol * nl;
-    leading_zero_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, stream>>>(
-        (const zc *)bf_dev, total, nl, l0_dev);
-    DSB_LAUNCH_CHECK();
-    DSB_CUDA(cudaMemcpyAsync(js.h_flag, l0_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-    DSB_CUDA(cudaStreamSynchronize(stream));
-    l0 = js.h_flag[0] >= nl ? 0 : js.h_flag[0];
-    static const bool no_trim = getenv("DSB_SVD_NOTRIM") != nullptr;  // diagnostic
-    if (no_trim) l0 = 0;
-  }
   const int nle = nl - l0;       // l columns kept per polarisation
   const int nsky = npol * nle;   // compact sky columns
   const int scols = nsky + svd_len;
@@ -1708,6 +1680,60 @@ static int svd_chain_impl(const void *bf_dev, const double *noisew_dev, int batc
     if (!chain && i < 2 * batch) continue;
     DSB_CHECK(hs[i] < max_sweeps, DSB_ERR_NUMERIC, "dsb_svd_chain: Jacobi pass %d of matrix %d did not converge",
               i / batch, i % batch);
+  }
+  return DSB_OK;
+}
+
+
+// temp_only: the single-SVD variant of BeamTransferTempSVD (beamtransfer.py:1549-1581): no image /
+// null-space passes, left singular vectors of the temperature columns of the whole whitened block.
+//
+// The leading zero l columns (l < m) are dropped from the arithmetic.  A call may stack blocks of
+// several m: matrices are processed in groups of equal l0, each group on its own, so the result of a
+// block does not depend on what else the call holds (a multi-GPU run, whose ranks stack different m,
+// writes bit for bit the files of a single process).
+static int svd_chain_impl(const void *bf_dev, const double *noisew_dev, int batch, int ntel, int npol, int nl,
+                          int svd_len, double rtol1, double polsvcut, void *beam_svd_dev, void *beam_ut_dev,
+                          void *invbeam_dev, double *sv_dev, int32_t *nmodes_dev, bool temp_only,
+                          void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool chain = npol > 1 && !temp_only;
+  DSB_CHECK(bf_dev && noisew_dev && beam_svd_dev && beam_ut_dev && sv_dev, DSB_ERR_INVALID,
+            "dsb_svd_chain: NULL argument");
+  DSB_CHECK(batch >= 0 && ntel > 0 && npol > 0 && nl > 0 && svd_len > 0 && svd_len <= ntel, DSB_ERR_INVALID,
+            "dsb_svd_chain: bad dimensions");
+  if (batch == 0) return DSB_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("dsb_svd_chain: no CUDA device available (there is no CPU fallback)");
+    return DSB_ERR_CUDA;
+  }
+  std::vector<int32_t> l0(batch, nl);
+  {
+    int32_t *l0_dev = nullptr;
+    DSB_CUDA(cudaMallocAsync((void **)&l0_dev, sizeof(int32_t) * batch, stream));
+    DSB_CUDA(cudaMemcpyAsync(l0_dev, l0.data(), sizeof(int32_t) * batch, cudaMemcpyHostToDevice, stream));
+    const size_t per = (size_t)ntel * npol * nl;
+    leading_zero_kernel<<<dim3((unsigned)std::min<size_t>((per + 255) / 256, 64), batch), 256, 0, stream>>>(
+        (const zc *)bf_dev, per, nl, l0_dev);
+    DSB_LAUNCH_CHECK();
+    DSB_CUDA(cudaMemcpyAsync(l0.data(), l0_dev, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, stream));
+    DSB_CUDA(cudaStreamSynchronize(stream));
+    cudaFreeAsync(l0_dev, stream);
+    static const bool no_trim = getenv("DSB_SVD_NOTRIM") != nullptr;  // diagnostic: keep every column
+    for (auto &v : l0)
+      if (no_trim || v >= nl) v = 0;  // an all-zero block keeps its columns (the chain returns no modes)
+  }
+  const size_t o_bf = (size_t)ntel * npol * nl, o_svd = (size_t)svd_len * npol * nl, o_ut = (size_t)svd_len * ntel,
+               o_inv = (size_t)npol * nl * svd_len;
+  for (int b0 = 0; b0 < batch;) {
+    int b1 = b0 + 1;
+    while (b1 < batch && l0[b1] == l0[b0]) ++b1;
+    DSB_TRY(svd_chain_group((const zc *)bf_dev + b0 * o_bf, noisew_dev + (size_t)b0 * ntel, b1 - b0, ntel, npol, nl,
+                            svd_len, rtol1, polsvcut, (zc *)beam_svd_dev + b0 * o_svd, (zc *)beam_ut_dev + b0 * o_ut,
+                            invbeam_dev ? (void *)((zc *)invbeam_dev + b0 * o_inv) : nullptr, sv_dev + (size_t)b0 * svd_len,
+                            nmodes_dev ? nmodes_dev + b0 : nullptr, chain, l0[b0], stream));
+    b0 = b1;
   }
   return DSB_OK;
 }
