@@ -297,10 +297,11 @@ def svd_section(tel, args, rank, world, dev, stream, with_cpu):
                 "peak": fp64_peak, "unit": "TFLOP/s", "peak_source": "nominal (not measured)",
                 "frac": flops_mine / (t_mine * 1e-3) / 1e12 / fp64_peak if t_mine > 0 else None,
                 "algorithmic_flops_rank0": flops_mine,
-                "note": "S5 counts one Gram product and three projections per block; the chain executes ~30 one-sided "
-                        "Jacobi sweeps of the augmented rows instead (no Gram matrix: the 1e-10 cut of SVD1 is not "
-                        "resolvable through B B^H in fp64), streaming every row pair from HBM once per tournament "
-                        "step -- it is bound by that traffic and by launch latency, not by the fp64 pipe"}
+                "note": "S5 counts one Gram product and three projections per block; the chain executes pivoted "
+                        "Householder reflections and ~25 block one-sided Jacobi sweeps of the compact rows [R | I] "
+                        "instead (no Gram matrix of the whole block: the 1e-10 cut of SVD1 is not resolvable through "
+                        "B B^H in fp64) -- roughly 100x the S5 flops; its Jacobi kernels run at ~45 % of the fp64 pipe, "
+                        "the reflections are BLAS-2 (memory) bound"}
     out = {
         "metric": "per-m SVD m-blocks/s", "unit": "m-blocks/s", "roofline": svd_roof,
         "value": len(ms_all) / (t_max * 1e-3) if t_max > 0 else None,
@@ -455,7 +456,9 @@ def main():
         "mmax": int(tel.mmax), "npol_sky": 4, "precision": args.precision,
         "sht": f"healpy map2alm(iter={int(tel.sht_iter)}, use_weights=False) on both arms",
         "l2": "per-step working set (ring spectra + product, several GB) is far larger than the 126 MB L2",
-        "sharding": "frequency per GPU; NCCL all-to-all of m-major blocks when N>1",
+        "sharding": "frequency per GPU; N>1: the pack kernel stores every m-block into its owner's memory over NVLink "
+                    "(fused freq->m exchange, complex64 on the links in fp32x3 as in BeamTransfer._generate_mfiles; "
+                    "NCCL all-to-all with --nccl-exchange)",
     }
 
     # ------------------------------------------------------------- reference arm
@@ -571,8 +574,12 @@ def main():
     if (world > 1 or args.force_scatter) and not args.nccl_exchange:
         # CUDA IPC must work on every rank (PeerScatter raises on all of them otherwise): fall back
         # to the NCCL all-to-all in that case
+        # fp32x3 results are fp32 numbers: they cross the links -- and stay in the owner's blocks -- as
+        # complex64, exactly as in BeamTransfer._generate_mfiles (widened when the m-files are written)
+        link_elem = 8 if args.precision == "fp32x3" else 16
+        link_kind = _lib.DSB_OUT_MMAJOR_C64 if link_elem == 8 else _lib.DSB_OUT_MMAJOR_C128
         try:
-            scatter = parallel.PeerScatter(comm, world * F, nb, np_inc, lside, mmax)
+            scatter = parallel.PeerScatter(comm, world * F, nb, np_inc, lside, mmax, elem_bytes=link_elem)
         except Exception as exc:  # noqa: BLE001
             sys.stderr.write(f"[bench] rank {rank}: peer scatter unavailable ({exc}); using the NCCL exchange\n")
             scatter = None
@@ -605,8 +612,7 @@ def main():
     def step_compute(st):
         """The kernels of one step (every nside bucket), enqueued on stream ``st``."""
         if scatter is not None:
-            fork_join(lambda b, s_: b[1].transfer_units_scatter(b[2], 4, True, mmax, eng.precision,
-                                                                _lib.DSB_OUT_MMAJOR_C128, gdims,
+            fork_join(lambda b, s_: b[1].transfer_units_scatter(b[2], 4, True, mmax, eng.precision, link_kind, gdims,
                                                                 scatter.block_ptrs, s_), st)
         else:
             fork_join(lambda b, s_: b[1].transfer_units(b[2], 4, True, mmax, eng.precision, _lib.DSB_OUT_MMAJOR_C128,
@@ -716,9 +722,10 @@ def main():
     exchange = None
     if scatter is not None:
         mlo, mhi = scatter.m_lo, scatter.m_hi
-        own_local = int((moff[mhi[rank]] - moff[mlo[rank]])) * 16
-        sent = int(total * 16 - own_local)
+        own_local = int((moff[mhi[rank]] - moff[mlo[rank]])) * link_elem
+        sent = int(total * link_elem - own_local)
         exchange = {"mode": "fused: pack kernel stores m-blocks into the owner's memory over NVLink (CUDA IPC)",
+                    "element": "complex64 (the fp32x3 result, exact)" if link_elem == 8 else "complex128",
                     "bytes_sent_per_gpu_per_step": sent, "pack_ms_per_step": stage_ms_pack,
                     "gbs_per_gpu_during_pack": sent / (stage_ms_pack * 1e-3) / 1e9 if stage_ms_pack > 0 else None,
                     "nvlink_peak_gbs": 900.0}
@@ -741,7 +748,7 @@ def main():
         hbm_peak, tf_peak, peak_src = 6650.0, 1400.0, "fallback"
     # measured DRAM traffic per step of each stage (ncu launch list of this same command, committed)
     traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(tpath) and F == 2 and args.precision == "fp32x3":
         with open(tpath) as fh:
             traffic = {k: v.get("dram_bytes_per_step") for k, v in json.load(fh).items() if isinstance(v, dict)}
@@ -824,9 +831,11 @@ def main():
                 out_host.copy_(out_dev, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
 
+        sc128 = None
         if scatter is not None:
             # the product a rank brings back to its host is the m range it owns, all frequencies
-            own_host = torch.empty(scatter.own_bytes // 16, dtype=torch.complex128, pin_memory=True)
+            sc128 = scatter if link_elem == 16 else parallel.PeerScatter(comm, world * F, nb, np_inc, lside, mmax)
+            own_host = torch.empty(sc128.own_bytes // 16, dtype=torch.complex128, pin_memory=True)
             d2h = own_host.numel() * 16
             cudart = ctypes.CDLL("libcudart.so")
 
@@ -836,9 +845,9 @@ def main():
                         if ns == nside:
                             plan.upload_beam(slot, b, stream)
                     plan.transfer_units_scatter(units, 4, True, mmax, eng.precision, _lib.DSB_OUT_MMAJOR_C128, gdims,
-                                                scatter.block_ptrs, stream)
-                scatter.fence()
-                cudart.cudaMemcpyAsync(ctypes.c_void_p(own_host.data_ptr()), ctypes.c_void_p(scatter.own_ptr),
+                                                sc128.block_ptrs, stream)
+                sc128.fence()
+                cudart.cudaMemcpyAsync(ctypes.c_void_p(own_host.data_ptr()), ctypes.c_void_p(sc128.own_ptr),
                                        ctypes.c_size_t(d2h), 2, ctypes.c_void_p(stream))
                 torch.cuda.current_stream().synchronize()
 
@@ -846,6 +855,8 @@ def main():
         e2e = {"value": world * units_per_step / (ms_e2e * 1e-3), "unit": "units/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
                "mode": "c128_dma"}
+        if sc128 is not None and sc128 is not scatter:
+            sc128.close()
         if scatter is not None and args.precision == "fp32x3" and not args.no_e2e_c64:
             # The same second way for the fused-exchange path: the owners' m-blocks are complex64 (half
             # the NVLink and PCIe bytes), each rank widens its own m range on its share of the host cores.
@@ -856,7 +867,8 @@ def main():
             del own_host  # keep the host footprint per rank bounded
             ok, scatter64 = 1, None
             try:
-                scatter64 = parallel.PeerScatter(comm, world * F, nb, np_inc, lside, mmax, elem_bytes=8)
+                scatter64 = scatter if link_elem == 8 else parallel.PeerScatter(comm, world * F, nb, np_inc, lside, mmax,
+                                                                                  elem_bytes=8)
                 stage64 = torch.empty(n_own, dtype=torch.complex64, pin_memory=True)
                 final_own = np.zeros(n_own, dtype=np.complex128)
             except Exception as exc:  # noqa: BLE001 -- agreed on by all ranks below
@@ -903,7 +915,7 @@ def main():
                                 "d2h_bytes_per_step": int(d2h // 2), "mode": "c64_widen"})
                 e2e["modes"] = modes
                 del stage64, final_own
-            if scatter64 is not None:
+            if scatter64 is not None and scatter64 is not scatter:
                 scatter64.close()
         if scatter is None and world == 1 and args.precision == "fp32x3" and not args.no_e2e_c64:
             # Second way through the same call: the fp32x3 product is fp32 on the device and the pack
@@ -1004,9 +1016,11 @@ def main():
     niter = int(tel.sht_iter)
     refine = {"sht_iter": niter, "ms_per_step": refine_ms.value / max(args.steps, 1),
               "ms_per_iteration": refine_ms.value / max(args.steps, 1) / max(niter, 1),
-              "what": "Jacobi refinement of the analysis (healpy map2alm iter): per pass one coefficient transpose, one "
-                      "synthesis contraction (tcgen05), the aliasing fold and one analysis contraction with the update "
-                      "fused into its epilogue; not part of the three stage times"}
+              "what": "Jacobi refinement of the analysis (healpy map2alm iter), coefficients kept in the operand layout: "
+                      "per pass one contraction (tcgen05) with the extended synthesis table -- ring functions of the "
+                      "aliasing cap rings plus the precomputed analysis-after-synthesis product over every other ring "
+                      "--, the aliasing fold of the cap rings, their analysis (contraction length = cap rings) and one "
+                      "streaming update kernel; not part of the three stage times"}
     if stdout_fd is not None:
         sys.stdout.flush()
         os.dup2(stdout_fd, 1)

@@ -33,6 +33,8 @@
 // pair fused in registers); rings of <= 16 pixels are summed directly.  Rings entirely
 // below the horizon are skipped, as is Stokes V of a pair of identical real beams
 // (identically zero, _fast_tools.pyx:158-162).
+#include <cstdlib>
+
 #include "dsb_common.cuh"
 #include "fft16.cuh"
 
@@ -659,7 +661,12 @@ static int launch_class(const dsb_plan::RingClass &cls, RingFFTParams<T> &P, con
   const int pitch = KIND == KIND_DIRECT ? 16 : F::PITCH;
   P.ph_cap = (lay.mcap + 2) & ~1;
   P.ch_cap = KIND == KIND_BLUESTEIN ? ((cls.max_n + 1) & ~1) : 0;
+  // diagnostics: DSB_RING_NPP=1 transforms one Stokes map per pass, DSB_RING_SMEM_KB sets the
+  // shared-memory target that decides how many units a CTA works on together
+  static const int npp_env = getenv("DSB_RING_NPP") ? atoi(getenv("DSB_RING_NPP")) : 0;
+  static const int smem_env = getenv("DSB_RING_SMEM_KB") ? atoi(getenv("DSB_RING_SMEM_KB")) : 64;
   int npp = lay.npol_sky >= 2 ? 2 : 1;
+  if (npp_env == 1) npp = 1;
   int tw_cap = KIND == KIND_DIRECT ? 16 : ((F::twtotal() + 1) & ~1);
   const size_t budget = 200 * 1024;
   auto need = [&](int npp_, int twc, int G) {
@@ -671,7 +678,7 @@ static int launch_class(const dsb_plan::RingClass &cls, RingFFTParams<T> &P, con
             "ring transform of length %d does not fit shared memory", F::L);
   // units per group: fill ~64 KB with sequences, more only helps the short rings
   int G = 1;
-  while (G < kMaxGroup && need(npp, tw_cap, 2 * G) <= 64 * 1024) G *= 2;
+  while (G < kMaxGroup && need(npp, tw_cap, 2 * G) <= (size_t)smem_env * 1024) G *= 2;
   P.npp = npp;
   P.tw_cap = tw_cap;
   P.fr_cap = G * cls.max_live * cls.max_n;

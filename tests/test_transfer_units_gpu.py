@@ -200,3 +200,39 @@ def test_full_size_units_against_c_oracle(nside, lside, nunits, precision, tol, 
     for i, s in enumerate(spec):
         if s[1] == s[2]:
             assert not res[i, 3].any() and np.abs(ref[i, 3]).max() == 0.0
+
+
+_CAP_SCRIPT = r"""
+import sys
+import numpy as np
+sys.path.insert(0, {root!r})
+sys.path.insert(0, {tests!r})
+import test_transfer_units_gpu as t
+rng = np.random.default_rng(77)
+nside, lside = 64, 95
+beams = [rng.standard_normal((12 * nside * nside, 2)) for _ in range(2)]
+spec = [((3.1, -1.7), 0, 1, 95), ((-9.0, 4.2), 1, 1, 88), ((0.0, 12.5), 0, 0, 70), ((20.3, 0.4), 1, 0, 95)]
+res, _, _ = t._run_units(nside, lside, spec, beams, True, 4, 1, niter=2)
+np.save({out!r}, res)
+"""
+
+
+def test_alias_cap_against_every_aliasing_ring(tmp_path):
+    """Production-precision refinement: only the rings next to the pole whose aliasing is above 1e-14
+    are synthesised and folded (Tables::kc, tables.cu::alias_cap_rows); DSB_ALIAS_EPS=0 keeps every
+    ring that can alias at all (n <= 2 mmax).  Both must agree to fp32 rounding -- far below the 1e-6
+    of the method -- on units that reach the largest lmax of their nside (lmax = 1.5 nside - 1)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for tag, env in (("cap", {}), ("all", {"DSB_ALIAS_EPS": "0"})):
+        out = str(tmp_path / f"res_{tag}.npy")
+        script = _CAP_SCRIPT.format(root=root, tests=os.path.join(root, "tests"), out=out)
+        subprocess.run([sys.executable, "-c", script], check=True, env=dict(os.environ, **env), cwd=root)
+        outs.append(np.load(out))
+    err = _relerr(outs[0], outs[1])
+    print("cap rings vs every aliasing ring:", err)
+    assert err <= 2e-7
