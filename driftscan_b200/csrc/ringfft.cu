@@ -661,24 +661,26 @@ static int launch_class(const dsb_plan::RingClass &cls, RingFFTParams<T> &P, con
   const int pitch = KIND == KIND_DIRECT ? 16 : F::PITCH;
   P.ph_cap = (lay.mcap + 2) & ~1;
   P.ch_cap = KIND == KIND_BLUESTEIN ? ((cls.max_n + 1) & ~1) : 0;
-  // diagnostics: DSB_RING_NPP=1 transforms one Stokes map per pass, DSB_RING_SMEM_KB sets the
-  // shared-memory target that decides how many units a CTA works on together
+  // Shared memory per CTA decides both the occupancy and the work between two barriers (units x maps
+  // transformed together).  Measured on the bench step (profiles/README.md, r02 ring experiments): two
+  // CTAs per SM with as many units per group as fit beat three CTAs with fewer, and a class whose two-map
+  // pass does not leave room for two CTAs (Bluestein, L = 2048) is better off with one map per pass.
+  // diagnostics: DSB_RING_NPP=1 forces one Stokes map per pass, DSB_RING_SMEM_KB sets the target.
   static const int npp_env = getenv("DSB_RING_NPP") ? atoi(getenv("DSB_RING_NPP")) : 0;
-  static const int smem_env = getenv("DSB_RING_SMEM_KB") ? atoi(getenv("DSB_RING_SMEM_KB")) : 64;
+  static const int smem_env = getenv("DSB_RING_SMEM_KB") ? atoi(getenv("DSB_RING_SMEM_KB")) : 0;
+  const size_t target = smem_env > 0 ? (size_t)smem_env * 1024 : (size_t)113 * 1024;  // 2 CTAs of 227 KB
   int npp = lay.npol_sky >= 2 ? 2 : 1;
-  if (npp_env == 1) npp = 1;
   int tw_cap = KIND == KIND_DIRECT ? 16 : ((F::twtotal() + 1) & ~1);
   const size_t budget = 200 * 1024;
   auto need = [&](int npp_, int twc, int G) {
     return cs * ((size_t)twc + P.ch_cap + P.ph_cap + (size_t)G * cls.max_live * cls.max_n + (size_t)G * npp_ * cls.max_live * pitch);
   };
   if (sizeof(T) == 8 && KIND != KIND_DIRECT) tw_cap = 0;  // fp64: twiddles stay in global memory (L1/L2)
-  if (need(npp, tw_cap, 1) > budget) npp = 1;
+  if (npp_env == 1 || need(npp, tw_cap, 1) > (sizeof(T) == 4 ? target : budget)) npp = 1;
   DSB_CHECK(need(npp, tw_cap, 1) <= budget, DSB_ERR_UNSUPPORTED,
             "ring transform of length %d does not fit shared memory", F::L);
-  // units per group: fill ~64 KB with sequences, more only helps the short rings
   int G = 1;
-  while (G < kMaxGroup && need(npp, tw_cap, 2 * G) <= (size_t)smem_env * 1024) G *= 2;
+  while (G < kMaxGroup && need(npp, tw_cap, 2 * G) <= target) G *= 2;
   P.npp = npp;
   P.tw_cap = tw_cap;
   P.fr_cap = G * cls.max_live * cls.max_n;

@@ -235,4 +235,4 @@ def test_alias_cap_against_every_aliasing_ring(tmp_path):
         outs.append(np.load(out))
     err = _relerr(outs[0], outs[1])
     print("cap rings vs every aliasing ring:", err)
-    assert err <= 2e-7
+    assert err <= 4e-7  # both sides carry fp32x3 rounding (1-2e-7 each)
