@@ -93,7 +93,7 @@ pack_mmajor_kernel(const PackParams pp, const UnitDev *__restrict__ units, const
     const CT *c_even = C + ((size_t)(2 * m) * ncols + col) * pp.NP;      // l - m even
     const CT *c_odd = C + ((size_t)(2 * m + 1) * ncols + col) * pp.NP;   // l - m odd
     const int lcut = ud.lmax - m;  // rows above the unit's lmax are zero (telescope.py:792-802)
-    for (int dl = lane; dl < nl; dl += 32) {
+    auto fetch1 = [&](int dl) {
       OT val;
       val.x = 0;
       val.y = 0;
@@ -103,7 +103,24 @@ pack_mmajor_kernel(const PackParams pp, const UnitDev *__restrict__ units, const
         val.x = c[n];
         val.y = c[n + pp.NP];
       }
-      orow[dl] = val;
+      return val;
+    };
+    if constexpr (sizeof(OT) == 8) {
+      // complex64 (the links of a multi-GPU run): two elements per lane, 16-byte stores -- 512 bytes per
+      // warp instruction as in the complex128 case; a row that starts on an odd element leads with one
+      const int lead = (reinterpret_cast<uintptr_t>(orow) & 8) ? 1 : 0;
+      if (lead && lane == 0 && nl > 0) orow[0] = fetch1(0);
+      for (int dl = lead + 2 * lane; dl < nl; dl += 64) {
+        const OT a = fetch1(dl);
+        if (dl + 1 < nl) {
+          const OT b = fetch1(dl + 1);
+          *reinterpret_cast<float4 *>(orow + dl) = make_float4(a.x, a.y, b.x, b.y);
+        } else {
+          orow[dl] = a;
+        }
+      }
+    } else {
+      for (int dl = lane; dl < nl; dl += 32) orow[dl] = fetch1(dl);
     }
   }
 }
