@@ -613,7 +613,7 @@ def main():
         """The kernels of one step (every nside bucket), enqueued on stream ``st``."""
         if scatter is not None:
             fork_join(lambda b, s_: b[1].transfer_units_scatter(b[2], 4, True, mmax, eng.precision, link_kind, gdims,
-                                                                scatter.block_ptrs, s_), st)
+                                                                scatter.block_ptrs, s_, m_start=scatter.m_start), st)
         else:
             fork_join(lambda b, s_: b[1].transfer_units(b[2], 4, True, mmax, eng.precision, _lib.DSB_OUT_MMAJOR_C128,
                                                         dims, out_dev.data_ptr(), False, s_), st)
@@ -716,6 +716,37 @@ def main():
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = world * units_per_step / (ms_step * 1e-3)
+
+    # N > 1, after the timed region: where a step's time goes on every rank -- the kernels of the step
+    # (compute + pack / NVLink scatter) and the wait at the fence (the slowest rank sets the pace)
+    per_rank = None
+    if world > 1 and scatter is not None and not args.no_fence:
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+        barrier()
+        for a, b, c in evs:
+            a.record()
+            if graph["g"] is not None:
+                graph["g"].replay()
+            else:
+                step_compute(stream)
+            b.record()
+            scatter.fence()
+            c.record()
+        barrier()
+        comp = sum(a.elapsed_time(b) for a, b, _ in evs) / args.steps
+        wait = sum(b.elapsed_time(c) for _, b, c in evs) / args.steps
+        t = torch.tensor([comp, wait] + [prof_ms[i] / max(args.steps, 1) for i in range(3)]
+                         + [refine_ms.value / max(args.steps, 1)], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = {"kernels_ms": [round(float(x[0]), 3) for x in allt], "fence_wait_ms": [round(float(x[1]), 3) for x in allt],
+                    "stage_ms_profiled_pass": {n: [round(float(x[2 + i]), 2) for x in allt]
+                                               for i, n in enumerate(("ring_fft", "legendre", "pack_scatter", "refinement"))},
+                    "channels": [[int((r + j * world) % (tel.nfreq // 2)), int(tel.nfreq - 1 - (r + j * world) % (tel.nfreq // 2))]
+                                 for r in range(world) for j in range((F + 1) // 2)],
+                    "what": "per rank, mean over the steps of a separate pass: device time of the step's kernels (pack and "
+                            "NVLink scatter included) and of the fence behind them (all-reduce of one element: "
+                            "the wait for the slowest rank)"}
 
     stage_ms_pack = prof_ms[2] / max(args.steps, 1)
     # ---- the frequency-major -> m-major exchange alone (N > 1): bytes each rank sends over NVLink
@@ -845,7 +876,7 @@ def main():
                         if ns == nside:
                             plan.upload_beam(slot, b, stream)
                     plan.transfer_units_scatter(units, 4, True, mmax, eng.precision, _lib.DSB_OUT_MMAJOR_C128, gdims,
-                                                sc128.block_ptrs, stream)
+                                                sc128.block_ptrs, stream, m_start=sc128.m_start)
                 sc128.fence()
                 cudart.cudaMemcpyAsync(ctypes.c_void_p(own_host.data_ptr()), ctypes.c_void_p(sc128.own_ptr),
                                        ctypes.c_size_t(d2h), 2, ctypes.c_void_p(stream))
@@ -885,7 +916,7 @@ def main():
                             if ns == nside:
                                 plan.upload_beam(slot, b, stream)
                         plan.transfer_units_scatter(units, 4, True, mmax, eng.precision, _lib.DSB_OUT_MMAJOR_C64,
-                                                    gdims, scatter64.block_ptrs, stream)
+                                                    gdims, scatter64.block_ptrs, stream, m_start=scatter64.m_start)
                     scatter64.fence()
                     pending = []
                     for a, b in zip(edges[:-1], edges[1:]):
@@ -1035,7 +1066,7 @@ def main():
             "launch_mode": ("CUDA graph of one step (%d kernels), replayed; stage times from a separate profiled "
                             "pass of direct launches" % graph["launches"]) if graph["g"] is not None
             else "direct launches", "cpu_baseline": cpu, "exchange": exchange, "svd": svd,
-            "refine": refine, "generate": gen, "multi_gpu_check": check,
+            "refine": refine, "generate": gen, "multi_gpu_check": check, "per_rank": per_rank,
         }
         print(json.dumps(line))
     if world > 1:

@@ -75,6 +75,7 @@ def _load():
         "dsb_plan_build_tables": (i32, [vp, i32, i32, i32, i32, vp]),
         "dsb_transfer_units": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, P(i64), vp, i32, vp]),
         "dsb_transfer_units_scatter": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, P(i64), vp, vp]),
+        "dsb_plan_set_scatter_start": (i32, [vp, i32]),
         "dsb_peer_alloc": (i32, [ctypes.c_size_t, P(vp), vp]),
         "dsb_peer_open": (i32, [vp, P(vp)]),
         "dsb_peer_close": (i32, [vp]),
@@ -234,9 +235,13 @@ class Plan:
         check(lib.dsb_plan_build_tables(self._h, lmax, mmax, int(spin2), precision, ctypes.c_void_p(stream or 0)))
 
     def transfer_units_scatter(self, units, npol_sky, polarised, mmax, precision, out_kind, dims, block_ptrs,
-                               stream=None):
+                               stream=None, m_start=None):
         """m-major output with block m written at device address ``block_ptrs[m]`` (uint64 array,
-        possibly peer memory): the pack kernel does the frequency -> m regrouping itself."""
+        possibly peer memory): the pack kernel does the frequency -> m regrouping itself.
+        ``m_start``: first block the pack kernel visits (``PeerScatter.m_start``: every rank begins at
+        another owner, so the senders never converge on one receiver)."""
+        if m_start is not None:
+            check(lib.dsb_plan_set_scatter_start(self._h, int(m_start)))
         units = np.ascontiguousarray(units, dtype=UNIT_DTYPE)
         d = (ctypes.c_int64 * len(dims))(*[int(x) for x in dims])
         bp = np.ascontiguousarray(block_ptrs, dtype=np.uint64)

@@ -327,6 +327,7 @@ class BeamTransfer(config.Reader):
                     bgrid.ravel().astype(np.int32), nslots if scatter else nfc, nb_inc, tel.lmax, tel.mmax,
                     0 if scatter else buf.data_ptr(), False, out_kind=out_kind, stream=stream,
                     block_ptrs=scatter.block_ptrs if scatter else None,
+                    m_start=scatter.m_start if scatter else None,
                 )
             # (source rank, first file row, rows, device address of block mi for that source)
             if scatter is not None:

@@ -639,6 +639,7 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
     pp.npol_out = npol_out;
     pp.mmax_out = mmax_out;
     pp.abs_ptrs = block_ptrs_host ? 1 : 0;
+    pp.m_rot = block_ptrs_host ? plan->scatter_start % (mmax_out + 1) : 0;
     void *pack_out = (tarray && out_is_host) ? (void *)stage : out_dev;
     if ((rc = launch_pack(pp, ud_dev, o0_dev, o1_dev, moff_dev, C0, C2, f64 ? 1 : 0, pack_out, stream)) !=
         DSB_OK)
@@ -682,6 +683,13 @@ extern "C" int dsb_transfer_units_scatter(dsb_plan *plan, const dsb_unit *units_
   DSB_CHECK(block_ptrs_host != nullptr, DSB_ERR_INVALID, "dsb_transfer_units_scatter: block_ptrs is NULL");
   return transfer_units_impl(plan, units_host, nunits, npol_sky, polarised, mmax, precision, out_kind, dims,
                              nullptr, 0, block_ptrs_host, stream_);
+}
+
+extern "C" int dsb_plan_set_scatter_start(dsb_plan *plan, int m_start) {
+  DSB_CHECK(plan != nullptr, DSB_ERR_INVALID, "dsb_plan_set_scatter_start: plan is NULL");
+  DSB_CHECK(m_start >= 0, DSB_ERR_INVALID, "dsb_plan_set_scatter_start: m_start %d is negative", m_start);
+  plan->scatter_start = m_start;
+  return DSB_OK;
 }
 
 // ---- peer (NVLink) buffers --------------------------------------------------------------

@@ -197,6 +197,7 @@ struct dsb_plan {
   // SHT settings of healpy.map2alm as cora.util.hputil calls it (telescope.py:1189,1300,1310):
   // Jacobi refinement passes and optional ring weights (multiplicative, one per fold ring)
   int sht_iter = 0;
+  int scatter_start = 0;  // first m-block of a scatter call's pack kernel (dsb_plan_set_scatter_start)
   std::vector<double> ring_weights;
   float *fold_scale = nullptr;  // [nfold] 2 x nphi (nphi on the equator): scale of the fused fold
   // workspace (grown on demand, capped by dsb_set_workspace_limit)
@@ -341,6 +342,7 @@ struct PackParams {
   int npol_out;
   int mmax_out;       // m-major: number of m blocks - 1
   int abs_ptrs;       // m-major: moff[m] is the device address of block m (scatter to peers)
+  int m_rot;          // m-major: CTA row y works on block (y + m_rot) mod (mmax_out + 1)
 };
 int launch_pack(const PackParams &pp, const UnitDev *units_dev, const int32_t *out0_dev,
                 const int32_t *out1_dev, const int64_t *moff_dev, const void *C0, const void *C2,

@@ -68,7 +68,10 @@ __global__ void __launch_bounds__(256)
 pack_mmajor_kernel(const PackParams pp, const UnitDev *__restrict__ units, const int32_t *__restrict__ out0,
                    const int32_t *__restrict__ out1, const int64_t *__restrict__ moff, const CT *__restrict__ C0,
                    const CT *__restrict__ C2, OT *__restrict__ out) {
-  const int m = blockIdx.y;
+  // blocks are visited cyclically from m_rot on (scatter mode: every rank of a multi-GPU run starts at
+  // another owner, see dsb_plan_set_scatter_start)
+  int m = blockIdx.y + pp.m_rot;
+  if (m > pp.mmax_out) m -= pp.mmax_out + 1;
   const int nl = pp.lside + 1 - m;
   if (nl <= 0) return;
   // block m lives at out + moff[m], or (scatter mode) at the absolute device address moff[m],

@@ -173,7 +173,7 @@ class TransferEngine:
 
     # ---- m-major output (BeamTransfer._generate_mfiles) ---------------------------
     def transfer_mmajor(self, bl, fi, lmax, fslot, bslot, nf, nb, lside, mmax, out_ptr, out_is_host,
-                        out_kind=_lib.DSB_OUT_MMAJOR_C128, stream=None, block_ptrs=None):
+                        out_kind=_lib.DSB_OUT_MMAJOR_C128, stream=None, block_ptrs=None, m_start=None):
         """Write the compact m-major beam_m blocks of the given units into ``out_ptr``
         (layout documented at DSB_OUT_MMAJOR_* in include/driftscan_b200.h), or -- ``block_ptrs``
         given -- block m at the device address ``block_ptrs[m]`` (possibly a peer GPU's memory:
@@ -185,7 +185,7 @@ class TransferEngine:
             dims = [nf, nb, npol, lside, mmax]
             if block_ptrs is not None:
                 plan.transfer_units_scatter(units, npol, tel._polarised_, mmax, self.precision, out_kind, dims,
-                                            block_ptrs, stream)
+                                            block_ptrs, stream, m_start=m_start)
             else:
                 plan.transfer_units(units, npol, tel._polarised_, mmax, self.precision, out_kind, dims, out_ptr,
                                     out_is_host, stream)

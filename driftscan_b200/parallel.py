@@ -188,6 +188,9 @@ class PeerScatter:
         else:
             _, m_lo, m_hi = split_counts(mmax + 1, comm.size)
         self.m_lo, self.m_hi = m_lo, m_hi
+        # first block of this rank's pack kernel: the range of the next rank, so that the ranks -- which
+        # step through the owners in lock step -- never store into the same receiver at the same time
+        self.m_start = int(m_lo[(comm.rank + 1) % comm.size]) if comm.size > 1 else 0
         own = int(per_m[m_lo[comm.rank] : m_hi[comm.rank]].sum()) * elem_bytes
         self.own_bytes = own
         ptr = ctypes.c_void_p()

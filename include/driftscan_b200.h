@@ -158,6 +158,15 @@ int dsb_transfer_units_scatter(dsb_plan *plan, const dsb_unit *units_host, int n
                                int polarised, int mmax, int precision, int out_kind, const int64_t *dims,
                                const uint64_t *block_ptrs_host, void *stream);
 
+/* First m-block the pack kernel of a scatter call visits (the mmax+1 blocks are visited cyclically
+ * from there; default 0).  The ranks of a multi-GPU run step through the owners in lock step: started
+ * at the same block they all store into the same receiver at the same time (7 senders on one NVLink
+ * ingress at N = 8: measured 9.4 ms for the pack kernel of the worst rank against 3.9 ms alone);
+ * rank r starting at the range of rank r+1 keeps the eight senders on eight different receivers
+ * -- the schedule of an all-to-all, which is what mpiutil.transpose_blocks
+ * (drift/core/beamtransfer.py:632) is. */
+int dsb_plan_set_scatter_start(dsb_plan *plan, int m_start);
+
 /* Peer buffers for the scatter above: the owner allocates (zero-filled) device memory and gets
  * a 64-byte CUDA IPC handle to publish; the other ranks of the node map it. */
 int dsb_peer_alloc(size_t bytes, void **dev_ptr, unsigned char *handle64);
