@@ -394,7 +394,9 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
               if (s == 2) nr = std::max(nr, nrows_mp(Lt[ct], m, 1 - p));
               nr = std::min(t.NP, std::max(32, (int)round_up(nr, 32)));
             }
-            for (int r0 = 0; r0 < nr; r0 += 128) items.push_back({2 * m + p, ct, std::min(128, nr - r0), s, r0});
+            // rings k < kmin[m] hold nothing for this m (production precision, Tables::kmin)
+            const int kbeg = f64 ? 0 : t.kmin[m];
+            for (int r0 = 0; r0 < nr; r0 += 128) items.push_back({2 * m + p, ct, std::min(128, nr - r0), s, r0, 0, kbeg});
           }
     }
 
@@ -428,7 +430,7 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
       }
       if (tflow) {
         citems = items;
-        for (auto &w : citems) w.klen = t.kc;
+        for (auto &w : citems) w.klen = t.kc, w.kbeg = 0;
       }
     }
 

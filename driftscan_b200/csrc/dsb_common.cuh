@@ -146,6 +146,9 @@ struct Tables {
   int synth = 0;
   int NPk = 0;
   int kc = 0, SR = 0;
+  // kmin[m] (host, production precision): fold rings k < kmin[m] hold nothing above 1e-15 of the
+  // largest table entry of that m (sin^m(theta) next to the pole): the analysis starts there
+  std::vector<int> kmin;
   double *s0_f64 = nullptr, *s2_f64 = nullptr;
   __nv_bfloat16 *s0_bf = nullptr, *s2_bf = nullptr;  // [3][nprob][SR][NPk or 2 NPk]
   size_t splane0 = 0, splane2 = 0;
@@ -282,6 +285,7 @@ struct WorkItem {
   int32_t spin;     // 0 or 2
   int32_t row0;     // first row (multiple of 16)
   int32_t klen;     // contraction length per operand role (multiple of 32); 0 = the launch's K
+  int32_t kbeg;     // first contraction index per role (multiple of 32): [kbeg, klen) is contracted
 };
 // One contraction launch:  C[prob][col][row] (+)= sum_k A[prob][k][col] * B[prob][row][k]
 //   analysis : A = ring spectra F (k = fold ring),  B = T tables, rows = l-index n, pitch NP

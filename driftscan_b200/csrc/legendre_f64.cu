@@ -43,7 +43,7 @@ contract_f64_kernel(const WorkItem *__restrict__ items, int nitems, const double
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
   for (int seg = 0; seg < nseg; ++seg)
-    for (int k0 = seg * d.kx; k0 < seg * d.kx + klen; k0 += F64_TK) {
+    for (int k0 = seg * d.kx + it.kbeg; k0 < seg * d.kx + klen; k0 += F64_TK) {
       for (int idx = threadIdx.x; idx < F64_TK * F64_TC; idx += 256) {
         const int kk = idx / F64_TC, c = idx % F64_TC;
         Fs[kk][c] = F[(size_t)(k0 + kk) * ncols + c];

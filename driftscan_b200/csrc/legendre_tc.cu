@@ -250,7 +250,7 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         const bool s2 = wi.spin == 2;
         const CUtensorMap *mA = s2 ? &mapA2 : &mapA0;
         const CUtensorMap *mB = s2 ? &mapB2 : &mapB0;
-        const int nkA = (wi.klen ? wi.klen : P.K0) / TC_KC;  // stages per role
+        const int nkA = ((wi.klen ? wi.klen : P.K0) - wi.kbeg) / TC_KC;  // stages per role
         const int nk = s2 ? 2 * nkA : nkA;                   // spin 2: W role then X role
         const uint32_t tx = TC_A_RAW + 3 * b_plane;
         for (int kc = 0; kc < nk; ++kc) {
@@ -262,13 +262,13 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
           mbar_expect_tx(&full[stage], load_b ? tx : (uint32_t)TC_A_RAW);
           // X role reads the spectra of the opposite fold parity
           const bool xrole = kc >= nkA;
-          tma_load_3d(mA, &full[stage], sR, wi.coltile * TC_M, (xrole ? kc - nkA : kc) * TC_KC,
+          tma_load_3d(mA, &full[stage], sR, wi.coltile * TC_M, wi.kbeg + (xrole ? kc - nkA : kc) * TC_KC,
                       xrole ? (wi.prob ^ 1) : wi.prob);
           if (load_b) {
 #pragma unroll
             for (int pl = 0; pl < 3; ++pl)
-              tma_load_4d(mB, &full[stage], sB + pl * b_plane, xrole ? P.kx + (kc - nkA) * TC_KC : kc * TC_KC, wi.row0,
-                          wi.prob, pl);
+              tma_load_4d(mB, &full[stage], sB + pl * b_plane,
+                          wi.kbeg + (xrole ? P.kx + (kc - nkA) * TC_KC : kc * TC_KC), wi.row0, wi.prob, pl);
           }
           if (++stage == P.nstages) {
             stage = 0;
@@ -288,7 +288,7 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       for (int it = blockIdx.x; it < P.nitems; it += gridDim.x, ++local) {
         const WorkItem wi = P.items[it];
         const bool s2 = wi.spin == 2;
-        const int nk = (s2 ? 2 : 1) * ((wi.klen ? wi.klen : P.K0) / TC_KC);
+        const int nk = (s2 ? 2 : 1) * (((wi.klen ? wi.klen : P.K0) - wi.kbeg) / TC_KC);
         const int cb = local & 1;
         const uint32_t cb_phase = (local >> 1) & 1;
         const uint32_t N = (uint32_t)((wi.nrows + 15) & ~15);
@@ -352,7 +352,7 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
     for (int it = blockIdx.x; it < P.nitems; it += gridDim.x, ++local) {
       const WorkItem wi = P.items[it];
       const bool s2 = wi.spin == 2;
-      const int nk = (s2 ? 2 : 1) * ((wi.klen ? wi.klen : P.K0) / TC_KC);
+      const int nk = (s2 ? 2 : 1) * (((wi.klen ? wi.klen : P.K0) - wi.kbeg) / TC_KC);
       const int cb = local & 1;
       const uint32_t cb_phase = (local >> 1) & 1;
       const int N = (wi.nrows + 15) & ~15;
@@ -459,7 +459,7 @@ legendre_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_const
     for (int it = blockIdx.x; it < P.nitems; it += gridDim.x) {
       const WorkItem wi = P.items[it];
       const bool s2 = wi.spin == 2;
-      const int nkA = (wi.klen ? wi.klen : P.K0) / TC_KC;
+      const int nkA = ((wi.klen ? wi.klen : P.K0) - wi.kbeg) / TC_KC;
       const int nk = s2 ? 2 * nkA : nkA;
       for (int kc = 0; kc < nk; ++kc) {
         const bool xrole = kc >= nkA;
@@ -668,7 +668,7 @@ extern "C" int dsb_debug_gemm_tc(int nprob, int K, int NP, int ncols, int nitems
   std::vector<WorkItem> items_h(nitems);
   for (int i = 0; i < nitems; ++i)
     items_h[i] = {items_host[5 * i], items_host[5 * i + 1], items_host[5 * i + 2], items_host[5 * i + 3],
-                  items_host[5 * i + 4], 0};
+                  items_host[5 * i + 4], 0, 0};
   DSB_CUDA(cudaMalloc(&F, nF * 4));
   DSB_CUDA(cudaMalloc(&T, nT * 2));
   DSB_CUDA(cudaMalloc(&C, nC * 4));

@@ -1726,13 +1726,29 @@ static int svd_chain_impl(const void *bf_dev, const double *noisew_dev, int batc
   }
   const size_t o_bf = (size_t)ntel * npol * nl, o_svd = (size_t)svd_len * npol * nl, o_ut = (size_t)svd_len * ntel,
                o_inv = (size_t)npol * nl * svd_len;
+  // Runs of equal l0 (one m each).  A run of at least kMinTrim matrices is trimmed and processed on its
+  // own; shorter runs (few frequencies per m) would leave the GPU idle one by one: neighbouring short
+  // runs are pooled and processed together with every column kept, where a block's result does not
+  // depend on its neighbours either.  Whether a run is trimmed depends on its own length only -- all
+  // frequencies of an m always arrive together -- so single- and multi-rank runs decide alike.
+  const int kMinTrim = 16;
   for (int b0 = 0; b0 < batch;) {
     int b1 = b0 + 1;
     while (b1 < batch && l0[b1] == l0[b0]) ++b1;
+    int lz = l0[b0];
+    if (b1 - b0 < kMinTrim) {
+      lz = 0;
+      while (b1 < batch) {  // extend over the following short runs
+        int b2 = b1 + 1;
+        while (b2 < batch && l0[b2] == l0[b1]) ++b2;
+        if (b2 - b1 >= kMinTrim) break;
+        b1 = b2;
+      }
+    }
     DSB_TRY(svd_chain_group((const zc *)bf_dev + b0 * o_bf, noisew_dev + (size_t)b0 * ntel, b1 - b0, ntel, npol, nl,
                             svd_len, rtol1, polsvcut, (zc *)beam_svd_dev + b0 * o_svd, (zc *)beam_ut_dev + b0 * o_ut,
                             invbeam_dev ? (void *)((zc *)invbeam_dev + b0 * o_inv) : nullptr, sv_dev + (size_t)b0 * svd_len,
-                            nmodes_dev ? nmodes_dev + b0 : nullptr, chain, l0[b0], stream));
+                            nmodes_dev ? nmodes_dev + b0 : nullptr, chain, lz, stream));
     b0 = b1;
   }
   return DSB_OK;

@@ -305,13 +305,44 @@ static int alias_cap_rows(const dsb_plan *plan, const Tables &t, const std::vect
 
 int build_tables(dsb_plan *plan, Tables &t, cudaStream_t stream) {
   const int nprob = 2 * (t.mmax + 1);
+  const int nfold = plan->nfold;
   t.Kp = plan->Kp;
   t.NP = (int)round_up(nrows_mp(t.lmax, 0, 0), 32);  // also the k-tile of the synthesis direction
   t.NPk = t.NP;
   t.plane0 = (size_t)nprob * t.NP * t.Kp;
   t.plane2 = (size_t)nprob * t.NP * 2 * t.Kp;
-  DSB_TRY((build_one<false, false>(plan, t, t.precision, t.plane0, &t.t0_f64, &t.t0_bf, stream)));
-  if (t.spin2) DSB_TRY((build_one<true, false>(plan, t, t.precision, t.plane2, &t.t2_f64, &t.t2_bf, stream)));
+  // amp[m][k] = max_l |lambda_lm(theta_k)| (spin 0; spin 2: W and X), a by-product of the build
+  const size_t namp = (size_t)(t.mmax + 1) * nfold;
+  double *amp_dev = nullptr;
+  DSB_CUDA(cudaMalloc(&amp_dev, 2 * namp * sizeof(double)));
+  std::vector<double> amp(2 * namp);
+  int rc = [&]() -> int {
+    DSB_CUDA(cudaMemsetAsync(amp_dev, 0, 2 * namp * sizeof(double), stream));
+    DSB_TRY((build_one<false, false>(plan, t, t.precision, t.plane0, &t.t0_f64, &t.t0_bf, stream, amp_dev)));
+    if (t.spin2)
+      DSB_TRY((build_one<true, false>(plan, t, t.precision, t.plane2, &t.t2_f64, &t.t2_bf, stream, amp_dev + namp)));
+    DSB_CUDA(cudaMemcpyAsync(amp.data(), amp_dev, 2 * namp * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    DSB_CUDA(cudaStreamSynchronize(stream));
+    return DSB_OK;
+  }();
+  cudaFree(amp_dev);
+  amp_dev = nullptr;
+  DSB_TRY(rc);
+  for (size_t i = 0; i < namp; ++i) amp[i] = std::max(amp[i], amp[namp + i]);
+  // first ring that matters for an m: next to the pole lambda_lm ~ sin^m(theta) vanishes; the ring
+  // spectra F_k are sums over the n_k pixels of a ring, so quad_k n_k amp bounds a ring's share
+  t.kmin.assign(t.mmax + 1, 0);
+  if (t.precision != DSB_PREC_FP64) {
+    static const bool no_kmin = getenv("DSB_NO_KMIN") != nullptr;  // diagnostic: contract every ring
+    for (int m = 0; m <= t.mmax && !no_kmin; ++m) {
+      double big = 0.0;
+      for (int k = 0; k < nfold; ++k)
+        big = std::max(big, amp[(size_t)m * nfold + k] * plan->rings_h[k].quad * plan->rings_h[k].nphi);
+      int k = 0;
+      while (k < nfold && amp[(size_t)m * nfold + k] * plan->rings_h[k].quad * plan->rings_h[k].nphi < 1e-15 * big) ++k;
+      t.kmin[m] = std::min(k / 32 * 32, std::max(0, t.Kp - 32));
+    }
+  }
   if (!t.synth) return DSB_OK;
   if (t.precision == DSB_PREC_FP64) {
     t.kc = plan->nfold;
@@ -323,26 +354,16 @@ int build_tables(dsb_plan *plan, Tables &t, cudaStream_t stream) {
     return DSB_OK;
   }
   // production precision: cap rings as ring functions + the precomputed product over all other rings
-  const int nfold = plan->nfold;
-  double *f0 = nullptr, *f2 = nullptr, *amp_dev = nullptr, *coef_dev = nullptr;
+  double *f0 = nullptr, *f2 = nullptr, *coef_dev = nullptr;
   auto cleanup = [&]() {
     cudaFree(f0);
     cudaFree(f2);
-    cudaFree(amp_dev);
     cudaFree(coef_dev);
   };
-  const size_t namp = (size_t)(t.mmax + 1) * nfold;
-  int rc = DSB_OK;
   auto body = [&]() -> int {
-    DSB_CUDA(cudaMalloc(&amp_dev, 2 * namp * sizeof(double)));
-    DSB_CUDA(cudaMemsetAsync(amp_dev, 0, 2 * namp * sizeof(double), stream));
     __nv_bfloat16 *none = nullptr;
-    DSB_TRY((build_one<false, false>(plan, t, DSB_PREC_FP64, t.plane0, &f0, &none, stream, amp_dev)));
-    if (t.spin2) DSB_TRY((build_one<true, false>(plan, t, DSB_PREC_FP64, t.plane2, &f2, &none, stream, amp_dev + namp)));
-    std::vector<double> amp(2 * namp);
-    DSB_CUDA(cudaMemcpyAsync(amp.data(), amp_dev, 2 * namp * sizeof(double), cudaMemcpyDeviceToHost, stream));
-    DSB_CUDA(cudaStreamSynchronize(stream));
-    for (size_t i = 0; i < namp; ++i) amp[i] = std::max(amp[i], amp[namp + i]);
+    DSB_TRY((build_one<false, false>(plan, t, DSB_PREC_FP64, t.plane0, &f0, &none, stream)));
+    if (t.spin2) DSB_TRY((build_one<true, false>(plan, t, DSB_PREC_FP64, t.plane2, &f2, &none, stream)));
     static const char *eps_env = getenv("DSB_ALIAS_EPS");  // diagnostic: 0 keeps every ring that can alias
     const double eps = eps_env ? atof(eps_env) : 1e-14;
     t.kc = alias_cap_rows(plan, t, amp, eps);
