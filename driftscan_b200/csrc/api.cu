@@ -539,7 +539,9 @@ static int transfer_units_impl(dsb_plan *plan, const dsb_unit *units_host, int n
     hc.lap(4);
     StageTimer timer(stream);
     timer.mark(0);
-    if ((rc = launch_ringfft(plan, lay, ud_dev, precision, wptr_dev, F0, F2, stream)) != DSB_OK) break;
+    if ((rc = launch_ringfft(plan, lay, ud_dev, precision, wptr_dev, F0, F2, stream, f64 ? nullptr : t.kmin_dev)) !=
+        DSB_OK)
+      break;
     timer.mark(1);
     hc.lap(5);
     // analysis: A = ring spectra, B = T tables (the tables may cover more m than this bucket)

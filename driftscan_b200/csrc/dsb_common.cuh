@@ -149,6 +149,7 @@ struct Tables {
   // kmin[m] (host, production precision): fold rings k < kmin[m] hold nothing above 1e-15 of the
   // largest table entry of that m (sin^m(theta) next to the pole): the analysis starts there
   std::vector<int> kmin;
+  int *kmin_dev = nullptr;  // the same on the device, [mmax + 1] (the ring kernel does not emit what is never read)
   double *s0_f64 = nullptr, *s2_f64 = nullptr;
   __nv_bfloat16 *s0_bf = nullptr, *s2_bf = nullptr;  // [3][nprob][SR][NPk or 2 NPk]
   size_t splane0 = 0, splane2 = 0;
@@ -269,8 +270,10 @@ struct UnitDev {
 // or [nprob][Kp][ncols2] float (fp32: stored once, roles derived by the tensor-core kernel).
 // units_dev[u].beam_i = index into wplanes_dev (pair weights), .beam_j = 1 if Stokes V of the pair is
 // identically zero.  wplanes_dev[pair] -> [nplane][npix] in the working precision.
+// kmin_dev (may be NULL): [mcap + 1], spectra of fold rings k < kmin[m] are not emitted (Tables::kmin)
 int launch_ringfft(dsb_plan *plan, const BucketLayout &lay, const UnitDev *units_dev, int precision,
-                   const void *const *wplanes_dev, void *F0, void *F2, cudaStream_t stream);
+                   const void *const *wplanes_dev, void *F0, void *F2, cudaStream_t stream,
+                   const int *kmin_dev = nullptr);
 int launch_pair_weights(dsb_plan *plan, int precision, int slot_i, int slot_j, int polarised, void *w,
                         cudaStream_t stream);
 int launch_bluestein_prepare16(dsb_plan *plan);

@@ -55,6 +55,7 @@ struct RingFFTParams {
   const cplx<T> *chirp;
   const cplx<T> *dhat;
   const UnitDev *units;
+  const int *kmin;  // [mcap + 1] first fold ring the analysis reads for an m (NULL: all)
   int nunits;
   const T *const *wplanes;  // per pair: [nplane][npix]
   int npix;
@@ -377,6 +378,7 @@ __device__ __forceinline__ void gather_emit(const RingCtx<T> &c) {
       gi = task - m * c.Gn;
     }
     if (m > c.us[gi].mmax) continue;
+    if (P.kmin && c.k < P.kmin[m]) continue;  // never read: the table holds nothing there for this m
     const int u = c.ug + gi;
     int kp = m;
     if (KIND == KIND_POW2)
@@ -700,8 +702,10 @@ static int launch_class(const dsb_plan::RingClass &cls, RingFFTParams<T> &P, con
 
 template <typename T>
 static int launch_t(dsb_plan *plan, const BucketLayout &lay, const UnitDev *units_dev, void *F0, void *F2,
-                    size_t plane0, size_t plane2, const T *const *wplanes_dev, cudaStream_t stream) {
+                    size_t plane0, size_t plane2, const T *const *wplanes_dev, cudaStream_t stream,
+                    const int *kmin_dev) {
   RingFFTParams<T> P;
+  P.kmin = kmin_dev;
   P.rings = plan->rings;
   P.trig = plan->trig;
   const bool f32 = sizeof(T) == 4;
@@ -774,13 +778,15 @@ static int launch_t(dsb_plan *plan, const BucketLayout &lay, const UnitDev *unit
 }
 
 int launch_ringfft(dsb_plan *plan, const BucketLayout &lay, const UnitDev *units_dev, int precision,
-                   const void *const *wplanes_dev, void *F0, void *F2, cudaStream_t stream) {
+                   const void *const *wplanes_dev, void *F0, void *F2, cudaStream_t stream, const int *kmin_dev) {
   const size_t nprob = 2 * ((size_t)lay.mcap + 1);
   const size_t plane0 = nprob * lay.Kp * lay.ncols0;  // fp64 layout only
   const size_t plane2 = nprob * 2 * lay.Kp * lay.ncols2;
   if (precision == DSB_PREC_FP64)
-    return launch_t<double>(plan, lay, units_dev, F0, F2, plane0, plane2, (const double *const *)wplanes_dev, stream);
-  return launch_t<float>(plan, lay, units_dev, F0, F2, plane0, plane2, (const float *const *)wplanes_dev, stream);
+    return launch_t<double>(plan, lay, units_dev, F0, F2, plane0, plane2, (const double *const *)wplanes_dev, stream,
+                            nullptr);
+  return launch_t<float>(plan, lay, units_dev, F0, F2, plane0, plane2, (const float *const *)wplanes_dev, stream,
+                         kmin_dev);
 }
 
 }  // namespace dsb

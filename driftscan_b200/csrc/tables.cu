@@ -253,6 +253,7 @@ void free_tables(Tables &t) {
   cudaFree(t.s2_f64);
   cudaFree(t.s0_bf);
   cudaFree(t.s2_bf);
+  cudaFree(t.kmin_dev);
   t = Tables();
 }
 
@@ -343,6 +344,9 @@ int build_tables(dsb_plan *plan, Tables &t, cudaStream_t stream) {
       t.kmin[m] = std::min(k / 32 * 32, std::max(0, t.Kp - 32));
     }
   }
+  DSB_CUDA(cudaMalloc(&t.kmin_dev, sizeof(int) * (t.mmax + 1)));
+  DSB_CUDA(cudaMemcpyAsync(t.kmin_dev, t.kmin.data(), sizeof(int) * (t.mmax + 1), cudaMemcpyHostToDevice, stream));
+  DSB_CUDA(cudaStreamSynchronize(stream));
   if (!t.synth) return DSB_OK;
   if (t.precision == DSB_PREC_FP64) {
     t.kc = plan->nfold;
