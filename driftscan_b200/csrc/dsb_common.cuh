@@ -203,7 +203,6 @@ struct dsb_plan {
   int sht_iter = 0;
   int scatter_start = 0;  // first m-block of a scatter call's pack kernel (dsb_plan_set_scatter_start)
   std::vector<double> ring_weights;
-  float *fold_scale = nullptr;  // [nfold] 2 x nphi (nphi on the equator): scale of the fused fold
   // workspace (grown on demand, capped by dsb_set_workspace_limit)
   void *ws = nullptr;
   size_t ws_bytes = 0;

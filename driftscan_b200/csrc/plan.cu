@@ -255,13 +255,6 @@ extern "C" int dsb_plan_create(int nside, const uint8_t *horizon_host, dsb_plan 
 
   DSB_CUDA(cudaMalloc(&plan->rings, sizeof(RingDesc) * nfold));
   DSB_CUDA(cudaMemcpy(plan->rings, plan->rings_h.data(), sizeof(RingDesc) * nfold, cudaMemcpyHostToDevice));
-  {
-    std::vector<float> fs(nfold);
-    for (int k = 0; k < nfold; ++k)
-      fs[k] = (float)((plan->rings_h[k].startS < 0 ? 1 : 2) * plan->rings_h[k].nphi);
-    DSB_CUDA(cudaMalloc(&plan->fold_scale, sizeof(float) * nfold));
-    DSB_CUDA(cudaMemcpy(plan->fold_scale, fs.data(), sizeof(float) * nfold, cudaMemcpyHostToDevice));
-  }
   DSB_CUDA(cudaMalloc(&plan->horizon, plan->npix));
   DSB_CUDA(cudaMemcpy(plan->horizon, horizon_host, plan->npix, cudaMemcpyHostToDevice));
   DSB_CUDA(cudaMalloc(&plan->trig, sizeof(double2) * ntrig));
@@ -344,7 +337,6 @@ extern "C" int dsb_plan_destroy(dsb_plan *plan) {
   }
   for (char *p : plan->graph_stage) cudaFreeHost(p);
   cudaFree(plan->rings);
-  cudaFree(plan->fold_scale);
   cudaFree(plan->horizon);
   cudaFree(plan->trig);
   cudaFree(plan->tw16_64);
