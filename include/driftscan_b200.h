@@ -65,7 +65,11 @@ int dsb_plan_destroy(dsb_plan *plan);
  * (drift/core/telescope.py:1189-1191, 1300-1302, 1310-1314; cora is external, its module
  * values are recalled as _weight = True, _iter = 2 and could not be verified offline).
  *   sht_iter     : Jacobi refinement passes a <- a + A(M - S a) of the analysis, 0 = plain
- *                  quadrature.  Each pass costs one synthesis and one analysis contraction.
+ *                  quadrature.  fp64: every ring is synthesised, folded (aliasing m' = m mod n
+ *                  on a ring of n pixels) and analysed again.  fp32x3: only the rings next to
+ *                  the pole whose aliasing reaches 1e-14 go that way (32 fold rings); on all
+ *                  others analysis after synthesis is a precomputed per-m table (DESIGN.md
+ *                  section 3, K5b) -- a pass costs about a quarter of the first analysis.
  *   ring_weights : NULL (use_weights=False: every ring weighs 4 pi / npix) or 2*nside
  *                  multiplicative weights, one per ring from the north pole to the equator
  *                  (the southern rings mirror them) -- the values 1 + w of healpy's
@@ -229,7 +233,10 @@ int dsb_debug_gemm_tc(int nprob, int K, int NP, int ncols, int nitems, const int
  * outputs (device, zero-filled beyond nmodes):
  *   beam_svd  c128 [batch][svd_len][npol][nl];  beam_ut c128 [batch][svd_len][ntel]
  *   invbeam   c128 [batch][npol][nl][svd_len] (may be NULL);  sv f64 [batch][svd_len]
- *   nmodes    int32 [batch] */
+ *   nmodes    int32 [batch]
+ * A call may stack the blocks of several m (the columns l < m of a block are identically zero
+ * and are dropped from the arithmetic): the result of a block does not depend on what else the
+ * call holds, so a multi-rank run writes the files of a single process bit for bit. */
 int dsb_svd_chain(const void *bf_dev, const double *noisew_dev, int batch, int ntel, int npol,
                   int nl, int svd_len, double rtol1, double polsvcut, void *beam_svd_dev,
                   void *beam_ut_dev, void *invbeam_dev, double *sv_dev, int32_t *nmodes_dev,
