@@ -107,6 +107,68 @@ class TransferEngine:
                 return None
         return fn(feed, freq)
 
+    # ---- SHT of real sky maps ---------------------------------------------------
+    def sphtrans_sky(self, skymap, lmax):
+        """``cora.util.hputil.sphtrans_sky``: a_lm (m >= 0) of real sky maps ``[nfreq, npix]`` or
+        ``[nfreq, npol, npix]`` (T, Q, U[, V]) -> ``[nfreq, (npol,) lmax + 1, lmax + 1]`` complex128, with
+        the plan's ``healpy.map2alm`` settings (``sht_iter``, ring weights) -- what
+        ``drift.pipeline.timestream.simulate`` (timestream.py:711-713) feeds the beam transfers with.
+
+        No kernel of its own: a sky map is a transfer unit with no fringe (zero baseline), no horizon
+        and unit prefactor.  With the partner "beam" (1, 0) the Stokes weights of
+        ``_construct_pol_real`` (_fast_tools.pyx:141-162) are w_I = b_theta, w_Q = b_theta, w_U = b_phi,
+        w_V = -b_phi (times i in the map), so the "beam" (T, -V) carries T and V through the spin-0 transform and the "beam"
+        (Q, U) carries Q, U through the spin-2 one; ``_transfer_single`` returns conj(a_lm) of the
+        conjugated map (telescope.py:1189-1191, 1300-1314), which for a real map is conj(a_lm)."""
+        skymap = np.asarray(skymap, dtype=np.float64)
+        pol = skymap.ndim == 3
+        nfreq, npix = skymap.shape[0], skymap.shape[-1]
+        nside = int(round(np.sqrt(npix / 12.0)))
+        if 12 * nside * nside != npix:
+            raise ValueError(f"{npix} is not a HEALPix map size")
+        npol = skymap.shape[1] if pol else 1
+        if pol and npol not in (3, 4):
+            raise ValueError("polarised sky maps hold (T, Q, U) or (T, Q, U, V)")
+        plan = _lib.Plan(nside, np.ones(npix, dtype=bool))
+        out = np.zeros((nfreq, npol, lmax + 1, lmax + 1), dtype=np.complex128)
+        try:
+            plan.set_sht(self.sht_iter, self._ring_weights(nside))
+            one = np.zeros((npix, 2))
+            one[:, 0] = 1.0
+            plan.upload_beam(2, one)
+            nun = 2 if pol else 1
+            units = np.zeros(nun, dtype=_lib.UNIT_DTYPE)
+            units["prefactor"] = 1.0
+            units["beam_j"] = 2
+            units["lmax"] = lmax
+            units["beam_i"] = np.arange(nun)
+            units["out0"] = np.arange(nun)
+            res = np.zeros((nun, 4, lmax + 1, 2 * lmax + 1), dtype=np.complex128)
+            for fi in range(nfreq):
+                a = np.zeros((npix, 2))
+                if pol:
+                    a[:, 0] = skymap[fi, 0]
+                    if npol == 4:
+                        a[:, 1] = -skymap[fi, 3]
+                    plan.upload_beam(0, a)
+                    plan.upload_beam(1, np.ascontiguousarray(skymap[fi, 1:3].T))
+                else:
+                    a[:, 0] = skymap[fi]
+                    plan.upload_beam(0, a)
+                plan.transfer_units(units, 4, True, lmax, self.precision, _lib.DSB_OUT_TARRAY_C128, [nun, 4, lmax],
+                                    res.ctypes.data, True)
+                out[fi, 0] = res[0, 0, :, : lmax + 1].conj()
+                if pol:
+                    out[fi, 1] = res[1, 1, :, : lmax + 1].conj()
+                    out[fi, 2] = res[1, 2, :, : lmax + 1].conj()
+                    if npol == 4:
+                        # Stokes V enters the unit as i (b_theta b'_phi - b_phi b'_theta) (_fast_tools.pyx:158-162):
+                        # the unit returns conj(-i a_lm) = i conj(a_lm)
+                        out[fi, 3] = 1.0j * res[0, 3, :, : lmax + 1].conj()
+        finally:
+            plan.close()
+        return out if pol else out[:, 0]
+
     # ---- unit tables -----------------------------------------------------------
     def _npol_compute(self):
         tel = self.tel

@@ -57,6 +57,14 @@ class Comm:
             pass
         return cls()
 
+    # A pickled object that holds a Comm (BeamTransfer inside a saved Timestream, as the reference
+    # pickles its manager) keeps no process-group handle: the view is taken again where it is loaded.
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self.__dict__.update(Comm.current().__dict__)
+
     @property
     def rank0(self):
         return self.rank == 0
