@@ -305,3 +305,37 @@ def test_undecodable_attribute_is_skipped(tmp_path):
     assert int(f.attrs["m"]) == 5 and "FLAGS" not in f.attrs
     assert np.array_equal(f["evals"][...], np.arange(4.0))
     f.close()
+
+
+def test_h5py_reads_what_h5lite_writes(tmp_path):
+    """Optional interoperability check (runs wherever h5py / libhdf5 exists; neither is installable in
+    the build or GPU images): contiguous and chunked + LZF datasets, complex
+    compound type, scalar / string / array attributes as the product files use them."""
+    h5py = pytest.importorskip("h5py")
+    from driftscan_b200.util import h5lite
+
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((5, 2, 7, 4, 9)) + 1j * rng.standard_normal((5, 2, 7, 4, 9))
+    sv = rng.standard_normal((5, 9))
+    name = str(tmp_path / "interop.hdf5")
+    with h5lite.File(name, "w") as f:
+        f.create_dataset("beam_m", data=a, chunks=(1, 1, 7, 4, 9), compression="lzf")
+        f.create_dataset("singularvalues", data=sv)
+        f.attrs["m"] = 14
+        f.attrs["frequencies"] = np.linspace(400.0, 450.0, 5)
+        f.attrs["FLAGS"] = "NotPositiveDefinite"
+    with h5py.File(name, "r") as f:
+        assert np.array_equal(f["beam_m"][:], a)
+        assert np.array_equal(f["singularvalues"][:], sv)
+        assert int(f.attrs["m"]) == 14
+        assert np.array_equal(f.attrs["frequencies"], np.linspace(400.0, 450.0, 5))
+        flags = f.attrs["FLAGS"]
+        assert (flags.decode() if isinstance(flags, bytes) else flags) == "NotPositiveDefinite"
+    # and the other way round
+    name2 = str(tmp_path / "interop2.hdf5")
+    with h5py.File(name2, "w") as f:
+        f.create_dataset("beam_m", data=a, chunks=(1, 1, 7, 4, 9), compression="lzf")
+        f.attrs["m"] = 3
+    with h5lite.File(name2, "r") as f:
+        assert np.array_equal(np.array(f["beam_m"][:]), a)
+        assert int(f.attrs["m"]) == 3
