@@ -426,6 +426,8 @@ def main():
     ap.add_argument("--no-svd", action="store_true", help="skip the per-m SVD measurement (second half of the metric)")
     ap.add_argument("--no-generate", action="store_true", help="skip the BeamTransfer.generate() wall-clock leg")
     ap.add_argument("--generate-freqs", type=int, default=2, help="channels per GPU in the generate() leg")
+    ap.add_argument("--generate-at-scale", action="store_true",
+                    help="run the generate() leg at N > 2 as well (it writes ~5 GB of products per channel and GPU)")
     ap.add_argument("--generate-lzf", action="store_true", help="also time generate() with the reference's chunked + LZF storage")
     ap.add_argument("--generate-dir", default=None, help="directory for the generate() leg's products (default: the system tmp)")
     ap.add_argument("--no-check", action="store_true", help="N > 1: skip the bit-exact check of the multi-GPU product path")
@@ -1036,8 +1038,11 @@ def main():
     # bit for bit against a single process on a small telescope (so a scaling run carries a
     # correctness result next to its timings)
     gen = check = None
-    if not args.no_generate:
+    if not args.no_generate and (world <= 2 or args.generate_at_scale):
         gen = generate_section(args, rank, world, comm)
+    elif not args.no_generate:
+        gen = {"skipped": f"N = {world}: the leg writes ~5 GB of m-files and ~5 GB of SVD files per channel "
+                          "(2 channels per GPU) to the temporary directory; run with --generate-at-scale"}
     if world > 1 and not args.no_check:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import check_generate_multi
