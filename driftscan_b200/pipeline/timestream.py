@@ -88,23 +88,23 @@ class Timestream(object):
                 print("******* m-files already generated ********")
             return
         tel = self.telescope
-        mmax, nfreq = tel.mmax, tel.nfreq
-        sfreq, efreq = comm.split_range(nfreq)
-        sm, em = comm.split_range(mmax + 1)
+        mmax = tel.mmax
+        f_lo, f_hi = comm.split_range(tel.nfreq)
+        m_lo, m_hi = comm.split_range(mmax + 1)
         ntime = self.ntime
-        row_mpairs = np.zeros((efreq - sfreq, 2, tel.npairs, mmax + 1), dtype=np.complex128)
-        for lfi, fi in enumerate(range(sfreq, efreq)):
-            row_mmodes = np.fft.fft(self.timestream_f(fi), axis=-1) / ntime
-            row_mpairs[lfi, 0, :, 0] = row_mmodes[:, 0]
-            for mi in range(1, mmax + 1):
-                row_mpairs[lfi, 0, :, mi] = row_mmodes[:, mi]
-                row_mpairs[lfi, 1, :, mi] = row_mmodes[:, -mi].conj()
+        # [local freq, +-, pair, m]: the + slot holds m = 0 .. mmax of the transform, the - slot the
+        # conjugates of m = -1 .. -mmax (its m = 0 entry stays empty)
+        packed = np.zeros((f_hi - f_lo, 2, tel.npairs, mmax + 1), dtype=np.complex128)
+        for k, fi in enumerate(range(f_lo, f_hi)):
+            spec = np.fft.fft(self.timestream_f(fi), axis=-1) / ntime
+            packed[k, 0] = spec[:, : mmax + 1]
+            packed[k, 1, :, 1:] = spec[:, : -(mmax + 1) : -1].conj()
         # every frequency of the m range this rank writes (mpiutil.transpose_blocks, timestream.py:165-167)
-        col_mmodes = _regroup(comm, row_mpairs, 0, 3, sm, em)  # [nfreq, 2, npairs, lm]
-        for lmi, mi in enumerate(range(sm, em)):
+        mine = _regroup(comm, packed, 0, 3, m_lo, m_hi)  # [nfreq, 2, npairs, local m]
+        for k, mi in enumerate(range(m_lo, m_hi)):
             os.makedirs(self._mdir(mi), exist_ok=True)
             with h5lite.File(self._mfile(mi), "w") as f:
-                f.create_dataset("mmode", data=np.ascontiguousarray(col_mmodes[..., lmi]))
+                f.create_dataset("mmode", data=np.ascontiguousarray(mine[..., k]))
                 f.attrs["m"] = mi
         comm.barrier()
         if comm.rank0:
@@ -174,82 +174,87 @@ def _regroup(comm, local, split_axis, take_axis, lo, hi):
     return np.concatenate([pieces[comm.rank] for pieces in everyone], axis=split_axis)
 
 
+def _sky_visibilities(comm, bt, maps, f_lo, f_hi, m_lo, m_hi, ntime):
+    """Sum of the sky maps -> a_lm on the device -> visibilities of every m through the beam transfers
+    -> ``[npairs, local freq, ntime]`` in FFT order of m (timestream.py:698-766)."""
+    tel = bt.telescope
+    lmax, mmax, nfreq, npol = tel.lmax, tel.mmax, tel.nfreq, tel.num_pol_sky
+    nloc = f_hi - f_lo
+    if nloc > 0:
+        sky = None
+        for name in maps:
+            with h5lite.File(name, "r") as f:
+                part = np.array(f["map"][f_lo:f_hi], dtype=np.float64)
+            sky = part if sky is None else sky + part
+        alm = tel.engine.sphtrans_sky(sky, lmax).reshape(nloc, npol * (lmax + 1), lmax + 1)
+    else:
+        alm = np.zeros((0, npol * (lmax + 1), lmax + 1), dtype=np.complex128)
+    # all frequencies of the local m; m beyond mmax is not observed (the reference trims in its transpose, :719-724)
+    alm_m = _regroup(comm, alm[..., : mmax + 1], 0, 2, m_lo, m_hi)
+    alm_m = np.moveaxis(alm_m, 2, 0).reshape(m_hi - m_lo, nfreq, npol, lmax + 1)
+    vis_m = np.stack([bt.project_vector_sky_to_telescope(mi, alm_m[k]) for k, mi in enumerate(range(m_lo, m_hi))]) \
+        if m_hi > m_lo else np.zeros((0, nfreq, bt.ntel), dtype=np.complex128)
+    # back to "my frequencies, every m": [m, +-, pair, local freq]
+    per_m = _regroup(comm, vis_m.transpose(0, 2, 1), 0, 2, f_lo, f_hi).reshape(mmax + 1, 2, tel.npairs, nloc)
+    out = np.zeros((tel.npairs, nloc, ntime), dtype=np.complex128)
+    out[..., : mmax + 1] = np.moveaxis(per_m[:, 0], 0, -1)
+    # negative m: the conjugate of the - slot only, no (-1)^m (timestream.py:763-765)
+    out[..., : -(mmax + 1) : -1] = np.moveaxis(per_m[1:, 1], 0, -1).conj()
+    return out
+
+
+def _noise_visibilities(comm, tel, shape, freqs, ndays, seed):
+    """Complex Gaussian noise per m with the telescope's noise power (timestream.py:769-796); the random
+    stream is the reference's: legacy ``np.random`` seeded with ``seed + rank``, one draw of
+    ``shape + (2,)`` normals."""
+    power = tel.noisepower(np.arange(tel.npairs)[:, None], np.asarray(freqs, dtype=int)[None, :], ndays=ndays)
+    power = power.reshape(tel.npairs, len(freqs))[:, :, None]
+    if seed is not None:
+        np.random.seed(seed + comm.rank)
+    draw = np.random.standard_normal(shape + (2,))
+    if seed is not None:
+        np.random.seed()
+    return (draw[..., 0] + 1.0j * draw[..., 1]) * np.sqrt(power / 2.0)
+
+
 def simulate(m, outdir, maps=[], ndays=None, resolution=0, seed=None, **kwargs):
     """Create a simulated timestream and save it to disk (timestream.py:645-829).
 
     ``m``: ProductManager (``m.beamtransfer``); ``maps``: HDF5 files with a ``map`` dataset
     ``[nfreq, npol, npix]`` whose sum is the sky; ``ndays``: None = the telescope's, 0 = noise free;
-    ``resolution``: seconds per sample, 0 = ``2 mmax + 1`` samples; ``seed``: noise seed (+ rank)."""
+    ``resolution``: seconds per sample, 0 = ``2 mmax + 1`` samples; ``seed``: noise seed (+ rank).
+    Returns the :class:`Timestream` (one ``timestream_f/<f>/timestream.hdf5`` per frequency)."""
     comm = parallel.Comm.current()
     bt = m.beamtransfer
     tel = bt.telescope
-    lmax, mmax, nfreq, npol = tel.lmax, tel.mmax, tel.nfreq, tel.num_pol_sky
-    projmaps = len(maps) > 0
-    sfreq, efreq = comm.split_range(nfreq)
-    lfreq = efreq - sfreq
-    local_freq = list(range(sfreq, efreq))
-    sm, em = comm.split_range(mmax + 1)
-    lm = em - sm
+    f_lo, f_hi = comm.split_range(tel.nfreq)
+    m_lo, m_hi = comm.split_range(tel.mmax + 1)
+    freqs = list(range(f_lo, f_hi))
     if ndays is None:
         ndays = tel.ndays
-    ntime = 2 * mmax + 1 if resolution == 0 else int(np.round(24 * 3600.0 / resolution))
+    ntime = 2 * tel.mmax + 1 if resolution == 0 else int(np.round(24 * 3600.0 / resolution))
 
-    col_vis = np.zeros((tel.npairs, lfreq, ntime), dtype=np.complex128)
-
-    if projmaps:
-        with h5lite.File(maps[0], "r") as f:
-            mapshape = f["map"].shape
-        if lfreq > 0:
-            row_map = np.zeros((lfreq,) + tuple(mapshape[1:]), dtype=np.float64)
-            for mapfile in maps:
-                with h5lite.File(mapfile, "r") as f:
-                    row_map += np.array(f["map"][sfreq:efreq])
-            row_alm = tel.engine.sphtrans_sky(row_map, lmax).reshape((lfreq, npol * (lmax + 1), lmax + 1))
-        else:
-            row_alm = np.zeros((lfreq, npol * (lmax + 1), lmax + 1), dtype=np.complex128)
-        # all frequencies of the local m (transpose_blocks trims m to mmax + 1 on the way, :722-724)
-        col_alm = _regroup(comm, row_alm[..., : mmax + 1], 0, 2, sm, em)  # [nfreq, npol (lmax+1), lm]
-        col_alm = np.transpose(col_alm, (2, 0, 1)).reshape(lm, nfreq, npol, lmax + 1)
-        vis_data = np.zeros((lm, nfreq, bt.ntel), dtype=np.complex128)
-        for mp, mi in enumerate(range(sm, em)):
-            vis_data[mp] = bt.project_vector_sky_to_telescope(mi, col_alm[mp])
-        row_vis = vis_data.transpose((0, 2, 1))  # [lm, ntel, nfreq]
-        col_vis_tmp = _regroup(comm, row_vis, 0, 2, sfreq, efreq).reshape(mmax + 1, 2, tel.npairs, lfreq)
-        col_vis[..., 0] = col_vis_tmp[0, 0]
-        for mi in range(1, mmax + 1):
-            col_vis[..., mi] = col_vis_tmp[mi, 0]
-            col_vis[..., -mi] = col_vis_tmp[mi, 1].conj()  # conjugate only, not (-1)^m (:763-765)
-        del col_vis_tmp
-
+    if len(maps) > 0:
+        vis_m = _sky_visibilities(comm, bt, maps, f_lo, f_hi, m_lo, m_hi, ntime)
+    else:
+        vis_m = np.zeros((tel.npairs, len(freqs), ntime), dtype=np.complex128)
     if ndays > 0:
-        noise_ps = tel.noisepower(np.arange(tel.npairs)[:, np.newaxis], np.array(local_freq)[np.newaxis, :],
-                                  ndays=ndays).reshape(tel.npairs, lfreq)[:, :, np.newaxis]
-        if seed is not None:
-            np.random.seed(seed + comm.rank)  # the rank: no correlated noise between frequency shards (:781-783)
-        noise_vis = (np.array([1.0, 1.0j]) * np.random.standard_normal(col_vis.shape + (2,))).sum(axis=-1)
-        noise_vis *= (noise_ps / 2.0) ** 0.5
-        if seed is not None:
-            np.random.seed()
-        col_vis += noise_vis
-        del noise_vis
+        vis_m += _noise_visibilities(comm, tel, vis_m.shape, freqs, ndays, seed)
 
-    vis_stream = np.fft.ifft(col_vis, axis=-1) * ntime
-    vis_stream = vis_stream.reshape(tel.npairs, lfreq, ntime)
-    tphi = np.linspace(0, 2 * np.pi, ntime, endpoint=False)
+    # m -> sidereal angle
+    stream = np.fft.ifft(vis_m, axis=-1) * ntime
+    phi = np.linspace(0, 2 * np.pi, ntime, endpoint=False)
 
-    tstream = Timestream(outdir, m)
-    for lfi, fi in enumerate(local_freq):
-        os.makedirs(tstream._fdir(fi), exist_ok=True)
-        with h5lite.File(tstream._ffile(fi), "w") as f:
-            f.create_dataset("timestream", data=np.ascontiguousarray(vis_stream[:, lfi]))
-            f.create_dataset("phi", data=tphi)
-            f.create_dataset("feedmap", data=tel.feedmap)
-            f.create_dataset("feedconj", data=tel.feedconj)
-            f.create_dataset("feedmask", data=tel.feedmask)
-            f.create_dataset("uniquepairs", data=tel.uniquepairs)
-            f.create_dataset("baselines", data=tel.baselines)
+    ts = Timestream(outdir, m)
+    for k, fi in enumerate(freqs):
+        os.makedirs(ts._fdir(fi), exist_ok=True)
+        with h5lite.File(ts._ffile(fi), "w") as f:
+            f.create_dataset("timestream", data=np.ascontiguousarray(stream[:, k]))
+            f.create_dataset("phi", data=phi)
+            for name in ("feedmap", "feedconj", "feedmask", "uniquepairs", "baselines"):  # telescope layout
+                f.create_dataset(name, data=getattr(tel, name))
             f.attrs["beamtransfer_path"] = os.path.abspath(bt.directory)
             f.attrs["ntime"] = ntime
-    tstream.save()
+    ts.save()
     comm.barrier()
-    return tstream
+    return ts
