@@ -312,6 +312,8 @@ def test_h5py_reads_what_h5lite_writes(tmp_path):
     the build or GPU images): contiguous and chunked + LZF datasets, complex
     compound type, scalar / string / array attributes as the product files use them."""
     h5py = pytest.importorskip("h5py")
+    if not hasattr(h5py, "version") or getattr(h5py, "__file__", None) is None:
+        pytest.skip("h5py here is the in-memory stand-in of tests/golden/make_golden.py, not the library")
     from driftscan_b200.util import h5lite
 
     rng = np.random.default_rng(3)
