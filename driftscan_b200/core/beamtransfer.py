@@ -25,7 +25,7 @@ import time
 import numpy as np
 
 from .. import config
-from ..util import h5lite, util
+from ..util import h5lite, truncate, util
 
 logger = logging.getLogger(__name__)
 
@@ -220,13 +220,15 @@ class BeamTransfer(config.Reader):
         tel, comm = self.telescope, self.comm
         from . import telescope as _telescope
 
-        if self.truncate:
-            # beamtransfer.py:549-555, 641-646 of the reference: caput's bit_truncate_max_complex and the
-            # bitshuffle + LZ4 filter, neither of which exists here
+        if self.truncate and comm.rank0:
+            # beamtransfer.py:549-555, 641-646 of the reference: caput's bit_truncate_max_complex, then the
+            # bitshuffle + LZ4 filter.  The truncation is applied (util/truncate.py restates caput's documented
+            # contract; caput is external: bit-pattern parity unpinned); the filter stays LZF.
             import warnings
 
-            warnings.warn("BeamTransfer: `truncate: true` is not implemented by driftscan_b200; the beam "
-                          "transfers are written at full precision with the LZF filter")
+            warnings.warn("BeamTransfer: `truncate: true` truncates the beam transfers to truncate_rel / "
+                          "truncate_maxl as documented for caput.truncate (bit patterns may differ from caput's) "
+                          "and writes them with the LZF filter, not bitshuffle + LZ4")
 
         if type(tel)._transfer_single is not _telescope.TransitTelescope._transfer_single:
             # fail loudly rather than ignore the user's unit: the m-files are produced by the device
@@ -300,6 +302,13 @@ class BeamTransfer(config.Reader):
             """``nfr`` frequencies of block ``mi`` at host address ``src_ptr`` -> f['beam_m'][rows]."""
             ds = f["beam_m"]
             n = nfr * per_m[mi]
+            if self.truncate:
+                # the reference truncates rows over l of the [m, f, +-, b, pol, l] array (beamtransfer.py:636-646)
+                data = np.frombuffer((ctypes.c_ubyte * (n * elem)).from_address(src_ptr), dtype=ndtype)
+                data = data.astype(np.complex128).reshape(-1, nl - mi)
+                truncate.bit_truncate_max_complex(data, self.truncate_rel, self.truncate_maxl)
+                ds[rows] = data.reshape((nfr, 2, nb_inc, np_inc, nl - mi))
+                return
             if isinstance(ds, h5lite.Dataset) and not isinstance(ds, h5lite._CompactDataset) and c64:
                 mm = ds._map()  # contiguous dataset: widen directly into the file mapping
                 _lib.widen_c64(src_ptr, mm.ctypes.data + rows.start * per_m[mi] * 16, n)
